@@ -1,0 +1,150 @@
+/* include/rkmh_gpu.h -- C ABI of the B200-native rkmh MinHash read-classification hot path.
+ *
+ * The reference (edawson/rkmh @ ea3d2e6) has no plugin/FFI interface: its hot path is the set of mkmh
+ * library calls made from the per-read loops of main_stream / main_filter / main_hash.  This header is
+ * the boundary a maintainer would bind instead of those loops (see INTEGRATION.md for the exact patch
+ * to src/rkmh.cpp).  Each entry point names the reference code it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions
+ *   - plain C: opaque context, plain pointers and sizes, int status (0 = ok, <0 = error; the text is in
+ *     rkg_last_error()).  No C++ or torch types cross this line.
+ *   - a context owns ONE GPU (one process per GPU; a multi-GPU host opens one context per device) and
+ *     all device memory; calls on one context must be serialised by the caller.
+ *   - sequences travel as a concatenated byte buffer `bases` plus `n + 1` int64 offsets; record i is
+ *     bases[offs[i] .. offs[i+1]).  Bytes are taken exactly as parsed from FASTA/FASTQ: upper-casing
+ *     (mkmh::to_upper, mkmh/mkmh.hpp:231-236) happens on the device.  Names never cross the boundary.
+ *   - host buffers may be pageable; buffers obtained from rkg_host_alloc() are pinned and make the
+ *     host<->device copies asynchronous.
+ *   - there is NO CPU fallback: every entry point fails with RKG_ERR_CUDA when no sm_100 device is usable.
+ *   - k-mer sizes 1..32 are supported (the reference accepts any int; its data sets use 10..21).
+ */
+#ifndef RKMH_GPU_H
+#define RKMH_GPU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RKG_OK            0
+#define RKG_ERR_ARG      -1   /* bad argument / unsupported parameter        */
+#define RKG_ERR_CUDA     -2   /* CUDA runtime error or no usable device      */
+#define RKG_ERR_STATE    -3   /* call order (e.g. classify before load_refs) */
+#define RKG_ERR_NOMEM    -4
+
+#define RKG_MAX_K        32
+#define RKG_MAX_NK       8
+
+typedef struct rkg_ctx rkg_ctx;
+typedef struct rkg_batch rkg_batch;   /* a read batch resident in device memory */
+
+/* Result of classifying one read: the argmax block of src/rkmh.cpp:874-883 (stream) and
+ * src/equiv.hpp:328-345 (filter), in a form both can be derived from:
+ *   stream : max_shared = best, max_id = ref_id, diff = best - prev
+ *   filter : max_shared = max(best,0), prev_best = max(prev,0), sample = (best > 0 ? ref_id : none) */
+typedef struct {
+    int32_t ref_id;      /* first reference index attaining the maximum shared count (0 if all are 0) */
+    int32_t best;        /* maximum over references of hash_intersection_size (mkmh/mkmh.hpp:822-840)  */
+    int32_t prev;        /* max of the counts at indices < ref_id; -1 when ref_id == 0                 */
+    int32_t sketch_len;  /* length of the read's sketch = min(s, #non-zero hashes) (mkmh.hpp:931-950) */
+} rkg_hit;
+
+/* ---- context ------------------------------------------------------------------------------------- */
+/* Replaces omp_set_num_threads() + the implicit process state (src/rkmh.cpp:734). */
+int  rkg_create(int device, rkg_ctx** ctx);
+void rkg_destroy(rkg_ctx* ctx);
+/* Error text of the last failing call on ctx (ctx == NULL: of the last failing rkg_create). */
+const char* rkg_last_error(const rkg_ctx* ctx);
+
+/* k-mer sizes in command-line order (-k repeatable, src/rkmh.cpp:675-677; hashes of each k are
+ * concatenated, mkmh/mkmh.hpp:689-711), sketch size -s, and the sizes of the lossy count tables
+ * (HASHTCounter, mkmh/HASHTCounter.cpp:12-15): 200000000 for stream (src/rkmh.cpp:739,742),
+ * 10000000 for filter (src/rkmh.cpp:1187-1188).  A size of 0 disables that table. */
+int rkg_set_params(rkg_ctx* ctx, const int* ks, int nk, int sketch_size,
+                   uint64_t read_table_size, uint64_t ref_table_size);
+
+/* Pinned host memory for batch buffers (replaces the per-record `new char[]` of parse_fastas,
+ * src/rkmh.cpp:238-263). */
+int rkg_host_alloc(rkg_ctx* ctx, size_t bytes, void** ptr);
+int rkg_host_free(rkg_ctx* ctx, void* ptr);
+
+/* ---- references ---------------------------------------------------------------------------------- */
+/* Hash + sketch every reference and build the HBM-resident (hash,rank) -> reference-bitset table.
+ * Replaces src/rkmh.cpp:815-838 (stream) and 1192-1246 (filter).
+ *   max_ref_occ <  0 : plain bottom-s sketches (no -I)
+ *   max_ref_occ >= 0 : the -I path: count reference hashes in the ref table first, then keep only
+ *                      hashes whose count is <= max_ref_occ (minhashes_frequency_filter,
+ *                      mkmh/mkmh.hpp:954-976).  per_sample_set = 0 counts every valid window
+ *                      occurrence (stream, mkmh.hpp:729-737); 1 counts each distinct hash once per
+ *                      reference, zero included (filter, src/rkmh.cpp:347-355). */
+int rkg_load_refs(rkg_ctx* ctx, const char* bases, const int64_t* offs, int nrefs,
+                  int max_ref_occ, int per_sample_set);
+/* Parity/debug: copy the reference sketches out (sketches is [nrefs * s], lens is [nrefs]). */
+int rkg_get_ref_sketches(rkg_ctx* ctx, uint64_t* sketches, int32_t* lens);
+
+/* ---- -M : read-set k-mer count table ------------------------------------------------------------- */
+/* Pass 1 of src/rkmh.cpp:904-910: hash every read and ++counts[hash % read_table_size] for every valid
+ * window (count_zeros = 0, mkmh/mkmh.hpp:729-737) or for every hash including the zeros of invalid
+ * windows (count_zeros = 1, filter: src/rkmh.cpp:331-336). */
+int rkg_count_reset(rkg_ctx* ctx);
+int rkg_count_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, int count_zeros);
+/* Device pointer and length (in int32 slots) of the read count table, so that a multi-GPU caller can
+ * all-reduce it (ncclAllReduce / torch.distributed.all_reduce, sum, int32) between pass 1 and pass 2:
+ * the `#pragma omp for` barrier at src/rkmh.cpp:910 is the only global point of the path. */
+int rkg_count_table(rkg_ctx* ctx, void** device_ptr, uint64_t* nslots);
+/* Parity/debug: counts[keys[i] % read_table_size] for n keys. */
+int rkg_count_lookup(rkg_ctx* ctx, const uint64_t* keys, int64_t n, int32_t* out);
+
+/* ---- classification ------------------------------------------------------------------------------ */
+/* hash -> (mask_by_frequency with min_occ when min_occ >= 0, mkmh/mkmh.hpp:898-908) -> bottom-s sketch
+ * -> intersection with every reference -> argmax.  Replaces the bodies of the per-read loops at
+ * src/rkmh.cpp:845-898, 911-948 and 1251-1298.  Host buffers in, host results out. */
+int rkg_classify_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads,
+                       int min_occ, rkg_hit* out);
+
+/* The same in two steps for callers that keep batches resident in HBM (and for kernel-only timing):
+ * upload once, classify any number of times, fetch results. */
+int rkg_batch_upload(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, rkg_batch** batch);
+int rkg_batch_classify(rkg_ctx* ctx, rkg_batch* batch, int min_occ);        /* asynchronous */
+int rkg_batch_count(rkg_ctx* ctx, rkg_batch* batch, int count_zeros);       /* asynchronous */
+int rkg_batch_results(rkg_ctx* ctx, rkg_batch* batch, rkg_hit* out);        /* synchronises  */
+int rkg_batch_free(rkg_ctx* ctx, rkg_batch* batch);
+int rkg_synchronize(rkg_ctx* ctx);
+
+/* ---- hash command -------------------------------------------------------------------------------- */
+/* Bottom-s sketches of nseq records (sorted ascending, duplicates kept, zeros dropped): calc_hashes +
+ * minhashes (mkmh/mkmh.hpp:689-711, 931-950), the intended behaviour of `rkmh hash` (src/rkmh.cpp:
+ * 2093-2105, README.md:114-117).  sketches is [nseq * s], lens is [nseq]. */
+int rkg_sketch_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nseq,
+                     int min_occ, uint64_t* sketches, int32_t* lens);
+/* Raw calc_hashes output (mkmh/mkmh.hpp:505-532, 689-711) of every record, concatenated; hash_offs
+ * receives nseq + 1 offsets into `hashes` (capacity: sum over records and k of max(len - k, 0)). */
+int rkg_hash_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nseq,
+                   uint64_t* hashes, int64_t* hash_offs);
+/* One large record whose k-mer start range [kmer_begin, kmer_end) of the whole record is handled by this
+ * context (sequence sharding for `hash` on a multi-GPU box; one k-mer size): `bases` holds record bytes
+ * [kmer_begin, min(kmer_end, record_len - k) + k), record_len is the length of the WHOLE record (so
+ * that the reference's len-k window count applies only at the true end).  Emits this shard's bottom-s
+ * multiset; the caller all-gathers the shards and calls rkg_merge_sketches. */
+int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t kmer_begin, int64_t kmer_end,
+                     int64_t record_len, uint64_t* sketch, int32_t* len);
+/* Multiset merge of `nparts` sorted sketches (parts is [nparts * s]) keeping the first s. */
+int rkg_merge_sketches(rkg_ctx* ctx, const uint64_t* parts, const int32_t* part_lens, int nparts,
+                       uint64_t* sketch, int32_t* len);
+
+/* ---- measurement --------------------------------------------------------------------------------- */
+/* Number of kernels this context has launched so far. */
+int64_t rkg_launch_count(const rkg_ctx* ctx);
+/* Per-kernel device time: when enabled every launch is bracketed by CUDA events on its stream. */
+int rkg_profile_enable(rkg_ctx* ctx, int on);
+/* Fills up to cap entries: kernel name, launches and total milliseconds since the last reset; returns
+ * the number of distinct kernels (synchronises the context). */
+typedef struct { const char* name; int64_t launches; double ms; } rkg_kernel_time;
+int rkg_profile_read(rkg_ctx* ctx, rkg_kernel_time* out, int cap, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RKMH_GPU_H */

@@ -1,0 +1,849 @@
+// rk_capi.cu -- implementation of include/rkmh_gpu.h: context, device buffers, kernel launches.
+// Host side only orchestrates; all arithmetic of the hot path runs in the kernels of rk_kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rkmh_gpu.h"
+#include "rk_kernels.cuh"
+
+using namespace rk;
+
+static_assert(sizeof(rkg_hit) == sizeof(Hit), "rkg_hit layout");
+static_assert(RKG_MAX_K == MAX_K && RKG_MAX_NK == MAX_NK, "limits");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum KernelId { K_INGEST, K_HASH, K_COUNT, K_COUNT_DISTINCT, K_SKETCH, K_MERGE, K_TABLE, K_CLASSIFY_GROUP,
+                K_CLASSIFY_BLOCK, K_NUM };
+const char* const kKernelNames[K_NUM] = {"ingest_kernel", "hash_kernel", "count_kernel", "count_distinct_kernel",
+                                         "sketch_kernel", "merge_kernel", "table_build_kernels",
+                                         "classify_group_kernel", "classify_block_kernel"};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct EventPair { cudaEvent_t a, b; int id; };
+
+}  // namespace
+
+struct rkg_batch {
+    DevBuf bases, offs, codes, nmask, hits, redo, scratch, misc;   // misc: [0] redo_count
+    i64 nseq = 0, total = 0, base0 = 0, max_ntotal = 0, max_len = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+};
+
+struct rkg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    std::string err;
+    KList kl{};
+    int kcsel = 0;
+    int kmax = 0, kmin = 0;
+    int s = 1000;
+    bool params_set = false;
+    u64 read_tbl_size = 0, ref_tbl_size = 0;
+    DevBuf read_counts, ref_counts;
+    CountTable read_ct{nullptr, {}}, ref_ct{nullptr, {}};
+    // references
+    bool refs_loaded = false;
+    int nrefs = 0;
+    DevBuf ref_sketches, ref_lens, tb_entries, tb_maxmult, tb_dupbase, tb_dupbits, tb_filter, tb_cursor;
+    RefTable tb{};
+    cudaStream_t stream = nullptr;
+    rkg_batch* slots[2] = {nullptr, nullptr};   // internal double buffer of rkg_classify_batch / count
+    // measurement
+    int64_t launches = 0;
+    bool profiling = false;
+    std::vector<EventPair> events;
+    double prof_ms[K_NUM] = {0};
+    int64_t prof_n[K_NUM] = {0};
+};
+
+namespace {
+
+int fail(rkg_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(ctx, RKG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+struct Timed {   // brackets one launch with events when profiling is on
+    rkg_ctx* c; cudaStream_t st; int id; EventPair ep{};
+    Timed(rkg_ctx* c_, cudaStream_t st_, int id_) : c(c_), st(st_), id(id_) {
+        ++c->launches;
+        if (c->profiling) {
+            cudaEventCreate(&ep.a); cudaEventCreate(&ep.b); ep.id = id;
+            cudaEventRecord(ep.a, st);
+        }
+    }
+    ~Timed() {
+        if (c->profiling) { cudaEventRecord(ep.b, st); c->events.push_back(ep); }
+    }
+};
+
+void profile_collect(rkg_ctx* c) {
+    for (auto& ep : c->events) {
+        cudaEventSynchronize(ep.b);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) { c->prof_ms[ep.id] += ms; c->prof_n[ep.id] += 1; }
+        cudaEventDestroy(ep.a); cudaEventDestroy(ep.b);
+    }
+    c->events.clear();
+}
+
+int next_pow2(i64 v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// Launch helper over the key-length-class template parameter.
+#define DISPATCH_KCSEL(sel, ...)                  \
+    switch (sel) {                                \
+        case 0: { constexpr int KS = 0; __VA_ARGS__; } break; \
+        case 1: { constexpr int KS = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int KS = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int KS = 3; __VA_ARGS__; } break; \
+        case 4: { constexpr int KS = 4; __VA_ARGS__; } break; \
+        case 5: { constexpr int KS = 5; __VA_ARGS__; } break; \
+        default: { constexpr int KS = 6; __VA_ARGS__; } break; \
+    }
+
+int batch_alloc(rkg_ctx* ctx, rkg_batch** out) {
+    rkg_batch* b = new rkg_batch();
+    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
+    *out = b;
+    return RKG_OK;
+}
+
+void batch_release(rkg_batch* b) {
+    if (!b) return;
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    b->bases.release(); b->offs.release(); b->codes.release(); b->nmask.release(); b->hits.release();
+    b->redo.release(); b->scratch.release(); b->misc.release();
+    if (b->done) cudaEventDestroy(b->done);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+// Copy reads [r0, r1) of the caller's buffers into the batch and pack them (asynchronous on b->stream).
+int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* offs, i64 r0, i64 r1) {
+    const i64 n = r1 - r0;
+    const i64 base0 = offs[r0], total = offs[r1] - base0;
+    b->nseq = n; b->total = total; b->base0 = base0;
+    const i64 nwords32 = (total + 31) / 32;
+    CK(b->bases.ensure((size_t)nwords32 * 32 + 64));
+    CK(b->offs.ensure(sizeof(i64) * (size_t)(n + 1)));
+    CK(b->codes.ensure(sizeof(u32) * (size_t)(2 * nwords32 + 8)));
+    CK(b->nmask.ensure(sizeof(u32) * (size_t)(nwords32 + 8)));
+    CK(b->hits.ensure(sizeof(Hit) * (size_t)std::max<i64>(n, 1)));
+    CK(b->redo.ensure(sizeof(int) * (size_t)std::max<i64>(n, 1)));
+    CK(b->misc.ensure(256));
+    if (total > 0) CK(cudaMemcpyAsync(b->bases.p, bases + base0, (size_t)total, cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(b->offs.p, offs + r0, sizeof(i64) * (size_t)(n + 1), cudaMemcpyHostToDevice, b->stream));
+    // the reader may touch one word past the end: keep the padding defined
+    CK(cudaMemsetAsync(b->codes.as<u32>() + 2 * nwords32, 0, sizeof(u32) * 8, b->stream));
+    CK(cudaMemsetAsync(b->nmask.as<u32>() + nwords32, 0xFF, sizeof(u32) * 8, b->stream));
+    // longest read of the batch (sizes the exact path's scratch); overlaps the copies above
+    i64 max_len = 0;
+    for (i64 r = r0; r < r1; ++r) max_len = std::max<i64>(max_len, offs[r + 1] - offs[r]);
+    b->max_len = max_len;
+    i64 mt = 0;
+    for (int j = 0; j < ctx->kl.nk; ++j) mt += std::max<i64>(max_len - ctx->kl.k[j], 0);
+    b->max_ntotal = mt;
+    if (nwords32 > 0) {
+        Timed t(ctx, b->stream, K_INGEST);
+        int grid = (int)std::min<i64>((nwords32 + 255) / 256, (i64)ctx->sm_count * 16);
+        ingest_kernel<<<grid, 256, 0, b->stream>>>(b->bases.as<unsigned char>(), total, b->codes.as<u32>(),
+                                                   b->nmask.as<u32>(), nwords32);
+    }
+    CK(cudaGetLastError());
+    return RKG_OK;
+}
+
+SeqBatch seq_view(const rkg_batch* b) {
+    SeqBatch sb;
+    sb.bases = b->bases.as<unsigned char>();
+    sb.offs = b->offs.as<i64>();
+    sb.codes = b->codes.as<u32>();
+    sb.nmask = b->nmask.as<u32>();
+    sb.nseq = b->nseq;
+    sb.total = b->total;
+    sb.base0 = b->base0;
+    return sb;
+}
+
+int launch_count(rkg_ctx* ctx, rkg_batch* b, CountTable ct, int count_zeros) {
+    if (b->nseq == 0) return RKG_OK;
+    Timed t(ctx, b->stream, K_COUNT);
+    int grid = (int)std::min<i64>((b->nseq + 7) / 8, (i64)ctx->sm_count * 8);
+    DISPATCH_KCSEL(ctx->kcsel, (count_kernel<KS><<<grid, 256, 0, b->stream>>>(seq_view(b), ctx->kl, ct, count_zeros)));
+    CK(cudaGetLastError());
+    return RKG_OK;
+}
+
+// Geometry of classify_group_kernel for this context, or ok = false when it cannot be used.
+struct GroupGeom { bool ok; int block, glog2, rwords, filter_words; size_t smem; };
+
+GroupGeom group_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
+    GroupGeom g{};
+    if (b->nseq == 0) return g;
+    const i64 mean_len = b->total / b->nseq;
+    i64 n = 0;
+    for (int j = 0; j < ctx->kl.nk; ++j) n += std::max<i64>(mean_len - ctx->kl.k[j], 0);
+    if (n > ctx->s || n > GROUP_MAX_KMERS) return g;     // typical read is not eligible: exact path for all
+    int glog2 = 5;                                        // ~8-12 k-mers per lane
+    while (glog2 > 3 && (n >> (glog2 - 1)) < 10) --glog2;
+    g.glog2 = glog2;
+    g.rwords = (ctx->nrefs + 1) / 2;
+    g.filter_words = (int)((1u << ctx->tb.filter_log2) / 32u);
+    for (int block : {1024, 512, 256}) {
+        int nwb = block / 32, gpw = 32 >> glog2;
+        size_t smem = (size_t)nwb * sizeof(GroupSmem) + (size_t)nwb * gpw * g.rwords * 4 + (size_t)nwb * gpw * 4 +
+                      (size_t)g.filter_words * 4;
+        if (smem <= ctx->smem_optin) { g.ok = true; g.block = block; g.smem = smem; return g; }
+    }
+    return g;
+}
+
+int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
+    if (b->nseq == 0) return RKG_OK;
+    CountTable ct = (min_occ >= 0) ? ctx->read_ct : CountTable{nullptr, {}};
+    if (min_occ >= 0 && ct.counts == nullptr)
+        return fail(ctx, RKG_ERR_STATE, "min_occ >= 0 needs a read count table (rkg_set_params read_table_size)");
+    SeqBatch sb = seq_view(b);
+    int* redo = b->redo.as<int>();
+    int* redo_count = b->misc.as<int>();
+    Hit* hits = b->hits.as<Hit>();
+    CK(cudaMemsetAsync(redo_count, 0, sizeof(int), b->stream));
+
+    GroupGeom gg = group_geometry(ctx, b);
+    if (gg.ok) {
+        Timed t(ctx, b->stream, K_CLASSIFY_GROUP);
+        int grid = ctx->sm_count;
+        DISPATCH_KCSEL(ctx->kcsel, {
+            CK(cudaFuncSetAttribute(classify_group_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gg.smem));
+            classify_group_kernel<KS><<<grid, gg.block, gg.smem, b->stream>>>(sb, ctx->kl, ctx->s, ct, min_occ, ctx->tb,
+                                                                               gg.glog2, gg.rwords, gg.filter_words,
+                                                                               redo, redo_count, hits);
+        });
+        CK(cudaGetLastError());
+    }
+    // exact path: the redo list of the group kernel, or every read when the group kernel was skipped
+    {
+        const int block = 512;
+        const int hs_cap = next_pow2(2 * (i64)std::min<i64>(ctx->s, std::max<i64>(b->max_ntotal, 1)));
+        const int rpad = (ctx->nrefs + 63) / 64 * 64;
+        const size_t budget = ctx->smem_optin / 2 - 1024;            // two blocks per SM
+        size_t fixed = (size_t)rpad * 4;
+        int hs_in_smem = ((size_t)hs_cap * 8 + fixed <= budget / 2) ? 1 : 0;
+        if (hs_in_smem) fixed += (size_t)hs_cap * 8;
+        i64 hbuf_cap = 0;
+        if (fixed + (size_t)b->max_ntotal * 8 <= budget) hbuf_cap = b->max_ntotal;
+        const size_t smem = fixed + (size_t)hbuf_cap * 8;
+        const i64 stride = (hbuf_cap >= b->max_ntotal) ? 0 : b->max_ntotal;
+        const int grid = ctx->sm_count * 2;
+        CK(b->scratch.ensure(sizeof(u64) * (size_t)grid * (size_t)(stride + hs_cap) + 64));
+        Timed t(ctx, b->stream, K_CLASSIFY_BLOCK);
+        DISPATCH_KCSEL(ctx->kcsel, {
+            CK(cudaFuncSetAttribute(classify_block_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            classify_block_kernel<KS><<<grid, block, smem, b->stream>>>(sb, ctx->kl, ctx->s, ct, min_occ, ctx->tb,
+                                                                         gg.ok ? redo : nullptr, gg.ok ? redo_count : nullptr,
+                                                                         b->nseq, (int)hbuf_cap, hs_cap, hs_in_smem, rpad,
+                                                                         b->scratch.as<u64>(), stride, hits);
+        });
+        CK(cudaGetLastError());
+    }
+    return RKG_OK;
+}
+
+// Sketch every sequence of a batch into d_sketches [nseq * s] / d_lens [nseq] (device pointers).
+int launch_sketch(rkg_ctx* ctx, rkg_batch* b, CountTable ct, int filter_mode, int occ, u64* d_sketches, int* d_lens,
+                  u64* d_sorted_all, const i64* d_all_offs) {
+    if (b->nseq == 0) return RKG_OK;
+    const int block = 512;
+    const int sort_cap = next_pow2(std::max<i64>(std::min<i64>(ctx->s, std::max<i64>(b->max_ntotal, 1)), 2));
+    const int sort_in_smem = ((size_t)sort_cap * 8 <= ctx->smem_optin - 4096) ? 1 : 0;
+    const size_t smem = sort_in_smem ? (size_t)sort_cap * 8 : 0;
+    i64 stride = std::max<i64>(b->max_ntotal, 1);
+    if (d_sorted_all) stride = next_pow2(stride);
+    const int grid = (int)std::min<i64>(b->nseq, (i64)ctx->sm_count * 2);
+    CK(b->scratch.ensure(sizeof(u64) * (size_t)grid * (size_t)(stride + sort_cap) + 64));
+    Timed t(ctx, b->stream, K_SKETCH);
+    DISPATCH_KCSEL(ctx->kcsel, {
+        CK(cudaFuncSetAttribute(sketch_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sketch_kernel<KS><<<grid, block, smem, b->stream>>>(seq_view(b), ctx->kl, ctx->s, ct, filter_mode, occ,
+                                                             b->scratch.as<u64>(), stride, sort_cap, sort_in_smem,
+                                                             d_sketches, d_lens, d_sorted_all, d_all_offs);
+    });
+    CK(cudaGetLastError());
+    return RKG_OK;
+}
+
+int ensure_slots(rkg_ctx* ctx) {
+    for (int i = 0; i < 2; ++i)
+        if (!ctx->slots[i]) { int rc = batch_alloc(ctx, &ctx->slots[i]); if (rc) return rc; }
+    return RKG_OK;
+}
+
+// Split [0, n) into chunks of bounded bytes / reads for the double-buffered host paths.
+std::vector<std::pair<i64, i64>> make_chunks(const int64_t* offs, i64 n, i64 max_bytes, i64 max_reads) {
+    std::vector<std::pair<i64, i64>> out;
+    i64 r0 = 0;
+    while (r0 < n) {
+        i64 hi = std::min<i64>(n, r0 + max_reads);
+        // largest r1 in (r0, hi] with offs[r1] - offs[r0] <= max_bytes (at least one read)
+        i64 lo = r0 + 1, best = r0 + 1;
+        while (lo <= hi) {
+            i64 mid = (lo + hi) / 2;
+            if (offs[mid] - offs[r0] <= max_bytes) { best = mid; lo = mid + 1; } else hi = mid - 1;
+        }
+        out.emplace_back(r0, best);
+        r0 = best;
+    }
+    return out;
+}
+
+constexpr i64 CHUNK_BYTES = 192LL << 20;
+constexpr i64 CHUNK_READS = 2LL << 20;
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int rkg_create(int device, rkg_ctx** out) {
+    rkg_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, RKG_ERR_ARG, "rkg_create: null output pointer");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, RKG_ERR_CUDA, "rkg_create: no CUDA device (%s); this library has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, RKG_ERR_ARG, "rkg_create: device %d of %d", device, ndev);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, RKG_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, RKG_ERR_CUDA, "rkg_create: device %d is sm_%d%d; this build targets sm_100a (B200) only",
+                    device, prop.major, prop.minor);
+    if ((e = cudaSetDevice(device)) != cudaSuccess)
+        return fail(nullptr, RKG_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    ctx = new rkg_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, RKG_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return RKG_OK;
+}
+
+void rkg_destroy(rkg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    profile_collect(ctx);
+    for (int i = 0; i < 2; ++i) batch_release(ctx->slots[i]);
+    for (DevBuf* d : {&ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
+                      &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor})
+        d->release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* rkg_last_error(const rkg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rkg_set_params(rkg_ctx* ctx, const int* ks, int nk, int sketch_size, uint64_t read_table_size,
+                   uint64_t ref_table_size) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ks || nk < 1 || nk > MAX_NK) return fail(ctx, RKG_ERR_ARG, "rkg_set_params: 1..%d k-mer sizes, got %d", MAX_NK, nk);
+    if (sketch_size < 1) return fail(ctx, RKG_ERR_ARG, "rkg_set_params: sketch size %d", sketch_size);
+    CK(cudaSetDevice(ctx->device));
+    KList kl{};
+    kl.nk = nk;
+    int kcsel = -1, kmax = 0, kmin = MAX_K;
+    for (int j = 0; j < nk; ++j) {
+        if (ks[j] < 1 || ks[j] > MAX_K)
+            return fail(ctx, RKG_ERR_ARG, "rkg_set_params: k = %d unsupported (1..%d)", ks[j], MAX_K);
+        kl.k[j] = ks[j];
+        kl.kc[j] = kclass_of(ks[j]);
+        kcsel = (kcsel == -1 || kcsel == kl.kc[j]) ? kl.kc[j] : 6;
+        kmax = std::max(kmax, ks[j]); kmin = std::min(kmin, ks[j]);
+    }
+    ctx->kl = kl; ctx->kcsel = kcsel; ctx->kmax = kmax; ctx->kmin = kmin; ctx->s = sketch_size;
+    ctx->refs_loaded = false;
+    auto setup = [&](uint64_t size, DevBuf& buf, CountTable& ct) -> cudaError_t {
+        ct.counts = nullptr;
+        if (size == 0) { buf.release(); return cudaSuccess; }
+        cudaError_t e = buf.ensure(sizeof(int) * size);
+        if (e != cudaSuccess) return e;
+        ct.counts = buf.as<int>();
+        ct.mod = make_fastmod(size);
+        return cudaMemsetAsync(buf.p, 0, sizeof(int) * size, ctx->stream);
+    };
+    if (read_table_size >= (1ULL << 62) || ref_table_size >= (1ULL << 62)) return fail(ctx, RKG_ERR_ARG, "table size");
+    CK(setup(read_table_size, ctx->read_counts, ctx->read_ct));
+    CK(setup(ref_table_size, ctx->ref_counts, ctx->ref_ct));
+    ctx->read_tbl_size = read_table_size; ctx->ref_tbl_size = ref_table_size;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->params_set = true;
+    return RKG_OK;
+}
+
+int rkg_host_alloc(rkg_ctx* ctx, size_t bytes, void** ptr) {
+    if (!ctx || !ptr) return RKG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return RKG_OK;
+}
+
+int rkg_host_free(rkg_ctx* ctx, void* ptr) {
+    if (!ctx) return RKG_ERR_ARG;
+    CK(cudaFreeHost(ptr));
+    return RKG_OK;
+}
+
+int rkg_synchronize(rkg_ctx* ctx) {
+    if (!ctx) return RKG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    return RKG_OK;
+}
+
+// ---- references -------------------------------------------------------------------------------------
+int rkg_load_refs(rkg_ctx* ctx, const char* bases, const int64_t* offs, int nrefs, int max_ref_occ, int per_sample_set) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_load_refs before rkg_set_params");
+    if (!bases || !offs || nrefs < 1) return fail(ctx, RKG_ERR_ARG, "rkg_load_refs: need at least one reference");
+    if (max_ref_occ >= 0 && ctx->ref_ct.counts == nullptr)
+        return fail(ctx, RKG_ERR_STATE, "max_ref_occ >= 0 needs a reference count table (rkg_set_params ref_table_size)");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_slots(ctx);
+    if (rc) return rc;
+    rkg_batch* b = ctx->slots[0];
+    CK(cudaStreamSynchronize(b->stream));
+    if ((rc = batch_fill(ctx, b, bases, offs, 0, nrefs))) return rc;
+    const int s = ctx->s;
+    ctx->nrefs = nrefs;
+    CK(ctx->ref_sketches.ensure(sizeof(u64) * (size_t)nrefs * s));
+    CK(ctx->ref_lens.ensure(sizeof(int) * (size_t)nrefs));
+    CK(cudaMemsetAsync(ctx->ref_sketches.p, 0, sizeof(u64) * (size_t)nrefs * s, b->stream));
+
+    int filter_mode = 0;
+    if (max_ref_occ >= 0) {
+        filter_mode = 1;
+        CK(cudaMemsetAsync(ctx->ref_ct.counts, 0, sizeof(int) * ctx->ref_tbl_size, b->stream));
+        if (!per_sample_set) {
+            if ((rc = launch_count(ctx, b, ctx->ref_ct, 0))) return rc;
+        } else {
+            // distinct hashes per reference (zero included): sort every hash of each reference, count run heads
+            std::vector<i64> all_offs(nrefs + 1, 0);
+            for (int r = 0; r < nrefs; ++r) {
+                i64 len = offs[r + 1] - offs[r], n = 0;
+                for (int j = 0; j < ctx->kl.nk; ++j) n += std::max<i64>(len - ctx->kl.k[j], 0);
+                all_offs[r + 1] = all_offs[r] + n;
+            }
+            DevBuf d_all, d_all_offs;
+            CK(d_all.ensure(sizeof(u64) * (size_t)std::max<i64>(all_offs[nrefs], 1)));
+            CK(d_all_offs.ensure(sizeof(i64) * (size_t)(nrefs + 1)));
+            CK(cudaMemcpyAsync(d_all_offs.p, all_offs.data(), sizeof(i64) * (size_t)(nrefs + 1), cudaMemcpyHostToDevice, b->stream));
+            rc = launch_sketch(ctx, b, CountTable{nullptr, {}}, 0, 0, ctx->ref_sketches.as<u64>(), ctx->ref_lens.as<int>(),
+                               d_all.as<u64>(), d_all_offs.as<i64>());
+            if (!rc) {
+                Timed t(ctx, b->stream, K_COUNT_DISTINCT);
+                count_distinct_kernel<<<std::min(nrefs, ctx->sm_count * 4), 256, 0, b->stream>>>(
+                    d_all.as<u64>(), d_all_offs.as<i64>(), nrefs, ctx->ref_ct);
+            }
+            cudaError_t e = cudaStreamSynchronize(b->stream);
+            d_all.release(); d_all_offs.release();
+            if (rc) return rc;
+            CK(e);
+        }
+    }
+    if ((rc = launch_sketch(ctx, b, ctx->ref_ct, filter_mode, max_ref_occ, ctx->ref_sketches.as<u64>(),
+                            ctx->ref_lens.as<int>(), nullptr, nullptr)))
+        return rc;
+
+    // table geometry
+    const i64 nent = (i64)nrefs * s;
+    const u32 cap = (u32)next_pow2(std::max<i64>(2 * nent, 1024));
+    const u32 nb = (u32)((nrefs + 63) / 64);
+    RefTable tb{};
+    tb.cap_mask = cap - 1; tb.nb = nb; tb.stride = 1 + nb; tb.nrefs = (u32)nrefs;
+    int flog2 = 10;
+    while (flog2 < 20 && (1LL << flog2) < 16 * nent) ++flog2;
+    tb.filter_log2 = (u32)flog2;
+    CK(ctx->tb_entries.ensure(sizeof(u64) * (size_t)cap * tb.stride));
+    CK(ctx->tb_maxmult.ensure(sizeof(u32) * (size_t)cap));
+    CK(ctx->tb_dupbase.ensure(sizeof(u32) * (size_t)cap));
+    CK(ctx->tb_dupbits.ensure(sizeof(u64) * (size_t)std::max<i64>(nent, 1) * nb));
+    CK(ctx->tb_filter.ensure(sizeof(u32) * ((size_t)1 << flog2) / 32));
+    CK(ctx->tb_cursor.ensure(256));
+    CK(cudaMemsetAsync(ctx->tb_entries.p, 0, sizeof(u64) * (size_t)cap * tb.stride, b->stream));
+    CK(cudaMemsetAsync(ctx->tb_maxmult.p, 0, sizeof(u32) * (size_t)cap, b->stream));
+    CK(cudaMemsetAsync(ctx->tb_dupbase.p, 0, sizeof(u32) * (size_t)cap, b->stream));
+    CK(cudaMemsetAsync(ctx->tb_dupbits.p, 0, sizeof(u64) * (size_t)std::max<i64>(nent, 1) * nb, b->stream));
+    CK(cudaMemsetAsync(ctx->tb_filter.p, 0, sizeof(u32) * ((size_t)1 << flog2) / 32, b->stream));
+    CK(cudaMemsetAsync(ctx->tb_cursor.p, 0, 256, b->stream));
+    tb.entries = ctx->tb_entries.as<u64>();
+    tb.maxmult = ctx->tb_maxmult.as<u32>();
+    tb.dup_base = ctx->tb_dupbase.as<u32>();
+    tb.dup_bits = ctx->tb_dupbits.as<u64>();
+    tb.filter = ctx->tb_filter.as<u32>();
+    {
+        Timed t(ctx, b->stream, K_TABLE);
+        int grid = (int)std::min<i64>((nent + 255) / 256, (i64)ctx->sm_count * 8);
+        table_insert_kernel<<<grid, 256, 0, b->stream>>>(ctx->ref_sketches.as<u64>(), ctx->ref_lens.as<int>(), nrefs, s, tb,
+                                                         ctx->tb_filter.as<u32>());
+        table_alloc_dup_kernel<<<(int)std::min<i64>((cap + 255) / 256, (i64)ctx->sm_count * 8), 256, 0, b->stream>>>(
+            tb, ctx->tb_cursor.as<u32>());
+        table_fill_dup_kernel<<<grid, 256, 0, b->stream>>>(ctx->ref_sketches.as<u64>(), ctx->ref_lens.as<int>(), nrefs, s, tb);
+        ctx->launches += 2;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(b->stream));
+    ctx->tb = tb;
+    ctx->refs_loaded = true;
+    return RKG_OK;
+}
+
+int rkg_get_ref_sketches(rkg_ctx* ctx, uint64_t* sketches, int32_t* lens) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->refs_loaded) return fail(ctx, RKG_ERR_STATE, "no references loaded");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(sketches, ctx->ref_sketches.p, sizeof(u64) * (size_t)ctx->nrefs * ctx->s, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lens, ctx->ref_lens.p, sizeof(int) * (size_t)ctx->nrefs, cudaMemcpyDeviceToHost));
+    return RKG_OK;
+}
+
+// ---- count table ------------------------------------------------------------------------------------
+int rkg_count_reset(rkg_ctx* ctx) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "no read count table (rkg_set_params read_table_size)");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(ctx->read_ct.counts, 0, sizeof(int) * ctx->read_tbl_size));
+    return RKG_OK;
+}
+
+int rkg_count_table(rkg_ctx* ctx, void** device_ptr, uint64_t* nslots) {
+    if (!ctx || !device_ptr || !nslots) return RKG_ERR_ARG;
+    if (!ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "no read count table");
+    *device_ptr = ctx->read_ct.counts;
+    *nslots = ctx->read_tbl_size;
+    return RKG_OK;
+}
+
+int rkg_count_lookup(rkg_ctx* ctx, const uint64_t* keys, int64_t n, int32_t* out) {
+    if (!ctx || !keys || !out) return RKG_ERR_ARG;
+    if (!ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "no read count table");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    for (int64_t i = 0; i < n; ++i) {   // parity/debug helper: one small copy per key
+        u64 slot = keys[i] % ctx->read_tbl_size;
+        CK(cudaMemcpy(out + i, ctx->read_ct.counts + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    return RKG_OK;
+}
+
+static int host_pipeline(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, int mode, int arg,
+                         rkg_hit* out) {
+    // mode 0: count (arg = count_zeros); mode 1: classify (arg = min_occ)
+    int rc = ensure_slots(ctx);
+    if (rc) return rc;
+    auto chunks = make_chunks(offs, nreads, CHUNK_BYTES, CHUNK_READS);
+    for (size_t c = 0; c < chunks.size(); ++c) {
+        rkg_batch* b = ctx->slots[c & 1];
+        CK(cudaStreamSynchronize(b->stream));     // the slot's previous chunk (c - 2) is finished
+        if ((rc = batch_fill(ctx, b, bases, offs, chunks[c].first, chunks[c].second))) return rc;
+        if (mode == 0) {
+            if ((rc = launch_count(ctx, b, ctx->read_ct, arg))) return rc;
+        } else {
+            if ((rc = launch_classify(ctx, b, arg))) return rc;
+            CK(cudaMemcpyAsync(out + chunks[c].first, b->hits.p, sizeof(Hit) * (size_t)b->nseq, cudaMemcpyDeviceToHost,
+                               b->stream));
+        }
+    }
+    for (int i = 0; i < 2; ++i) CK(cudaStreamSynchronize(ctx->slots[i]->stream));
+    return RKG_OK;
+}
+
+int rkg_count_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, int count_zeros) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_count_batch before rkg_set_params");
+    if (!ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "no read count table (rkg_set_params read_table_size)");
+    if (nreads < 0 || !offs || (!bases && nreads > 0)) return fail(ctx, RKG_ERR_ARG, "rkg_count_batch: bad buffers");
+    if (nreads == 0) return RKG_OK;
+    CK(cudaSetDevice(ctx->device));
+    return host_pipeline(ctx, bases, offs, nreads, 0, count_zeros, nullptr);
+}
+
+// ---- classification ---------------------------------------------------------------------------------
+int rkg_classify_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, int min_occ, rkg_hit* out) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->refs_loaded) return fail(ctx, RKG_ERR_STATE, "rkg_classify_batch before rkg_load_refs");
+    if (nreads < 0 || !offs || (!bases && nreads > 0) || (!out && nreads > 0))
+        return fail(ctx, RKG_ERR_ARG, "rkg_classify_batch: bad buffers");
+    if (nreads == 0) return RKG_OK;
+    CK(cudaSetDevice(ctx->device));
+    return host_pipeline(ctx, bases, offs, nreads, 1, min_occ, out);
+}
+
+int rkg_batch_upload(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, rkg_batch** batch) {
+    if (!ctx || !batch) return RKG_ERR_ARG;
+    if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_batch_upload before rkg_set_params");
+    if (nreads < 0 || !offs || (!bases && nreads > 0)) return fail(ctx, RKG_ERR_ARG, "rkg_batch_upload: bad buffers");
+    CK(cudaSetDevice(ctx->device));
+    rkg_batch* b = nullptr;
+    int rc = batch_alloc(ctx, &b);
+    if (rc) return rc;
+    if ((rc = batch_fill(ctx, b, bases, offs, 0, nreads))) { batch_release(b); return rc; }
+    CK(cudaStreamSynchronize(b->stream));
+    *batch = b;
+    return RKG_OK;
+}
+
+int rkg_batch_classify(rkg_ctx* ctx, rkg_batch* batch, int min_occ) {
+    if (!ctx || !batch) return RKG_ERR_ARG;
+    if (!ctx->refs_loaded) return fail(ctx, RKG_ERR_STATE, "rkg_batch_classify before rkg_load_refs");
+    CK(cudaSetDevice(ctx->device));
+    return launch_classify(ctx, batch, min_occ);
+}
+
+int rkg_batch_count(rkg_ctx* ctx, rkg_batch* batch, int count_zeros) {
+    if (!ctx || !batch) return RKG_ERR_ARG;
+    if (!ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "no read count table");
+    CK(cudaSetDevice(ctx->device));
+    return launch_count(ctx, batch, ctx->read_ct, count_zeros);
+}
+
+int rkg_batch_results(rkg_ctx* ctx, rkg_batch* batch, rkg_hit* out) {
+    if (!ctx || !batch || !out) return RKG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, batch->hits.p, sizeof(Hit) * (size_t)batch->nseq, cudaMemcpyDeviceToHost, batch->stream));
+    CK(cudaStreamSynchronize(batch->stream));
+    return RKG_OK;
+}
+
+int rkg_batch_free(rkg_ctx* ctx, rkg_batch* batch) {
+    if (!ctx) return RKG_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    batch_release(batch);
+    return RKG_OK;
+}
+
+// ---- hash command -----------------------------------------------------------------------------------
+int rkg_sketch_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nseq, int min_occ,
+                     uint64_t* sketches, int32_t* lens) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_sketch_batch before rkg_set_params");
+    if (nseq < 0 || !offs || (!bases && nseq > 0) || !sketches || !lens) return fail(ctx, RKG_ERR_ARG, "rkg_sketch_batch: bad buffers");
+    if (min_occ >= 0 && !ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "min_occ >= 0 needs a read count table");
+    if (nseq == 0) return RKG_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_slots(ctx);
+    if (rc) return rc;
+    rkg_batch* b = ctx->slots[0];
+    DevBuf d_sk, d_len;
+    auto chunks = make_chunks(offs, nseq, CHUNK_BYTES, 1 << 16);
+    for (auto& ch : chunks) {
+        CK(cudaStreamSynchronize(b->stream));
+        if ((rc = batch_fill(ctx, b, bases, offs, ch.first, ch.second))) break;
+        const size_t n = (size_t)(ch.second - ch.first);
+        if (d_sk.ensure(sizeof(u64) * n * ctx->s) != cudaSuccess || d_len.ensure(sizeof(int) * n) != cudaSuccess) {
+            rc = fail(ctx, RKG_ERR_NOMEM, "rkg_sketch_batch: device allocation failed");
+            break;
+        }
+        cudaMemsetAsync(d_sk.p, 0, sizeof(u64) * n * ctx->s, b->stream);
+        CountTable ct = (min_occ >= 0) ? ctx->read_ct : CountTable{nullptr, {}};
+        if ((rc = launch_sketch(ctx, b, ct, min_occ >= 0 ? 2 : 0, min_occ, d_sk.as<u64>(), d_len.as<int>(), nullptr, nullptr))) break;
+        cudaMemcpyAsync(sketches + (size_t)ch.first * ctx->s, d_sk.p, sizeof(u64) * n * ctx->s, cudaMemcpyDeviceToHost, b->stream);
+        cudaMemcpyAsync(lens + ch.first, d_len.p, sizeof(int) * n, cudaMemcpyDeviceToHost, b->stream);
+        if (cudaStreamSynchronize(b->stream) != cudaSuccess) { rc = fail(ctx, RKG_ERR_CUDA, "rkg_sketch_batch: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    }
+    cudaStreamSynchronize(b->stream);
+    d_sk.release(); d_len.release();
+    return rc;
+}
+
+int rkg_hash_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nseq, uint64_t* hashes, int64_t* hash_offs) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_hash_batch before rkg_set_params");
+    if (nseq < 0 || !offs || (!bases && nseq > 0) || !hashes || !hash_offs) return fail(ctx, RKG_ERR_ARG, "rkg_hash_batch: bad buffers");
+    hash_offs[0] = 0;
+    for (int64_t r = 0; r < nseq; ++r) {
+        i64 len = offs[r + 1] - offs[r], n = 0;
+        for (int j = 0; j < ctx->kl.nk; ++j) n += std::max<i64>(len - ctx->kl.k[j], 0);
+        hash_offs[r + 1] = hash_offs[r] + n;
+    }
+    if (nseq == 0) return RKG_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_slots(ctx);
+    if (rc) return rc;
+    rkg_batch* b = ctx->slots[0];
+    DevBuf d_h, d_ho;
+    auto chunks = make_chunks(offs, nseq, 64LL << 20, CHUNK_READS);
+    for (auto& ch : chunks) {
+        CK(cudaStreamSynchronize(b->stream));
+        if ((rc = batch_fill(ctx, b, bases, offs, ch.first, ch.second))) break;
+        const i64 n = ch.second - ch.first;
+        const i64 h0 = hash_offs[ch.first], nh = hash_offs[ch.second] - h0;
+        if (d_h.ensure(sizeof(u64) * (size_t)std::max<i64>(nh, 1)) != cudaSuccess || d_ho.ensure(sizeof(i64) * (size_t)(n + 1)) != cudaSuccess) {
+            rc = fail(ctx, RKG_ERR_NOMEM, "rkg_hash_batch: device allocation failed");
+            break;
+        }
+        std::vector<i64> rel(n + 1);
+        for (i64 i = 0; i <= n; ++i) rel[i] = hash_offs[ch.first + i] - h0;
+        cudaMemcpyAsync(d_ho.p, rel.data(), sizeof(i64) * (size_t)(n + 1), cudaMemcpyHostToDevice, b->stream);
+        for (int kidx = 0; kidx < ctx->kl.nk; ++kidx) {
+            Timed t(ctx, b->stream, K_HASH);
+            int grid = (int)std::min<i64>((n + 7) / 8, (i64)ctx->sm_count * 8);
+            DISPATCH_KCSEL(ctx->kl.kc[kidx], (hash_kernel<(KS < 6 ? KS : 0)><<<grid, 256, 0, b->stream>>>(
+                                                 seq_view(b), ctx->kl, kidx, d_h.as<u64>(), d_ho.as<i64>())));
+        }
+        cudaMemcpyAsync(hashes + h0, d_h.p, sizeof(u64) * (size_t)nh, cudaMemcpyDeviceToHost, b->stream);
+        if (cudaStreamSynchronize(b->stream) != cudaSuccess) { rc = fail(ctx, RKG_ERR_CUDA, "rkg_hash_batch: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    }
+    cudaStreamSynchronize(b->stream);
+    d_h.release(); d_ho.release();
+    return rc;
+}
+
+int rkg_merge_sketches(rkg_ctx* ctx, const uint64_t* parts, const int32_t* part_lens, int nparts, uint64_t* sketch, int32_t* len) {
+    if (!ctx || !parts || !part_lens || nparts < 1 || !sketch || !len) return RKG_ERR_ARG;
+    if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_merge_sketches before rkg_set_params");
+    CK(cudaSetDevice(ctx->device));
+    const int s = ctx->s, P = next_pow2(std::max(s, 2));
+    DevBuf d_parts, d_lens, d_out, d_len, d_scr;
+    int rc = RKG_OK;
+    do {
+        if (d_parts.ensure(sizeof(u64) * (size_t)nparts * s) || d_lens.ensure(sizeof(int) * (size_t)nparts) ||
+            d_out.ensure(sizeof(u64) * (size_t)s) || d_len.ensure(sizeof(int)) || d_scr.ensure(sizeof(u64) * (size_t)P)) {
+            rc = fail(ctx, RKG_ERR_NOMEM, "rkg_merge_sketches: device allocation failed");
+            break;
+        }
+        cudaMemcpyAsync(d_parts.p, parts, sizeof(u64) * (size_t)nparts * s, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_lens.p, part_lens, sizeof(int) * (size_t)nparts, cudaMemcpyHostToDevice, ctx->stream);
+        const int in_smem = ((size_t)P * 8 <= ctx->smem_optin - 1024) ? 1 : 0;
+        const size_t smem = in_smem ? (size_t)P * 8 : 0;
+        {
+            Timed t(ctx, ctx->stream, K_MERGE);
+            cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            merge_kernel<<<1, 512, smem, ctx->stream>>>(d_parts.as<u64>(), d_lens.as<int>(), nparts, s, P, d_out.as<u64>(),
+                                                        d_len.as<int>(), d_scr.as<u64>(), in_smem);
+        }
+        cudaMemcpyAsync(len, d_len.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = fail(ctx, RKG_ERR_CUDA, "merge: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        cudaMemcpy(sketch, d_out.p, sizeof(u64) * (size_t)(*len), cudaMemcpyDeviceToHost);
+    } while (0);
+    d_parts.release(); d_lens.release(); d_out.release(); d_len.release(); d_scr.release();
+    return rc;
+}
+
+int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t kmer_begin, int64_t kmer_end,
+                     int64_t record_len, uint64_t* sketch, int32_t* len) {
+    if (!ctx || !bases || !sketch || !len) return RKG_ERR_ARG;
+    if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_sketch_shard before rkg_set_params");
+    if (ctx->kl.nk != 1) return fail(ctx, RKG_ERR_ARG, "rkg_sketch_shard: exactly one k-mer size");
+    // The shard is cut into pieces of PIECE k-mer starts; each piece is an ordinary record whose last
+    // k-mer would be dropped by the len-k rule, so a piece carries k bases of right context, except the
+    // piece that holds the true end of the record.
+    const int k = ctx->kl.k[0];
+    const i64 last_start = record_len - k;            // k-mer starts [0, record_len - k) exist
+    kmer_end = std::min<i64>(kmer_end, last_start);
+    *len = 0;
+    if (kmer_end <= kmer_begin) return RKG_OK;
+    const i64 PIECE = 1 << 20;
+    std::vector<int64_t> offs;
+    std::vector<char> buf;
+    // pieces overlap, so they are materialised into a staging buffer (k bytes of overlap per MiB)
+    for (i64 p0 = kmer_begin; p0 < kmer_end; p0 += PIECE) {
+        i64 p1 = std::min<i64>(p0 + PIECE, kmer_end);
+        i64 b0 = p0 - kmer_begin, b1 = (p1 - kmer_begin) + k;     // bytes [b0, b1): p1 - p0 starts + k
+        if (b1 > nbytes) return fail(ctx, RKG_ERR_ARG, "rkg_sketch_shard: shard buffer too short");
+        offs.push_back((int64_t)buf.size());
+        buf.insert(buf.end(), bases + b0, bases + b1);
+    }
+    offs.push_back((int64_t)buf.size());
+    const int nparts = (int)offs.size() - 1;
+    std::vector<uint64_t> parts((size_t)nparts * ctx->s);
+    std::vector<int32_t> lens(nparts);
+    int rc = rkg_sketch_batch(ctx, buf.data(), offs.data(), nparts, -1, parts.data(), lens.data());
+    if (rc) return rc;
+    // merge in groups so that one launch never holds more than 64 parts
+    while ((int)lens.size() > 1) {
+        std::vector<uint64_t> np; std::vector<int32_t> nl;
+        for (size_t i = 0; i < lens.size(); i += 64) {
+            int cnt = (int)std::min<size_t>(64, lens.size() - i);
+            std::vector<uint64_t> o(ctx->s); int32_t ol = 0;
+            rc = rkg_merge_sketches(ctx, parts.data() + i * ctx->s, lens.data() + i, cnt, o.data(), &ol);
+            if (rc) return rc;
+            np.insert(np.end(), o.begin(), o.end()); nl.push_back(ol);
+        }
+        parts.swap(np); lens.swap(nl);
+    }
+    *len = lens[0];
+    std::memcpy(sketch, parts.data(), sizeof(uint64_t) * (size_t)lens[0]);
+    return RKG_OK;
+}
+
+// ---- measurement ------------------------------------------------------------------------------------
+int64_t rkg_launch_count(const rkg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int rkg_profile_enable(rkg_ctx* ctx, int on) {
+    if (!ctx) return RKG_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    profile_collect(ctx);
+    ctx->profiling = on != 0;
+    return RKG_OK;
+}
+
+int rkg_profile_read(rkg_ctx* ctx, rkg_kernel_time* out, int cap, int reset) {
+    if (!ctx) return RKG_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    profile_collect(ctx);
+    int n = 0;
+    for (int i = 0; i < K_NUM; ++i) {
+        if (ctx->prof_n[i] == 0) continue;
+        if (out && n < cap) { out[n].name = kKernelNames[i]; out[n].launches = ctx->prof_n[i]; out[n].ms = ctx->prof_ms[i]; }
+        ++n;
+    }
+    if (reset) for (int i = 0; i < K_NUM; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
+    return n;
+}
+
+}  // extern "C"

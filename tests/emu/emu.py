@@ -1,0 +1,88 @@
+"""tests/emu/emu.py -- ctypes face of tests/emu/libemu.so (TEST INFRASTRUCTURE ONLY): the product's kernel
+source compiled for the CPU by g++ against tests/emu/cuda_emu.h."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+HIT = np.dtype([("ref_id", "<i4"), ("best", "<i4"), ("prev", "<i4"), ("sketch_len", "<i4")])
+
+
+def pack(seqs):
+    offs = np.zeros(len(seqs) + 1, dtype=np.int64)
+    if seqs:
+        offs[1:] = np.cumsum([len(s) for s in seqs])
+    return np.frombuffer(b"".join(seqs) + b"\0", dtype=np.uint8).copy(), offs
+
+
+class Emu:
+    def __init__(self):
+        subprocess.check_call(["make", "-C", HERE, "libemu.so"], stdout=subprocess.DEVNULL)
+        self.lib = lib = C.CDLL(os.path.join(HERE, "libemu.so"))
+        lib.emu_fastmod.argtypes = [C.c_uint64, C.c_uint64]
+        lib.emu_fastmod.restype = C.c_uint64
+        lib.emu_kmer_hash.argtypes = [C.c_char_p, C.c_int]
+        lib.emu_kmer_hash.restype = C.c_uint64
+        P, I, L, U = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+        lib.emu_hash.argtypes = [P, P, L, P, I, P, P, I]
+        lib.emu_count.argtypes = [P, P, L, P, I, P, U, I, I]
+        lib.emu_sketch.argtypes = [P, P, L, P, I, I, P, U, I, I, P, P, I, I]
+        lib.emu_merge.argtypes = [P, P, I, I, P, P, I, I]
+        lib.emu_classify.argtypes = [P, P, I, P, P, L, P, I, I, P, U, I, I, I, I, I, I, P, P, P, P]
+
+    def hash(self, seqs, ks, block=64):
+        bases, offs = pack(seqs)
+        ks = np.atleast_1d(np.asarray(ks, np.int32))
+        n = sum(max(len(s) - int(k), 0) for s in seqs for k in ks)
+        out = np.zeros(max(n, 1), np.uint64)
+        ho = np.zeros(len(seqs) + 1, np.int64)
+        self.lib.emu_hash(bases.ctypes.data, offs.ctypes.data, len(seqs), ks.ctypes.data, len(ks), out.ctypes.data,
+                          ho.ctypes.data, block)
+        return out[:n], ho
+
+    def count(self, seqs, ks, counts, count_zeros=False, block=64):
+        bases, offs = pack(seqs)
+        ks = np.atleast_1d(np.asarray(ks, np.int32))
+        self.lib.emu_count(bases.ctypes.data, offs.ctypes.data, len(seqs), ks.ctypes.data, len(ks), counts.ctypes.data,
+                           C.c_uint64(counts.size), int(count_zeros), block)
+
+    def sketch(self, seqs, ks, s, counts=None, mode=0, occ=0, block=64, force_global_sort=False):
+        bases, offs = pack(seqs)
+        ks = np.atleast_1d(np.asarray(ks, np.int32))
+        sk = np.zeros((len(seqs), s), np.uint64)
+        lens = np.zeros(len(seqs), np.int32)
+        self.lib.emu_sketch(bases.ctypes.data, offs.ctypes.data, len(seqs), ks.ctypes.data, len(ks), s,
+                            counts.ctypes.data if counts is not None else None,
+                            C.c_uint64(counts.size if counts is not None else 0), mode, occ,
+                            sk.ctypes.data, lens.ctypes.data, block, int(force_global_sort))
+        return sk, lens
+
+    def merge(self, parts, lens, s, block=64, in_smem=True):
+        parts = np.ascontiguousarray(parts, np.uint64)
+        lens = np.ascontiguousarray(lens, np.int32)
+        out = np.zeros(s, np.uint64)
+        n = np.zeros(1, np.int32)
+        self.lib.emu_merge(parts.ctypes.data, lens.ctypes.data, len(lens), s, out.ctypes.data, n.ctypes.data, block,
+                           int(in_smem))
+        return out[:n[0]]
+
+    def classify(self, refs, reads, ks, s, counts=None, min_occ=-1, path=1, glog2=4, block=64, hbuf_global=False,
+                 hs_global=False):
+        rb, ro = pack(refs)
+        qb, qo = pack(reads)
+        ks = np.atleast_1d(np.asarray(ks, np.int32))
+        hits = np.zeros(max(len(reads), 1), HIT)
+        rsk = np.zeros((len(refs), s), np.uint64)
+        rl = np.zeros(len(refs), np.int32)
+        redo = np.zeros(1, np.int32)
+        self.lib.emu_classify(rb.ctypes.data, ro.ctypes.data, len(refs), qb.ctypes.data, qo.ctypes.data, len(reads),
+                              ks.ctypes.data, len(ks), s, counts.ctypes.data if counts is not None else None,
+                              C.c_uint64(counts.size if counts is not None else 0), min_occ, path, glog2, block,
+                              int(hbuf_global), int(hs_global), hits.ctypes.data, rsk.ctypes.data, rl.ctypes.data,
+                              redo.ctypes.data)
+        return hits[:len(reads)], rsk, rl, int(redo[0])

@@ -1,0 +1,236 @@
+// tests/emu/emu_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the product's kernel source (rkmh_b200/csrc/rk_kernels.cuh) with g++ against the CPU stand-in
+// of tests/emu/cuda_emu.h and drives the kernels the way rk_capi.cu does, on plain host memory.  Used by
+// tests/test_emu.py to check the kernel LOGIC against the oracle in the GPU-less build container.
+#include "cuda_emu.h"
+EMU_DEFINE_STATE
+
+#include <algorithm>
+#include <vector>
+
+#include "../../rkmh_b200/csrc/rk_kernels.cuh"
+
+using namespace rk;
+
+namespace {
+
+struct HostBatch {
+    std::vector<unsigned char> bases;
+    std::vector<i64> offs;
+    std::vector<u32> codes, nmask;
+    i64 nseq = 0, total = 0, max_ntotal = 0;
+    SeqBatch view() const {
+        SeqBatch sb;
+        sb.bases = bases.data(); sb.offs = offs.data(); sb.codes = codes.data(); sb.nmask = nmask.data();
+        sb.nseq = nseq; sb.total = total; sb.base0 = offs.empty() ? 0 : offs[0];
+        return sb;
+    }
+};
+
+KList make_klist(const int* ks, int nk, int* kcsel) {
+    KList kl{};
+    kl.nk = nk;
+    int sel = -1;
+    for (int j = 0; j < nk; ++j) {
+        kl.k[j] = ks[j]; kl.kc[j] = kclass_of(ks[j]);
+        sel = (sel == -1 || sel == kl.kc[j]) ? kl.kc[j] : 6;
+    }
+    *kcsel = sel;
+    return kl;
+}
+
+void fill_batch(HostBatch& b, const char* bases, const i64* offs, i64 n, const KList& kl, int block) {
+    b.nseq = n; b.total = offs[n] - offs[0];
+    i64 nwords32 = (b.total + 31) / 32;
+    b.bases.assign((size_t)nwords32 * 32 + 64, 0);
+    std::copy(bases + offs[0], bases + offs[n], b.bases.begin());
+    b.offs.assign(offs, offs + n + 1);
+    b.codes.assign((size_t)2 * nwords32 + 8, 0);
+    b.nmask.assign((size_t)nwords32 + 8, 0xFFFFFFFFu);
+    i64 max_len = 0;
+    for (i64 r = 0; r < n; ++r) max_len = std::max(max_len, offs[r + 1] - offs[r]);
+    b.max_ntotal = 0;
+    for (int j = 0; j < kl.nk; ++j) b.max_ntotal += std::max<i64>(max_len - kl.k[j], 0);
+    if (nwords32 > 0) {
+        unsigned char* pb = b.bases.data(); u32* pc = b.codes.data(); u32* pm = b.nmask.data(); i64 tot = b.total;
+        emu::launch(dim3(2), dim3(block), 0, [=] { ingest_kernel(pb, tot, pc, pm, nwords32); });
+    }
+}
+
+int next_pow2(i64 v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+template <typename F> void dispatch(int sel, F&& f) {
+    switch (sel) {
+        case 0: f(KcTag<0>()); break; case 1: f(KcTag<1>()); break; case 2: f(KcTag<2>()); break;
+        case 3: f(KcTag<3>()); break; case 4: f(KcTag<4>()); break; case 5: f(KcTag<5>()); break;
+        default: f(KcTag<6>()); break;
+    }
+}
+
+struct HostTable {
+    std::vector<u64> entries, dup_bits;
+    std::vector<u32> maxmult, dup_base, filter, cursor;
+    RefTable tb{};
+};
+
+void run_sketch(const HostBatch& b, const KList& kl, int kcsel, int s, CountTable ct, int filter_mode, int occ, int block,
+                int grid, int force_global_sort, u64* sketches, int* lens) {
+    const int sort_cap = next_pow2(std::max<i64>(std::min<i64>(s, std::max<i64>(b.max_ntotal, 1)), 2));
+    const int sort_in_smem = force_global_sort ? 0 : 1;
+    const i64 stride = std::max<i64>(b.max_ntotal, 1);
+    std::vector<u64> scratch((size_t)grid * (size_t)(stride + sort_cap) + 8);
+    SeqBatch sb = b.view();
+    u64* ps = scratch.data();
+    dispatch(kcsel, [&](auto tag) {
+        constexpr int KS = decltype(tag)::value;
+        emu::launch(dim3(grid), dim3(block), (size_t)sort_cap * 8, [=] {
+            sketch_kernel<KS>(sb, kl, s, ct, filter_mode, occ, ps, stride, sort_cap, sort_in_smem, sketches, lens, nullptr, nullptr);
+        });
+    });
+}
+
+void build_table(HostTable& ht, const u64* sketches, const int* lens, int nrefs, int s, int block) {
+    const i64 nent = (i64)nrefs * s;
+    const u32 cap = (u32)next_pow2(std::max<i64>(2 * nent, 1024));
+    const u32 nb = (u32)((nrefs + 63) / 64);
+    RefTable& tb = ht.tb;
+    tb.cap_mask = cap - 1; tb.nb = nb; tb.stride = 1 + nb; tb.nrefs = (u32)nrefs;
+    int flog2 = 10;
+    while (flog2 < 20 && (1LL << flog2) < 16 * nent) ++flog2;
+    tb.filter_log2 = (u32)flog2;
+    ht.entries.assign((size_t)cap * tb.stride, 0); ht.maxmult.assign(cap, 0); ht.dup_base.assign(cap, 0);
+    ht.dup_bits.assign((size_t)std::max<i64>(nent, 1) * nb, 0); ht.filter.assign(((size_t)1 << flog2) / 32, 0);
+    ht.cursor.assign(64, 0);
+    tb.entries = ht.entries.data(); tb.maxmult = ht.maxmult.data(); tb.dup_base = ht.dup_base.data();
+    tb.dup_bits = ht.dup_bits.data(); tb.filter = ht.filter.data();
+    RefTable t = tb; u32* f = ht.filter.data(); u32* cur = ht.cursor.data();
+    emu::launch(dim3(2), dim3(block), 0, [=] { table_insert_kernel(sketches, lens, nrefs, s, t, f); });
+    emu::launch(dim3(2), dim3(block), 0, [=] { table_alloc_dup_kernel(t, cur); });
+    emu::launch(dim3(2), dim3(block), 0, [=] { table_fill_dup_kernel(sketches, lens, nrefs, s, t); });
+}
+
+}  // namespace
+
+extern "C" {
+
+// raw calc_hashes of every record (concatenated, per-k order), out_offs has nseq + 1 entries
+int emu_hash(const char* bases, const i64* offs, i64 nseq, const int* ks, int nk, u64* out, i64* out_offs, int block) {
+    int kcsel; KList kl = make_klist(ks, nk, &kcsel);
+    HostBatch b; fill_batch(b, bases, offs, nseq, kl, block);
+    out_offs[0] = 0;
+    for (i64 r = 0; r < nseq; ++r) {
+        i64 len = offs[r + 1] - offs[r], n = 0;
+        for (int j = 0; j < nk; ++j) n += std::max<i64>(len - ks[j], 0);
+        out_offs[r + 1] = out_offs[r] + n;
+    }
+    SeqBatch sb = b.view();
+    for (int kidx = 0; kidx < nk; ++kidx)
+        dispatch(kl.kc[kidx], [&](auto tag) {
+            constexpr int KS = decltype(tag)::value;
+            emu::launch(dim3(2), dim3(block), 0, [=] { hash_kernel<(KS < 6 ? KS : 0)>(sb, kl, kidx, out, out_offs); });
+        });
+    return 0;
+}
+
+int emu_count(const char* bases, const i64* offs, i64 nseq, const int* ks, int nk, int* counts, u64 size, int count_zeros,
+              int block) {
+    int kcsel; KList kl = make_klist(ks, nk, &kcsel);
+    HostBatch b; fill_batch(b, bases, offs, nseq, kl, block);
+    CountTable ct{counts, make_fastmod(size)};
+    SeqBatch sb = b.view();
+    dispatch(kcsel, [&](auto tag) {
+        constexpr int KS = decltype(tag)::value;
+        emu::launch(dim3(2), dim3(block), 0, [=] { count_kernel<KS>(sb, kl, ct, count_zeros); });
+    });
+    return 0;
+}
+
+int emu_sketch(const char* bases, const i64* offs, i64 nseq, const int* ks, int nk, int s, const int* counts, u64 size,
+               int filter_mode, int occ, u64* sketches, int* lens, int block, int force_global_sort) {
+    int kcsel; KList kl = make_klist(ks, nk, &kcsel);
+    HostBatch b; fill_batch(b, bases, offs, nseq, kl, block);
+    CountTable ct{const_cast<int*>(counts), make_fastmod(size ? size : 1)};
+    run_sketch(b, kl, kcsel, s, ct, counts ? filter_mode : 0, occ, block, 2, force_global_sort, sketches, lens);
+    return 0;
+}
+
+int emu_merge(const u64* parts, const int* part_lens, int nparts, int s, u64* out, int* out_len, int block, int in_smem) {
+    const int P = next_pow2(std::max(s, 2));
+    std::vector<u64> scr(P);
+    u64* ps = scr.data();
+    emu::launch(dim3(1), dim3(block), (size_t)P * 8, [=] { merge_kernel(parts, part_lens, nparts, s, P, out, out_len, ps, in_smem); });
+    return 0;
+}
+
+// Full classification: refs -> sketches -> table; reads -> group kernel (optional) -> block kernel.
+// path: 0 = block kernel for every read, 1 = group kernel + block kernel on its redo list.
+// hbuf_mode: 0 = hashes in shared memory when they fit, 1 = force global scratch; hs_smem likewise.
+int emu_classify(const char* ref_bases, const i64* ref_offs, int nrefs, const char* bases, const i64* offs, i64 nreads,
+                 const int* ks, int nk, int s, const int* counts, u64 size, int min_occ, int path, int glog2, int block,
+                 int hbuf_global, int hs_global, Hit* out, u64* ref_sketches_out, int* ref_lens_out, int* redo_count_out) {
+    int kcsel; KList kl = make_klist(ks, nk, &kcsel);
+    HostBatch rb; fill_batch(rb, ref_bases, ref_offs, nrefs, kl, block);
+    std::vector<u64> rsk((size_t)nrefs * s, 0); std::vector<int> rlen(nrefs, 0);
+    run_sketch(rb, kl, kcsel, s, CountTable{nullptr, {}}, 0, 0, block, 2, 0, rsk.data(), rlen.data());
+    if (ref_sketches_out) std::copy(rsk.begin(), rsk.end(), ref_sketches_out);
+    if (ref_lens_out) std::copy(rlen.begin(), rlen.end(), ref_lens_out);
+    HostTable ht; build_table(ht, rsk.data(), rlen.data(), nrefs, s, block);
+
+    HostBatch b; fill_batch(b, bases, offs, nreads, kl, block);
+    CountTable ct{const_cast<int*>(counts), make_fastmod(size ? size : 1)};
+    if (!counts) min_occ = -1;
+    SeqBatch sb = b.view();
+    RefTable tb = ht.tb;
+    std::vector<int> redo((size_t)std::max<i64>(nreads, 1)); int redo_count = 0;
+    int* predo = redo.data(); int* pcount = &redo_count;
+    const int grid = 2;
+    if (path == 1) {
+        const int nwb = block / 32, gpw = 32 >> glog2, rwords = (nrefs + 1) / 2;
+        const int filter_words = (int)((1u << tb.filter_log2) / 32u);
+        size_t smem = (size_t)nwb * sizeof(GroupSmem) + (size_t)nwb * gpw * rwords * 4 + (size_t)nwb * gpw * 4 + (size_t)filter_words * 4;
+        dispatch(kcsel, [&](auto tag) {
+            constexpr int KS = decltype(tag)::value;
+            emu::launch(dim3(grid), dim3(block), smem, [=] {
+                classify_group_kernel<KS>(sb, kl, s, ct, min_occ, tb, glog2, rwords, filter_words, predo, pcount, out);
+            });
+        });
+    }
+    if (redo_count_out) *redo_count_out = redo_count;
+    {
+        const int hs_cap = next_pow2(2 * (i64)std::min<i64>(s, std::max<i64>(b.max_ntotal, 1)));
+        const int rpad = (nrefs + 63) / 64 * 64;
+        const int hs_in_smem = hs_global ? 0 : 1;
+        const i64 hbuf_cap = hbuf_global ? 0 : b.max_ntotal;
+        const i64 stride = hbuf_global ? std::max<i64>(b.max_ntotal, 1) : 0;
+        size_t smem = (size_t)hbuf_cap * 8 + (hs_in_smem ? (size_t)hs_cap * 8 : 0) + (size_t)rpad * 4;
+        std::vector<u64> scratch((size_t)grid * (size_t)(stride + hs_cap) + 8);
+        u64* ps = scratch.data();
+        const int* list = (path == 1) ? predo : nullptr;
+        dispatch(kcsel, [&](auto tag) {
+            constexpr int KS = decltype(tag)::value;
+            emu::launch(dim3(grid), dim3(block), smem, [=] {
+                classify_block_kernel<KS>(sb, kl, s, ct, min_occ, tb, list, pcount, nreads, (int)hbuf_cap, hs_cap, hs_in_smem,
+                                          rpad, ps, stride, out);
+            });
+        });
+    }
+    return 0;
+}
+
+// host-side arithmetic checks
+u64 emu_fastmod(u64 n, u64 d) { FastMod f = make_fastmod(d); return fastmod(n, f); }
+
+u64 emu_kmer_hash(const char* kmer, int k) {   // canonical hash of one window through the rolling window code
+    u64 result = 0;
+    dispatch(kclass_of(k), [&](auto tag) {
+        constexpr int KC = decltype(tag)::value < 6 ? decltype(tag)::value : 0;
+        KmerWindow<KC> w; w.reset();
+        for (int i = 0; i < k; ++i) w.push(base_code((u32)(unsigned char)kmer[i]), !base_valid((u32)(unsigned char)kmer[i]), k,
+                                           win_top_shift(k), win_top_mask(k));
+        result = w.hash(k);
+    });
+    return result;
+}
+
+}  // extern "C"
