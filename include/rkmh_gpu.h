@@ -107,6 +107,12 @@ int rkg_classify_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int
 /* The same in two steps for callers that keep batches resident in HBM (and for kernel-only timing):
  * upload once, classify any number of times, fetch results. */
 int rkg_batch_upload(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, rkg_batch** batch);
+/* Re-run the ingest kernel (upper-case / 2-bit pack / invalid-base mask) on the resident ASCII bases;
+ * rkg_batch_upload already did it once.  Asynchronous. */
+int rkg_batch_ingest(rkg_ctx* ctx, rkg_batch* batch);
+/* Issue this batch's work on the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores the
+ * batch's own stream), so that the caller's events bracket the kernels. */
+int rkg_batch_set_stream(rkg_ctx* ctx, rkg_batch* batch, void* cuda_stream);
 int rkg_batch_classify(rkg_ctx* ctx, rkg_batch* batch, int min_occ);        /* asynchronous */
 int rkg_batch_count(rkg_ctx* ctx, rkg_batch* batch, int count_zeros);       /* asynchronous */
 int rkg_batch_results(rkg_ctx* ctx, rkg_batch* batch, rkg_hit* out);        /* synchronises  */

@@ -51,9 +51,9 @@ struct EventPair { cudaEvent_t a, b; int id; };
 struct rkg_batch {
     DevBuf bases, offs, codes, nmask, hits, redo, scratch, misc;   // misc: [0] redo_count
     i64 nseq = 0, total = 0, base0 = 0, max_ntotal = 0, max_len = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // the stream every operation of this batch is issued on
+    cudaStream_t own_stream = nullptr;   // created with the batch; `stream` may be redirected to a caller's stream
     cudaEvent_t done = nullptr;
-    bool busy = false;
 };
 
 struct rkg_ctx {
@@ -140,7 +140,8 @@ int next_pow2(i64 v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 int batch_alloc(rkg_ctx* ctx, rkg_batch** out) {
     rkg_batch* b = new rkg_batch();
-    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
+    b->stream = b->own_stream;
     CK(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
     *out = b;
     return RKG_OK;
@@ -152,8 +153,21 @@ void batch_release(rkg_batch* b) {
     b->bases.release(); b->offs.release(); b->codes.release(); b->nmask.release(); b->hits.release();
     b->redo.release(); b->scratch.release(); b->misc.release();
     if (b->done) cudaEventDestroy(b->done);
-    if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->own_stream) cudaStreamDestroy(b->own_stream);
     delete b;
+}
+
+// 2-bit pack + invalid-base mask of the batch's resident ASCII bases.
+int launch_ingest(rkg_ctx* ctx, rkg_batch* b) {
+    const i64 nwords32 = (b->total + 31) / 32;
+    if (nwords32 > 0) {
+        Timed t(ctx, b->stream, K_INGEST);
+        int grid = (int)std::min<i64>((nwords32 + 255) / 256, (i64)ctx->sm_count * 16);
+        ingest_kernel<<<grid, 256, 0, b->stream>>>(b->bases.as<unsigned char>(), b->total, b->codes.as<u32>(),
+                                                   b->nmask.as<u32>(), nwords32);
+    }
+    CK(cudaGetLastError());
+    return RKG_OK;
 }
 
 // Copy reads [r0, r1) of the caller's buffers into the batch and pack them (asynchronous on b->stream).
@@ -181,14 +195,7 @@ int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* off
     i64 mt = 0;
     for (int j = 0; j < ctx->kl.nk; ++j) mt += std::max<i64>(max_len - ctx->kl.k[j], 0);
     b->max_ntotal = mt;
-    if (nwords32 > 0) {
-        Timed t(ctx, b->stream, K_INGEST);
-        int grid = (int)std::min<i64>((nwords32 + 255) / 256, (i64)ctx->sm_count * 16);
-        ingest_kernel<<<grid, 256, 0, b->stream>>>(b->bases.as<unsigned char>(), total, b->codes.as<u32>(),
-                                                   b->nmask.as<u32>(), nwords32);
-    }
-    CK(cudaGetLastError());
-    return RKG_OK;
+    return launch_ingest(ctx, b);
 }
 
 SeqBatch seq_view(const rkg_batch* b) {
@@ -648,6 +655,20 @@ int rkg_batch_count(rkg_ctx* ctx, rkg_batch* batch, int count_zeros) {
     if (!ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "no read count table");
     CK(cudaSetDevice(ctx->device));
     return launch_count(ctx, batch, ctx->read_ct, count_zeros);
+}
+
+int rkg_batch_ingest(rkg_ctx* ctx, rkg_batch* batch) {
+    if (!ctx || !batch) return RKG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return launch_ingest(ctx, batch);
+}
+
+int rkg_batch_set_stream(rkg_ctx* ctx, rkg_batch* batch, void* cuda_stream) {
+    if (!ctx || !batch) return RKG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(batch->stream));
+    batch->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : batch->own_stream;
+    return RKG_OK;
 }
 
 int rkg_batch_results(rkg_ctx* ctx, rkg_batch* batch, rkg_hit* out) {

@@ -1,0 +1,106 @@
+"""CPU tests of the kernel LOGIC: rkmh_b200/csrc/rk_kernels.cuh compiled by g++ against the CUDA stand-in
+of tests/emu/cuda_emu.h, compared with the oracle.  The same kernels are checked on the B200 by the
+`-m gpu` tests; this keeps logic regressions visible in the GPU-less container."""
+import random
+
+import numpy as np
+import pytest
+
+from rkmh_b200.fastx import load_sequences
+from tests.util import data_path
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from tests.emu.emu import Emu
+    return Emu()
+
+
+def test_fastmod_exact(emu):
+    rnd = random.Random(1)
+    for d in [200_000_000, 10_000_000, 3, 7, 1_000_003, 2**31 - 1, 2**40 + 15, 1 << 20, 640_000]:
+        for n in [0, 1, d - 1, d, d + 1, 2**64 - 1, 2**63] + [rnd.getrandbits(64) for _ in range(50)]:
+            assert emu.lib.emu_fastmod(n, d) == n % d
+
+
+def test_rolling_murmur_all_k(emu, oracle):
+    rnd = random.Random(2)
+    for k in range(1, 33):
+        for _ in range(10):
+            km = "".join(rnd.choice("ACGT") for _ in range(k)).encode()
+            assert emu.lib.emu_kmer_hash(km, k) == oracle.calc_hash(km)
+
+
+@pytest.mark.parametrize("ks", [[8], [4], [9, 16], [17], [25], [32], [12, 20]])
+def test_hash_kernel(emu, oracle, ks):
+    _, seqs, _ = load_sequences([data_path("awkward_reads.fq.gz")])
+    h, _ = emu.hash(seqs, ks)
+    exp = np.concatenate([oracle.calc_hashes(oracle.to_upper(s), ks) for s in seqs])
+    assert np.array_equal(h, exp)
+
+
+def _classify_case(emu, oracle, ref_files, read_file, ks, s, nreads=None, nrefs=None, **kw):
+    _, refs, _ = load_sequences([data_path(f) for f in ref_files])
+    _, reads, _ = load_sequences([data_path(read_file)])
+    reads = reads[:nreads] if nreads else reads
+    refs = refs[:nrefs] if nrefs else refs
+    hits, rsk, rl, redo = emu.classify(refs, reads, ks, s, **kw)
+    osk, ol = oracle.sketch_batch(refs, ks, s)
+    oh = oracle.classify_batch(reads, ks, s, osk, ol)
+    assert np.array_equal(rsk, osk) and np.array_equal(rl, ol)
+    for f in ("ref_id", "best", "prev", "sketch_len"):
+        assert np.array_equal(hits[f], oh[f]), f
+    return redo
+
+
+@pytest.mark.parametrize("kw", [dict(path=0), dict(path=1, glog2=3), dict(path=1, glog2=5),
+                                dict(path=0, hbuf_global=True, hs_global=True)])
+def test_classify_awkward(emu, oracle, kw):
+    _classify_case(emu, oracle, ["awkward_refs.fa.gz"], "awkward_reads.fq.gz", [8], 50, **kw)
+
+
+def test_classify_small_sketch_and_multik(emu, oracle):
+    _classify_case(emu, oracle, ["awkward_refs.fa.gz"], "awkward_reads.fq.gz", [8], 10, path=1, glog2=4)
+    _classify_case(emu, oracle, ["awkward_refs.fa.gz"], "awkward_reads.fq.gz", [6, 17], 20, path=1, glog2=4)
+
+
+def test_classify_fixtures(emu, oracle):
+    assert _classify_case(emu, oracle, ["hpv_16_allFasta.fa.gz"], "minION25.fq.gz", [10], 1000, nreads=4, path=1) == 4
+    assert _classify_case(emu, oracle, ["all_pave_ref.fa.gz"], "z1.fq.gz", [12], 1000, nreads=48, nrefs=70, path=1,
+                          glog2=4) == 0
+    _classify_case(emu, oracle, ["zika.fa.gz", "dengue.fa.gz", "yellow_fever.fa.gz", "hpv_16.fa.gz"], "z1.fq.gz", [20],
+                   2000, nreads=64, path=1, glog2=4)
+
+
+def test_count_mask_and_filters(emu, oracle):
+    _, refs, _ = load_sequences([data_path("new_refs.fa.gz")])
+    _, reads, _ = load_sequences([data_path("mix2k.fq.gz")])
+    reads = reads[:120]
+    size = 1_000_003
+    c1 = np.zeros(size, np.int32)
+    emu.count(reads, [12], c1)
+    c2 = np.zeros(size, np.int32)
+    oracle.count_batch(reads, [12], c2)
+    assert np.array_equal(c1, c2)
+    for path in (0, 1):
+        hits, _, _, _ = emu.classify(refs, reads, [12], 1000, counts=c1, min_occ=2, path=path, glog2=5)
+        osk, ol = oracle.sketch_batch(refs, [12], 1000)
+        oh = oracle.classify_batch(reads, [12], 1000, osk, ol, counts=c2, min_occ=2)
+        for f in ("ref_id", "best", "prev", "sketch_len"):
+            assert np.array_equal(hits[f], oh[f]), (path, f)
+    sk, ln = emu.sketch(refs, [12], 1000, counts=c1, mode=1, occ=3)
+    osk, ol = oracle.sketch_batch(refs, [12], 1000, counts=c2, mode=1, occ=3)
+    assert np.array_equal(sk, osk) and np.array_equal(ln, ol)
+
+
+def test_sketch_and_merge(emu, oracle):
+    _, refs, _ = load_sequences([data_path("new_refs.fa.gz")])
+    refs = refs[:4]
+    for s, kw in ((300, dict(force_global_sort=True)), (20000, {}), (1000, {})):
+        sk, ln = emu.sketch(refs, [12], s, **kw)
+        osk, ol = oracle.sketch_batch(refs, [12], s)
+        assert np.array_equal(sk, osk) and np.array_equal(ln, ol)
+    parts, pl = oracle.sketch_batch(refs, [12], 1000)
+    whole = oracle.minhashes(np.concatenate([oracle.calc_hashes(oracle.to_upper(r), [12]) for r in refs]), 1000)
+    assert np.array_equal(emu.merge(parts, pl, 1000), whole)
+    assert np.array_equal(emu.merge(parts, pl, 1000, in_smem=False), whole)

@@ -1,0 +1,268 @@
+"""GPU parity tests (run on the B200 with `-m gpu`): every call goes through the C ABI
+(include/rkmh_gpu.h) and is compared with the oracle / golden vectors of the real reference."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from rkmh_b200.fastx import load_sequences
+from tests.golden.make_golden import CLI_CASES, LIB_CASES, sketch_checksum
+from tests.util import data_path, golden_cli_output
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import rkmh_b200
+    ctx = rkmh_b200.RkmhGpu(0)
+    yield ctx
+    ctx.close()
+
+
+def _pack(seqs):
+    from rkmh_b200 import pack_sequences
+    return pack_sequences(seqs)
+
+
+def _fields(h):
+    return np.stack([h["ref_id"], h["best"], h["prev"], h["sketch_len"]], axis=1)
+
+
+# ---- hashing -------------------------------------------------------------------------------------------
+def test_calc_hashes_full_dump(gpu, lib_vectors):
+    _, qs, _ = load_sequences([data_path("minION25.fq.gz")])
+    gpu.set_params([10], 1000)
+    h, ho = gpu.calc_hashes(*_pack(qs[:1]))
+    assert np.array_equal(h, lib_vectors["dump/minion0_k10"])
+    _, rs, _ = load_sequences([data_path("all_pave_ref.fa.gz")])
+    gpu.set_params([12], 1000)
+    h, ho = gpu.calc_hashes(*_pack(rs[:1]))
+    assert np.array_equal(h, lib_vectors["dump/pave0_k12"])
+    sk, ln = gpu.sketch_batch(*_pack(rs[:1]))
+    assert np.array_equal(sk[0, :ln[0]], lib_vectors["dump/pave0_k12_sketch"])
+
+
+def test_calc_hash_kats(gpu, kats):
+    for kat in kats["calc_hash"]:
+        km = kat["kmer"].encode()
+        if len(km) > 32:
+            continue
+        gpu.set_params([len(km)], 10)
+        h, _ = gpu.calc_hashes(*_pack([km + b"A"]))
+        assert int(h[0]) == int(kat["hash"]), kat["kmer"]
+
+
+@pytest.mark.parametrize("k", list(range(1, 33)))
+def test_calc_hashes_every_k_vs_oracle(gpu, oracle, k):
+    rng = np.random.default_rng(100 + k)
+    seqs = []
+    for n in (k, k + 1, k + 2, 40, 151, 1000):
+        s = rng.choice(np.frombuffer(b"ACGTacgtNnRY-*", np.uint8), size=n, p=[.22, .22, .22, .22, .02, .02, .02, .02, .01, .01, .005, .005, .005, .005])
+        seqs.append(s.tobytes())
+    gpu.set_params([k], 100)
+    h, ho = gpu.calc_hashes(*_pack(seqs))
+    exp = np.concatenate([oracle.calc_hashes(oracle.to_upper(s), [k]) for s in seqs])
+    assert np.array_equal(h, exp)
+
+
+def test_multi_k_order(gpu, oracle):
+    _, qs, _ = load_sequences([data_path("awkward_reads.fq.gz")])
+    ks = [12, 5, 20, 16, 32, 9]
+    gpu.set_params(ks, 100)
+    h, ho = gpu.calc_hashes(*_pack(qs))
+    exp = np.concatenate([oracle.calc_hashes(oracle.to_upper(s), ks) for s in qs])
+    assert np.array_equal(h, exp)
+
+
+# ---- sketches and classification vs the real mkmh vectors ---------------------------------------------------
+@pytest.mark.parametrize("case", sorted(LIB_CASES))
+def test_against_real_mkmh_vectors(gpu, lib_vectors, case):
+    ref_files, read_file, ks, s = LIB_CASES[case]
+    _, rs, _ = load_sequences([data_path(f) for f in ref_files])
+    _, qs, _ = load_sequences([data_path(read_file)])
+    gpu.set_params(ks, s)
+    gpu.load_refs(*_pack(rs))
+    sk, lens = gpu.ref_sketches()
+    assert np.array_equal(lens, lib_vectors[case + "/ref_len"])
+    x = np.array([sketch_checksum(sk[i, :lens[i]]) for i in range(len(rs))], np.uint64)
+    assert np.array_equal(x, lib_vectors[case + "/ref_sketch_x"])
+    if case + "/ref_sketches" in lib_vectors:
+        assert np.array_equal(sk, lib_vectors[case + "/ref_sketches"])
+    hits = gpu.classify_batch(*_pack(qs))
+    assert np.array_equal(_fields(hits), lib_vectors[case + "/hits"])
+    # the resident-batch path gives the same records
+    b = gpu.upload(*_pack(qs))
+    b.classify()
+    assert np.array_equal(_fields(b.results()), lib_vectors[case + "/hits"])
+    b.free()
+    # read sketches through the `hash` entry point
+    rsk, rl = gpu.sketch_batch(*_pack(qs))
+    assert np.array_equal(rl, lib_vectors[case + "/hits"][:, 3])
+    rx = np.array([sketch_checksum(rsk[i, :rl[i]]) for i in range(len(qs))], np.uint64)
+    assert np.array_equal(rx, lib_vectors[case + "/read_sketch_x"])
+
+
+# ---- whole commands vs the real CLI's stdout ------------------------------------------------------------------
+def _parse(argv):
+    opt = {"r": [], "f": [], "k": [], "s": 1000, "M": -1, "N": -1, "D": 0, "I": None}
+    it = iter(argv[1:])
+    for a in it:
+        v = next(it)
+        key = a[1]
+        if key in "rf":
+            opt[key].append(data_path(v))
+        elif key == "k":
+            opt["k"].append(int(v))
+        else:
+            opt[key] = int(v)
+    return opt
+
+
+@pytest.mark.parametrize("name", sorted(CLI_CASES))
+def test_cli_output_md5(gpu, cli_manifest, name):
+    import rkmh_b200.api as api
+    which, argv = CLI_CASES[name]
+    o = _parse(argv)
+    if which == "filter":
+        out = api.run_filter(o["r"], o["f"], o["k"], o["s"], o["M"], o["N"], o["D"],
+                             100000 if o["I"] is None else o["I"], ctx=gpu)
+    else:
+        out = api.run_stream(o["r"], o["f"], o["k"], o["s"], o["M"], o["N"], o["D"], o["I"], ctx=gpu)
+    gold = golden_cli_output(name)
+    if out != gold:
+        a, b = out.splitlines(), gold.splitlines()
+        diff = [(i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y][:3]
+        pytest.fail(f"{name}: {len(a)} vs {len(b)} lines; first diffs {diff}")
+    assert hashlib.md5(out).hexdigest() == cli_manifest[name]["md5"]
+
+
+# ---- edge cases ----------------------------------------------------------------------------------------------
+def test_edge_cases_vs_oracle(gpu, oracle):
+    _, rs, _ = load_sequences([data_path("awkward_refs.fa.gz")])
+    reads = [b"A" * 200, b"ACGT" * 50, b"N" * 60, b"ACGTACGTA", b"ACGTACGT", b"ACG", b"", b"acgtacgtacgtnacgtacgtacgt",
+             b"GATTACA" * 30, b"G" * 9 + b"{}|~" + b"C" * 20, rs[0], rs[1] + rs[1]]
+    for ks, s in (([8], 50), ([8], 5), ([8, 4], 1000), ([31], 16), ([2], 3)):
+        gpu.set_params(ks, s)
+        gpu.load_refs(*_pack(rs))
+        osk, ol = oracle.sketch_batch(rs, ks, s)
+        sk, ln = gpu.ref_sketches()
+        assert np.array_equal(sk, osk) and np.array_equal(ln, ol)
+        hits = gpu.classify_batch(*_pack(reads))
+        exp = oracle.classify_batch(reads, ks, s, osk, ol)
+        assert np.array_equal(_fields(hits), _fields(exp)), (ks, s)
+    # empty batch
+    assert len(gpu.classify_batch(np.zeros(1, np.uint8), np.zeros(1, np.int64))) == 0
+
+
+def test_errors_are_loud(gpu):
+    import rkmh_b200
+    with pytest.raises(rkmh_b200.RkmhError):
+        gpu.set_params([33], 100)
+    with pytest.raises(rkmh_b200.RkmhError):
+        gpu.set_params([], 100)
+    gpu.set_params([12], 100)
+    with pytest.raises(rkmh_b200.RkmhError):
+        gpu.classify_batch(*_pack([b"ACGTACGTACGTACGTAC"]))       # no references loaded
+    with pytest.raises(rkmh_b200.RkmhError):
+        gpu.count_batch(*_pack([b"ACGTACGTACGTACGTAC"]))          # no count table configured
+
+
+def _synthetic_reads(rng, refs, n, length, sub=0.005, nrate=0.001, random_frac=0.1):
+    from rkmh_b200.synth import sample_reads
+    return sample_reads(rng, refs, n, length, sub, nrate, random_frac)
+
+
+def test_random_reads_vs_oracle(gpu, oracle):
+    """seeded cfg2-like reads at a size the oracle finishes in seconds; both kernels are exercised"""
+    _, rs, _ = load_sequences([data_path("all_pave_ref.fa.gz")])
+    rng = np.random.default_rng(2)
+    bases, offs = _synthetic_reads(rng, rs, 3000, 150)
+    reads = [bases[offs[i]:offs[i + 1]].tobytes() for i in range(len(offs) - 1)]
+    reads[5] = b"A" * 150                      # duplicates inside one read
+    reads[6] = (b"GTTAACTACCATCATTCATT" * 8)[:150]
+    bases, offs = _pack(reads)
+    gpu.set_params([12], 1000)
+    gpu.load_refs(*_pack(rs))
+    sk, ln = gpu.ref_sketches()
+    hits = gpu.classify_batch(bases, offs)
+    exp = oracle.classify_batch(reads, [12], 1000, sk, ln)
+    assert np.array_equal(_fields(hits), _fields(exp))
+    # long reads, sketch smaller than the read
+    genome = b"".join(rs[:3])                   # 24 kb of concatenated genomes to cut 10 kb reads from
+    bases, offs = _synthetic_reads(rng, [genome, genome[5000:] + genome[:5000]], 40, 10000, sub=0.04)
+    reads = [bases[offs[i]:offs[i + 1]].tobytes() for i in range(len(offs) - 1)]
+    hits = gpu.classify_batch(bases, offs)
+    exp = oracle.classify_batch(reads, [12], 1000, sk, ln)
+    assert np.array_equal(_fields(hits), _fields(exp))
+
+
+def test_count_table_vs_oracle(gpu, oracle):
+    _, rs, _ = load_sequences([data_path("new_refs.fa.gz")])
+    _, qs, _ = load_sequences([data_path("mix2k.fq.gz")])
+    qs = qs[:600]
+    size = 200_000_000
+    gpu.set_params([12], 1000, read_table_size=size)
+    gpu.load_refs(*_pack(rs))
+    gpu.count_reset()
+    gpu.count_batch(*_pack(qs))
+    counts = np.zeros(size, np.int32)
+    oracle.count_batch(qs, [12], counts)
+    allh = np.concatenate([oracle.calc_hashes(oracle.to_upper(q), [12]) for q in qs[:50]])
+    probe = allh[allh != 0][::7]
+    assert np.array_equal(gpu.count_lookup(probe), counts[(probe % np.uint64(size)).astype(np.int64)])
+    t = gpu.count_table_tensor()
+    assert int(t.sum().item()) == int(counts.sum())
+    sk, ln = gpu.ref_sketches()
+    for m in (1, 3, 10):
+        hits = gpu.classify_batch(*_pack(qs), min_occ=m)
+        exp = oracle.classify_batch(qs, [12], 1000, sk, ln, counts=counts, min_occ=m)
+        assert np.array_equal(_fields(hits), _fields(exp)), m
+
+
+def test_sharded_sketch_equals_whole(gpu, oracle):
+    """`hash` of one record split over shards + merge == minhashes of the whole record."""
+    rng = np.random.default_rng(5)
+    seq = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=3_000_000, p=[.2475, .2475, .2475, .2475, .01])
+    k, s = 21, 10000
+    gpu.set_params([k], s)
+    whole, wl = gpu.sketch_batch(seq, np.array([0, seq.size], np.int64))
+    nk = seq.size - k
+    parts, lens = [], []
+    nshard = 4
+    for r in range(nshard):
+        b, e = nk * r // nshard, nk * (r + 1) // nshard
+        sk = gpu.sketch_shard(seq[b:min(e + k, seq.size)], b, e, seq.size)
+        row = np.zeros(s, np.uint64)
+        row[:len(sk)] = sk
+        parts.append(row)
+        lens.append(len(sk))
+    merged = gpu.merge_sketches(np.stack(parts), lens)
+    assert np.array_equal(merged, whole[0, :wl[0]])
+    ref = oracle.minhashes(oracle.calc_hashes(seq[:400_000].tobytes(), [k]), s)
+    part, pl = gpu.sketch_batch(seq[:400_000], np.array([0, 400_000], np.int64))
+    assert np.array_equal(part[0, :pl[0]], ref)
+
+
+def test_full_size_properties(gpu, oracle):
+    """BASELINE config 2 at a tenth of its size (1 M reads) through size-independent properties: results do not
+    depend on batch order or chunking, a spot sample equals the oracle, and every best <= sketch_len <= s."""
+    _, rs, _ = load_sequences([data_path("all_pave_ref.fa.gz")])
+    rng = np.random.default_rng(22)
+    n = 1_000_000
+    bases, offs = _synthetic_reads(rng, rs, n, 150)
+    gpu.set_params([12], 1000)
+    gpu.load_refs(*_pack(rs))
+    hits = gpu.classify_batch(bases, offs)
+    assert (hits["best"] <= hits["sketch_len"]).all() and (hits["sketch_len"] <= 138).all()
+    assert (hits["prev"] < np.maximum(hits["best"], 0) + (hits["ref_id"] == 0)).all()
+    # reversed read order gives reversed results
+    mat = bases.reshape(n, 150)[::-1].copy()
+    hits_r = gpu.classify_batch(mat.reshape(-1), offs)
+    assert np.array_equal(_fields(hits_r), _fields(hits)[::-1])
+    # a spot sample against the oracle
+    idx = rng.choice(n, 400, replace=False)
+    reads = [bases[offs[i]:offs[i + 1]].tobytes() for i in idx]
+    sk, ln = gpu.ref_sketches()
+    exp = oracle.classify_batch(reads, [12], 1000, sk, ln)
+    assert np.array_equal(_fields(hits[idx]), _fields(exp))
