@@ -126,7 +126,7 @@ void profile_collect(rkg_ctx* c) {
 
 int next_pow2(i64 v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-// Launch helper over the key-length-class template parameter.
+// Launch helper over the key-length-variant template parameter (NUM_KV = mixed variants).
 #define DISPATCH_KCSEL(sel, ...)                  \
     switch (sel) {                                \
         case 0: { constexpr int KS = 0; __VA_ARGS__; } break; \
@@ -135,7 +135,11 @@ int next_pow2(i64 v) { int p = 1; while (p < v) p <<= 1; return p; }
         case 3: { constexpr int KS = 3; __VA_ARGS__; } break; \
         case 4: { constexpr int KS = 4; __VA_ARGS__; } break; \
         case 5: { constexpr int KS = 5; __VA_ARGS__; } break; \
-        default: { constexpr int KS = 6; __VA_ARGS__; } break; \
+        case 6: { constexpr int KS = 6; __VA_ARGS__; } break; \
+        case 7: { constexpr int KS = 7; __VA_ARGS__; } break; \
+        case 8: { constexpr int KS = 8; __VA_ARGS__; } break; \
+        case 9: { constexpr int KS = 9; __VA_ARGS__; } break; \
+        default: { constexpr int KS = NUM_KV; __VA_ARGS__; } break; \
     }
 
 int batch_alloc(rkg_ctx* ctx, rkg_batch** out) {
@@ -228,7 +232,7 @@ GroupGeom group_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
     const i64 mean_len = b->total / b->nseq;
     i64 n = 0;
     for (int j = 0; j < ctx->kl.nk; ++j) n += std::max<i64>(mean_len - ctx->kl.k[j], 0);
-    if (n > ctx->s || n > GROUP_MAX_KMERS) return g;     // typical read is not eligible: exact path for all
+    if (n > ctx->s || n > GROUP_MAX_KMERS || ctx->nrefs > 65000) return g;   // typical read is not eligible: exact path for all
     int glog2 = 5;                                        // ~8-12 k-mers per lane
     while (glog2 > 3 && (n >> (glog2 - 1)) < 10) --glog2;
     g.glog2 = glog2;
@@ -406,10 +410,12 @@ int rkg_set_params(rkg_ctx* ctx, const int* ks, int nk, int sketch_size, uint64_
         if (ks[j] < 1 || ks[j] > MAX_K)
             return fail(ctx, RKG_ERR_ARG, "rkg_set_params: k = %d unsupported (1..%d)", ks[j], MAX_K);
         kl.k[j] = ks[j];
-        kl.kc[j] = kclass_of(ks[j]);
-        kcsel = (kcsel == -1 || kcsel == kl.kc[j]) ? kl.kc[j] : 6;
+        kl.kv[j] = kvariant_of(ks[j]);
+        kl.ksum += ks[j];
+        kcsel = (kcsel == -1 || kcsel == kl.kv[j]) ? kl.kv[j] : NUM_KV;
         kmax = std::max(kmax, ks[j]); kmin = std::min(kmin, ks[j]);
     }
+    kl.kmax = kmax;
     ctx->kl = kl; ctx->kcsel = kcsel; ctx->kmax = kmax; ctx->kmin = kmin; ctx->s = sketch_size;
     ctx->refs_loaded = false;
     auto setup = [&](uint64_t size, DevBuf& buf, CountTable& ct) -> cudaError_t {
@@ -752,7 +758,7 @@ int rkg_hash_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t
         for (int kidx = 0; kidx < ctx->kl.nk; ++kidx) {
             Timed t(ctx, b->stream, K_HASH);
             int grid = (int)std::min<i64>((n + 7) / 8, (i64)ctx->sm_count * 8);
-            DISPATCH_KCSEL(ctx->kl.kc[kidx], (hash_kernel<(KS < 6 ? KS : 0)><<<grid, 256, 0, b->stream>>>(
+            DISPATCH_KCSEL(ctx->kl.kv[kidx], (hash_kernel<(KS < NUM_KV ? KS : 0)><<<grid, 256, 0, b->stream>>>(
                                                  seq_view(b), ctx->kl, kidx, d_h.as<u64>(), d_ho.as<i64>())));
         }
         cudaMemcpyAsync(hashes + h0, d_h.p, sizeof(u64) * (size_t)nh, cudaMemcpyDeviceToHost, b->stream);

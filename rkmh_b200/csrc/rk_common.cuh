@@ -87,33 +87,51 @@ constexpr u64 MM_C2 = 0x4cf5ad432745937fULL;
 RK_HD u64 mm_mix_k1(u64 k1) { k1 *= MM_C1; k1 = rotl64(k1, 31); k1 *= MM_C2; return k1; }
 RK_HD u64 mm_mix_k2(u64 k2) { k2 *= MM_C2; k2 = rotl64(k2, 33); k2 *= MM_C1; return k2; }
 
-// Key-length classes: which of body blocks / tail words exist is fixed per class, so each kernel
-// instantiation carries no length-dependent branches.
-//   KC 0: 1..8   tail k1            KC 3: 17..24  body + tail k1
-//   KC 1: 9..15  tail k1,k2         KC 4: 25..31  body + tail k1,k2
-//   KC 2: 16     body               KC 5: 32      body, body
-inline int kclass_of(int k) { return k <= 8 ? 0 : k <= 15 ? 1 : k == 16 ? 2 : k <= 24 ? 3 : k <= 31 ? 4 : 5; }
-template <int KC> struct KWords { static constexpr int N = (KC == 0) ? 1 : (KC <= 2) ? 2 : (KC == 3) ? 3 : 4; };
+// Key-length variants.  A k-mer of k bytes is held in NW = ceil(k/4) 32-bit registers; which Murmur body
+// blocks / tail words exist is fixed per variant, so each kernel instantiation carries no length-dependent
+// branches:
+//   KV  k       NW  Murmur                      KV  k       NW  Murmur
+//   0   1..4    1   tail k1                     5   17..20   5   body + tail k1
+//   1   5..8    2   tail k1                     6   21..24   6   body + tail k1
+//   2   9..12   3   tail k1,k2(32 bit)          7   25..28   7   body + tail k1,k2(32 bit)
+//   3   13..15  4   tail k1,k2                  8   29..31   8   body + tail k1,k2
+//   4   16      4   body                        9   32       8   body, body
+constexpr int NUM_KV = 10;
+inline int kvariant_of(int k) {
+    return k <= 4 ? 0 : k <= 8 ? 1 : k <= 12 ? 2 : k <= 15 ? 3 : k == 16 ? 4 : k <= 20 ? 5 : k <= 24 ? 6 : k <= 28 ? 7 : k <= 31 ? 8 : 9;
+}
+template <int KV> struct KVar {
+    static constexpr int NW = (KV == 0) ? 1 : (KV == 1) ? 2 : (KV == 2) ? 3 : (KV <= 4) ? 4 : (KV == 5) ? 5 : (KV == 6) ? 6 : (KV == 7) ? 7 : 8;
+    static constexpr int BODIES = (KV <= 3) ? 0 : (KV <= 8) ? 1 : 2;
+    static constexpr bool TAIL = (KV != 4 && KV != 9);
+};
 
-template <int KC>
-RK_HD u64 murmur_kmer(const u64* w, int k) {
+RK_HD u64 pack64(u32 lo, u32 hi) { return ((u64)hi << 32) | (u64)lo; }
+
+// w[0..NW): the k key bytes little-endian, bytes beyond k zero.
+template <int KV>
+RK_HD u64 murmur_kmer(const u32* w, int k) {
     u64 h1 = MURMUR_SEED, h2 = MURMUR_SEED;
-    if (KC >= 2) {                                   // murmur3.cpp:248-259, first block
-        h1 ^= mm_mix_k1(w[0]);
+    if constexpr (KVar<KV>::BODIES >= 1) {           // murmur3.cpp:248-259
+        h1 ^= mm_mix_k1(pack64(w[0], w[1]));
         h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
-        h2 ^= mm_mix_k2(w[1]);
+        h2 ^= mm_mix_k2(pack64(w[2], w[3]));
         h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
     }
-    if (KC == 5) {                                   // second block (k = 32)
-        h1 ^= mm_mix_k1(w[2]);
+    if constexpr (KVar<KV>::BODIES == 2) {
+        h1 ^= mm_mix_k1(pack64(w[4], w[5]));
         h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
-        h2 ^= mm_mix_k2(w[3]);
+        h2 ^= mm_mix_k2(pack64(w[6], w[7]));
         h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
     }
-    if (KC == 1) h2 ^= mm_mix_k2(w[1]);              // tail, murmur3.cpp:269-289
-    if (KC == 4) h2 ^= mm_mix_k2(w[3]);
-    if (KC == 0 || KC == 1) h1 ^= mm_mix_k1(w[0]);
-    if (KC == 3 || KC == 4) h1 ^= mm_mix_k1(w[2]);
+    if constexpr (KVar<KV>::TAIL) {                  // murmur3.cpp:269-289
+        constexpr int T = KVar<KV>::NW - 4 * KVar<KV>::BODIES;   // 1..4 tail registers
+        constexpr int B = 4 * KVar<KV>::BODIES;
+        if constexpr (T == 4) h2 ^= mm_mix_k2(pack64(w[B + 2], w[B + 3]));
+        if constexpr (T == 3) h2 ^= mm_mix_k2((u64)w[B + 2]);
+        if constexpr (T >= 2) h1 ^= mm_mix_k1(pack64(w[B], w[B + 1]));
+        if constexpr (T == 1) h1 ^= mm_mix_k1((u64)w[B]);
+    }
     h1 ^= (u64)k; h2 ^= (u64)k;                      // murmur3.cpp:294-305
     h1 += h2; h2 += h1;
     h1 = fmix64(h1); h2 = fmix64(h2);
@@ -122,9 +140,11 @@ RK_HD u64 murmur_kmer(const u64* w, int k) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// 2-bit base codes.  code = (ascii >> 1) & 3 gives A=0 C=1 T=2 G=3 for either case, the complement is
-// code ^ 2, and the ASCII letter is byte `code` of 0x47544341 ("ACTG" little-endian).
-constexpr u32 CODE_TO_ASCII = 0x47544341u;
+// 2-bit base codes.  code = (ascii >> 1) & 3 gives A=0 C=1 T=2 G=3 for either case and the complement is
+// code ^ 2.  One byte-permute turns a code into both ASCII letters Murmur needs: byte 0 = the base,
+// byte 1 = its complement (bytes 2,3 are don't-care).
+constexpr u32 CODE_TO_ASCII = 0x47544341u;   // "ACTG"
+constexpr u32 CODE_TO_COMP = 0x43414754u;    // "TGAC"
 
 RK_HD u32 base_code(u32 ascii) { return (ascii >> 1) & 3u; }
 // Exactly the bytes canonical() accepts (valid_dna[], mkmh.hpp:137-152): A C G T a c g t.
@@ -132,21 +152,40 @@ RK_HD bool base_valid(u32 ascii) {
     u32 u = ascii & 0xDFu;
     return u == 'A' || u == 'C' || u == 'G' || u == 'T';
 }
-RK_HD u32 code_ascii(u32 code) {
+
+RK_HD u32 byte_perm(u32 a, u32 b, u32 sel) {
 #if defined(__CUDA_ARCH__)
-    return __byte_perm(CODE_TO_ASCII, 0u, 0x4440u | code);
+    return __byte_perm(a, b, sel);
 #else
-    return (CODE_TO_ASCII >> (8 * code)) & 0xFFu;
+    u64 src = ((u64)b << 32) | a;
+    u32 r = 0;
+    for (int i = 0; i < 4; ++i) r |= (u32)((src >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
 #endif
+}
+RK_HD u32 code_letters(u32 code) { return byte_perm(CODE_TO_ASCII, CODE_TO_COMP, code * 0x11u + 0x40u); }
+
+// Byte-permute selectors of the rolling window for a given k (uniform per launch).
+struct WinSel { u32 f_last, r_last, r_first; };
+RK_HD WinSel make_winsel(int k) {
+    const int p = (k - 1) & 3;                       // index of the newest base's byte in the last register
+    // one 16-bit selector per value of p, packed in a 64-bit constant (no local-memory table)
+    const int sh = 16 * p;
+    WinSel s;
+    s.f_last = (u32)(0x4321342133413334ULL >> sh) & 0xFFFFu;
+    s.r_last = (u32)(0x6543754377437773ULL >> sh) & 0xFFFFu;
+    s.r_first = (k <= 4) ? ((u32)(0x6541754177417771ULL >> sh) & 0xFFFFu) : 0x6541u;   // single-register window
+    return s;
 }
 
 // Rolling window over one strand pair.  f[] holds the forward k-mer as the k ASCII bytes Murmur reads
-// (byte 0 = first base); r[] holds the reverse complement (byte 0 = complement of the LAST base).
-// `run` counts the valid bases seen since the last invalid one; a window is hashable iff run >= k.
-template <int KC>
+// (byte 0 = first base); r[] holds the reverse complement (byte 0 = complement of the LAST base).  Bytes
+// beyond k stay zero.  `run` counts the valid bases seen since the last invalid one; a window is hashable
+// iff run >= k (canonical(), mkmh.hpp:182-188).
+template <int KV>
 struct KmerWindow {
-    static constexpr int NW = KWords<KC>::N;
-    u64 f[NW], r[NW];
+    static constexpr int NW = KVar<KV>::NW;
+    u32 f[NW], r[NW];
     int run;
 
     RK_HD void reset() {
@@ -155,17 +194,17 @@ struct KmerWindow {
         run = 0;
     }
 
-    // k is the k-mer size, top_shift = 8 * ((k - 1) & 7), top_mask keeps the low ((k-1)&7)+1 bytes.
-    RK_HD void push(u32 code, bool invalid, int k, int top_shift, u64 top_mask) {
-        (void)k;
-        u64 a = code_ascii(code), c = code_ascii(code ^ 2u);
+    RK_HD void push(u32 code, bool invalid, const WinSel& ws) {
+        const u32 ac = code_letters(code);
 #pragma unroll
-        for (int i = 0; i < NW - 1; ++i) f[i] = (f[i] >> 8) | (f[i + 1] << 56);
-        f[NW - 1] = (f[NW - 1] >> 8) | (a << top_shift);
+        for (int i = 0; i < NW - 1; ++i) f[i] = byte_perm(f[i], f[i + 1], 0x4321u);
+        f[NW - 1] = byte_perm(f[NW - 1], ac, ws.f_last);
+        if constexpr (NW > 1) {
+            r[NW - 1] = byte_perm(r[NW - 2], r[NW - 1], ws.r_last);
 #pragma unroll
-        for (int i = NW - 1; i > 0; --i) r[i] = (r[i] << 8) | (r[i - 1] >> 56);
-        r[0] = (r[0] << 8) | c;
-        r[NW - 1] &= top_mask;
+            for (int i = NW - 2; i > 0; --i) r[i] = byte_perm(r[i - 1], r[i], 0x6543u);
+        }
+        r[0] = byte_perm(ac, r[0], ws.r_first);
         run = invalid ? 0 : run + 1;
     }
 
@@ -173,12 +212,9 @@ struct KmerWindow {
     // (mkmh.hpp:515-528).
     RK_HD u64 hash(int k) const {
         if (run < k) return 0;
-        u64 hf = murmur_kmer<KC>(f, k), hr = murmur_kmer<KC>(r, k);
+        u64 hf = murmur_kmer<KV>(f, k), hr = murmur_kmer<KV>(r, k);
         return hf < hr ? hf : hr;
     }
 };
-
-RK_HD int win_top_shift(int k) { return 8 * ((k - 1) & 7); }
-RK_HD u64 win_top_mask(int k) { int b = ((k - 1) & 7) + 1; return b == 8 ? ~0ULL : ((1ULL << (8 * b)) - 1); }
 
 }  // namespace rk

@@ -32,7 +32,7 @@ struct SeqBatch {
     i64 base0;                    // offs[] are offsets into the caller's buffer; the batch starts at base0
 };
 
-struct KList { int nk; int k[MAX_NK]; int kc[MAX_NK]; };
+struct KList { int nk; int k[MAX_NK]; int kv[MAX_NK]; int kmax; int ksum; };   // kv = kvariant_of(k)
 
 struct CountTable {
     int* counts;      // nullptr = absent
@@ -97,22 +97,29 @@ ingest_kernel(const unsigned char* __restrict__ bases, i64 total, u32* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sequential reader of packed bases for one thread.
+// Sequential reader of packed bases for one thread: a 64-bit shift register of 2-bit codes and a 32-bit
+// one of invalid-base flags, refilled every 32 bases.  Threads that walk their chunks in lock step refill
+// on the same iteration, so the refill branch does not diverge.
 struct BaseReader {
     const u32* codes; const u32* nmask;
-    i64 pos; u32 cw, mw;
-    RK_D void init(const u32* c, const u32* m, i64 p) {
-        codes = c; nmask = m; pos = p;
-        cw = c[p >> 4]; mw = m[p >> 5];
+    i64 pos; u64 cw; u32 mw; int left;
+    RK_D void refill() {
+        const u32* c = codes + (pos >> 4);
+        const u32 sh = 2u * ((u32)pos & 15u);
+        u32 c0 = c[0], c1 = c[1], c2 = c[2];
+        u32 lo = __funnelshift_r(c0, c1, sh), hi = __funnelshift_r(c1, c2, sh);
+        cw = ((u64)hi << 32) | lo;
+        const u32* m = nmask + (pos >> 5);
+        mw = __funnelshift_r(m[0], m[1], (u32)pos & 31u);
+        left = 32;
     }
+    RK_D void init(const u32* c, const u32* m, i64 p) { codes = c; nmask = m; pos = p; refill(); }
     RK_D void next(u32& code, bool& invalid) {
-        code = (cw >> (2 * ((u32)pos & 15u))) & 3u;
-        invalid = (mw >> ((u32)pos & 31u)) & 1u;
-        ++pos;
-        if (((u32)pos & 15u) == 0) {
-            cw = codes[pos >> 4];
-            if (((u32)pos & 31u) == 0) mw = nmask[pos >> 5];
-        }
+        if (left == 0) refill();
+        code = (u32)cw & 3u;
+        invalid = mw & 1u;
+        cw >>= 2; mw >>= 1;
+        ++pos; --left;
     }
 };
 
@@ -128,11 +135,11 @@ template <int KC, typename F>
 RK_D void hash_range(const u32* codes, const u32* nmask, i64 seq_begin, i64 c0, i64 c1, int k, F&& emit) {
     BaseReader rd; rd.init(codes, nmask, seq_begin + c0);
     KmerWindow<KC> win; win.reset();
-    const int ts = win_top_shift(k); const u64 tm = win_top_mask(k);
+    const WinSel ws = make_winsel(k);
     u32 code; bool inv;
-    for (int j = 0; j < k - 1; ++j) { rd.next(code, inv); win.push(code, inv, k, ts, tm); }
+    for (int j = 0; j < k - 1; ++j) { rd.next(code, inv); win.push(code, inv, ws); }
     for (i64 i = c0; i < c1; ++i) {
-        rd.next(code, inv); win.push(code, inv, k, ts, tm);
+        rd.next(code, inv); win.push(code, inv, ws);
         emit(i, win.hash(k));
     }
 }
@@ -147,24 +154,29 @@ RK_D void team_hash(const u32* codes, const u32* nmask, i64 seq_begin, i64 n, in
     }
 }
 
-// Dispatch on the key-length class.  KCSEL 0..5: every k of the list is of that class (no switch in
-// the instantiation); KCSEL 6: mixed classes, switch per k.
+// Dispatch on the key-length variant.  KCSEL 0..9: every k of the list is of that variant (no switch in
+// the instantiation); KCSEL 10 (= NUM_KV): mixed variants, switch per k.
 template <int KCSEL, typename F>
-RK_D void team_hash_k(int kc, const u32* codes, const u32* nmask, i64 seq_begin, i64 n, int k, int tid, int nthreads,
+RK_D void team_hash_k(int kv, const u32* codes, const u32* nmask, i64 seq_begin, i64 n, int k, int tid, int nthreads,
                       int chunk, F&& emit) {
-    if (KCSEL < 6) { team_hash<(KCSEL < 6 ? KCSEL : 0)>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); return; }
-    switch (kc) {
+    if (KCSEL < NUM_KV) { team_hash<(KCSEL < NUM_KV ? KCSEL : 0)>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); return; }
+    switch (kv) {
         case 0: team_hash<0>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
         case 1: team_hash<1>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
         case 2: team_hash<2>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
         case 3: team_hash<3>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
         case 4: team_hash<4>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
-        default: team_hash<5>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
+        case 5: team_hash<5>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
+        case 6: team_hash<6>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
+        case 7: team_hash<7>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
+        case 8: team_hash<8>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
+        default: team_hash<9>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
     }
 }
 
 RK_D i64 nkmers(i64 len, int k) { return len - k > 0 ? len - k : 0; }   // len - k windows, SURVEY F7
 RK_D i64 nkmers_total(i64 len, const KList& kl) {
+    if (len >= kl.kmax) return (i64)kl.nk * len - kl.ksum;
     i64 n = 0;
     for (int j = 0; j < kl.nk; ++j) n += nkmers(len, kl.k[j]);
     return n;
@@ -204,7 +216,7 @@ count_kernel(SeqBatch sb, KList kl, CountTable ct, int count_zeros) {
         i64 beg = sb.offs[s] - sb.base0, len = sb.offs[s + 1] - sb.offs[s];
         for (int j = 0; j < kl.nk; ++j) {
             const int k = kl.k[j];
-            team_hash_k<KCSEL>(kl.kc[j], sb.codes, sb.nmask, beg, nkmers(len, k), k, lane, 32, 8,
+            team_hash_k<KCSEL>(kl.kv[j], sb.codes, sb.nmask, beg, nkmers(len, k), k, lane, 32, 8,
                                [&](i64, u64 h) {
                                    if (h != 0 || count_zeros) atomicAdd(&ct.counts[fastmod(h, ct.mod)], 1);
                                });
@@ -352,7 +364,7 @@ sketch_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int filter_mode, int 
         for (int j = 0; j < kl.nk; ++j) {
             const int k = kl.k[j];
             i64 nj = nkmers(len, k);
-            team_hash_k<KCSEL>(kl.kc[j], sb.codes, sb.nmask, beg, nj, k, threadIdx.x, blockDim.x, 9,
+            team_hash_k<KCSEL>(kl.kv[j], sb.codes, sb.nmask, beg, nj, k, threadIdx.x, blockDim.x, 9,
                                [&](i64 i, u64 h) {
                                    if (h != 0 && filter_mode != 0) {
                                        int freq = ct.counts[fastmod(h, ct.mod)];
@@ -586,7 +598,7 @@ classify_block_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, 
         for (int j = 0; j < kl.nk; ++j) {
             const int k = kl.k[j];
             i64 nj = nkmers(len, k);
-            team_hash_k<KCSEL>(kl.kc[j], sb.codes, sb.nmask, beg, nj, k, threadIdx.x, blockDim.x, 9,
+            team_hash_k<KCSEL>(kl.kv[j], sb.codes, sb.nmask, beg, nj, k, threadIdx.x, blockDim.x, 9,
                                [&](i64 i, u64 h) {
                                    h = apply_min_occ(h, ct, min_occ);
                                    H[base + i] = h;
@@ -710,14 +722,13 @@ classify_group_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, 
                     atomicOr(&gflag_all[wib * gpw + hg], 2u);
                 } else {
                     atomicOr(&gflag_all[wib * gpw + hg], 1u);
-                    const u64* row = tb.entries + (i64)slot * tb.stride + 1;
-                    for (u32 w = 0; w < tb.nb; ++w) {
-                        u64 bits = row[w];
+                    const u32* row = reinterpret_cast<const u32*>(tb.entries + (i64)slot * tb.stride + 1);
+                    for (u32 w = 0; w < 2 * tb.nb; ++w) {
+                        u32 bits = row[w];
                         while (bits) {
-                            int b = __ffsll((long long)bits) - 1;
+                            const int b = __ffs((int)bits) - 1;
                             bits &= bits - 1;
-                            int j = (int)w * 64 + b;
-                            atomicAdd(&hc[j >> 1], 1u << (16 * (j & 1)));
+                            atomicAdd(&hc[16 * w + (b >> 1)], 1u << (16 * (b & 1)));   // reference 32 w + b
                         }
                     }
                 }
@@ -746,16 +757,16 @@ classify_group_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, 
             auto body = [&](auto kc_tag) {
                 constexpr int KC = decltype(kc_tag)::value;
                 BaseReader rd; KmerWindow<KC> win; win.reset();
-                const int ts = win_top_shift(k); const u64 tm = win_top_mask(k);
+                const WinSel ws = make_winsel(k);
                 u32 code; bool inv;
                 if (c0 < c1) {
                     rd.init(sb.codes, sb.nmask, beg + c0);
-                    for (int w = 0; w < k - 1; ++w) { rd.next(code, inv); win.push(code, inv, k, ts, tm); }
+                    for (int w = 0; w < k - 1; ++w) { rd.next(code, inv); win.push(code, inv, ws); }
                 }
                 for (int i = 0; i < cmax; ++i) {
                     u64 h = 0;
                     if (c0 + i < c1) {
-                        rd.next(code, inv); win.push(code, inv, k, ts, tm);
+                        rd.next(code, inv); win.push(code, inv, ws);
                         h = apply_min_occ(win.hash(k), ct, min_occ);
                     }
                     bool cand = false;
@@ -776,10 +787,12 @@ classify_group_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, 
                     }
                 }
             };
-            if (KCSEL < 6) { body(KcTag<(KCSEL < 6 ? KCSEL : 0)>()); }
-            else switch (kl.kc[j]) {
+            if (KCSEL < NUM_KV) { body(KcTag<(KCSEL < NUM_KV ? KCSEL : 0)>()); }
+            else switch (kl.kv[j]) {
                 case 0: body(KcTag<0>()); break; case 1: body(KcTag<1>()); break; case 2: body(KcTag<2>()); break;
-                case 3: body(KcTag<3>()); break; case 4: body(KcTag<4>()); break; default: body(KcTag<5>()); break;
+                case 3: body(KcTag<3>()); break; case 4: body(KcTag<4>()); break; case 5: body(KcTag<5>()); break;
+                case 6: body(KcTag<6>()); break; case 7: body(KcTag<7>()); break; case 8: body(KcTag<8>()); break;
+                default: body(KcTag<9>()); break;
             }
         }
         while (qn > 0) drain(min(qn, 32));
@@ -793,21 +806,24 @@ classify_group_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, 
             } else if (!(flag & 1u)) {
                 if (l == 0) { Hit hh; hh.ref_id = 0; hh.best = 0; hh.prev = -1; hh.sketch_len = nz; out[rid] = hh; }
             } else {
-                u64 best = 0;
-                for (int j = l; j < (int)tb.nrefs; j += G) {
-                    u32 c = (cnt[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-                    u64 key = ((u64)c << 32) | (u64)(0xFFFFFFFFu - (u32)j);
-                    best = key > best ? key : best;
+                // argmax of src/rkmh.cpp:874-883 on 32-bit keys (count << 16 | 0xFFFF - index): the largest key is the
+                // first reference with the highest count
+                u32 best = 0;
+                for (int w = l; w < rwords; w += G) {
+                    const u32 pair = cnt[w];
+                    const u32 j = 2u * (u32)w;
+                    best = max(best, max((pair << 16) | (0xFFFFu - j), (pair & 0xFFFF0000u) | (0xFFFEu - j)));
                 }
-                for (int d = G >> 1; d >= 1; d >>= 1) {
-                    u64 o = __shfl_xor_sync(gmask, best, d);
-                    best = o > best ? o : best;
-                }
-                const int id = (int)(0xFFFFFFFFu - (u32)(best & 0xFFFFFFFFu));
+                for (int d = G >> 1; d >= 1; d >>= 1) best = max(best, __shfl_xor_sync(gmask, best, d));
+                const int id = (int)(0xFFFFu - (best & 0xFFFFu));
                 int prev = -1;
-                for (int j = l; j < id; j += G) prev = max(prev, (int)((cnt[j >> 1] >> (16 * (j & 1))) & 0xFFFFu));
+                for (int w = l; 2 * w < id; w += G) {
+                    const u32 pair = cnt[w];
+                    prev = max(prev, (int)(pair & 0xFFFFu));
+                    if (2 * w + 1 < id) prev = max(prev, (int)(pair >> 16));
+                }
                 for (int d = G >> 1; d >= 1; d >>= 1) prev = max(prev, __shfl_xor_sync(gmask, prev, d));
-                if (l == 0) { Hit hh; hh.ref_id = id; hh.best = (int)(best >> 32); hh.prev = prev; hh.sketch_len = nz; out[rid] = hh; }
+                if (l == 0) { Hit hh; hh.ref_id = id; hh.best = (int)(best >> 16); hh.prev = prev; hh.sketch_len = nz; out[rid] = hh; }
             }
         }
         __syncwarp();

@@ -33,8 +33,9 @@ KList make_klist(const int* ks, int nk, int* kcsel) {
     kl.nk = nk;
     int sel = -1;
     for (int j = 0; j < nk; ++j) {
-        kl.k[j] = ks[j]; kl.kc[j] = kclass_of(ks[j]);
-        sel = (sel == -1 || sel == kl.kc[j]) ? kl.kc[j] : 6;
+        kl.k[j] = ks[j]; kl.kv[j] = kvariant_of(ks[j]);
+        kl.ksum += ks[j]; kl.kmax = std::max(kl.kmax, ks[j]);
+        sel = (sel == -1 || sel == kl.kv[j]) ? kl.kv[j] : NUM_KV;
     }
     *kcsel = sel;
     return kl;
@@ -64,7 +65,9 @@ template <typename F> void dispatch(int sel, F&& f) {
     switch (sel) {
         case 0: f(KcTag<0>()); break; case 1: f(KcTag<1>()); break; case 2: f(KcTag<2>()); break;
         case 3: f(KcTag<3>()); break; case 4: f(KcTag<4>()); break; case 5: f(KcTag<5>()); break;
-        default: f(KcTag<6>()); break;
+        case 6: f(KcTag<6>()); break; case 7: f(KcTag<7>()); break; case 8: f(KcTag<8>()); break;
+        case 9: f(KcTag<9>()); break;
+        default: f(KcTag<NUM_KV>()); break;
     }
 }
 
@@ -126,9 +129,9 @@ int emu_hash(const char* bases, const i64* offs, i64 nseq, const int* ks, int nk
     }
     SeqBatch sb = b.view();
     for (int kidx = 0; kidx < nk; ++kidx)
-        dispatch(kl.kc[kidx], [&](auto tag) {
+        dispatch(kl.kv[kidx], [&](auto tag) {
             constexpr int KS = decltype(tag)::value;
-            emu::launch(dim3(2), dim3(block), 0, [=] { hash_kernel<(KS < 6 ? KS : 0)>(sb, kl, kidx, out, out_offs); });
+            emu::launch(dim3(2), dim3(block), 0, [=] { hash_kernel<(KS < NUM_KV ? KS : 0)>(sb, kl, kidx, out, out_offs); });
         });
     return 0;
 }
@@ -223,11 +226,12 @@ u64 emu_fastmod(u64 n, u64 d) { FastMod f = make_fastmod(d); return fastmod(n, f
 
 u64 emu_kmer_hash(const char* kmer, int k) {   // canonical hash of one window through the rolling window code
     u64 result = 0;
-    dispatch(kclass_of(k), [&](auto tag) {
-        constexpr int KC = decltype(tag)::value < 6 ? decltype(tag)::value : 0;
+    dispatch(kvariant_of(k), [&](auto tag) {
+        constexpr int KC = decltype(tag)::value < NUM_KV ? decltype(tag)::value : 0;
         KmerWindow<KC> w; w.reset();
-        for (int i = 0; i < k; ++i) w.push(base_code((u32)(unsigned char)kmer[i]), !base_valid((u32)(unsigned char)kmer[i]), k,
-                                           win_top_shift(k), win_top_mask(k));
+        const WinSel ws = make_winsel(k);
+        for (int i = 0; i < k + 3; ++i) w.push(base_code((u32)'G'), false, ws);   // junk first: bytes beyond k must stay zero
+        for (int i = 0; i < k; ++i) w.push(base_code((u32)(unsigned char)kmer[i]), !base_valid((u32)(unsigned char)kmer[i]), ws);
         result = w.hash(k);
     });
     return result;
