@@ -69,23 +69,88 @@ RK_HD u64 fastmod(u64 n, const FastMod& f) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// MurmurHash3_x64_128, first output word only, over a key of k <= 32 bytes held little-endian in
-// w[0..3] (bytes beyond k are zero).  Returns the value mkmh compares and stores:
+// MurmurHash3_x64_128 (murmur3.cpp:234-312), first output word only, over a key of k <= 32 bytes held
+// little-endian in 32-bit registers (bytes beyond k are zero).  Returns the value mkmh compares and stores:
 // (uint64)out32[0] << 32 | out32[1], i.e. the first 64-bit word with its halves swapped.
-RK_HD u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
+//
+// All 64-bit arithmetic is spelled on 32-bit halves: a 64 x 64 -> 64 multiply by a constant is exactly three
+// integer multiply-adds (IMAD.WIDE + 2 IMAD) and a rotate is two funnel shifts.  Left to itself the compiler
+// turns rotl(x * c, r) into two full multiplies and adds an extra add per product (~40% more instructions).
+struct W64 { u32 lo, hi; };
 
-RK_HD u64 fmix64(u64 v) {  // murmur3.cpp:58-67
-    v ^= v >> 33; v *= 0xff51afd7ed558ccdULL;
-    v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL;
-    v ^= v >> 33;
-    return v;
+RK_HD W64 w64(u32 lo, u32 hi) { W64 r; r.lo = lo; r.hi = hi; return r; }
+
+template <u64 C>
+RK_HD W64 mul_c(W64 a) {
+    constexpr u32 clo = (u32)C, chi = (u32)(C >> 32);
+    W64 r;
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(r.lo), "=r"(r.hi) : "r"(a.lo), "r"(clo));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r.hi) : "r"(a.lo), "r"(chi));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r.hi) : "r"(a.hi), "r"(clo));
+#else
+    u64 v = (((u64)a.hi << 32) | a.lo) * C;
+    r.lo = (u32)v; r.hi = (u32)(v >> 32);
+#endif
+    return r;
+}
+// the same for an operand whose upper half is known to be zero (a 1..4 byte tail word)
+template <u64 C>
+RK_HD W64 mul_c_lo(u32 alo) {
+    constexpr u32 clo = (u32)C, chi = (u32)(C >> 32);
+    W64 r;
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(r.lo), "=r"(r.hi) : "r"(alo), "r"(clo));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(r.hi) : "r"(alo), "r"(chi));
+#else
+    u64 v = (u64)alo * C;
+    r.lo = (u32)v; r.hi = (u32)(v >> 32);
+#endif
+    return r;
+}
+
+RK_HD u32 fshl(u32 lo, u32 hi, u32 n) {   // upper word of (hi:lo) << n, 0 < n < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, n);
+#else
+    return (hi << n) | (lo >> (32 - n));
+#endif
+}
+template <int R>
+RK_HD W64 rotl_c(W64 a) {
+    if (R == 32) return w64(a.hi, a.lo);
+    if (R < 32) return w64(fshl(a.hi, a.lo, R), fshl(a.lo, a.hi, R));
+    return w64(fshl(a.lo, a.hi, R - 32), fshl(a.hi, a.lo, R - 32));
+}
+RK_HD W64 add64(W64 a, W64 b) {
+    W64 r;
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=r"(r.lo), "=r"(r.hi) : "r"(a.lo), "r"(a.hi), "r"(b.lo), "r"(b.hi));
+#else
+    u64 v = (((u64)a.hi << 32) | a.lo) + (((u64)b.hi << 32) | b.lo);
+    r.lo = (u32)v; r.hi = (u32)(v >> 32);
+#endif
+    return r;
+}
+RK_HD W64 xor64(W64 a, W64 b) { return w64(a.lo ^ b.lo, a.hi ^ b.hi); }
+RK_HD W64 xorshr33(W64 a) { return w64(a.lo ^ (a.hi >> 1), a.hi); }   // v ^= v >> 33
+
+RK_HD W64 fmix64(W64 v) {  // murmur3.cpp:58-67
+    v = xorshr33(v); v = mul_c<0xff51afd7ed558ccdULL>(v);
+    v = xorshr33(v); v = mul_c<0xc4ceb9fe1a85ec53ULL>(v);
+    return xorshr33(v);
 }
 
 constexpr u64 MM_C1 = 0x87c37b91114253d5ULL;
 constexpr u64 MM_C2 = 0x4cf5ad432745937fULL;
 
-RK_HD u64 mm_mix_k1(u64 k1) { k1 *= MM_C1; k1 = rotl64(k1, 31); k1 *= MM_C2; return k1; }
-RK_HD u64 mm_mix_k2(u64 k2) { k2 *= MM_C2; k2 = rotl64(k2, 33); k2 *= MM_C1; return k2; }
+RK_HD W64 mm_mix_k1(W64 k1) { return mul_c<MM_C2>(rotl_c<31>(mul_c<MM_C1>(k1))); }
+RK_HD W64 mm_mix_k2(W64 k2) { return mul_c<MM_C1>(rotl_c<33>(mul_c<MM_C2>(k2))); }
+RK_HD W64 mm_mix_k1_lo(u32 k1) { return mul_c<MM_C2>(rotl_c<31>(mul_c_lo<MM_C1>(k1))); }
+RK_HD W64 mm_mix_k2_lo(u32 k2) { return mul_c<MM_C1>(rotl_c<33>(mul_c_lo<MM_C2>(k2))); }
+// h = h * 5 + c  (murmur3.cpp:255,259)
+template <u32 ADD>
+RK_HD W64 mul5_add(W64 h) { return add64(mul_c<5ULL>(h), w64(ADD, 0u)); }
 
 // Key-length variants.  A k-mer of k bytes is held in NW = ceil(k/4) 32-bit registers; which Murmur body
 // blocks / tail words exist is fixed per variant, so each kernel instantiation carries no length-dependent
@@ -106,37 +171,35 @@ template <int KV> struct KVar {
     static constexpr bool TAIL = (KV != 4 && KV != 9);
 };
 
-RK_HD u64 pack64(u32 lo, u32 hi) { return ((u64)hi << 32) | (u64)lo; }
-
 // w[0..NW): the k key bytes little-endian, bytes beyond k zero.
 template <int KV>
 RK_HD u64 murmur_kmer(const u32* w, int k) {
-    u64 h1 = MURMUR_SEED, h2 = MURMUR_SEED;
+    W64 h1 = w64(MURMUR_SEED, 0u), h2 = w64(MURMUR_SEED, 0u);
     if constexpr (KVar<KV>::BODIES >= 1) {           // murmur3.cpp:248-259
-        h1 ^= mm_mix_k1(pack64(w[0], w[1]));
-        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
-        h2 ^= mm_mix_k2(pack64(w[2], w[3]));
-        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+        h1 = xor64(h1, mm_mix_k1(w64(w[0], w[1])));
+        h1 = rotl_c<27>(h1); h1 = add64(h1, h2); h1 = mul5_add<0x52dce729u>(h1);
+        h2 = xor64(h2, mm_mix_k2(w64(w[2], w[3])));
+        h2 = rotl_c<31>(h2); h2 = add64(h2, h1); h2 = mul5_add<0x38495ab5u>(h2);
     }
     if constexpr (KVar<KV>::BODIES == 2) {
-        h1 ^= mm_mix_k1(pack64(w[4], w[5]));
-        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
-        h2 ^= mm_mix_k2(pack64(w[6], w[7]));
-        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+        h1 = xor64(h1, mm_mix_k1(w64(w[4], w[5])));
+        h1 = rotl_c<27>(h1); h1 = add64(h1, h2); h1 = mul5_add<0x52dce729u>(h1);
+        h2 = xor64(h2, mm_mix_k2(w64(w[6], w[7])));
+        h2 = rotl_c<31>(h2); h2 = add64(h2, h1); h2 = mul5_add<0x38495ab5u>(h2);
     }
     if constexpr (KVar<KV>::TAIL) {                  // murmur3.cpp:269-289
         constexpr int T = KVar<KV>::NW - 4 * KVar<KV>::BODIES;   // 1..4 tail registers
         constexpr int B = 4 * KVar<KV>::BODIES;
-        if constexpr (T == 4) h2 ^= mm_mix_k2(pack64(w[B + 2], w[B + 3]));
-        if constexpr (T == 3) h2 ^= mm_mix_k2((u64)w[B + 2]);
-        if constexpr (T >= 2) h1 ^= mm_mix_k1(pack64(w[B], w[B + 1]));
-        if constexpr (T == 1) h1 ^= mm_mix_k1((u64)w[B]);
+        if constexpr (T == 4) h2 = xor64(h2, mm_mix_k2(w64(w[B + 2], w[B + 3])));
+        if constexpr (T == 3) h2 = xor64(h2, mm_mix_k2_lo(w[B + 2]));
+        if constexpr (T >= 2) h1 = xor64(h1, mm_mix_k1(w64(w[B], w[B + 1])));
+        if constexpr (T == 1) h1 = xor64(h1, mm_mix_k1_lo(w[B]));
     }
-    h1 ^= (u64)k; h2 ^= (u64)k;                      // murmur3.cpp:294-305
-    h1 += h2; h2 += h1;
+    h1.lo ^= (u32)k; h2.lo ^= (u32)k;                // murmur3.cpp:294-305 (len < 2^32)
+    h1 = add64(h1, h2); h2 = add64(h2, h1);
     h1 = fmix64(h1); h2 = fmix64(h2);
-    h1 += h2;
-    return (h1 << 32) | (h1 >> 32);
+    h1 = add64(h1, h2);
+    return ((u64)h1.lo << 32) | (u64)h1.hi;          // halves swapped, see above
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -102,7 +102,8 @@ ingest_kernel(const unsigned char* __restrict__ bases, i64 total, u32* __restric
 // on the same iteration, so the refill branch does not diverge.
 struct BaseReader {
     const u32* codes; const u32* nmask;
-    i64 pos; u64 cw; u32 mw; int left;
+    i64 pos;            // position of the first base held in the shift registers
+    u64 cw; u32 mw; int left;
     RK_D void refill() {
         const u32* c = codes + (pos >> 4);
         const u32 sh = 2u * ((u32)pos & 15u);
@@ -115,11 +116,11 @@ struct BaseReader {
     }
     RK_D void init(const u32* c, const u32* m, i64 p) { codes = c; nmask = m; pos = p; refill(); }
     RK_D void next(u32& code, bool& invalid) {
-        if (left == 0) refill();
+        if (left == 0) { pos += 32; refill(); }
         code = (u32)cw & 3u;
         invalid = mw & 1u;
         cw >>= 2; mw >>= 1;
-        ++pos; --left;
+        --left;
     }
 };
 
@@ -653,17 +654,18 @@ classify_block_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, 
 // warp and probed 32 at a time, so the L2 probes run with full lanes.  Per-reference counts live in
 // shared memory as packed 16-bit counters.
 //
-// A read is handed to classify_block_kernel through `redo` instead when it is not eligible, or when two
-// of its table hits are the same hash (multiset semantics need ranks) or its hits overflow
-// the per-warp dedupe set.  The result is therefore exact for every input.
+// Multiset semantics: a per-warp shared-memory set counts how often each table slot was hit by
+// the read, so the r-th copy of a hash is looked up at rank r.  A read is handed to classify_block_kernel
+// through `redo` instead when it is not eligible or when its hits overflow that set.  The result is
+// therefore exact for every input.
 constexpr int GROUP_MAX_KMERS = 2048;
 constexpr int GQ = 64;      // per-warp candidate ring
-constexpr int GDS = 256;    // per-warp dedupe set (u32 keys)
+constexpr int GDS = 128;    // per-warp set of the table slots hit so far: key + number of copies seen
 
 struct GroupSmem {           // per-warp scratch
     u64 qh[GQ];
     u32 qg[GQ];
-    u32 ds[GDS];
+    u32 d[2 * GDS];          // [0, GDS): keys, [GDS, 2 GDS): counts
 };
 
 template <int KC>
@@ -696,40 +698,68 @@ classify_group_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, 
 
     for (int i = threadIdx.x; i < filter_words; i += blockDim.x) filt[i] = tb.filter[i];
     for (int i = threadIdx.x; i < nwb * gpw * rwords + nwb * gpw; i += blockDim.x) cnt_all[i] = 0;
-    for (int i = lane; i < GDS; i += 32) wsm->ds[i] = 0;
+    for (int i = lane; i < 2 * GDS; i += 32) wsm->d[i] = 0;
     __syncthreads();
 
     const i64 gwarp = (i64)blockIdx.x * nwb + wib, nwarps = (i64)gridDim.x * nwb;
     int qhead = 0, qn = 0;
 
+    // Lanes cooperate on the reference bitsets of the hits of one drain: a row of nw32 32-bit words is spread
+    // over min(nw32, 32) lanes, so the serial part is the number of set bits of ONE word, not of the whole row.
+    const int nw32 = 2 * (int)tb.nb;
+    const int lanes_per_hit = nw32 < 32 ? nw32 : 32;
+    const int hits_per_round = 32 / lanes_per_hit;
+    const int my_sub = lane / lanes_per_hit, my_word = lane - my_sub * lanes_per_hit;
+
     auto drain = [&](int m) {                // probe the first m (<= 32) queued candidates
+        const u64* row = nullptr;
+        u32 hg = 0;
         if (lane < m) {
             int qi = (qhead + lane) & (GQ - 1);
             u64 h = wsm->qh[qi];
-            u32 hg = wsm->qg[qi];
+            hg = wsm->qg[qi];
             int slot = table_find(tb, h);
             if (slot >= 0) {
-                u32 key = (((u32)slot << 3) | hg) + 1u, p = (key * 0x9E3779B1u) >> 24;   // GDS = 256
-                bool fresh = false;
-                for (int tries = 0; tries < GDS / 2; ++tries) {
-                    u32 old = atomicCAS(&wsm->ds[p], 0u, key);
-                    if (old == 0u) { fresh = true; break; }
-                    if (old == key) break;
+                // multiplicity inside the read's sketch: the r-th copy of a hash counts for the references that hold
+                // more than r copies (sum of min(multiplicities), mkmh.hpp:822-840)
+                u32 key = (((u32)slot << 3) | hg) + 1u, p = (key * 0x9E3779B1u) >> 25;   // GDS = 128
+                bool found = false;
+                for (int tries = 0; tries < GDS; ++tries) {
+                    u32 old = atomicCAS(&wsm->d[p], 0u, key);
+                    if (old == 0u || old == key) { found = true; break; }
                     p = (p + 1) & (GDS - 1);
                 }
-                u32* hc = cnt_all + (size_t)(wib * gpw + hg) * rwords;
-                if (!fresh) {
-                    atomicOr(&gflag_all[wib * gpw + hg], 2u);
+                if (!found) {
+                    atomicOr(&gflag_all[wib * gpw + hg], 2u);          // set overflow: exact path
                 } else {
                     atomicOr(&gflag_all[wib * gpw + hg], 1u);
-                    const u32* row = reinterpret_cast<const u32*>(tb.entries + (i64)slot * tb.stride + 1);
-                    for (u32 w = 0; w < 2 * tb.nb; ++w) {
-                        u32 bits = row[w];
-                        while (bits) {
-                            const int b = __ffs((int)bits) - 1;
-                            bits &= bits - 1;
-                            atomicAdd(&hc[16 * w + (b >> 1)], 1u << (16 * (b & 1)));   // reference 32 w + b
-                        }
+                    const u32 rank = atomicAdd(&wsm->d[GDS + p], 1u);
+                    row = table_row(tb, slot, rank);
+                }
+            }
+        }
+        __syncwarp();
+        // compact the hit rows into the ring slots this drain has just consumed
+        const u32 hitmask = __ballot_sync(0xffffffffu, row != nullptr);
+        const int nh = __popc(hitmask);
+        if (row != nullptr) {
+            int qi = (qhead + __popc(hitmask & ((1u << lane) - 1u))) & (GQ - 1);
+            wsm->qh[qi] = (u64)(size_t)row;
+            wsm->qg[qi] = hg;
+        }
+        __syncwarp();
+        for (int base = 0; base < nh; base += hits_per_round) {
+            const int hi = base + my_sub;
+            if (hi < nh && my_sub < hits_per_round) {
+                const int qi = (qhead + hi) & (GQ - 1);
+                const u32* r32 = reinterpret_cast<const u32*>((size_t)wsm->qh[qi]);
+                u32* hc = cnt_all + (size_t)(wib * gpw + wsm->qg[qi]) * rwords;
+                for (int w = my_word; w < nw32; w += 32) {
+                    u32 bits = r32[w];
+                    while (bits) {
+                        const int b = __ffs((int)bits) - 1;
+                        bits &= bits - 1;
+                        atomicAdd(&hc[16 * w + (b >> 1)], 1u << (16 * (b & 1)));   // reference 32 w + b
                     }
                 }
             }
@@ -830,7 +860,7 @@ classify_group_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, 
         const u32 anyflag = __ballot_sync(0xffffffffu, flag != 0);
         if (anyflag) {                        // some group of this warp touched counters / the dedupe set
             if (flag) { for (int i = l; i < rwords; i += G) cnt[i] = 0; if (l == 0) *gflag = 0; }
-            for (int i = lane; i < GDS; i += 32) wsm->ds[i] = 0;
+            for (int i = lane; i < 2 * GDS; i += 32) wsm->d[i] = 0;
         }
         __syncwarp();
     }
