@@ -1,0 +1,330 @@
+// rkmh_main.cpp -- the `rkmh` command line (classify / stream / filter / hash) on top of the C ABI
+// (include/rkmh_gpu.h).  Host side only: option parsing with the reference's letters and defaults
+// (reference src/rkmh.cpp:626-720, 1037-1123, 1963-2037), FASTA/FASTQ parsing into pinned batch buffers,
+// sharding of read chunks over the GPUs of the box, and formatting of the reference's exact output lines.
+// Every arithmetic step of the hot path runs in the CUDA library; there is no CPU fallback.
+//
+// Extra, non-reference option: -g/--gpus N (default: RKMH_GPUS or 1) shards reads over N GPUs.  -t is accepted
+// and ignored (the reference's OpenMP thread count).
+#include <getopt.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/rkmh_gpu.h"
+#include "fastx.hpp"
+
+#ifdef RKMH_WITH_NCCL
+#include <cuda_runtime.h>
+#include <nccl.h>
+#endif
+
+using rkhost::SeqSet;
+
+namespace {
+
+constexpr uint64_t STREAM_TABLE = 200000000ULL;   // src/rkmh.cpp:739,742
+constexpr uint64_t FILTER_TABLE = 10000000ULL;    // src/rkmh.cpp:1187-1188
+
+struct Options {
+    std::vector<const char*> refs, reads;
+    std::vector<int> ks;
+    int sketch = 1000, threads = 1, min_occ = -1, min_matches = -1, min_diff = 0, max_samples = 100000;
+    bool do_read_depth = false, do_ref_depth = false, hash_sketch_given = false;
+    int gpus = 1;
+};
+
+void usage(const char* argv0) {
+    fprintf(stderr,
+            "Usage: %s { classify | stream | filter | hash } [options]\n"
+            "    classify: match each read to the reference it most closely resembles using MinHash sketches.\n"
+            "    stream:   the same (classify forwards to stream, as in the reference).\n"
+            "    filter:   spit out reads that meet thresholds for match to ref, uniqueness, etc.\n"
+            "    hash:     compute the MinHash sketches of a set of reads and/or references.\n"
+            "Options:\n"
+            "  --reference/-r <REF>      reference FASTA/FASTQ (repeatable)\n"
+            "  --fasta/-f <FASTAFILE>    reads (repeatable)\n"
+            "  --kmer/-k <KMERSIZE>      k-mer size, 1..32 (repeatable; default 16)\n"
+            "  --sketch-size/-s <N>      sketch size (default 1000)\n"
+            "  --threads/-t <N>          accepted for compatibility, ignored\n"
+            "  --min-kmer-occurence/-M <N>  only use read k-mers seen at least N times in the read set\n"
+            "  --min-matches/-N <N>      flag/filter reads with fewer than N matches\n"
+            "  --min-diff/-D <N>         flag/filter reads whose best match is not N better than the runner-up\n"
+            "  --max-samples/-I <N>      drop reference k-mers seen more than N times in the reference set\n"
+            "  --gpus/-g <N>             shard reads over N B200s (default $RKMH_GPUS or 1)\n",
+            argv0);
+}
+
+[[noreturn]] void die(rkg_ctx* ctx, const char* what) {
+    fprintf(stderr, "rkmh: %s: %s\n", what, rkg_last_error(ctx));
+    exit(2);
+}
+#define RK(ctx, call) do { if ((call) != RKG_OK) die(ctx, #call); } while (0)
+
+// getopt loop shared by stream/classify and filter (same letters in the reference; `d` and unknown letters
+// print the usage and abort(), 'h' / '?' print it and exit(1)).
+void parse_common(int argc, char** argv, Options& o, const char* optstring) {
+    static struct option long_options[] = {
+        {"help", no_argument, 0, 'h'},           {"kmer", no_argument, 0, 'k'},   // sic: the reference declares --kmer no_argument
+        {"fasta", required_argument, 0, 'f'},    {"reference", required_argument, 0, 'r'},
+        {"sketch-size", required_argument, 0, 's'}, {"ref-sketch", required_argument, 0, 'S'},
+        {"threads", required_argument, 0, 't'},  {"min-kmer-occurence", required_argument, 0, 'M'},
+        {"min-matches", required_argument, 0, 'N'}, {"min-diff", required_argument, 0, 'D'},
+        {"max-samples", required_argument, 0, 'I'}, {"pre-reads", required_argument, 0, 'F'},
+        {"pre-references", required_argument, 0, 'R'}, {"read-kmer-map-file", required_argument, 0, 'p'},
+        {"ref-kmer-map-file", required_argument, 0, 'q'}, {"in-stream", no_argument, 0, 'i'},
+        {"output-reads", no_argument, 0, 'z'},   {"merge-sketch", no_argument, 0, 'm'},
+        {"gpus", required_argument, 0, 'g'},     {0, 0, 0, 0}};
+    optind = 2;
+    for (;;) {
+        int idx = 0;
+        int c = getopt_long(argc, argv, optstring, long_options, &idx);
+        if (c == -1) break;
+        switch (c) {
+            case 'm': case 'i': case 'z': break;                       // parsed, no effect (reference: same)
+            case 'F': case 'R': case 'p': case 'q': case 'S': break;   // parsed, no effect
+            case 't': o.threads = atoi(optarg); break;
+            case 'r': o.refs.push_back(optarg); break;
+            case 'f': o.reads.push_back(optarg); break;
+            case 'k': if (optarg) o.ks.push_back(atoi(optarg)); break;
+            case 'N': o.min_matches = atoi(optarg); break;
+            case 'D': o.min_diff = atoi(optarg); break;
+            case 's': o.sketch = atoi(optarg); o.hash_sketch_given = true; break;
+            case 'M': o.min_occ = atoi(optarg); o.do_read_depth = true; break;
+            case 'I': o.max_samples = atoi(optarg); o.do_ref_depth = true; break;
+            case 'g': o.gpus = atoi(optarg); break;
+            case '?': case 'h': usage(argv[0]); exit(1);
+            default: usage(argv[0]); abort();
+        }
+    }
+    if (o.ks.empty()) {
+        fprintf(stderr, "No kmer size(s) provided. Will use a default kmer size of 16.\n");
+        o.ks.push_back(16);
+    }
+}
+
+void load_all(const std::vector<const char*>& files, SeqSet& set, bool keep_qual) {
+    for (const char* f : files)
+        if (!rkhost::read_fastx(f, set, keep_qual)) { fprintf(stderr, "rkmh: cannot open %s\n", f); exit(2); }
+}
+
+// One context per GPU, parameters and references replicated on each.
+struct Fleet {
+    std::vector<rkg_ctx*> ctx;
+    void open(int n) {
+        for (int d = 0; d < n; ++d) {
+            rkg_ctx* c = nullptr;
+            if (rkg_create(d, &c) != RKG_OK) { fprintf(stderr, "rkmh: %s\n", rkg_last_error(nullptr)); exit(2); }
+            ctx.push_back(c);
+        }
+    }
+    ~Fleet() { for (auto c : ctx) rkg_destroy(c); }
+    template <typename F> void each(F&& f) {
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < ctx.size(); ++d) th.emplace_back([&, d] { f((int)d, ctx[d]); });
+        for (auto& t : th) t.join();
+    }
+};
+
+// The only global point of the path: sum the per-GPU read count tables (src/rkmh.cpp:910, the barrier between
+// pass 1 and pass 2).
+void allreduce_counts(Fleet& fl) {
+    if (fl.ctx.size() < 2) return;
+#ifdef RKMH_WITH_NCCL
+    const int n = (int)fl.ctx.size();
+    std::vector<ncclComm_t> comms(n);
+    std::vector<int> devs(n);
+    for (int d = 0; d < n; ++d) devs[d] = d;
+    if (ncclCommInitAll(comms.data(), n, devs.data()) != ncclSuccess) { fprintf(stderr, "rkmh: ncclCommInitAll failed\n"); exit(2); }
+    ncclGroupStart();
+    for (int d = 0; d < n; ++d) {
+        void* p = nullptr; uint64_t slots = 0;
+        RK(fl.ctx[d], rkg_count_table(fl.ctx[d], &p, &slots));
+        cudaSetDevice(d);
+        ncclAllReduce(p, p, slots, ncclInt32, ncclSum, comms[d], 0);
+    }
+    ncclGroupEnd();
+    for (int d = 0; d < n; ++d) { cudaSetDevice(d); cudaStreamSynchronize(0); ncclCommDestroy(comms[d]); }
+#else
+    fprintf(stderr, "rkmh: -M with more than one GPU needs the NCCL build (make WITH_NCCL=1)\n");
+    exit(2);
+#endif
+}
+
+// Reads are sharded over the GPUs in contiguous ranges; every range goes through rkg_classify_batch.
+void shard(size_t n, int parts, int d, size_t& lo, size_t& hi) { lo = n * d / parts; hi = n * (d + 1) / parts; }
+
+void append_int(std::string& s, long long v) { char b[24]; int n = snprintf(b, sizeof b, "%lld", v); s.append(b, n); }
+
+void setup_refs(Fleet& fl, const Options& o, const SeqSet& refs, uint64_t table, bool filter_mode) {
+    const bool use_i = filter_mode ? (o.max_samples < 100000) : o.do_ref_depth;
+    fl.each([&](int, rkg_ctx* c) {
+        RK(c, rkg_set_params(c, o.ks.data(), (int)o.ks.size(), o.sketch, o.do_read_depth ? table : 0, use_i ? table : 0));
+        RK(c, rkg_load_refs(c, refs.bases.data(), refs.offs.data(), (int)refs.size(), use_i ? o.max_samples : -1,
+                            filter_mode ? 1 : 0));
+    });
+}
+
+std::vector<rkg_hit> classify_all(Fleet& fl, const Options& o, const SeqSet& reads, bool count_zeros) {
+    const int G = (int)fl.ctx.size();
+    const size_t n = reads.size();
+    std::vector<rkg_hit> hits(n);
+    if (o.do_read_depth) {                              // pass 1: global k-mer count table
+        fl.each([&](int d, rkg_ctx* c) {
+            size_t lo, hi; shard(n, G, d, lo, hi);
+            RK(c, rkg_count_reset(c));
+            if (hi > lo) RK(c, rkg_count_batch(c, reads.bases.data(), reads.offs.data() + lo, (int64_t)(hi - lo), count_zeros));
+        });
+        allreduce_counts(fl);
+    }
+    fl.each([&](int d, rkg_ctx* c) {
+        size_t lo, hi; shard(n, G, d, lo, hi);
+        if (hi > lo)
+            RK(c, rkg_classify_batch(c, reads.bases.data(), reads.offs.data() + lo, (int64_t)(hi - lo),
+                                     o.do_read_depth ? o.min_occ : -1, hits.data() + lo));
+    });
+    return hits;
+}
+
+// ---- stream / classify: src/rkmh.cpp:584-989 ------------------------------------------------------------
+int main_stream(int argc, char** argv) {
+    if (argc <= 2) { usage(argv[0]); exit(1); }
+    Options o;
+    const char* env = getenv("RKMH_GPUS");
+    if (env) o.gpus = atoi(env);
+    parse_common(argc, argv, o, "zmhdk:f:r:s:S:t:M:N:I:R:F:p:q:iD:g:");
+    SeqSet refs, reads;
+    load_all(o.refs, refs, false);
+    load_all(o.reads, reads, false);
+    if (refs.size() == 0) { fprintf(stderr, "rkmh: no reference sequences (the reference binary is undefined here)\n"); return 2; }
+    Fleet fl; fl.open(std::max(1, o.gpus));
+    setup_refs(fl, o, refs, STREAM_TABLE, false);
+    std::vector<rkg_hit> hits = classify_all(fl, o, reads, false);
+    std::string out;
+    out.reserve(1 << 22);
+    for (size_t i = 0; i < reads.size(); ++i) {          // src/rkmh.cpp:884-893
+        const rkg_hit& h = hits[i];
+        const int diff = h.best - h.prev;
+        const bool depth_fail = h.sketch_len <= o.min_matches, match_fail = h.best < o.min_matches, diff_ok = diff > o.min_diff;
+        out += refs.names[h.ref_id]; out += '\t'; out += reads.names[i]; out += '\t';
+        append_int(out, h.best); out += '\t'; append_int(out, o.sketch);
+        if (depth_fail) out += "FAIL:DEPTH";
+        out += '\t'; if (match_fail) out += "FAIL:MATCHES";
+        out += '\t'; if (!diff_ok) out += "FAIL:DIFF";
+        out += '\n';
+        if (out.size() > (1 << 22) - 4096) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+    }
+    fwrite(out.data(), 1, out.size(), stdout);
+    return 0;
+}
+
+// ---- filter: src/rkmh.cpp:996-1424 (intended flow) ----------------------------------------------
+int main_filter(int argc, char** argv) {
+    if (argc <= 2) { usage(argv[0]); exit(1); }
+    Options o;
+    const char* env = getenv("RKMH_GPUS");
+    if (env) o.gpus = atoi(env);
+    parse_common(argc, argv, o, "hdk:f:r:s:S:t:M:N:I:R:F:p:q:iD:g:");
+    SeqSet refs, reads;
+    load_all(o.refs, refs, false);
+    load_all(o.reads, reads, true);
+    if (refs.size() == 0) { fprintf(stderr, "rkmh: no reference sequences\n"); return 2; }
+    Fleet fl; fl.open(std::max(1, o.gpus));
+    setup_refs(fl, o, refs, FILTER_TABLE, true);
+    std::vector<rkg_hit> hits = classify_all(fl, o, reads, true);
+    std::string out;
+    for (size_t i = 0; i < reads.size(); ++i) {          // src/rkmh.cpp:1289-1309, src/equiv.hpp:328-352
+        const rkg_hit& h = hits[i];
+        const int best = std::max(h.best, 0), prev = std::max(h.prev, 0);
+        if (!(h.sketch_len > 0) || best < o.min_matches || !(best - prev > o.min_diff)) continue;
+        out += '>'; out += reads.names[i]; out += '\n';
+        const char* s = reads.bases.data() + reads.offs[i];
+        for (int64_t j = 0, L = reads.offs[i + 1] - reads.offs[i]; j < L; ++j) {
+            signed char ch = (signed char)s[j];
+            out += (char)((int)ch - 91 > 0 ? ch - 32 : ch);      // to_upper, mkmh.hpp:231-236
+        }
+        out += "\n+\n"; out += reads.quals[i]; out += '\n';
+        if (out.size() > (1 << 22)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+    }
+    fwrite(out.data(), 1, out.size(), stdout);
+    return 0;
+}
+
+// ---- hash: src/rkmh.cpp:1931-2116; with -s the intended behaviour (README.md:114-117), without it HEAD's ---------
+int main_hash(int argc, char** argv) {
+    if (argc <= 2) { usage(argv[0]); exit(1); }
+    Options o;
+    o.sketch = 0;
+    const char* env = getenv("RKMH_GPUS");
+    if (env) o.gpus = atoi(env);
+    parse_common(argc, argv, o, "hdk:f:r:s:S:t:M:N:I:R:F:p:q:iD:g:mwcKTo:");
+    fprintf(stderr, "Using a kmer size of %d\n", o.ks[0]);
+    SeqSet seqs;
+    load_all(o.refs, seqs, false);                        // -r is accepted here (HEAD aborts on it)
+    load_all(o.reads, seqs, false);
+    Fleet fl; fl.open(1);
+    rkg_ctx* c = fl.ctx[0];
+    const bool sketch_mode = o.sketch > 0;
+    RK(c, rkg_set_params(c, o.ks.data(), (int)o.ks.size(), sketch_mode ? o.sketch : 1, 0, 0));
+    std::string out;
+    const size_t n = seqs.size();
+    if (sketch_mode) {
+        std::vector<uint64_t> sk(n * (size_t)o.sketch);
+        std::vector<int32_t> lens(n);
+        if (n) RK(c, rkg_sketch_batch(c, seqs.bases.data(), seqs.offs.data(), (int64_t)n, -1, sk.data(), lens.data()));
+        for (size_t i = 0; i < n; ++i) {                  // print_hashes format, mkmh.hpp:1438-1449
+            out += seqs.names[i]; out += '\t';
+            for (int j = 0; j < lens[i]; ++j) { if (j) out += '\t'; char b[24]; out.append(b, snprintf(b, sizeof b, "%llu", (unsigned long long)sk[i * o.sketch + j])); }
+            out += '\n';
+            if (out.size() > (1 << 22)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+        }
+    } else {                                              // HEAD-literal: every hash, unsorted, zeros included
+        size_t total = 0;
+        for (size_t i = 0; i < n; ++i)
+            for (int k : o.ks) total += (size_t)std::max<int64_t>(seqs.offs[i + 1] - seqs.offs[i] - k, 0);
+        std::vector<uint64_t> h(std::max<size_t>(total, 1));
+        std::vector<int64_t> ho(n + 1);
+        if (n) RK(c, rkg_hash_batch(c, seqs.bases.data(), seqs.offs.data(), (int64_t)n, h.data(), ho.data()));
+        for (size_t i = 0; i < n; ++i) {
+            out += seqs.names[i]; out += '\t';
+            for (int64_t j = ho[i]; j < ho[i + 1]; ++j) { if (j > ho[i]) out += '\t'; char b[24]; out.append(b, snprintf(b, sizeof b, "%llu", (unsigned long long)h[j])); }
+            out += '\n';
+            if (out.size() > (1 << 22)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+        }
+    }
+    fwrite(out.data(), 1, out.size(), stdout);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    if (argc <= 1) { usage(argv[0]); exit(1); }
+    const std::string cmd = argv[1];
+    if (cmd == "classify") {
+        fprintf(stderr, "CLASSIFY COMMAND IS TEMPORARILY UNAVAILABLE: TRY rkmh stream INSTEAD.\n");   // src/rkmh.cpp:2746
+        return main_stream(argc, argv);
+    }
+    if (cmd == "stream") return main_stream(argc, argv);
+    if (cmd == "filter") return main_filter(argc, argv);
+    if (cmd == "hash") return main_hash(argc, argv);
+    if (cmd == "parse") {            // host-only debugging aid: dump the records the parser sees (no GPU needed)
+        for (int i = 2; i < argc; ++i) {
+            SeqSet set;
+            if (!rkhost::read_fastx(argv[i], set, true)) { fprintf(stderr, "rkmh: cannot open %s\n", argv[i]); return 2; }
+            for (size_t r = 0; r < set.size(); ++r) {
+                fwrite(set.names[r].data(), 1, set.names[r].size(), stdout); fputc('\t', stdout);
+                fwrite(set.bases.data() + set.offs[r], 1, (size_t)(set.offs[r + 1] - set.offs[r]), stdout); fputc('\t', stdout);
+                fwrite(set.quals[r].data(), 1, set.quals[r].size(), stdout); fputc('\n', stdout);
+            }
+        }
+        return 0;
+    }
+    usage(argv[0]);
+    return 1;
+}

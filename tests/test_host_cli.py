@@ -1,0 +1,110 @@
+"""The C++ `rkmh` front-end: its FASTA/FASTQ parser (CPU) and, on the GPU box, its stdout against the real
+reference CLI's golden outputs."""
+import gzip
+import hashlib
+import os
+import subprocess
+
+import pytest
+
+from rkmh_b200.fastx import read_fastx
+from tests.golden.make_golden import CLI_CASES
+from tests.util import DATA, ROOT, golden_cli_output
+
+BIN = os.path.join(ROOT, "rkmh_b200", "bin", "rkmh")
+
+
+@pytest.fixture(scope="module")
+def rkmh_bin():
+    if not os.path.exists(BIN):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "rkmh_b200", "host")], stdout=subprocess.DEVNULL)
+    return BIN
+
+
+def _dump(path):
+    return b"".join(n + b"\t" + s + b"\t" + q + b"\n" for n, s, q in read_fastx(path))
+
+
+@pytest.mark.parametrize("name", ["awkward_refs.fa.gz", "awkward_reads.fq.gz", "minION25.fq.gz", "hpv_16_allFasta.fa.gz",
+                                  "z1.fq.gz", "zika.refs.fa.gz"])
+def test_cpp_parser_matches_python_parser(rkmh_bin, name):
+    path = os.path.join(DATA, name)
+    out = subprocess.run([rkmh_bin, "parse", path], stdout=subprocess.PIPE, check=True).stdout
+    assert out == _dump(path)
+
+
+def test_parser_odd_inputs(rkmh_bin, tmp_path):
+    """header without newline, '>' inside a sequence line, CRLF, truncated quality, empty file, no final newline"""
+    cases = {
+        "a.fa": b">s1 desc\nACGT\nAC>s2\nGG\r\nTT\r\n>s3",
+        "b.fq": b"@r1\nACGT\n+\nIIII\n@r2\nAC\nGT\n+r2\nII\nII\n@r3\nACGTA\n+\nIII",
+        "c.fa": b"",
+        "d.fa": b"junk before\n>x\nacgtn\n\n\n>y\tcomment\n\nAC GT\n",
+        "e.fq": b"@q\nACGT\n+\n@@@@\n@q2\nAC\n+\n@I",
+    }
+    for fn, payload in cases.items():
+        p = tmp_path / fn
+        p.write_bytes(payload)
+        out = subprocess.run([rkmh_bin, "parse", str(p)], stdout=subprocess.PIPE, check=True).stdout
+        assert out == _dump(str(p)), fn
+        pz = tmp_path / (fn + ".gz")
+        with gzip.open(pz, "wb") as fh:
+            fh.write(payload)
+        outz = subprocess.run([rkmh_bin, "parse", str(pz)], stdout=subprocess.PIPE, check=True).stdout
+        assert outz == out, fn
+
+
+def test_usage_and_exit_codes(rkmh_bin):
+    assert subprocess.run([rkmh_bin], stderr=subprocess.PIPE).returncode == 1
+    assert subprocess.run([rkmh_bin, "stream"], stderr=subprocess.PIPE).returncode == 1
+    assert subprocess.run([rkmh_bin, "stream", "-h"], stderr=subprocess.PIPE).returncode == 1
+    # an option letter without a case aborts, as the reference does (src/rkmh.cpp:716-718)
+    assert subprocess.run([rkmh_bin, "stream", "-d"], stderr=subprocess.PIPE).returncode < 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CLI_CASES))
+def test_cli_stdout_equals_reference(rkmh_bin, cli_manifest, name):
+    _, argv = CLI_CASES[name]
+    res = subprocess.run([rkmh_bin] + argv + ["-t", "1"], cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert res.returncode == 0, res.stderr.decode()[-400:]
+    gold = golden_cli_output(name)
+    if res.stdout != gold:
+        a, b = res.stdout.splitlines(), gold.splitlines()
+        diff = [(i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y][:3]
+        pytest.fail(f"{name}: {len(a)} vs {len(b)} lines; first diffs {diff}")
+    assert hashlib.md5(res.stdout).hexdigest() == cli_manifest[name]["md5"]
+
+
+@pytest.mark.gpu
+def test_hash_command(rkmh_bin, oracle):
+    """`rkmh hash -s` prints name + sorted sketch; without -s every hash in window order (HEAD's behaviour)."""
+    import numpy as np
+    from rkmh_b200.fastx import load_sequences
+    path = os.path.join(DATA, "new_refs.fa.gz")
+    names, seqs, _ = load_sequences([path])
+    res = subprocess.run([rkmh_bin, "hash", "-f", path, "-k", "21", "-s", "500"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    lines = res.stdout.splitlines()
+    assert len(lines) == len(names)
+    for ln, nm, sq in zip(lines, names, seqs):
+        f = ln.split(b"\t")
+        assert f[0] == nm
+        exp = oracle.minhashes(oracle.calc_hashes(oracle.to_upper(sq), [21]), 500)
+        assert np.array_equal(np.array([int(x) for x in f[1:]], np.uint64), exp)
+    res = subprocess.run([rkmh_bin, "hash", "-f", path, "-k", "12"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    f = res.stdout.splitlines()[0].split(b"\t")
+    exp = oracle.calc_hashes(oracle.to_upper(seqs[0]), [12])
+    assert np.array_equal(np.array([int(x) for x in f[1:]], np.uint64), exp)
+
+
+@pytest.mark.gpu
+def test_two_gpus_same_output(rkmh_bin, cli_manifest):
+    """read sharding over 2 GPUs (incl. the NCCL all-reduce of the -M table) does not change stdout"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    for name in ("pave_z1_k12", "newrefs_mix2k_M20_N10"):
+        _, argv = CLI_CASES[name]
+        res = subprocess.run([rkmh_bin] + argv + ["-g", "2"], cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert res.returncode == 0, res.stderr.decode()[-400:]
+        assert hashlib.md5(res.stdout).hexdigest() == cli_manifest[name]["md5"]
