@@ -7,6 +7,7 @@
 // Extra, non-reference option: -g/--gpus N (default: RKMH_GPUS or 1) shards reads over N GPUs.  -t is accepted
 // and ignored (the reference's OpenMP thread count).
 #include <getopt.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -140,16 +141,35 @@ void allreduce_counts(Fleet& fl) {
     std::vector<ncclComm_t> comms(n);
     std::vector<int> devs(n);
     for (int d = 0; d < n; ++d) devs[d] = d;
-    if (ncclCommInitAll(comms.data(), n, devs.data()) != ncclSuccess) { fprintf(stderr, "rkmh: ncclCommInitAll failed\n"); exit(2); }
-    ncclGroupStart();
+    auto nccl_ok = [](ncclResult_t r, const char* what) {
+        if (r != ncclSuccess) { fprintf(stderr, "rkmh: %s: %s\n", what, ncclGetErrorString(r)); exit(2); }
+    };
+    // NCCL may print its version banner on stdout (NCCL_DEBUG=VERSION); stdout is the result stream, so send
+    // anything the library prints during initialisation to stderr instead.
+    fflush(stdout);
+    const int saved_stdout = dup(1);
+    dup2(2, 1);
+    nccl_ok(ncclCommInitAll(comms.data(), n, devs.data()), "ncclCommInitAll");
+    fflush(stdout);
+    dup2(saved_stdout, 1);
+    close(saved_stdout);
+    std::vector<cudaStream_t> streams(n);
+    for (int d = 0; d < n; ++d) { cudaSetDevice(d); cudaDeviceSynchronize(); cudaStreamCreate(&streams[d]); }
+    nccl_ok(ncclGroupStart(), "ncclGroupStart");
     for (int d = 0; d < n; ++d) {
         void* p = nullptr; uint64_t slots = 0;
         RK(fl.ctx[d], rkg_count_table(fl.ctx[d], &p, &slots));
         cudaSetDevice(d);
-        ncclAllReduce(p, p, slots, ncclInt32, ncclSum, comms[d], 0);
+        nccl_ok(ncclAllReduce(p, p, (size_t)slots, ncclInt32, ncclSum, comms[d], streams[d]), "ncclAllReduce");
     }
-    ncclGroupEnd();
-    for (int d = 0; d < n; ++d) { cudaSetDevice(d); cudaStreamSynchronize(0); ncclCommDestroy(comms[d]); }
+    nccl_ok(ncclGroupEnd(), "ncclGroupEnd");
+    for (int d = 0; d < n; ++d) {
+        cudaSetDevice(d);
+        cudaError_t e = cudaStreamSynchronize(streams[d]);
+        if (e != cudaSuccess) { fprintf(stderr, "rkmh: all-reduce failed: %s\n", cudaGetErrorString(e)); exit(2); }
+        cudaStreamDestroy(streams[d]);
+        ncclCommDestroy(comms[d]);
+    }
 #else
     fprintf(stderr, "rkmh: -M with more than one GPU needs the NCCL build (make WITH_NCCL=1)\n");
     exit(2);
