@@ -107,8 +107,9 @@ int rkg_classify_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int
 /* The same in two steps for callers that keep batches resident in HBM (and for kernel-only timing):
  * upload once, classify any number of times, fetch results. */
 int rkg_batch_upload(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, rkg_batch** batch);
-/* Re-run the ingest kernel (upper-case / 2-bit pack / invalid-base mask) on the resident ASCII bases;
- * rkg_batch_upload already did it once.  Asynchronous. */
+/* Run the ingest kernel (upper-case / 2-bit pack / invalid-base mask) on the resident ASCII bases.  The
+ * other batch calls run it on demand; on the memoised path (below) the classification and count kernels
+ * read the ASCII bases themselves and this call launches nothing.  Asynchronous. */
 int rkg_batch_ingest(rkg_ctx* ctx, rkg_batch* batch);
 /* Issue this batch's work on the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores the
  * batch's own stream), so that the caller's events bracket the kernels. */
@@ -118,6 +119,18 @@ int rkg_batch_count(rkg_ctx* ctx, rkg_batch* batch, int count_zeros);       /* a
 int rkg_batch_results(rkg_ctx* ctx, rkg_batch* batch, rkg_hit* out);        /* synchronises  */
 int rkg_batch_free(rkg_ctx* ctx, rkg_batch* batch);
 int rkg_synchronize(rkg_ctx* ctx);
+
+/* ---- memoised hashing (single k <= 12) ----------------------------------------------------------- */
+/* calc_hash (mkmh/mkmh.hpp:505-532) is a pure function of the k-mer; for a single k <= 12 its domain has
+ * 4^k <= 16.7 M points, so rkg_load_refs runs the hashing kernel once over every k-mer and the read-side
+ * kernels (rkg_classify_batch / rkg_count_batch and their rkg_batch_* forms) look hashes up in an
+ * L2-resident table instead of recomputing 2 x MurmurHash3_x64_128 per window.  Results are bit-identical;
+ * the read count table (rkg_count_table) keeps the reference's layout.  On by default (environment
+ * RKMH_NO_MEMO=1 or rkg_set_memo(ctx, 0) force the Murmur path for every k); a change takes effect at
+ * the next rkg_load_refs.  After all-reducing the table obtained from rkg_count_table, call
+ * rkg_count_table again before any later all-reduce: the call marks the table as changed. */
+int rkg_set_memo(rkg_ctx* ctx, int enable);
+int rkg_memo_active(const rkg_ctx* ctx);
 
 /* ---- hash command -------------------------------------------------------------------------------- */
 /* Bottom-s sketches of nseq records (sorted ascending, duplicates kept, zeros dropped): calc_hashes +

@@ -16,6 +16,7 @@ RKG_SYMBOLS = [
     "rkg_count_lookup", "rkg_classify_batch", "rkg_batch_upload", "rkg_batch_classify", "rkg_batch_count",
     "rkg_batch_results", "rkg_batch_ingest", "rkg_batch_set_stream", "rkg_batch_free", "rkg_synchronize", "rkg_sketch_batch", "rkg_hash_batch",
     "rkg_sketch_shard", "rkg_merge_sketches", "rkg_launch_count", "rkg_profile_enable", "rkg_profile_read",
+    "rkg_set_memo", "rkg_memo_active",
 ]
 
 
@@ -64,6 +65,8 @@ def load():
     lib.rkg_hash_batch.argtypes = [P, P, P, L, P, P]
     lib.rkg_sketch_shard.argtypes = [P, P, L, L, L, L, P, P]
     lib.rkg_merge_sketches.argtypes = [P, P, P, I, P, P]
+    lib.rkg_set_memo.argtypes = [P, I]
+    lib.rkg_memo_active.argtypes = [P]
     lib.rkg_launch_count.argtypes = [P]
     lib.rkg_launch_count.restype = L
     lib.rkg_profile_enable.argtypes = [P, I]

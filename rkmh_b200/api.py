@@ -136,6 +136,13 @@ class RkmhGpu:
         self._check(self.lib.rkg_get_ref_sketches(self.handle, sk.ctypes.data, lens.ctypes.data))
         return sk, lens
 
+    def set_memo(self, enable=True):
+        """Memoised hashing for a single k <= 12 (include/rkmh_gpu.h); takes effect at the next load_refs."""
+        self._check(self.lib.rkg_set_memo(self.handle, int(enable)))
+
+    def memo_active(self):
+        return bool(self.lib.rkg_memo_active(self.handle))
+
     # -- -M count table ---------------------------------------------------------------------------
     def count_reset(self):
         self._check(self.lib.rkg_count_reset(self.handle))

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -12,6 +13,7 @@
 
 #include "../../include/rkmh_gpu.h"
 #include "rk_kernels.cuh"
+#include "rk_memo.cuh"
 
 using namespace rk;
 
@@ -23,10 +25,13 @@ namespace {
 thread_local std::string g_create_error;
 
 enum KernelId { K_INGEST, K_HASH, K_COUNT, K_COUNT_DISTINCT, K_SKETCH, K_MERGE, K_TABLE, K_CLASSIFY_GROUP,
-                K_CLASSIFY_BLOCK, K_NUM };
+                K_CLASSIFY_BLOCK, K_MEMO_BUILD, K_MEMO_MAINT, K_COUNT_MEMO, K_CLASSIFY_MEMO_WARP, K_CLASSIFY_MEMO_BLOCK,
+                K_NUM };
 const char* const kKernelNames[K_NUM] = {"ingest_kernel", "hash_kernel", "count_kernel", "count_distinct_kernel",
                                          "sketch_kernel", "merge_kernel", "table_build_kernels",
-                                         "classify_group_kernel", "classify_block_kernel"};
+                                         "classify_group_kernel", "classify_block_kernel", "memo_build_kernels",
+                                         "memo_fold_apply_kernels", "count_memo_kernel", "classify_memo_warp_kernel",
+                                         "classify_memo_block_kernel"};
 
 struct DevBuf {
     void* p = nullptr;
@@ -51,6 +56,7 @@ struct EventPair { cudaEvent_t a, b; int id; };
 struct rkg_batch {
     DevBuf bases, offs, codes, nmask, hits, redo, scratch, misc;   // misc: [0] redo_count
     i64 nseq = 0, total = 0, base0 = 0, max_ntotal = 0, max_len = 0;
+    bool packed = false;                 // codes / nmask hold this batch (ingest_kernel has run)
     cudaStream_t stream = nullptr;       // the stream every operation of this batch is issued on
     cudaStream_t own_stream = nullptr;   // created with the batch; `stream` may be redirected to a caller's stream
     cudaEvent_t done = nullptr;
@@ -76,6 +82,14 @@ struct rkg_ctx {
     RefTable tb{};
     cudaStream_t stream = nullptr;
     rkg_batch* slots[2] = {nullptr, nullptr};   // internal double buffer of rkg_classify_batch / count
+    // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
+    bool memo_enabled = true, memo_ready = false;
+    DevBuf memo_tab, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc;
+    Memo memo{};
+    bool memo_pending = false;           // code_counts holds increments not yet folded into the read count table
+    int memo_pending_zeros = 0;
+    bool memo_occ_stale = true;          // the read count table changed since FAILM was baked
+    int memo_occ = INT_MIN;              // min_occ currently baked into the FAILM flags (INT_MIN: none)
     // measurement
     int64_t launches = 0;
     bool profiling = false;
@@ -171,10 +185,14 @@ int launch_ingest(rkg_ctx* ctx, rkg_batch* b) {
                                                    b->nmask.as<u32>(), nwords32);
     }
     CK(cudaGetLastError());
+    b->packed = true;
     return RKG_OK;
 }
 
-// Copy reads [r0, r1) of the caller's buffers into the batch and pack them (asynchronous on b->stream).
+// The Murmur-path kernels read the packed codes; the memoised path reads the ASCII bases and never needs them.
+int ensure_packed(rkg_ctx* ctx, rkg_batch* b) { return b->packed ? RKG_OK : launch_ingest(ctx, b); }
+
+// Copy reads [r0, r1) of the caller's buffers into the batch (asynchronous on b->stream); packing is done on demand.
 int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* offs, i64 r0, i64 r1) {
     const i64 n = r1 - r0;
     const i64 base0 = offs[r0], total = offs[r1] - base0;
@@ -199,7 +217,8 @@ int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* off
     i64 mt = 0;
     for (int j = 0; j < ctx->kl.nk; ++j) mt += std::max<i64>(max_len - ctx->kl.k[j], 0);
     b->max_ntotal = mt;
-    return launch_ingest(ctx, b);
+    b->packed = false;
+    return RKG_OK;
 }
 
 SeqBatch seq_view(const rkg_batch* b) {
@@ -214,8 +233,111 @@ SeqBatch seq_view(const rkg_batch* b) {
     return sb;
 }
 
+// ---- memoised path (rk_memo.cuh) ---------------------------------------------------------------------------
+// Build hash / rank / REF tables over all 4^k codes.  Called at the end of rkg_load_refs (the reference table exists).
+int memo_build(rkg_ctx* ctx, cudaStream_t st) {
+    ctx->memo_ready = false;
+    if (!ctx->memo_enabled || ctx->kl.nk != 1 || ctx->kl.k[0] > MEMO_MAX_K) return RKG_OK;
+    const int k = ctx->kl.k[0];
+    const u32 ncodes = 1u << (2 * k);
+    const int bucket_bits = std::max(2 * k - 8, 0);
+    const u32 nb = 1u << bucket_bits;
+    CK(ctx->memo_tab.ensure(sizeof(u32) * (size_t)ncodes));
+    CK(ctx->memo_ref.ensure(sizeof(u32) * (size_t)ncodes));
+    CK(ctx->memo_hash.ensure(sizeof(u64) * (size_t)ncodes));
+    CK(ctx->memo_tmp.ensure(sizeof(u32) * ((size_t)3 * nb + ncodes)));
+    CK(ctx->memo_misc.ensure(256));
+    u32* bcount = ctx->memo_tmp.as<u32>();
+    u32* bstart = bcount + nb; u32* bfill = bstart + nb; u32* bcodes = bfill + nb;
+    CK(cudaMemsetAsync(bcount, 0, sizeof(u32) * (size_t)nb, st));
+    CK(cudaMemsetAsync(ctx->memo_ref.p, 0, sizeof(u32) * (size_t)ncodes, st));
+    CK(cudaMemsetAsync(ctx->memo_misc.p, 0, 256, st));
+    Memo mm{};
+    mm.tab = ctx->memo_tab.as<u32>(); mm.ref = ctx->memo_ref.as<u32>(); mm.hash = ctx->memo_hash.as<u64>();
+    mm.inval = ctx->memo_misc.as<unsigned long long>();
+    int* err = ctx->memo_misc.as<int>() + 8;
+    mm.ncodes = ncodes; mm.kmask = (1u << k) - 1u; mm.k = k;
+    mm.code_counts = nullptr;
+    if (ctx->read_ct.counts) {
+        CK(ctx->memo_counts.ensure(sizeof(int) * (size_t)ncodes));
+        CK(cudaMemsetAsync(ctx->memo_counts.p, 0, sizeof(int) * (size_t)ncodes, st));
+        mm.code_counts = ctx->memo_counts.as<int>();
+    }
+    {
+        Timed t(ctx, st, K_MEMO_BUILD);
+        const int grid = (int)std::min<i64>(((i64)ncodes + 255) / 256, (i64)ctx->sm_count * 16);
+        u64* hash = ctx->memo_hash.as<u64>();
+        switch (kvariant_of(k)) {
+            case 0: memo_hash_kernel<0><<<grid, 256, 0, st>>>(k, ncodes, hash, bcount, bucket_bits); break;
+            case 1: memo_hash_kernel<1><<<grid, 256, 0, st>>>(k, ncodes, hash, bcount, bucket_bits); break;
+            default: memo_hash_kernel<2><<<grid, 256, 0, st>>>(k, ncodes, hash, bcount, bucket_bits); break;
+        }
+        memo_scan_kernel<<<1, 1024, 0, st>>>(bcount, bstart, bfill, nb, err);
+        memo_scatter_kernel<<<grid, 256, 0, st>>>(ncodes, hash, bstart, bfill, bcodes, bucket_bits);
+        memo_rank_kernel<<<(int)std::min<i64>(nb, (i64)ctx->sm_count * 8), 256, 0, st>>>(hash, bcount, bstart, bcodes, nb, ctx->tb,
+                                                                                        mm.tab, mm.ref);
+        ctx->launches += 3;
+    }
+    CK(cudaGetLastError());
+    int herr = 0;
+    CK(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (herr) return RKG_OK;          // a hash bucket larger than the sort capacity: keep the Murmur path (still exact)
+    ctx->memo = mm;
+    ctx->memo_ready = true;
+    ctx->memo_pending = false; ctx->memo_occ_stale = true; ctx->memo_occ = INT_MIN;
+    return RKG_OK;
+}
+
+// Fold the per-code counters of pass 1 into the read count table (the table the reference keeps, rkmh.cpp:738-743).
+int memo_flush(rkg_ctx* ctx) {
+    if (!ctx->memo_ready || !ctx->memo_pending) return RKG_OK;
+    CK(cudaDeviceSynchronize());
+    {
+        Timed t(ctx, ctx->stream, K_MEMO_MAINT);
+        const int grid = (int)std::min<i64>(((i64)ctx->memo.ncodes + 255) / 256, (i64)ctx->sm_count * 16);
+        memo_fold_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->memo, ctx->read_ct, ctx->memo_pending_zeros);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->memo_pending = false;
+    ctx->memo_occ_stale = true;
+    return RKG_OK;
+}
+
+// Make the FAILM flags of the table reflect (read count table, min_occ) before a classification pass.
+int memo_prepare(rkg_ctx* ctx, int min_occ) {
+    int rc = memo_flush(ctx);
+    if (rc) return rc;
+    const int want = min_occ >= 0 ? min_occ : INT_MIN;
+    if (want == ctx->memo_occ && !(want != INT_MIN && ctx->memo_occ_stale)) return RKG_OK;
+    CK(cudaDeviceSynchronize());
+    {
+        Timed t(ctx, ctx->stream, K_MEMO_MAINT);
+        const int grid = (int)std::min<i64>(((i64)ctx->memo.ncodes + 255) / 256, (i64)ctx->sm_count * 16);
+        memo_apply_occ_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->memo, ctx->read_ct, min_occ);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->memo_occ = want;
+    ctx->memo_occ_stale = false;
+    return RKG_OK;
+}
+
 int launch_count(rkg_ctx* ctx, rkg_batch* b, CountTable ct, int count_zeros) {
     if (b->nseq == 0) return RKG_OK;
+    if (ctx->memo_ready && ctx->memo.code_counts && ct.counts == ctx->read_ct.counts) {
+        if (ctx->memo_pending && ctx->memo_pending_zeros != count_zeros) { int rc = memo_flush(ctx); if (rc) return rc; }
+        ctx->memo_pending = true; ctx->memo_pending_zeros = count_zeros;
+        const int wpr = (b->total / b->nseq > 2048) ? 8 : 1;            // a block per long read, a warp per short one
+        const i64 teams = (b->nseq + 0) * 1;
+        const int grid = (int)std::min<i64>((teams * wpr + 7) / 8, (i64)ctx->sm_count * 8);
+        Timed t(ctx, b->stream, K_COUNT_MEMO);
+        count_memo_kernel<<<grid, 256, 0, b->stream>>>(seq_view(b), ctx->memo, count_zeros, wpr);
+        CK(cudaGetLastError());
+        return RKG_OK;
+    }
+    { int rc = ensure_packed(ctx, b); if (rc) return rc; }
     Timed t(ctx, b->stream, K_COUNT);
     int grid = (int)std::min<i64>((b->nseq + 7) / 8, (i64)ctx->sm_count * 8);
     DISPATCH_KCSEL(ctx->kcsel, (count_kernel<KS><<<grid, 256, 0, b->stream>>>(seq_view(b), ctx->kl, ct, count_zeros)));
@@ -247,6 +369,34 @@ GroupGeom group_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
     return g;
 }
 
+// Geometry of the two memoised classification kernels for this batch, or ok = false (Murmur path instead).
+struct MemoGeom { bool ok, use_warp; int warp_block, rwords; size_t warp_smem; int vcap, hs_cap, rpad; size_t block_smem; i64 scratch_stride; };
+
+MemoGeom memo_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
+    MemoGeom g{};
+    // block kernel: [vcap values][MEMO_BINS histogram][2 hs_cap hit set][rpad counters] in u32, two blocks per SM
+    g.hs_cap = next_pow2(2 * (i64)std::min<i64>(ctx->s, std::max<i64>(b->max_ntotal, 1)));
+    g.rpad = (ctx->nrefs + 63) / 64 * 64;
+    const size_t budget = ctx->smem_optin / 2 - 2048;
+    const size_t fixed = 4 * ((size_t)MEMO_BINS + 2 * (size_t)g.hs_cap + (size_t)g.rpad);
+    if (fixed + 4096 > budget) return g;
+    const i64 room = (i64)((budget - fixed) / 4);
+    g.vcap = (int)std::min<i64>(std::max<i64>(b->max_ntotal, 1), room);
+    g.scratch_stride = (b->max_ntotal > g.vcap) ? b->max_ntotal : 0;
+    g.block_smem = fixed + 4 * (size_t)g.vcap;
+    g.ok = true;
+    // warp kernel: the typical read keeps all its k-mers (n <= s)
+    const i64 mean_n = std::max<i64>(b->total / b->nseq - ctx->kl.k[0], 0);
+    g.rwords = (ctx->nrefs + 1) / 2;
+    if (mean_n <= ctx->s && ctx->nrefs <= 65000) {
+        for (int block : {1024, 512, 256}) {
+            const size_t smem = (size_t)(block / 32) * (sizeof(MemoWarpSmem) + (size_t)g.rwords * 4);
+            if (smem <= ctx->smem_optin) { g.use_warp = true; g.warp_block = block; g.warp_smem = smem; break; }
+        }
+    }
+    return g;
+}
+
 int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
     if (b->nseq == 0) return RKG_OK;
     CountTable ct = (min_occ >= 0) ? ctx->read_ct : CountTable{nullptr, {}};
@@ -257,6 +407,32 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
     int* redo_count = b->misc.as<int>();
     Hit* hits = b->hits.as<Hit>();
     CK(cudaMemsetAsync(redo_count, 0, sizeof(int), b->stream));
+
+    if (ctx->memo_ready) {
+        MemoGeom mg = memo_geometry(ctx, b);
+        if (mg.ok) {
+            int rc = memo_prepare(ctx, min_occ);
+            if (rc) return rc;
+            if (mg.use_warp) {
+                Timed t(ctx, b->stream, K_CLASSIFY_MEMO_WARP);
+                CK(cudaFuncSetAttribute(classify_memo_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg.warp_smem));
+                classify_memo_warp_kernel<<<ctx->sm_count, mg.warp_block, mg.warp_smem, b->stream>>>(
+                    sb, ctx->s, ctx->memo, ctx->tb, mg.rwords, redo, redo_count, hits);
+                CK(cudaGetLastError());
+            }
+            const int grid = ctx->sm_count * 2;
+            CK(b->scratch.ensure(sizeof(u32) * (size_t)grid * (size_t)mg.scratch_stride + 64));
+            Timed t(ctx, b->stream, K_CLASSIFY_MEMO_BLOCK);
+            CK(cudaFuncSetAttribute(classify_memo_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg.block_smem));
+            classify_memo_block_kernel<<<grid, 256, mg.block_smem, b->stream>>>(
+                sb, ctx->s, ctx->memo, ctx->tb, mg.use_warp ? redo : nullptr, mg.use_warp ? redo_count : nullptr, b->nseq,
+                mg.vcap, mg.hs_cap, mg.rpad, b->scratch.as<u32>(), mg.scratch_stride, hits);
+            CK(cudaGetLastError());
+            return RKG_OK;
+        }
+    }
+    { int rc = memo_flush(ctx); if (rc) return rc; }
+    { int rc = ensure_packed(ctx, b); if (rc) return rc; }
 
     GroupGeom gg = group_geometry(ctx, b);
     if (gg.ok) {
@@ -302,6 +478,8 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
 int launch_sketch(rkg_ctx* ctx, rkg_batch* b, CountTable ct, int filter_mode, int occ, u64* d_sketches, int* d_lens,
                   u64* d_sorted_all, const i64* d_all_offs) {
     if (b->nseq == 0) return RKG_OK;
+    { int rc = memo_flush(ctx); if (rc) return rc; }       // the count filter reads the read count table itself
+    { int rc = ensure_packed(ctx, b); if (rc) return rc; }
     const int block = 512;
     const int sort_cap = next_pow2(std::max<i64>(std::min<i64>(ctx->s, std::max<i64>(b->max_ntotal, 1)), 2));
     const int sort_in_smem = ((size_t)sort_cap * 8 <= ctx->smem_optin - 4096) ? 1 : 0;
@@ -372,6 +550,7 @@ int rkg_create(int device, rkg_ctx** out) {
         return fail(nullptr, RKG_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     ctx = new rkg_ctx();
     ctx->device = device;
+    { const char* nm = getenv("RKMH_NO_MEMO"); ctx->memo_enabled = !(nm && nm[0] && nm[0] != '0'); }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -389,7 +568,8 @@ void rkg_destroy(rkg_ctx* ctx) {
     profile_collect(ctx);
     for (int i = 0; i < 2; ++i) batch_release(ctx->slots[i]);
     for (DevBuf* d : {&ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
-                      &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor})
+                      &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
+                      &ctx->memo_tab, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc})
         d->release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -418,6 +598,7 @@ int rkg_set_params(rkg_ctx* ctx, const int* ks, int nk, int sketch_size, uint64_
     kl.kmax = kmax;
     ctx->kl = kl; ctx->kcsel = kcsel; ctx->kmax = kmax; ctx->kmin = kmin; ctx->s = sketch_size;
     ctx->refs_loaded = false;
+    ctx->memo_ready = false;
     auto setup = [&](uint64_t size, DevBuf& buf, CountTable& ct) -> cudaError_t {
         ct.counts = nullptr;
         if (size == 0) { buf.release(); return cudaSuccess; }
@@ -468,6 +649,8 @@ int rkg_load_refs(rkg_ctx* ctx, const char* bases, const int64_t* offs, int nref
     if (rc) return rc;
     rkg_batch* b = ctx->slots[0];
     CK(cudaStreamSynchronize(b->stream));
+    ctx->memo_ready = false;                  // the reference side always goes through the hashing kernels
+    ctx->refs_loaded = false;
     if ((rc = batch_fill(ctx, b, bases, offs, 0, nrefs))) return rc;
     const int s = ctx->s;
     ctx->nrefs = nrefs;
@@ -549,6 +732,7 @@ int rkg_load_refs(rkg_ctx* ctx, const char* bases, const int64_t* offs, int nref
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(b->stream));
     ctx->tb = tb;
+    if ((rc = memo_build(ctx, b->stream))) return rc;
     ctx->refs_loaded = true;
     return RKG_OK;
 }
@@ -568,13 +752,25 @@ int rkg_count_reset(rkg_ctx* ctx) {
     if (!ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "no read count table (rkg_set_params read_table_size)");
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
-    CK(cudaMemset(ctx->read_ct.counts, 0, sizeof(int) * ctx->read_tbl_size));
+    // on the context's own stream and waited for: the batch streams are non-blocking, a legacy-stream memset would
+    // not be ordered before the count kernels that follow
+    CK(cudaMemsetAsync(ctx->read_ct.counts, 0, sizeof(int) * ctx->read_tbl_size, ctx->stream));
+    if (ctx->memo_ready && ctx->memo.code_counts) {
+        CK(cudaMemsetAsync(ctx->memo.code_counts, 0, sizeof(int) * (size_t)ctx->memo.ncodes, ctx->stream));
+        CK(cudaMemsetAsync(ctx->memo.inval, 0, sizeof(unsigned long long), ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->memo_pending = false;
+    ctx->memo_occ_stale = true;
     return RKG_OK;
 }
 
 int rkg_count_table(rkg_ctx* ctx, void** device_ptr, uint64_t* nslots) {
     if (!ctx || !device_ptr || !nslots) return RKG_ERR_ARG;
     if (!ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "no read count table");
+    CK(cudaSetDevice(ctx->device));
+    { int rc = memo_flush(ctx); if (rc) return rc; }
+    ctx->memo_occ_stale = true;               // the caller may all-reduce the table in place
     *device_ptr = ctx->read_ct.counts;
     *nslots = ctx->read_tbl_size;
     return RKG_OK;
@@ -584,6 +780,7 @@ int rkg_count_lookup(rkg_ctx* ctx, const uint64_t* keys, int64_t n, int32_t* out
     if (!ctx || !keys || !out) return RKG_ERR_ARG;
     if (!ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "no read count table");
     CK(cudaSetDevice(ctx->device));
+    { int rc = memo_flush(ctx); if (rc) return rc; }
     CK(cudaDeviceSynchronize());
     for (int64_t i = 0; i < n; ++i) {   // parity/debug helper: one small copy per key
         u64 slot = keys[i] % ctx->read_tbl_size;
@@ -666,6 +863,7 @@ int rkg_batch_count(rkg_ctx* ctx, rkg_batch* batch, int count_zeros) {
 int rkg_batch_ingest(rkg_ctx* ctx, rkg_batch* batch) {
     if (!ctx || !batch) return RKG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->memo_ready) return RKG_OK;       // the memoised kernels read the ASCII bases themselves (fused ingest)
     return launch_ingest(ctx, batch);
 }
 
@@ -755,6 +953,7 @@ int rkg_hash_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t
         std::vector<i64> rel(n + 1);
         for (i64 i = 0; i <= n; ++i) rel[i] = hash_offs[ch.first + i] - h0;
         cudaMemcpyAsync(d_ho.p, rel.data(), sizeof(i64) * (size_t)(n + 1), cudaMemcpyHostToDevice, b->stream);
+        if ((rc = ensure_packed(ctx, b))) break;
         for (int kidx = 0; kidx < ctx->kl.nk; ++kidx) {
             Timed t(ctx, b->stream, K_HASH);
             int grid = (int)std::min<i64>((n + 7) / 8, (i64)ctx->sm_count * 8);
@@ -846,6 +1045,17 @@ int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t km
     std::memcpy(sketch, parts.data(), sizeof(uint64_t) * (size_t)lens[0]);
     return RKG_OK;
 }
+
+int rkg_set_memo(rkg_ctx* ctx, int enable) {
+    if (!ctx) return RKG_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    { int rc = memo_flush(ctx); if (rc) return rc; }
+    ctx->memo_enabled = enable != 0;
+    if (!enable) ctx->memo_ready = false;
+    return RKG_OK;
+}
+
+int rkg_memo_active(const rkg_ctx* ctx) { return ctx && ctx->memo_ready ? 1 : 0; }
 
 // ---- measurement ------------------------------------------------------------------------------------
 int64_t rkg_launch_count(const rkg_ctx* ctx) { return ctx ? ctx->launches : 0; }

@@ -1,0 +1,518 @@
+// rk_memo.cuh -- the memoised path of the rkmh hot path for a single k <= 12.
+//
+// calc_hash (mkmh.hpp:505-532) is a pure function of the k-mer, and for k <= 12 its whole domain has
+// 4^k <= 16,777,216 points.  The hashing kernel (murmur_kmer, rk_common.cuh) is therefore run ONCE over every
+// k-mer when the references are loaded, and the per-read kernels look results up in a table that stays resident
+// in the 126 MB L2 instead of recomputing 2 x MurmurHash3_x64_128 per window:
+//
+//   hash[c]  u64  canonical hash of k-mer code c                              (mkmh.hpp:517-524)
+//   tab[c]   u32  (rank << 8) | flags; rank = number of codes whose hash is smaller, so that "the s smallest
+//                 hashes, duplicates kept" (minhashes, mkmh.hpp:931-950) is "the s smallest ranks"
+//                 REF   the hash is a member of some reference sketch          (hash_intersection_size)
+//                 ZERO  the hash is 0, the reference's "invalid" sentinel      
+//                 FAILM counts[hash % size] < min_occ                          (mask_by_frequency, mkmh.hpp:898)
+//   ref[rank] u32  slot + 1 of the hash in the (hash, rank) -> bitset table     (equal hash <=> equal rank)
+//   code_counts[c] int32  -M pass 1 counters per code; folded into counts[hash % size] (HASHTCounter.cpp:46)
+//
+// A k-mer code is the pair of bit planes of its 2-bit base codes: bit j = low code bit of base j, bit k + j =
+// high code bit of base j.  The per-read kernels read the ASCII bases as parsed (no ingest pass): a warp turns 32
+// bases into three 32-bit planes with three ballots, and the code of the window that starts at lane l is two
+// funnel shifts.  Results are bit-identical to the Murmur path for every input (tests: memo on/off).
+#pragma once
+#include "rk_kernels.cuh"
+
+namespace rk {
+
+constexpr int MEMO_MAX_K = 12;
+constexpr u32 MEMO_REF = 1u, MEMO_ZERO = 2u, MEMO_FAILM = 4u;
+constexpr u32 MEMO_SKIP = 0xFFFFFFFFu;          // "window does not count": never a real entry (5 flag bits unused)
+constexpr int MEMO_BUCKET_CAP = 1024;           // rank build: largest hash bucket that is sorted in shared memory
+constexpr int MEMO_BINS = 4096;                 // radix-select histogram (12 bits of the 24-bit rank per level)
+
+struct Memo {
+    u32* tab;
+    u32* ref;
+    const u64* hash;
+    int* code_counts;               // nullptr when the context has no read count table
+    unsigned long long* inval;      // windows with an invalid base seen by the count pass (count_zeros mode)
+    u32 ncodes;
+    u32 kmask;                      // (1 << k) - 1
+    int k;
+};
+
+#ifdef RK_EMU
+RK_D u32 warp_sum(u32 v) { for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d); return v; }
+RK_D u32 warp_max(u32 v) { for (int d = 16; d >= 1; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d)); return v; }
+#else
+RK_D u32 warp_sum(u32 v) { return __reduce_add_sync(0xffffffffu, v); }
+RK_D u32 warp_max(u32 v) { return __reduce_max_sync(0xffffffffu, v); }
+#endif
+
+// Exactly the bytes canonical() accepts (valid_dna[], mkmh.hpp:137-152) as one bit test: A C G T a c g t.
+RK_D bool memo_base_invalid(u32 ch) {
+    const u32 u = (ch & 0xDFu) - 65u;                       // 'A' -> 0 ... 'Z' -> 25 for either case
+    return u > 19u || !((0x00080045u >> u) & 1u);           // bits 0 (A), 2 (C), 6 (G), 19 (T)
+}
+
+// ------------------------------------------------------------------------------------------------
+// One warp walks the k-mer starts [s0, s1) of the sequence p[0, len), 32 starts per round, and calls
+// f(pos, code, in_range, valid) on every lane (warp-convergent).  Bases beyond len read as invalid.
+template <typename F>
+RK_D void memo_stream(const unsigned char* __restrict__ p, i64 len, int k, u32 kmask, i64 s0, i64 s1, int lane, F&& f) {
+    if (s0 >= s1) return;
+    auto load = [&](i64 base) -> u32 { const i64 i = base + lane; return i < len ? (u32)p[i] : 0u; };
+    u32 c0, c1, cv;
+    {
+        const u32 ch = load(s0), c2 = base_code(ch);
+        c0 = __ballot_sync(0xffffffffu, c2 & 1u); c1 = __ballot_sync(0xffffffffu, c2 & 2u);
+        cv = __ballot_sync(0xffffffffu, memo_base_invalid(ch));
+    }
+    u32 chn = load(s0 + 32);
+    for (i64 base = s0; base < s1; base += 32) {
+        const u32 c2 = base_code(chn);
+        const u32 n0 = __ballot_sync(0xffffffffu, c2 & 1u), n1 = __ballot_sync(0xffffffffu, c2 & 2u);
+        const u32 nv = __ballot_sync(0xffffffffu, memo_base_invalid(chn));
+        chn = load(base + 64);                                  // in flight while this round is processed
+        const u32 f0 = __funnelshift_r(c0, n0, (u32)lane) & kmask;
+        const u32 f1 = __funnelshift_r(c1, n1, (u32)lane) & kmask;
+        const u32 fv = __funnelshift_r(cv, nv, (u32)lane) & kmask;
+        const i64 pos = base + lane;
+        const bool in = pos < s1;
+        f(pos, f0 | (f1 << k), in, in && fv == 0u);
+        c0 = n0; c1 = n1; cv = nv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Table construction (once per rkg_load_refs).
+
+// canonical hash of k-mer code c through the hashing kernel's Murmur (mkmh.hpp:515-524)
+template <int KV>
+RK_D u64 memo_code_hash(u32 c, int k) {
+    constexpr int NW = KVar<KV>::NW;
+    u32 f[NW], r[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) { f[i] = 0; r[i] = 0; }
+#pragma unroll
+    for (int j = 0; j < 4 * NW; ++j) {
+        if (j < k) {
+            const u32 cf = ((c >> j) & 1u) | (((c >> (k + j)) & 1u) << 1);
+            f[j >> 2] |= (code_letters(cf) & 0xFFu) << (8 * (j & 3));
+            const int src = k - 1 - j;                          // reverse complement: byte j = complement of base k-1-j
+            const u32 cr = ((c >> src) & 1u) | (((c >> (k + src)) & 1u) << 1);
+            r[j >> 2] |= ((code_letters(cr) >> 8) & 0xFFu) << (8 * (j & 3));
+        }
+    }
+    const u64 hf = murmur_kmer<KV>(f, k), hr = murmur_kmer<KV>(r, k);
+    return hf < hr ? hf : hr;
+}
+
+RK_D u32 memo_bucket(u64 h, int bucket_bits) { return bucket_bits ? (u32)(h >> (64 - bucket_bits)) : 0u; }
+
+template <int KV>
+__global__ void __launch_bounds__(256)
+memo_hash_kernel(int k, u32 ncodes, u64* __restrict__ hash, u32* __restrict__ bucket_count, int bucket_bits) {
+    for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < ncodes; c += gridDim.x * blockDim.x) {
+        const u64 h = memo_code_hash<KV>(c, k);
+        hash[c] = h;
+        atomicAdd(&bucket_count[memo_bucket(h, bucket_bits)], 1u);
+    }
+}
+
+// exclusive scan of nb (<= 65536) bucket counts by one block of 1024 threads; also resets the fill cursors
+__global__ void __launch_bounds__(1024)
+memo_scan_kernel(const u32* __restrict__ count, u32* __restrict__ start, u32* __restrict__ fill, u32 nb, int* __restrict__ err) {
+    __shared__ u32 part[1024];
+    const u32 per = (nb + 1023u) / 1024u, b0 = threadIdx.x * per;
+    u32 sum = 0, mx = 0;
+    for (u32 i = 0; i < per; ++i) if (b0 + i < nb) { sum += count[b0 + i]; mx = max(mx, count[b0 + i]); }
+    if (mx > (u32)MEMO_BUCKET_CAP) *err = 1;
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        u32 v = ((int)threadIdx.x >= d) ? part[threadIdx.x - d] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    u32 run = part[threadIdx.x] - sum;
+    for (u32 i = 0; i < per; ++i) if (b0 + i < nb) { start[b0 + i] = run; fill[b0 + i] = 0; run += count[b0 + i]; }
+}
+
+__global__ void __launch_bounds__(256)
+memo_scatter_kernel(u32 ncodes, const u64* __restrict__ hash, const u32* __restrict__ start, u32* __restrict__ fill,
+                    u32* __restrict__ codes, int bucket_bits) {
+    for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < ncodes; c += gridDim.x * blockDim.x) {
+        const u32 b = memo_bucket(hash[c], bucket_bits);
+        codes[start[b] + atomicAdd(&fill[b], 1u)] = c;
+    }
+}
+
+// One block per hash bucket: sort the bucket by hash in shared memory; rank = start + index of the first equal hash.
+__global__ void __launch_bounds__(256)
+memo_rank_kernel(const u64* __restrict__ hash, const u32* __restrict__ count, const u32* __restrict__ start,
+                 const u32* __restrict__ codes, u32 nb, RefTable tb, u32* __restrict__ tab, u32* __restrict__ ref) {
+    __shared__ u64 key[MEMO_BUCKET_CAP];
+    __shared__ u32 val[MEMO_BUCKET_CAP];
+    for (u32 b = blockIdx.x; b < nb; b += gridDim.x) {
+        const int n = (int)min(count[b], (u32)MEMO_BUCKET_CAP);
+        const u32 st = start[b];
+        int cap = 2; while (cap < n) cap <<= 1;
+        for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+            if (i < n) { const u32 c = codes[st + i]; val[i] = c; key[i] = hash[c]; } else { val[i] = 0; key[i] = ~0ULL; }
+        }
+        for (int size = 2; size <= cap; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (int t = threadIdx.x; t < (cap >> 1); t += blockDim.x) {
+                    const int lo = ((t / stride) * (stride << 1)) + (t % stride), hi = lo + stride;
+                    const bool up = ((lo & size) == 0);
+                    const u64 x = key[lo], y = key[hi];
+                    if ((x > y) == up) { key[lo] = y; key[hi] = x; const u32 v = val[lo]; val[lo] = val[hi]; val[hi] = v; }
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const u64 h = key[i];
+            int first = i;
+            while (first > 0 && key[first - 1] == h) --first;
+            const u32 rank = st + (u32)first;
+            u32 flags = 0;
+            if (h == 0) flags |= MEMO_ZERO;
+            else if (tb.entries != nullptr) {
+                const int slot = table_find(tb, h);
+                if (slot >= 0) { flags |= MEMO_REF; ref[rank] = (u32)slot + 1u; }
+            }
+            tab[val[i]] = (rank << 8) | flags;
+        }
+        __syncthreads();
+    }
+}
+
+// -M pass 1 epilogue: counts[hash % size] += code_counts[code]  (HASHTCounter::increment, HASHTCounter.cpp:46-58)
+__global__ void __launch_bounds__(256)
+memo_fold_kernel(Memo mm, CountTable ct, int count_zeros) {
+    for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < mm.ncodes; c += gridDim.x * blockDim.x) {
+        const int n = mm.code_counts[c];
+        if (n == 0) continue;
+        mm.code_counts[c] = 0;
+        const u64 h = mm.hash[c];
+        if (h != 0 || count_zeros) atomicAdd(&ct.counts[fastmod(h, ct.mod)], n);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long inv = *mm.inval;
+        *mm.inval = 0;
+        if (count_zeros && inv) atomicAdd(&ct.counts[0], (int)inv);     // an invalid window hashes to 0 (rkmh.cpp:331-336)
+    }
+}
+
+// bake mask_by_frequency (mkmh.hpp:898-908) for the current table and min_occ into the FAILM flag (min_occ < 0: clear)
+__global__ void __launch_bounds__(256)
+memo_apply_occ_kernel(Memo mm, CountTable ct, int min_occ) {
+    for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < mm.ncodes; c += gridDim.x * blockDim.x) {
+        const u32 t = mm.tab[c];
+        u32 fail = 0;
+        if (min_occ >= 0 && ct.counts != nullptr) {
+            const u64 h = mm.hash[c];
+            if (h != 0 && !(min_occ <= ct.counts[fastmod(h, ct.mod)])) fail = MEMO_FAILM;
+        }
+        const u32 nt = (t & ~MEMO_FAILM) | fail;
+        if (nt != t) mm.tab[c] = nt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// count_memo_kernel: -M pass 1.  `wpr` warps share one read (1 for short reads, a whole block for long ones).
+__global__ void __launch_bounds__(256)
+count_memo_kernel(SeqBatch sb, Memo mm, int count_zeros, int wpr) {
+    const int lane = threadIdx.x & 31;
+    const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((i64)gridDim.x * blockDim.x) >> 5;
+    const i64 team = gw / wpr, nteams = nw / wpr;
+    const int wt = (int)(gw % wpr);
+    u32 inv = 0;
+    for (i64 s = team; s < sb.nseq; s += nteams) {
+        const i64 beg = sb.offs[s] - sb.base0, len = sb.offs[s + 1] - sb.offs[s];
+        const i64 n = nkmers(len, mm.k);
+        const i64 per = ((((n + 31) >> 5) + wpr - 1) / wpr) << 5;          // k-mer starts per warp, whole rounds
+        const i64 s0 = (i64)wt * per, s1 = min(n, s0 + per);
+        memo_stream(sb.bases + beg, len, mm.k, mm.kmask, s0, s1, lane, [&](i64, u32 code, bool in, bool valid) {
+            if (valid) atomicAdd(&mm.code_counts[code], 1);
+            else if (in) ++inv;
+        });
+    }
+    if (count_zeros) {
+        inv = warp_sum(inv);
+        if (lane == 0 && inv) atomicAdd(mm.inval, (unsigned long long)inv);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// classify_memo_warp_kernel: one warp per read whose sketch is "every counted k-mer" (number of k-mers <= s).
+// Members of a reference sketch (REF) are queued per warp and resolved 32 at a time: table slot from ref[rank], copy
+// number inside the read from a per-warp set (multiset semantics), bitset rows spread over the lanes into
+// packed 16-bit per-reference counters.  Reads with more k-mers than s, or whose hits overflow the set, go to the
+// block kernel through `redo`.
+constexpr int MQ = 64;      // per-warp candidate ring
+constexpr int MDS = 128;    // per-warp set of the table slots hit so far: key + number of copies seen
+
+struct MemoWarpSmem {
+    u64 q[MQ];
+    u32 d[2 * MDS];          // [0, MDS): keys, [MDS, 2 MDS): counts
+};
+
+__global__ void __launch_bounds__(1024, 1)
+classify_memo_warp_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, int rwords,
+                          int* __restrict__ redo, int* __restrict__ redo_count, Hit* __restrict__ out) {
+#ifdef RK_EMU
+    unsigned char* dsm = reinterpret_cast<unsigned char*>(EMU_DYN_SMEM());
+#else
+    extern __shared__ __align__(16) unsigned char dsm[];
+#endif
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    MemoWarpSmem* wsm = reinterpret_cast<MemoWarpSmem*>(dsm) + wib;
+    u32* cnt = reinterpret_cast<u32*>(reinterpret_cast<MemoWarpSmem*>(dsm) + nwb) + (size_t)wib * rwords;
+
+    for (int i = lane; i < rwords; i += 32) cnt[i] = 0;
+    for (int i = lane; i < 2 * MDS; i += 32) wsm->d[i] = 0;
+    __syncwarp();
+
+    const int nw32 = 2 * (int)tb.nb;
+    const int lanes_per_hit = nw32 < 32 ? nw32 : 32;
+    const int hits_per_round = 32 / lanes_per_hit;
+    const int my_sub = lane / lanes_per_hit, my_word = lane - my_sub * lanes_per_hit;
+    const int k = mm.k;
+
+    const i64 gwarp = (i64)blockIdx.x * nwb + wib, nwarps = (i64)gridDim.x * nwb;
+    for (i64 rid = gwarp; rid < sb.nseq; rid += nwarps) {
+        const i64 beg = sb.offs[rid] - sb.base0, len = sb.offs[rid + 1] - sb.offs[rid];
+        const i64 n = nkmers(len, k);
+        if (n > s) {                                         // the sketch is a strict subset: block kernel
+            if (lane == 0) redo[atomicAdd(redo_count, 1)] = (int)rid;
+            continue;
+        }
+        int qhead = 0, qn = 0;
+        bool dirty = false, overflow = false;
+        u32 nz = 0;
+
+        auto drain = [&](int m) {                            // resolve the first m (<= 32) queued candidates
+            const u64* row = nullptr;
+            bool over = false;
+            if (lane < m) {
+                const u32 rank = (u32)wsm->q[(qhead + lane) & (MQ - 1)];
+                const u32 key = mm.ref[rank];                // slot + 1
+                u32 p = (key * 0x9E3779B1u) >> 25;           // MDS = 128
+                bool found = false;
+                for (int tries = 0; tries < MDS; ++tries) {
+                    const u32 old = atomicCAS(&wsm->d[p], 0u, key);
+                    if (old == 0u || old == key) { found = true; break; }
+                    p = (p + 1) & (MDS - 1);
+                }
+                if (!found) over = true;
+                else row = table_row(tb, (int)key - 1, atomicAdd(&wsm->d[MDS + p], 1u));
+            }
+            __syncwarp();
+            if (__ballot_sync(0xffffffffu, over)) overflow = true;
+            const u32 hitmask = __ballot_sync(0xffffffffu, row != nullptr);
+            const int nh = __popc(hitmask);
+            if (row != nullptr) wsm->q[(qhead + __popc(hitmask & ((1u << lane) - 1u))) & (MQ - 1)] = (u64)(size_t)row;
+            __syncwarp();
+            for (int base = 0; base < nh; base += hits_per_round) {
+                const int hi = base + my_sub;
+                if (hi < nh && my_sub < hits_per_round) {
+                    const u32* r32 = reinterpret_cast<const u32*>((size_t)wsm->q[(qhead + hi) & (MQ - 1)]);
+                    for (int w = my_word; w < nw32; w += 32) {
+                        u32 bits = r32[w];
+                        while (bits) {
+                            const int b = __ffs((int)bits) - 1;
+                            bits &= bits - 1;
+                            atomicAdd(&cnt[16 * w + (b >> 1)], 1u << (16 * (b & 1)));   // reference 32 w + b
+                        }
+                    }
+                }
+            }
+            qhead = (qhead + m) & (MQ - 1);
+            qn -= m;
+            dirty = true;
+            __syncwarp();
+        };
+
+        memo_stream(sb.bases + beg, len, k, mm.kmask, 0, n, lane, [&](i64, u32 code, bool, bool valid) {
+            u32 m = MEMO_ZERO;
+            if (valid) m = __ldg(&mm.tab[code]);
+            const bool counted = !(m & (MEMO_ZERO | MEMO_FAILM));
+            nz += counted;
+            const bool cand = counted && (m & MEMO_REF);
+            const u32 bal = __ballot_sync(0xffffffffu, cand);
+            if (bal) {
+                if (cand) wsm->q[(qhead + qn + __popc(bal & ((1u << lane) - 1u))) & (MQ - 1)] = (u64)(m >> 8);
+                qn += __popc(bal);
+                __syncwarp();
+                if (qn >= 32) drain(32);
+            }
+        });
+        while (qn > 0) drain(min(qn, 32));
+
+        nz = warp_sum(nz);
+        if (overflow) {
+            if (lane == 0) redo[atomicAdd(redo_count, 1)] = (int)rid;
+        } else if (!dirty) {
+            if (lane == 0) { Hit hh; hh.ref_id = 0; hh.best = 0; hh.prev = -1; hh.sketch_len = (int)nz; out[rid] = hh; }
+        } else {
+            // argmax of src/rkmh.cpp:874-883 on 32-bit keys (count << 16 | 0xFFFF - index): the largest key is the
+            // first reference with the highest count
+            u32 best = 0;
+            for (int w = lane; w < rwords; w += 32) {
+                const u32 pair = cnt[w], j = 2u * (u32)w;
+                best = max(best, max((pair << 16) | (0xFFFFu - j), (pair & 0xFFFF0000u) | (0xFFFEu - j)));
+            }
+            best = warp_max(best);
+            const int id = (int)(0xFFFFu - (best & 0xFFFFu));
+            u32 prev1 = 0;                                   // max of (count + 1) before the winner, 0 = none
+            for (int w = lane; 2 * w < id; w += 32) {
+                const u32 pair = cnt[w];
+                prev1 = max(prev1, (pair & 0xFFFFu) + 1u);
+                if (2 * w + 1 < id) prev1 = max(prev1, (pair >> 16) + 1u);
+            }
+            prev1 = warp_max(prev1);
+            if (lane == 0) { Hit hh; hh.ref_id = id; hh.best = (int)(best >> 16); hh.prev = (int)prev1 - 1; hh.sketch_len = (int)nz; out[rid] = hh; }
+        }
+        if (dirty) {
+            __syncwarp();
+            for (int i = lane; i < rwords; i += 32) cnt[i] = 0;
+            for (int i = lane; i < 2 * MDS; i += 32) wsm->d[i] = 0;
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// classify_memo_block_kernel: one block per read (grid-stride over `list`, or over every read when list is null).
+// Exact for every input.  The read's table values (rank | flags, MEMO_SKIP for windows that do not count) are kept in
+// shared memory (or L2 scratch for very long reads); the bottom-s multiset is a two-level radix select on the 24-bit
+// rank; its REF members are resolved against the reference table exactly like the Murmur path does.
+//
+// Dynamic shared memory (u32 units): [vcap values][MEMO_BINS histogram][hs_cap keys][hs_cap counts][rpad counters]
+struct MemoBlockScratch { u32 part[32]; u32 bin, before; int nz, take; ArgmaxScratch as; };
+
+// the bin in which the running count of hist[0, MEMO_BINS) reaches `target` (1-based), and the count before it
+RK_D void memo_find_bin(const u32* hist, u32 target, MemoBlockScratch* bs) {
+    const int per = MEMO_BINS / (int)blockDim.x, b0 = (int)threadIdx.x * per;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    u32 sum = 0;
+    for (int i = 0; i < per; ++i) sum += hist[b0 + i];
+    u32 incl = sum;
+    for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) bs->part[wib] = incl;
+    __syncthreads();
+    u32 woff = 0;
+    for (int w = 0; w < nwb; ++w) if (w < wib) woff += bs->part[w];
+    const u32 excl = woff + incl - sum;
+    if (excl < target && target <= excl + sum) {
+        u32 run = excl;
+        for (int i = 0; i < per; ++i) {
+            const u32 c = hist[b0 + i];
+            if (run + c >= target) { bs->bin = (u32)(b0 + i); bs->before = run; break; }
+            run += c;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 2)
+classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* __restrict__ list,
+                           const int* __restrict__ nlist_ptr, i64 nseq, int vcap, int hs_cap, int rpad,
+                           u32* __restrict__ scratch, i64 scratch_stride, Hit* __restrict__ out) {
+#ifdef RK_EMU
+    unsigned char* dsm = reinterpret_cast<unsigned char*>(EMU_DYN_SMEM());
+#else
+    extern __shared__ __align__(16) unsigned char dsm[];
+#endif
+    __shared__ MemoBlockScratch bs;
+    u32* vals_smem = reinterpret_cast<u32*>(dsm);
+    u32* hist = vals_smem + vcap;
+    u32* hs_keys = hist + MEMO_BINS;
+    u32* hs_cnt = hs_keys + hs_cap;
+    u32* counts = hs_cnt + hs_cap;
+    const u32 hs_mask = (u32)hs_cap - 1;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    const int k = mm.k;
+
+    const i64 nlist = list ? (i64)*nlist_ptr : nseq;
+    for (i64 q = blockIdx.x; q < nlist; q += gridDim.x) {
+        const i64 rid = list ? (i64)list[q] : q;
+        const i64 beg = sb.offs[rid] - sb.base0, len = sb.offs[rid + 1] - sb.offs[rid];
+        const i64 n = nkmers(len, k);
+        u32* V = (n <= vcap) ? vals_smem : scratch + (i64)blockIdx.x * scratch_stride;
+        if (threadIdx.x == 0) { bs.nz = 0; bs.take = 0; }
+        for (int i = threadIdx.x; i < MEMO_BINS; i += blockDim.x) hist[i] = 0;
+        for (int i = threadIdx.x; i < 2 * hs_cap; i += blockDim.x) hs_keys[i] = 0;
+        for (int i = threadIdx.x; i < rpad; i += blockDim.x) counts[i] = 0;
+        __syncthreads();
+        // ---- pass 1: table values of every window, histogram of the top 12 rank bits ----------------------
+        {
+            const i64 per = ((((n + 31) >> 5) + nwb - 1) / nwb) << 5;
+            const i64 s0 = (i64)wib * per, s1 = min(n, s0 + per);
+            u32 local_nz = 0;
+            memo_stream(sb.bases + beg, len, k, mm.kmask, s0, s1, lane, [&](i64 pos, u32 code, bool in, bool valid) {
+                u32 m = MEMO_SKIP;
+                if (valid) { m = __ldg(&mm.tab[code]); if (m & (MEMO_ZERO | MEMO_FAILM)) m = MEMO_SKIP; }
+                if (in) V[pos] = m;
+                if (m != MEMO_SKIP) { ++local_nz; atomicAdd(&hist[m >> 20], 1u); }
+            });
+            local_nz = warp_sum(local_nz);
+            if (lane == 0 && local_nz) atomicAdd(&bs.nz, (int)local_nz);
+        }
+        __syncthreads();
+        const int nz = bs.nz;
+        const int L = nz < s ? nz : s;
+        // ---- bottom-s threshold: rank T, of which `need` copies belong to the sketch -----------------------
+        u32 T = 0xFFFFFFFFu; int need = 0;
+        if (nz > s) {
+            memo_find_bin(hist, (u32)s, &bs);
+            const u32 b1 = bs.bin, before1 = bs.before;
+            __syncthreads();
+            for (int i = threadIdx.x; i < MEMO_BINS; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            for (i64 i = threadIdx.x; i < n; i += blockDim.x) {
+                const u32 m = V[i];
+                if (m != MEMO_SKIP && (m >> 20) == b1) atomicAdd(&hist[(m >> 8) & 0xFFFu], 1u);
+            }
+            __syncthreads();
+            memo_find_bin(hist, (u32)s - before1, &bs);
+            T = (b1 << 12) | bs.bin;
+            need = s - (int)before1 - (int)bs.before;
+            __syncthreads();
+        }
+        // ---- resolve the REF members of the sketch ----------------------------------------------------------
+        for (i64 i = threadIdx.x; i < n; i += blockDim.x) {
+            const u32 m = V[i];
+            if (m == MEMO_SKIP) continue;
+            const u32 rank = m >> 8;
+            if (rank > T) continue;
+            if (rank == T && !(atomicAdd(&bs.take, 1) < need)) continue;
+            if (!(m & MEMO_REF)) continue;
+            const u32 key = mm.ref[rank];                    // slot + 1
+            u32 p = (key * 0x9E3779B1u) & hs_mask;
+            for (;;) {
+                const u32 old = atomicCAS(&hs_keys[p], 0u, key);
+                if (old == 0u || old == key) break;
+                p = (p + 1) & hs_mask;
+            }
+            const u64* row = table_row(tb, (int)key - 1, atomicAdd(&hs_cnt[p], 1u));
+            if (row == nullptr) continue;
+            for (u32 w = 0; w < tb.nb; ++w) {
+                u64 bits = row[w];
+                while (bits) {
+                    const int b = __ffsll((long long)bits) - 1;
+                    bits &= bits - 1;
+                    atomicAdd(&counts[w * 64 + b], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        block_argmax(counts, (int)tb.nrefs, &bs.as, &out[rid], L);
+    }
+}
+
+}  // namespace rk

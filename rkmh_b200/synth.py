@@ -76,3 +76,64 @@ def write_fastq(path, bases, offs, prefix="r"):
                 parts.append(qual)
                 parts.append(b"\n")
             fh.write(b"".join(parts))
+
+
+def ont_reads(rng, genomes, n, length, sub=0.04, ins=0.03, dele=0.03, chunk=2048):
+    """cfg3-style long reads: each read is a circular walk on one uniformly chosen genome (random start, random
+    strand) with ONT-like errors: `sub` substitutions, `ins` inserted random bases, `dele` skipped genome bases.
+    Fixed output length.  Returns (bases uint8 [n * length], offs int64 [n + 1])."""
+    gs = upper_refs(genomes)
+    bases = np.empty(n * length, np.uint8)
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        gi = rng.integers(0, len(gs), m)
+        u = rng.random((m, length), dtype=np.float32)
+        is_ins = u < ins
+        step = np.where(is_ins, 0, 1 + (u > 1.0 - dele)).astype(np.int32)      # 0 = inserted base, 2 = one base skipped
+        walk = np.cumsum(step, axis=1, dtype=np.int32) - step
+        blk = np.empty((m, length), np.uint8)
+        for g in np.unique(gi):
+            rows = np.nonzero(gi == g)[0]
+            G = gs[g]
+            start = rng.integers(0, G.size, rows.size)
+            src = (start[:, None] + walk[rows]) % G.size
+            seg = G[src]
+            rev = rng.random(rows.size) < 0.5
+            seg[rev] = _COMP[seg[rev][:, ::-1]]
+            blk[rows] = seg
+        noise = is_ins | (rng.random((m, length), dtype=np.float32) < sub)
+        blk[noise] = _ACGT[rng.integers(0, 4, int(noise.sum()))]
+        bases[c0 * length:(c0 + m) * length] = blk.reshape(-1)
+    return bases, np.arange(n + 1, dtype=np.int64) * length
+
+
+def background_reads(rng, n, length, gc=0.41, chunk=1 << 18):
+    """cfg4-style "human-like" background: order-0 random bases with the given GC fraction."""
+    p = np.array([(1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2])     # A C G T
+    bases = np.empty(n * length, np.uint8)
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        bases[c0 * length:(c0 + m) * length] = _ACGT[rng.choice(4, size=m * length, p=p)]
+    return bases, np.arange(n + 1, dtype=np.int64) * length
+
+
+def mixed_reads(rng, refs, n, length, viral_frac=0.05, gc=0.41):
+    """cfg4: `viral_frac` of the reads sampled from the references as in cfg2, the rest background; shuffled."""
+    nv = int(round(n * viral_frac))
+    vb, _ = sample_reads(rng, refs, nv, length, random_frac=0.0)
+    bb, _ = background_reads(rng, n - nv, length, gc)
+    mat = np.concatenate([vb.reshape(nv, length), bb.reshape(n - nv, length)])
+    perm = rng.permutation(n)
+    return np.ascontiguousarray(mat[perm]).reshape(-1), np.arange(n + 1, dtype=np.int64) * length, perm < nv
+
+
+def random_genome(rng, nbases, n_run_rate=1e-5, n_run_len=1000, chunk=1 << 26):
+    """cfg5: one uniform ACGT sequence with ~1 % of its bases inside runs of N."""
+    out = np.empty(nbases, np.uint8)
+    for c0 in range(0, nbases, chunk):
+        m = min(chunk, nbases - c0)
+        out[c0:c0 + m] = _ACGT[rng.integers(0, 4, m, dtype=np.uint8)]
+    nruns = int(nbases * n_run_rate)
+    for st in rng.integers(0, max(nbases - n_run_len, 1), nruns):
+        out[st:st + n_run_len] = ord("N")
+    return out

@@ -34,6 +34,8 @@ class Emu:
         lib.emu_sketch.argtypes = [P, P, L, P, I, I, P, U, I, I, P, P, I, I]
         lib.emu_merge.argtypes = [P, P, I, I, P, P, I, I]
         lib.emu_classify.argtypes = [P, P, I, P, P, L, P, I, I, P, U, I, I, I, I, I, I, P, P, P, P]
+        lib.emu_count_memo.argtypes = [P, P, L, I, P, U, I, I, I]
+        lib.emu_classify_memo.argtypes = [P, P, I, P, P, L, I, I, P, U, I, I, I, I, P, P]
 
     def hash(self, seqs, ks, block=64):
         bases, offs = pack(seqs)
@@ -86,3 +88,22 @@ class Emu:
                               int(hbuf_global), int(hs_global), hits.ctypes.data, rsk.ctypes.data, rl.ctypes.data,
                               redo.ctypes.data)
         return hits[:len(reads)], rsk, rl, int(redo[0])
+
+    # ---- memoised path (rk_memo.cuh) ----
+    def count_memo(self, seqs, k, counts, count_zeros=False, wpr=1, block=64):
+        bases, offs = pack(seqs)
+        rc = self.lib.emu_count_memo(bases.ctypes.data, offs.ctypes.data, len(seqs), int(k), counts.ctypes.data,
+                                     C.c_uint64(counts.size), int(count_zeros), int(wpr), block)
+        assert rc == 0
+
+    def classify_memo(self, refs, reads, k, s, counts=None, min_occ=-1, path=1, block=64, vcap_limit=0):
+        rb, ro = pack(refs)
+        qb, qo = pack(reads)
+        hits = np.zeros(max(len(reads), 1), HIT)
+        redo = np.zeros(1, np.int32)
+        rc = self.lib.emu_classify_memo(rb.ctypes.data, ro.ctypes.data, len(refs), qb.ctypes.data, qo.ctypes.data, len(reads),
+                                        int(k), int(s), counts.ctypes.data if counts is not None else None,
+                                        C.c_uint64(counts.size if counts is not None else 0), min_occ, path, block,
+                                        vcap_limit, hits.ctypes.data, redo.ctypes.data)
+        assert rc == 0
+        return hits[:len(reads)], int(redo[0])

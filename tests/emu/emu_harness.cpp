@@ -10,6 +10,7 @@ EMU_DEFINE_STATE
 #include <vector>
 
 #include "../../rkmh_b200/csrc/rk_kernels.cuh"
+#include "../../rkmh_b200/csrc/rk_memo.cuh"
 
 using namespace rk;
 
@@ -220,6 +221,98 @@ int emu_classify(const char* ref_bases, const i64* ref_offs, int nrefs, const ch
     }
     return 0;
 }
+
+// ---- memoised path (rk_memo.cuh) -------------------------------------------------------------------------
+struct HostMemo {
+    std::vector<u32> tab, ref, tmp;
+    std::vector<u64> hash;
+    std::vector<int> code_counts;
+    unsigned long long inval = 0;
+    int err = 0;
+    Memo mm{};
+};
+
+static void build_memo(HostMemo& hm, int k, const RefTable& tb, int block) {
+    const u32 ncodes = 1u << (2 * k);
+    const int bucket_bits = std::max(2 * k - 8, 0);
+    const u32 nb = 1u << bucket_bits;
+    hm.tab.assign(ncodes, 0); hm.ref.assign(ncodes, 0); hm.hash.assign(ncodes, 0); hm.code_counts.assign(ncodes, 0);
+    hm.tmp.assign((size_t)3 * nb + ncodes, 0);
+    u32* bcount = hm.tmp.data(); u32* bstart = bcount + nb; u32* bfill = bstart + nb; u32* bcodes = bfill + nb;
+    u64* hash = hm.hash.data(); u32* tab = hm.tab.data(); u32* ref = hm.ref.data(); int* err = &hm.err;
+    dispatch(kvariant_of(k), [&](auto tag) {
+        constexpr int KV = decltype(tag)::value <= 2 ? decltype(tag)::value : 2;
+        emu::launch(dim3(2), dim3(block), 0, [=] { memo_hash_kernel<KV>(k, ncodes, hash, bcount, bucket_bits); });
+    });
+    emu::launch(dim3(1), dim3(1024), 0, [=] { memo_scan_kernel(bcount, bstart, bfill, nb, err); });
+    emu::launch(dim3(2), dim3(block), 0, [=] { memo_scatter_kernel(ncodes, hash, bstart, bfill, bcodes, bucket_bits); });
+    emu::launch(dim3(2), dim3(block), 0, [=] { memo_rank_kernel(hash, bcount, bstart, bcodes, nb, tb, tab, ref); });
+    hm.mm.tab = tab; hm.mm.ref = ref; hm.mm.hash = hash; hm.mm.code_counts = hm.code_counts.data();
+    hm.mm.inval = &hm.inval; hm.mm.ncodes = ncodes; hm.mm.kmask = (1u << k) - 1u; hm.mm.k = k;
+}
+
+extern "C" {
+
+// -M pass 1 through the memoised count kernel + fold; counts must be zero-initialised by the caller
+int emu_count_memo(const char* bases, const i64* offs, i64 nseq, int k, int* counts, u64 size, int count_zeros, int wpr,
+                   int block) {
+    int ks[1] = {k}; int kcsel; KList kl = make_klist(ks, 1, &kcsel);
+    HostBatch b; fill_batch(b, bases, offs, nseq, kl, block);
+    HostMemo hm; RefTable none{}; build_memo(hm, k, none, block);
+    if (hm.err) return -1;
+    CountTable ct{counts, make_fastmod(size)};
+    SeqBatch sb = b.view(); Memo mm = hm.mm;
+    emu::launch(dim3(2), dim3(block), 0, [=] { count_memo_kernel(sb, mm, count_zeros, wpr); });
+    emu::launch(dim3(2), dim3(block), 0, [=] { memo_fold_kernel(mm, ct, count_zeros); });
+    return 0;
+}
+
+// path: 0 = block kernel for every read, 1 = warp kernel + block kernel on its redo list.  vcap_limit > 0 caps the
+// shared-memory value buffer (forces the global scratch for longer reads).
+int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, const char* bases, const i64* offs, i64 nreads,
+                      int k, int s, const int* counts, u64 size, int min_occ, int path, int block, int vcap_limit,
+                      Hit* out, int* redo_count_out) {
+    int ks[1] = {k}; int kcsel; KList kl = make_klist(ks, 1, &kcsel);
+    HostBatch rb; fill_batch(rb, ref_bases, ref_offs, nrefs, kl, block);
+    std::vector<u64> rsk((size_t)nrefs * s, 0); std::vector<int> rlen(nrefs, 0);
+    run_sketch(rb, kl, kcsel, s, CountTable{nullptr, {}}, 0, 0, block, 2, 0, rsk.data(), rlen.data());
+    HostTable ht; build_table(ht, rsk.data(), rlen.data(), nrefs, s, block);
+    HostMemo hm; build_memo(hm, k, ht.tb, block);
+    if (hm.err) return -1;
+    HostBatch b; fill_batch(b, bases, offs, nreads, kl, block);
+    CountTable ct{const_cast<int*>(counts), make_fastmod(size ? size : 1)};
+    if (!counts) min_occ = -1;
+    Memo mm = hm.mm;
+    emu::launch(dim3(2), dim3(block), 0, [=] { memo_apply_occ_kernel(mm, ct, min_occ); });
+    SeqBatch sb = b.view();
+    RefTable tb = ht.tb;
+    std::vector<int> redo((size_t)std::max<i64>(nreads, 1)); int redo_count = 0;
+    int* predo = redo.data(); int* pcount = &redo_count;
+    const int grid = 2;
+    if (path == 1) {
+        const int rwords = (nrefs + 1) / 2;
+        size_t smem = (size_t)(block / 32) * (sizeof(MemoWarpSmem) + (size_t)rwords * 4);
+        emu::launch(dim3(grid), dim3(block), smem, [=] { classify_memo_warp_kernel(sb, s, mm, tb, rwords, predo, pcount, out); });
+    }
+    if (redo_count_out) *redo_count_out = redo_count;
+    {
+        const int hs_cap = next_pow2(2 * (i64)std::min<i64>(s, std::max<i64>(b.max_ntotal, 1)));
+        const int rpad = (nrefs + 63) / 64 * 64;
+        int vcap = (int)std::max<i64>(b.max_ntotal, 1);
+        if (vcap_limit > 0) vcap = std::min(vcap, vcap_limit);
+        const i64 stride = (b.max_ntotal > vcap) ? b.max_ntotal : 0;
+        size_t smem = 4 * ((size_t)vcap + MEMO_BINS + 2 * (size_t)hs_cap + rpad);
+        std::vector<u32> scratch((size_t)grid * (size_t)stride + 8);
+        u32* ps = scratch.data();
+        const int* list = (path == 1) ? predo : nullptr;
+        emu::launch(dim3(grid), dim3(block), smem, [=] {
+            classify_memo_block_kernel(sb, s, mm, tb, list, pcount, nreads, vcap, hs_cap, rpad, ps, stride, out);
+        });
+    }
+    return 0;
+}
+
+}  // extern "C"
 
 // host-side arithmetic checks
 u64 emu_fastmod(u64 n, u64 d) { FastMod f = make_fastmod(d); return fastmod(n, f); }

@@ -104,3 +104,52 @@ def test_sketch_and_merge(emu, oracle):
     whole = oracle.minhashes(np.concatenate([oracle.calc_hashes(oracle.to_upper(r), [12]) for r in refs]), 1000)
     assert np.array_equal(emu.merge(parts, pl, 1000), whole)
     assert np.array_equal(emu.merge(parts, pl, 1000, in_smem=False), whole)
+
+
+# ---- memoised path (rk_memo.cuh): same results as the oracle, through the table build + streaming kernels ----------
+def _memo_case(emu, oracle, refs, reads, k, s, counts=None, min_occ=-1, **kw):
+    hits, redo = emu.classify_memo(refs, reads, k, s, counts=counts, min_occ=min_occ, **kw)
+    osk, ol = oracle.sketch_batch(refs, [k], s)
+    oh = oracle.classify_batch(reads, [k], s, osk, ol, counts=counts, min_occ=min_occ if counts is not None else 0)
+    for f in ("ref_id", "best", "prev", "sketch_len"):
+        assert np.array_equal(hits[f], oh[f]), (f, kw)
+    return redo
+
+
+@pytest.mark.parametrize("kw", [dict(path=0), dict(path=1), dict(path=0, vcap_limit=16), dict(path=1, block=128)])
+def test_memo_classify_awkward(emu, oracle, kw):
+    _, refs, _ = load_sequences([data_path("awkward_refs.fa.gz")])
+    _, reads, _ = load_sequences([data_path("awkward_reads.fq.gz")])
+    reads = reads + [b"A" * 70, b"ACGT" * 20, b"N" * 40, b"ACGTACGTA", b"ACGTACGT", b"", b"acgtacgtacgtnacgtacgtacgt",
+                     b"G" * 9 + b"{}|~" + b"C" * 20, refs[0], refs[1] + refs[1]]
+    for k, s in ((8, 50), (8, 5), (5, 1000), (3, 7)):
+        _memo_case(emu, oracle, refs, reads, k, s, **kw)
+
+
+def test_memo_classify_fixtures(emu, oracle):
+    _, refs, _ = load_sequences([data_path("hpv_16_allFasta.fa.gz")])
+    _, reads, _ = load_sequences([data_path("minION25.fq.gz")])
+    assert _memo_case(emu, oracle, refs, reads[:3], 8, 300, path=1) == 3        # long reads: all through the block kernel
+    _, short, _ = load_sequences([data_path("z1.fq.gz")])
+    assert _memo_case(emu, oracle, refs, short[:40], 8, 1000, path=1) == 0
+
+
+def test_memo_count_and_min_occ(emu, oracle):
+    _, refs, _ = load_sequences([data_path("new_refs.fa.gz")])
+    _, reads, _ = load_sequences([data_path("mix2k.fq.gz")])
+    reads = reads[:60] + [b"ACGTNNACGTTTGACCA" * 9, b"N" * 50]
+    size = 10_007
+    for zeros in (False, True):
+        c1 = np.zeros(size, np.int32)
+        emu.count_memo(reads, 8, c1, count_zeros=zeros, wpr=1)
+        c2 = np.zeros(size, np.int32)
+        oracle.count_batch(reads, [8], c2, valid_only=not zeros)
+        assert np.array_equal(c1, c2), zeros
+        c3 = np.zeros(size, np.int32)
+        emu.count_memo(reads, 8, c3, count_zeros=zeros, wpr=2)
+        assert np.array_equal(c3, c2), zeros
+    c = np.zeros(size, np.int32)
+    oracle.count_batch(reads, [8], c)
+    for m in (1, 30, 200):
+        for path in (0, 1):
+            _memo_case(emu, oracle, refs[:4], reads, 8, 200, counts=c, min_occ=m, path=path)

@@ -12,10 +12,13 @@ from tests.util import data_path, golden_cli_output
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def gpu():
+@pytest.fixture(scope="module", params=["memo", "murmur"])
+def gpu(request):
+    """Every test runs twice: with the memoised path (single k <= 12, include/rkmh_gpu.h) and with the Murmur
+    kernels forced for every k."""
     import rkmh_b200
     ctx = rkmh_b200.RkmhGpu(0)
+    ctx.set_memo(request.param == "memo")
     yield ctx
     ctx.close()
 
@@ -266,3 +269,44 @@ def test_full_size_properties(gpu, oracle):
     sk, ln = gpu.ref_sketches()
     exp = oracle.classify_batch(reads, [12], 1000, sk, ln)
     assert np.array_equal(_fields(hits[idx]), _fields(exp))
+
+
+def test_memo_path_is_taken_and_matches_murmur(oracle):
+    """The memoised kernels run for a single k <= 12 and give the same records as the Murmur kernels: short reads
+    (warp kernel), long reads (block kernel, bottom-s by rank), with and without -M."""
+    import rkmh_b200
+    from rkmh_b200.synth import ont_reads
+    _, rs, _ = load_sequences([data_path("all_pave_ref.fa.gz")])
+    _, hpv, _ = load_sequences([data_path("hpv_16_allFasta.fa.gz")])
+    rng = np.random.default_rng(77)
+    sb, so = _synthetic_reads(rng, rs, 20000, 150)
+    lb, lo = ont_reads(rng, hpv, 300, 10000)
+    res = {}
+    for memo in (True, False):
+        with rkmh_b200.RkmhGpu(0) as g:
+            g.set_memo(memo)
+            g.set_params([12], 1000, read_table_size=rkmh_b200.STREAM_TABLE_SIZE)
+            g.load_refs(*_pack(rs))
+            assert g.memo_active() == memo
+            g.profile_enable(True)
+            out = [_fields(g.classify_batch(sb, so)), _fields(g.classify_batch(lb, lo))]
+            g.count_reset()
+            g.count_batch(lb, lo)
+            g.count_batch(sb, so)
+            t = g.count_table_tensor()
+            out.append(int(t.sum().item()))
+            for m in (2, 40):
+                out.append(_fields(g.classify_batch(lb, lo, min_occ=m)))
+                out.append(_fields(g.classify_batch(sb, so, min_occ=m)))
+            out.append(_fields(g.classify_batch(sb, so)))          # -M off again: FAILM flags cleared
+            names = set(g.profile_read())
+            assert ("classify_memo_warp_kernel" in names) == memo and ("classify_group_kernel" in names) == (not memo)
+            assert ("count_memo_kernel" in names) == memo
+            res[memo] = out
+    for a, b in zip(res[True], res[False]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(res[True][0], res[True][-1])
+    sk, ln = oracle.sketch_batch(rs, [12], 1000)
+    reads = [lb[lo[i]:lo[i + 1]].tobytes() for i in range(12)]
+    exp = oracle.classify_batch(reads, [12], 1000, sk, ln)
+    assert np.array_equal(res[True][1][:12], _fields(exp))
