@@ -26,12 +26,13 @@ thread_local std::string g_create_error;
 
 enum KernelId { K_INGEST, K_HASH, K_COUNT, K_COUNT_DISTINCT, K_SKETCH, K_MERGE, K_TABLE, K_CLASSIFY_GROUP,
                 K_CLASSIFY_BLOCK, K_MEMO_BUILD, K_MEMO_MAINT, K_COUNT_MEMO, K_CLASSIFY_MEMO_WARP, K_CLASSIFY_MEMO_BLOCK,
+                K_CLASSIFY_MEMO_TILE,
                 K_NUM };
 const char* const kKernelNames[K_NUM] = {"ingest_kernel", "hash_kernel", "count_kernel", "count_distinct_kernel",
                                          "sketch_kernel", "merge_kernel", "table_build_kernels",
                                          "classify_group_kernel", "classify_block_kernel", "memo_build_kernels",
                                          "memo_fold_apply_kernels", "count_memo_kernel", "classify_memo_warp_kernel",
-                                         "classify_memo_block_kernel"};
+                                         "classify_memo_block_kernel", "classify_memo_tile_kernel"};
 
 struct DevBuf {
     void* p = nullptr;
@@ -83,8 +84,8 @@ struct rkg_ctx {
     cudaStream_t stream = nullptr;
     rkg_batch* slots[2] = {nullptr, nullptr};   // internal double buffer of rkg_classify_batch / count
     // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
-    bool memo_enabled = true, memo_ready = false;
-    DevBuf memo_tab, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc;
+    bool memo_enabled = true, memo_ready = false, tile_kernel = false;
+    DevBuf memo_tab, memo_tab2, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc;
     Memo memo{};
     bool memo_pending = false;           // code_counts holds increments not yet folded into the read count table
     int memo_pending_zeros = 0;
@@ -243,6 +244,7 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     const int bucket_bits = std::max(2 * k - 8, 0);
     const u32 nb = 1u << bucket_bits;
     CK(ctx->memo_tab.ensure(sizeof(u32) * (size_t)ncodes));
+    CK(ctx->memo_tab2.ensure(sizeof(u32) * (size_t)ncodes));
     CK(ctx->memo_ref.ensure(sizeof(u32) * (size_t)ncodes));
     CK(ctx->memo_hash.ensure(sizeof(u64) * (size_t)ncodes));
     CK(ctx->memo_tmp.ensure(sizeof(u32) * ((size_t)3 * nb + ncodes)));
@@ -253,7 +255,7 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     CK(cudaMemsetAsync(ctx->memo_ref.p, 0, sizeof(u32) * (size_t)ncodes, st));
     CK(cudaMemsetAsync(ctx->memo_misc.p, 0, 256, st));
     Memo mm{};
-    mm.tab = ctx->memo_tab.as<u32>(); mm.ref = ctx->memo_ref.as<u32>(); mm.hash = ctx->memo_hash.as<u64>();
+    mm.tab = ctx->memo_tab.as<u32>(); mm.tab2 = ctx->memo_tab2.as<u32>(); mm.ref = ctx->memo_ref.as<u32>(); mm.hash = ctx->memo_hash.as<u64>();
     mm.inval = ctx->memo_misc.as<unsigned long long>();
     int* err = ctx->memo_misc.as<int>() + 8;
     mm.ncodes = ncodes; mm.kmask = (1u << k) - 1u; mm.k = k;
@@ -276,7 +278,8 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
         memo_scatter_kernel<<<grid, 256, 0, st>>>(ncodes, hash, bstart, bfill, bcodes, bucket_bits);
         memo_rank_kernel<<<(int)std::min<i64>(nb, (i64)ctx->sm_count * 8), 256, 0, st>>>(hash, bcount, bstart, bcodes, nb, ctx->tb,
                                                                                         mm.tab, mm.ref);
-        ctx->launches += 3;
+        memo_tab2_kernel<<<grid, 256, 0, st>>>(mm);
+        ctx->launches += 4;
     }
     CK(cudaGetLastError());
     int herr = 0;
@@ -370,7 +373,7 @@ GroupGeom group_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
 }
 
 // Geometry of the two memoised classification kernels for this batch, or ok = false (Murmur path instead).
-struct MemoGeom { bool ok, use_warp; int warp_block, rwords; size_t warp_smem; int vcap, hs_cap, rpad; size_t block_smem; i64 scratch_stride; };
+struct MemoGeom { bool ok, use_warp, use_tile; int warp_block, rwords; size_t warp_smem; int vcap, hs_cap, rpad; size_t block_smem; i64 scratch_stride; };
 
 MemoGeom memo_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
     MemoGeom g{};
@@ -393,6 +396,10 @@ MemoGeom memo_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
             const size_t smem = (size_t)(block / 32) * (sizeof(MemoWarpSmem) + (size_t)g.rwords * 4);
             if (smem <= ctx->smem_optin) { g.use_warp = true; g.warp_block = block; g.warp_smem = smem; break; }
         }
+        // thread per read: enough reads per shared-memory tile to fill the block
+        // (experimental, RKMH_TILE=1: measured 2x slower than the warp kernel on config 2 -- latency bound)
+        g.use_tile = ctx->tile_kernel && g.use_warp && ctx->tb.nb <= 4 && b->total / b->nseq <= 400 &&
+                     TILE_SMEM + 2048 <= ctx->smem_optin;
     }
     return g;
 }
@@ -413,10 +420,37 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
         if (mg.ok) {
             int rc = memo_prepare(ctx, min_occ);
             if (rc) return rc;
-            if (mg.use_warp) {
+            if (mg.use_tile) {                               // short reads, <= 256 references: a thread per read
+                Timed t(ctx, b->stream, K_CLASSIFY_MEMO_TILE);
+                const int grid = ctx->sm_count * 2;
+#define RK_TILE_LAUNCH(NWV)                                                                                              \
+    do {                                                                                                                 \
+        CK(cudaFuncSetAttribute(classify_memo_tile_kernel<NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM)); \
+        classify_memo_tile_kernel<NWV><<<grid, TILE_THREADS, TILE_SMEM, b->stream>>>(sb, ctx->s, ctx->memo, ctx->tb, redo, \
+                                                                                      redo_count, hits);                \
+    } while (0)
+                switch (ctx->tb.nb) {
+                    case 1: RK_TILE_LAUNCH(2); break;
+                    case 2: RK_TILE_LAUNCH(4); break;
+                    case 3: RK_TILE_LAUNCH(6); break;
+                    default: RK_TILE_LAUNCH(8); break;
+                }
+#undef RK_TILE_LAUNCH
+                CK(cudaGetLastError());
+            } else if (mg.use_warp && ctx->tb.nb <= 4) {     // <= 256 references: bitset rows in registers
                 Timed t(ctx, b->stream, K_CLASSIFY_MEMO_WARP);
-                CK(cudaFuncSetAttribute(classify_memo_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg.warp_smem));
-                classify_memo_warp_kernel<<<ctx->sm_count, mg.warp_block, mg.warp_smem, b->stream>>>(
+                const int grid = ctx->sm_count;
+                switch (ctx->tb.nb) {
+                    case 1: classify_memo_warp_kernel<2><<<grid, 1024, 0, b->stream>>>(sb, ctx->s, ctx->memo, ctx->tb, redo, redo_count, hits); break;
+                    case 2: classify_memo_warp_kernel<4><<<grid, 1024, 0, b->stream>>>(sb, ctx->s, ctx->memo, ctx->tb, redo, redo_count, hits); break;
+                    case 3: classify_memo_warp_kernel<6><<<grid, 1024, 0, b->stream>>>(sb, ctx->s, ctx->memo, ctx->tb, redo, redo_count, hits); break;
+                    default: classify_memo_warp_kernel<8><<<grid, 1024, 0, b->stream>>>(sb, ctx->s, ctx->memo, ctx->tb, redo, redo_count, hits); break;
+                }
+                CK(cudaGetLastError());
+            } else if (mg.use_warp) {
+                Timed t(ctx, b->stream, K_CLASSIFY_MEMO_WARP);
+                CK(cudaFuncSetAttribute(classify_memo_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg.warp_smem));
+                classify_memo_wide_kernel<<<ctx->sm_count, mg.warp_block, mg.warp_smem, b->stream>>>(
                     sb, ctx->s, ctx->memo, ctx->tb, mg.rwords, redo, redo_count, hits);
                 CK(cudaGetLastError());
             }
@@ -551,6 +585,7 @@ int rkg_create(int device, rkg_ctx** out) {
     ctx = new rkg_ctx();
     ctx->device = device;
     { const char* nm = getenv("RKMH_NO_MEMO"); ctx->memo_enabled = !(nm && nm[0] && nm[0] != '0'); }
+    { const char* tk = getenv("RKMH_TILE"); ctx->tile_kernel = tk && tk[0] && tk[0] != '0'; }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -569,7 +604,7 @@ void rkg_destroy(rkg_ctx* ctx) {
     for (int i = 0; i < 2; ++i) batch_release(ctx->slots[i]);
     for (DevBuf* d : {&ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
                       &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
-                      &ctx->memo_tab, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc})
+                      &ctx->memo_tab, &ctx->memo_tab2, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc})
         d->release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

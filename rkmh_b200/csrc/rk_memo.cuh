@@ -30,7 +30,8 @@ constexpr int MEMO_BUCKET_CAP = 1024;           // rank build: largest hash buck
 constexpr int MEMO_BINS = 4096;                 // radix-select histogram (12 bits of the 24-bit rank per level)
 
 struct Memo {
-    u32* tab;
+    u32* tab;                       // indexed by the plane code (warp-streaming kernels)
+    u32* tab2;                      // the same entries indexed by the rolling code (thread-per-read tile kernel)
     u32* ref;
     const u64* hash;
     int* code_counts;               // nullptr when the context has no read count table
@@ -43,9 +44,11 @@ struct Memo {
 #ifdef RK_EMU
 RK_D u32 warp_sum(u32 v) { for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d); return v; }
 RK_D u32 warp_max(u32 v) { for (int d = 16; d >= 1; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d)); return v; }
+RK_D u32 warp_or(u32 v) { for (int d = 16; d >= 1; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d); return v; }
 #else
 RK_D u32 warp_sum(u32 v) { return __reduce_add_sync(0xffffffffu, v); }
 RK_D u32 warp_max(u32 v) { return __reduce_max_sync(0xffffffffu, v); }
+RK_D u32 warp_or(u32 v) { return __reduce_or_sync(0xffffffffu, v); }
 #endif
 
 // Exactly the bytes canonical() accepts (valid_dna[], mkmh.hpp:137-152) as one bit test: A C G T a c g t.
@@ -105,6 +108,22 @@ RK_D u64 memo_code_hash(u32 c, int k) {
     }
     const u64 hf = murmur_kmer<KV>(f, k), hr = murmur_kmer<KV>(r, k);
     return hf < hr ? hf : hr;
+}
+
+// rolling code of the k-mer with plane code c: base j at bits 2 (k-1-j) (the newest base in the low bits)
+RK_HD u32 memo_roll_code(u32 c, int k) {
+    u32 r = 0;
+    for (int j = 0; j < k; ++j) {
+        const u32 c2 = ((c >> j) & 1u) | (((c >> (k + j)) & 1u) << 1);
+        r |= c2 << (2 * (k - 1 - j));
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+memo_tab2_kernel(Memo mm) {
+    for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < mm.ncodes; c += gridDim.x * blockDim.x)
+        mm.tab2[memo_roll_code(c, mm.k)] = mm.tab[c];
 }
 
 RK_D u32 memo_bucket(u64 h, int bucket_bits) { return bucket_bits ? (u32)(h >> (64 - bucket_bits)) : 0u; }
@@ -218,7 +237,7 @@ memo_apply_occ_kernel(Memo mm, CountTable ct, int min_occ) {
             if (h != 0 && !(min_occ <= ct.counts[fastmod(h, ct.mod)])) fail = MEMO_FAILM;
         }
         const u32 nt = (t & ~MEMO_FAILM) | fail;
-        if (nt != t) mm.tab[c] = nt;
+        if (nt != t) { mm.tab[c] = nt; mm.tab2[memo_roll_code(c, mm.k)] = nt; }
     }
 }
 
@@ -248,11 +267,11 @@ count_memo_kernel(SeqBatch sb, Memo mm, int count_zeros, int wpr) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// classify_memo_warp_kernel: one warp per read whose sketch is "every counted k-mer" (number of k-mers <= s).
-// Members of a reference sketch (REF) are queued per warp and resolved 32 at a time: table slot from ref[rank], copy
-// number inside the read from a per-warp set (multiset semantics), bitset rows spread over the lanes into
-// packed 16-bit per-reference counters.  Reads with more k-mers than s, or whose hits overflow the set, go to the
-// block kernel through `redo`.
+// classify_memo_wide_kernel: the warp-per-read kernel for MORE than 256 references (see classify_memo_warp_kernel
+// below for the common case).  Members of a reference sketch (REF) are queued per warp and resolved 32 at a time:
+// table slot from ref[rank], copy number inside the read from a per-warp set (multiset semantics),
+// bitset rows spread over the lanes into packed 16-bit per-reference counters.  Reads with more k-mers than s, or
+// whose hits overflow the set, go to the block kernel through `redo`.
 constexpr int MQ = 64;      // per-warp candidate ring
 constexpr int MDS = 128;    // per-warp set of the table slots hit so far: key + number of copies seen
 
@@ -262,7 +281,7 @@ struct MemoWarpSmem {
 };
 
 __global__ void __launch_bounds__(1024, 1)
-classify_memo_warp_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, int rwords,
+classify_memo_wide_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, int rwords,
                           int* __restrict__ redo, int* __restrict__ redo_count, Hit* __restrict__ out) {
 #ifdef RK_EMU
     unsigned char* dsm = reinterpret_cast<unsigned char*>(EMU_DYN_SMEM());
@@ -386,6 +405,416 @@ classify_memo_warp_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, int rwords,
     }
 }
 
+// Column sums of the 32 x (32 NW) bit matrix held one row per lane, reduced on the fly to what the scan of
+// src/rkmh.cpp:874-883 reports: best = largest column sum, id = first column attaining it, prev = largest sum at a
+// smaller index (0 when there is none but id > 0, -1 when id == 0).  Columns are visited in index order, and only
+// those that can win: when some column is set in two rows (OR over lanes of row & exclusive-prefix-OR of rows), only
+// such columns are counted (popc of a ballot); the columns with a single row matter through `prev` alone.
+template <int NW>
+RK_D void memo_scan_rows(const u32 (&x)[NW], int lane, int& best, int& id, int& prev) {
+    u32 any[NW], two[NW];
+    u32 any_all = 0, two_all = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        any[w] = warp_or(x[w]);
+        two[w] = 0;
+        if (any[w] & (any[w] - 1u)) {                        // at least two columns or rows could overlap: exact test
+            u32 v = __shfl_up_sync(0xffffffffu, x[w], 1);
+            if (lane < 1) v = 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v |= t; }
+            two[w] = warp_or(x[w] & v);
+        } else if (any[w]) {                                 // one column: it is shared iff two lanes hold it
+            two[w] = __popc(__ballot_sync(0xffffffffu, x[w] != 0u)) >= 2 ? any[w] : 0u;
+        }
+        any_all |= any[w]; two_all |= two[w];
+    }
+    best = 0; id = 0; prev = -1;
+    if (!any_all) return;
+    if (!two_all) {                                          // every column sum is 0 or 1
+#pragma unroll
+        for (int w = NW - 1; w >= 0; --w) if (any[w]) id = 32 * w + __ffs((int)any[w]) - 1;
+        best = 1; prev = id == 0 ? -1 : 0;
+        return;
+    }
+    int idw = 0; u32 idbit = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        u32 u = two[w];
+        while (u) {
+            const u32 low = u & (0u - u);
+            u ^= low;
+            const int c = __popc(__ballot_sync(0xffffffffu, (x[w] & low) != 0u));
+            if (c > best) { prev = best; best = c; idw = w; idbit = low; }
+        }
+    }
+    id = 32 * idw + __ffs((int)idbit) - 1;
+    // columns before the winner that were not counted hold 1 (any) or 0
+    bool single_before = false;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        if (w < idw) single_before |= any[w] != 0u;
+        else if (w == idw) single_before |= (any[w] & (idbit - 1u)) != 0u;
+    }
+    prev = id == 0 ? -1 : max(prev, single_before ? 1 : 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// classify_memo_warp_kernel: one warp per read whose sketch is "every counted k-mer" (number of k-mers <= s), for
+// at most 256 references (NW = number of 32-bit words of a reference bitset row, 2..8).
+//
+//   1. the warp streams the read 32 windows at a time (three ballots turn 32 ASCII bases into bit planes, two funnel
+//      shifts give a lane its window's code) and looks the code up in the L2-resident table;
+//   2. the ranks of the REF windows are compacted into one lane each (reads with more than 32 of them take the block
+//      kernel: 0.1 % of the config-2 reads);
+//   3. each lane fetches its hit's reference bitset row (table slot from ref[rank]; the copy number of a hash that
+//      occurs more than once in the read is its position among equal keys, __match_any_sync -- multiset semantics,
+//      SURVEY F10) into registers;
+//   4. for every reference some hit belongs to, in index order, count = popc(ballot(bit)) -- and the running
+//      best / previous-best scan of src/rkmh.cpp:874-883 is applied on the fly.  No counters, no shared-memory
+//      atomics, nothing to clear between reads.
+constexpr int MEMO_WARP_MAX_KMERS = 1 << 20;
+
+template <int NW>
+__global__ void __launch_bounds__(1024, 1)
+classify_memo_warp_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
+                          int* __restrict__ redo, int* __restrict__ redo_count, Hit* __restrict__ out) {
+    __shared__ u32 qs[32][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    u32* q = qs[wib];
+    const int k = mm.k;
+    const u32 kmask = mm.kmask;
+    const u32 lt = (1u << lane) - 1u;
+    const u32* __restrict__ tab = mm.tab;
+
+    const i64 gwarp = (i64)blockIdx.x * nwb + wib, nwarps = (i64)gridDim.x * nwb;
+    for (i64 rid = gwarp; rid < sb.nseq; rid += nwarps) {
+        const i64 beg = sb.offs[rid] - sb.base0, len64 = sb.offs[rid + 1] - sb.offs[rid];
+        const i64 n64 = nkmers(len64, k);
+        if (n64 > s || n64 > MEMO_WARP_MAX_KMERS) {          // the sketch is a strict subset: block kernel
+            if (lane == 0) redo[atomicAdd(redo_count, 1)] = (int)rid;
+            continue;
+        }
+        const unsigned char* __restrict__ p = sb.bases + beg;
+        const int len = (int)len64, n = (int)n64;
+        // ---- 1 + 2: stream the windows, compact the REF ranks -------------------------------------------------
+        int nc = 0;
+        u32 nz = 0;
+        if (n > 0) {
+            u32 c0, c1, cv;
+            {
+                const u32 ch = lane < len ? (u32)p[lane] : 0u, c2 = base_code(ch);
+                c0 = __ballot_sync(0xffffffffu, c2 & 1u); c1 = __ballot_sync(0xffffffffu, c2 & 2u);
+                cv = __ballot_sync(0xffffffffu, memo_base_invalid(ch));
+            }
+            u32 chn = 32 + lane < len ? (u32)p[32 + lane] : 0u;
+            for (int base = 0; base < n; base += 32) {
+                const u32 c2 = base_code(chn);
+                const u32 n0 = __ballot_sync(0xffffffffu, c2 & 1u), n1 = __ballot_sync(0xffffffffu, c2 & 2u);
+                const u32 nv = __ballot_sync(0xffffffffu, memo_base_invalid(chn));
+                chn = base + 64 + lane < len ? (u32)p[base + 64 + lane] : 0u;     // in flight while this round is processed
+                const u32 f0 = __funnelshift_r(c0, n0, (u32)lane) & kmask;
+                const u32 f1 = __funnelshift_r(c1, n1, (u32)lane) & kmask;
+                const u32 fv = __funnelshift_r(cv, nv, (u32)lane) & kmask;
+                u32 m = MEMO_ZERO;
+                if (base + lane < n && fv == 0u) m = __ldg(&tab[f0 | (f1 << k)]);
+                nz += !(m & (MEMO_ZERO | MEMO_FAILM));
+                const bool cand = (m & (MEMO_REF | MEMO_ZERO | MEMO_FAILM)) == MEMO_REF;
+                const u32 bal = __ballot_sync(0xffffffffu, cand);
+                if (bal) {
+                    const int at = nc + __popc(bal & lt);
+                    if (cand && at < 32) q[at] = m >> 8;
+                    nc += __popc(bal);
+                }
+                c0 = n0; c1 = n1; cv = nv;
+            }
+        }
+        if (nc > 32) {
+            if (lane == 0) redo[atomicAdd(redo_count, 1)] = (int)rid;
+            __syncwarp();
+            continue;
+        }
+        nz = warp_sum(nz);
+        int best = 0, id = 0, prev = -1;
+        if (nc > 0) {
+            __syncwarp();
+            // ---- 3: one hit per lane: its reference bitset row ----------------------------------------------------
+            u32 x[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) x[w] = 0;
+            const bool has = lane < nc;
+            const u32 active = __ballot_sync(0xffffffffu, has);
+            if (has) {
+                const u32 key = __ldg(&mm.ref[q[lane]]);             // slot + 1
+                const u32 same = __match_any_sync(active, key);
+                const u64* row = table_row(tb, (int)key - 1, (u32)__popc(same & lt));
+                if (row != nullptr) {
+#pragma unroll
+                    for (int w = 0; w < NW / 2; ++w) { const u64 v = __ldg(&row[w]); x[2 * w] = (u32)v; x[2 * w + 1] = (u32)(v >> 32); }
+                }
+            }
+            // ---- 4: per-reference counts + the scan of src/rkmh.cpp:874-883 -----------------------------------------
+            memo_scan_rows<NW>(x, lane, best, id, prev);
+            __syncwarp();
+        }
+        if (lane == 0) { Hit hh; hh.ref_id = id; hh.best = best; hh.prev = prev; hh.sketch_len = (int)nz; out[rid] = hh; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// classify_memo_tile_kernel: ONE THREAD PER READ for short reads (the config-2 shape), at most 256 references.
+//
+// A block stages a tile of consecutive reads (their ASCII bases, <= TILE_BYTES) in shared memory with one TMA bulk
+// copy (cp.async.bulk + mbarrier) and then every thread walks its own read:
+//   1. per base: byte -> (2-bit code, invalid flag) through a 256-entry shared-memory table, roll the 2k-bit code,
+//      look the table entry up in L2 (eight lookups in flight per thread); entries that are members of a reference
+//      sketch (REF) go to the thread's candidate list in shared memory;
+//   2. per candidate: table slot (ref[rank]), copy number inside the read (a 64-bit Bloom word decides whether the
+//      earlier candidates have to be compared at all -- multiset semantics), bitset row of the
+//      (hash, copy) pair, added into BIT-SLICED per-reference counters held in registers (plane p of word w = bit p
+//      of the counts of references 32 w .. 32 w + 31);
+//   3. the scan of src/rkmh.cpp:874-883 on the bit-sliced counters: most significant plane first, the set of
+//      references that can still hold the maximum shrinks; its lowest index is the winner, and the same walk over
+//      the references before it gives the previous best.
+// No warp-level cooperation at all: the per-read cost is ~25 thread-instructions per base instead of ~8 warp-
+// instructions.  Reads that do not fit (more k-mers than s, more than TILE_LIST candidates, a count above 31, longer
+// than a tile) are handed to the block kernel through `redo`.
+constexpr int TILE_THREADS = 384;
+constexpr int TILE_BYTES = 61440;
+constexpr int TILE_LIST = 32;
+constexpr int TILE_PLANES = 5;
+constexpr size_t TILE_SMEM = (size_t)TILE_BYTES + (size_t)TILE_LIST * TILE_THREADS * 4;
+
+struct TileCtl { i64 b0; int m; int skip; };
+
+template <int NW>
+__global__ void __launch_bounds__(TILE_THREADS, 2)
+classify_memo_tile_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
+                          int* __restrict__ redo, int* __restrict__ redo_count, Hit* __restrict__ out) {
+#ifdef RK_EMU
+    unsigned char* dsm = reinterpret_cast<unsigned char*>(EMU_DYN_SMEM());
+#else
+    extern __shared__ __align__(128) unsigned char dsm[];
+#endif
+    __shared__ u32 lut[256];
+    __shared__ TileCtl ctl;
+    __shared__ __align__(8) unsigned long long bar;
+    unsigned char* rd = dsm;
+    u32* lists = reinterpret_cast<u32*>(dsm + TILE_BYTES);
+    const int t = threadIdx.x;
+    const int k = mm.k;
+    const u32 cmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+    const u32* __restrict__ tab2 = mm.tab2;
+
+    for (int b = t; b < 256; b += TILE_THREADS) lut[b] = base_code((u32)b) | (memo_base_invalid((u32)b) ? 0x80000000u : 0u);
+#ifndef RK_EMU
+    const u32 bar_addr = (u32)__cvta_generic_to_shared(&bar);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_addr), "r"(1) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    u32 phase = 0;
+#endif
+    __syncthreads();
+
+    for (i64 t0 = (i64)blockIdx.x * TILE_THREADS; t0 < sb.nseq; t0 += (i64)gridDim.x * TILE_THREADS) {
+        const i64 rend = min(sb.nseq, t0 + (i64)TILE_THREADS);
+        i64 r = t0;
+        while (r < rend) {
+            // ---- the next run of reads that fits in the tile ----------------------------------------------------
+            if (t == 0) {
+                const i64 b0 = sb.offs[r];
+                const i64 lim = (i64)TILE_BYTES - 32;
+                int lo = 1, hi = (int)(rend - r), m = 0;
+                while (lo <= hi) {                           // largest m with offs[r + m] - b0 <= lim
+                    const int mid = (lo + hi) >> 1;
+                    if (sb.offs[r + mid] - b0 <= lim) { m = mid; lo = mid + 1; } else hi = mid - 1;
+                }
+                ctl.b0 = b0; ctl.m = m; ctl.skip = 0;
+                if (m == 0) { redo[atomicAdd(redo_count, 1)] = (int)r; ctl.skip = 1; }   // one read longer than a tile
+            }
+            __syncthreads();
+            const int m = ctl.m;
+            if (ctl.skip) { r += 1; __syncthreads(); continue; }
+            const i64 gb0 = ctl.b0 - sb.base0;               // first byte of the run in sb.bases
+            const i64 ga = gb0 & ~(i64)15;                   // 16-byte aligned start of the copy
+            const int shift = (int)(gb0 - ga);
+            const int nbytes = (int)(sb.offs[r + m] - ctl.b0);
+            const u32 copy_bytes = (u32)((shift + nbytes + 15) & ~15);
+#ifdef RK_EMU
+            for (u32 i = (u32)t; i < copy_bytes; i += TILE_THREADS) rd[i] = sb.bases[ga + i];
+            __syncthreads();
+#else
+            if (t == 0) {
+                const u32 dst = (u32)__cvta_generic_to_shared(rd);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the previous tile was read through the generic proxy
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_addr), "r"(copy_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(dst), "l"(sb.bases + ga), "r"(copy_bytes), "r"(bar_addr) : "memory");
+            }
+            {
+                u32 done = 0;
+                while (!done) {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done) : "r"(bar_addr), "r"(phase) : "memory");
+                }
+                phase ^= 1u;
+            }
+#endif
+            if (t < m) {
+                const i64 rid = r + t;
+                const i64 o0 = sb.offs[rid], o1 = sb.offs[rid + 1];
+                const unsigned char* rp = rd + shift + (int)(o0 - ctl.b0);
+                const int len = (int)(o1 - o0);
+                const int n = len - k > 0 ? len - k : 0;
+                u32* mylist = lists + t;
+                bool give_up = n > s;
+                int nc = 0;
+                u32 nz = 0;
+                if (!give_up) {
+                    // ---- 1: walk the read; window ending at base i starts at i - k + 1 and counts iff i < len - 1 --------
+                    const int lim = len - 1;
+                    u32 c = 0;
+                    int lastinv = -1;
+                    for (int i0 = 0; i0 < lim; i0 += 8) {
+                        u32 mv[8];
+                        if (i0 + 8 <= lim) {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int i = i0 + u;
+                                const u32 e = lut[rp[i]];
+                                c = ((c << 2) | e) & cmask;
+                                if ((int)e < 0) lastinv = i;
+                                mv[u] = MEMO_ZERO;
+                                if (i - lastinv >= k) mv[u] = __ldg(&tab2[c]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int i = i0 + u;
+                                mv[u] = MEMO_ZERO;
+                                if (i < lim) {
+                                    const u32 e = lut[rp[i]];
+                                    c = ((c << 2) | e) & cmask;
+                                    if ((int)e < 0) lastinv = i;
+                                    if (i - lastinv >= k) mv[u] = __ldg(&tab2[c]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const u32 mval = mv[u];
+                            nz += !(mval & (MEMO_ZERO | MEMO_FAILM));
+                            if ((mval & (MEMO_REF | MEMO_ZERO | MEMO_FAILM)) == MEMO_REF) {
+                                if (nc < TILE_LIST) mylist[nc * TILE_THREADS] = mval >> 8;
+                                ++nc;
+                            }
+                        }
+                    }
+                    if (nc > TILE_LIST) give_up = true;
+                }
+                int best = 0, id = 0, prev = -1;
+                if (!give_up && nc > 0) {
+                    // ---- 2: candidates -> table slots -> bitset rows -> bit-sliced counters --------------------------------
+                    for (int j = 0; j < nc; ++j) mylist[j * TILE_THREADS] = __ldg(&mm.ref[mylist[j * TILE_THREADS]]);   // slot + 1
+                    u32 P[TILE_PLANES][NW];
+#pragma unroll
+                    for (int pl = 0; pl < TILE_PLANES; ++pl)
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) P[pl][w] = 0;
+                    unsigned long long bloom = 0;
+                    u32 carry_out = 0;
+                    for (int j0 = 0; j0 < nc; j0 += 2) {
+                        const u64* rowp[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            rowp[u] = nullptr;
+                            const int j = j0 + u;
+                            if (j < nc) {
+                                const u32 key = mylist[j * TILE_THREADS];
+                                const unsigned long long bit = 1ULL << ((key * 0x9E3779B1u) >> 26);
+                                u32 copy = 0;
+                                if (bloom & bit) for (int jj = 0; jj < j; ++jj) copy += mylist[jj * TILE_THREADS] == key;
+                                bloom |= bit;
+                                rowp[u] = table_row(tb, (int)key - 1, copy);
+                            }
+                        }
+                        u32 x[2][NW];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+#pragma unroll
+                            for (int w = 0; w < NW / 2; ++w) {
+                                const u64 v = rowp[u] ? __ldg(&rowp[u][w]) : 0ULL;
+                                x[u][2 * w] = (u32)v; x[u][2 * w + 1] = (u32)(v >> 32);
+                            }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+#pragma unroll
+                            for (int w = 0; w < NW; ++w) {
+                                u32 cy = x[u][w];
+                                if (cy) {
+#pragma unroll
+                                    for (int pl = 0; pl < TILE_PLANES; ++pl) { const u32 tt = P[pl][w] & cy; P[pl][w] ^= cy; cy = tt; }
+                                    carry_out |= cy;
+                                }
+                            }
+                    }
+                    if (carry_out) give_up = true;           // some count reached 2^TILE_PLANES
+                    else {
+                        // ---- 3: first index of the maximum, and the maximum before it ------------------------------------
+                        u32 cand[NW];
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) cand[w] = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int pl = TILE_PLANES - 1; pl >= 0; --pl) {
+                            u32 tsel[NW], any = 0;
+#pragma unroll
+                            for (int w = 0; w < NW; ++w) { tsel[w] = cand[w] & P[pl][w]; any |= tsel[w]; }
+                            if (any) {
+                                best |= 1 << pl;
+#pragma unroll
+                                for (int w = 0; w < NW; ++w) cand[w] = tsel[w];
+                            }
+                        }
+                        if (best > 0) {
+                            int idw = 0;
+#pragma unroll
+                            for (int w = NW - 1; w >= 0; --w) if (cand[w]) idw = w;
+                            u32 cw = 0;
+#pragma unroll
+                            for (int w = 0; w < NW; ++w) if (w == idw) cw = cand[w];
+                            const int idb = __ffs((int)cw) - 1;
+                            id = 32 * idw + idb;
+                            if (id > 0) {
+                                u32 below[NW];
+#pragma unroll
+                                for (int w = 0; w < NW; ++w) below[w] = w < idw ? 0xFFFFFFFFu : (w == idw ? ((1u << idb) - 1u) : 0u);
+                                int pbest = 0;
+#pragma unroll
+                                for (int pl = TILE_PLANES - 1; pl >= 0; --pl) {
+                                    u32 tsel[NW], any = 0;
+#pragma unroll
+                                    for (int w = 0; w < NW; ++w) { tsel[w] = below[w] & P[pl][w]; any |= tsel[w]; }
+                                    if (any) {
+                                        pbest |= 1 << pl;
+#pragma unroll
+                                        for (int w = 0; w < NW; ++w) below[w] = tsel[w];
+                                    }
+                                }
+                                prev = pbest;
+                            }
+                        }
+                    }
+                }
+                if (give_up) redo[atomicAdd(redo_count, 1)] = (int)rid;
+                else { Hit hh; hh.ref_id = id; hh.best = best; hh.prev = prev; hh.sketch_len = (int)nz; out[rid] = hh; }
+            }
+            __syncthreads();                                 // the tile is reused by the next run
+            r += m;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // classify_memo_block_kernel: one block per read (grid-stride over `list`, or over every read when list is null).
 // Exact for every input.  The read's table values (rank | flags, MEMO_SKIP for windows that do not count) are kept in
@@ -484,32 +913,72 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
             need = s - (int)before1 - (int)bs.before;
             __syncthreads();
         }
-        // ---- resolve the REF members of the sketch ----------------------------------------------------------
-        for (i64 i = threadIdx.x; i < n; i += blockDim.x) {
-            const u32 m = V[i];
-            if (m == MEMO_SKIP) continue;
-            const u32 rank = m >> 8;
-            if (rank > T) continue;
-            if (rank == T && !(atomicAdd(&bs.take, 1) < need)) continue;
-            if (!(m & MEMO_REF)) continue;
-            const u32 key = mm.ref[rank];                    // slot + 1
-            u32 p = (key * 0x9E3779B1u) & hs_mask;
-            for (;;) {
-                const u32 old = atomicCAS(&hs_keys[p], 0u, key);
-                if (old == 0u || old == key) break;
-                p = (p + 1) & hs_mask;
+        // ---- resolve the REF members of the sketch: 32 windows per warp step ---------------------------------
+        const bool small = tb.nb == 1;
+        u32 vp[5][2];
+#pragma unroll
+        for (int pl = 0; pl < 5; ++pl) { vp[pl][0] = 0; vp[pl][1] = 0; }
+        int vsteps = 0;
+        auto flush_planes = [&]() {
+            for (u32 j = 0; j < tb.nrefs; ++j) {
+                u32 c = 0;
+#pragma unroll
+                for (int pl = 0; pl < 5; ++pl) c |= (((j < 32 ? vp[pl][0] : vp[pl][1]) >> (j & 31)) & 1u) << pl;
+                c = warp_sum(c);
+                if (lane == 0 && c) atomicAdd(&counts[j], c);
             }
-            const u64* row = table_row(tb, (int)key - 1, atomicAdd(&hs_cnt[p], 1u));
-            if (row == nullptr) continue;
-            for (u32 w = 0; w < tb.nb; ++w) {
-                u64 bits = row[w];
-                while (bits) {
-                    const int b = __ffsll((long long)bits) - 1;
-                    bits &= bits - 1;
-                    atomicAdd(&counts[w * 64 + b], 1u);
+#pragma unroll
+            for (int pl = 0; pl < 5; ++pl) { vp[pl][0] = 0; vp[pl][1] = 0; }
+        };
+        for (i64 i0 = (i64)wib * 32; i0 < n; i0 += (i64)nwb * 32) {
+            const i64 i = i0 + lane;
+            const u32 m = i < n ? V[i] : MEMO_SKIP;
+            const u64* row = nullptr;
+            if (m != MEMO_SKIP) {
+                const u32 rank = m >> 8;
+                const bool member = rank < T || (rank == T && atomicAdd(&bs.take, 1) < need);
+                if (member && (m & MEMO_REF)) {
+                    const u32 key = mm.ref[rank];                // slot + 1
+                    u32 p = (key * 0x9E3779B1u) & hs_mask;
+                    for (;;) {
+                        const u32 old = atomicCAS(&hs_keys[p], 0u, key);
+                        if (old == 0u || old == key) break;
+                        p = (p + 1) & hs_mask;
+                    }
+                    row = table_row(tb, (int)key - 1, atomicAdd(&hs_cnt[p], 1u));
+                }
+            }
+            if (small) {
+                // <= 64 references: every lane adds its row into private bit-sliced counters (plane p = bit p of the
+                // per-reference counts), flushed to the shared counters every 31 steps and at the end of the read
+                if (row != nullptr) {
+                    const u64 v = row[0];
+                    u32 cy0 = (u32)v, cy1 = (u32)(v >> 32);
+#pragma unroll
+                    for (int pl = 0; pl < 5; ++pl) {
+                        const u32 t0 = vp[pl][0] & cy0, t1 = vp[pl][1] & cy1;
+                        vp[pl][0] ^= cy0; vp[pl][1] ^= cy1;
+                        cy0 = t0; cy1 = t1;
+                    }
+                }
+                if (++vsteps == 31) { flush_planes(); vsteps = 0; }
+                continue;
+            }
+            if (!__any_sync(0xffffffffu, row != nullptr)) continue;
+            // column sums of this step's rows: one shared-memory add per reference that occurs, not per set bit
+            const u32* r32 = reinterpret_cast<const u32*>(row);
+            for (u32 w = 0; w < 2u * tb.nb; ++w) {
+                const u32 xw = row ? r32[w] : 0u;
+                u32 u = warp_or(xw);
+                while (u) {
+                    const u32 low = u & (0u - u);
+                    u ^= low;
+                    const u32 c = (u32)__popc(__ballot_sync(0xffffffffu, (xw & low) != 0u));
+                    if (lane == 0) atomicAdd(&counts[32u * w + (u32)__ffs((int)low) - 1u], c);
                 }
             }
         }
+        if (small && vsteps) flush_planes();
         __syncthreads();
         block_argmax(counts, (int)tb.nrefs, &bs.as, &out[rid], L);
     }

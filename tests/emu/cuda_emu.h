@@ -132,6 +132,16 @@ static inline unsigned __ballot_sync(unsigned mask, int p) {
     w.bar(mask).wait();
     return r;
 }
+static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
+    mask &= emu_warp_mask_all();
+    emu::Warp& w = *emu::t_block->warps[emu::t_warp];
+    w.slot[emu::t_lane] = v;
+    w.bar(mask).wait();
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) if ((mask >> i & 1) && (unsigned)w.slot[i] == v) r |= 1u << i;
+    w.bar(mask).wait();
+    return r;
+}
 static inline int __any_sync(unsigned mask, int p) { return __ballot_sync(mask, p) != 0; }
 static inline int __all_sync(unsigned mask, int p) { return __ballot_sync(mask, p) == (mask & emu_warp_mask_all()); }
 

@@ -224,7 +224,7 @@ int emu_classify(const char* ref_bases, const i64* ref_offs, int nrefs, const ch
 
 // ---- memoised path (rk_memo.cuh) -------------------------------------------------------------------------
 struct HostMemo {
-    std::vector<u32> tab, ref, tmp;
+    std::vector<u32> tab, tab2, ref, tmp;
     std::vector<u64> hash;
     std::vector<int> code_counts;
     unsigned long long inval = 0;
@@ -236,7 +236,7 @@ static void build_memo(HostMemo& hm, int k, const RefTable& tb, int block) {
     const u32 ncodes = 1u << (2 * k);
     const int bucket_bits = std::max(2 * k - 8, 0);
     const u32 nb = 1u << bucket_bits;
-    hm.tab.assign(ncodes, 0); hm.ref.assign(ncodes, 0); hm.hash.assign(ncodes, 0); hm.code_counts.assign(ncodes, 0);
+    hm.tab.assign(ncodes, 0); hm.tab2.assign(ncodes, 0); hm.ref.assign(ncodes, 0); hm.hash.assign(ncodes, 0); hm.code_counts.assign(ncodes, 0);
     hm.tmp.assign((size_t)3 * nb + ncodes, 0);
     u32* bcount = hm.tmp.data(); u32* bstart = bcount + nb; u32* bfill = bstart + nb; u32* bcodes = bfill + nb;
     u64* hash = hm.hash.data(); u32* tab = hm.tab.data(); u32* ref = hm.ref.data(); int* err = &hm.err;
@@ -247,8 +247,10 @@ static void build_memo(HostMemo& hm, int k, const RefTable& tb, int block) {
     emu::launch(dim3(1), dim3(1024), 0, [=] { memo_scan_kernel(bcount, bstart, bfill, nb, err); });
     emu::launch(dim3(2), dim3(block), 0, [=] { memo_scatter_kernel(ncodes, hash, bstart, bfill, bcodes, bucket_bits); });
     emu::launch(dim3(2), dim3(block), 0, [=] { memo_rank_kernel(hash, bcount, bstart, bcodes, nb, tb, tab, ref); });
-    hm.mm.tab = tab; hm.mm.ref = ref; hm.mm.hash = hash; hm.mm.code_counts = hm.code_counts.data();
+    hm.mm.tab = tab; hm.mm.tab2 = hm.tab2.data(); hm.mm.ref = ref; hm.mm.hash = hash; hm.mm.code_counts = hm.code_counts.data();
     hm.mm.inval = &hm.inval; hm.mm.ncodes = ncodes; hm.mm.kmask = (1u << k) - 1u; hm.mm.k = k;
+    Memo mm = hm.mm;
+    emu::launch(dim3(2), dim3(block), 0, [=] { memo_tab2_kernel(mm); });
 }
 
 extern "C" {
@@ -289,10 +291,25 @@ int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, con
     std::vector<int> redo((size_t)std::max<i64>(nreads, 1)); int redo_count = 0;
     int* predo = redo.data(); int* pcount = &redo_count;
     const int grid = 2;
-    if (path == 1) {
+    if (path == 3 && tb.nb <= 4) {       // thread per read (tile kernel)
+        switch (tb.nb) {
+            case 1: emu::launch(dim3(grid), dim3(TILE_THREADS), TILE_SMEM, [=] { classify_memo_tile_kernel<2>(sb, s, mm, tb, predo, pcount, out); }); break;
+            case 2: emu::launch(dim3(grid), dim3(TILE_THREADS), TILE_SMEM, [=] { classify_memo_tile_kernel<4>(sb, s, mm, tb, predo, pcount, out); }); break;
+            case 3: emu::launch(dim3(grid), dim3(TILE_THREADS), TILE_SMEM, [=] { classify_memo_tile_kernel<6>(sb, s, mm, tb, predo, pcount, out); }); break;
+            default: emu::launch(dim3(grid), dim3(TILE_THREADS), TILE_SMEM, [=] { classify_memo_tile_kernel<8>(sb, s, mm, tb, predo, pcount, out); }); break;
+        }
+    } else if (path == 1 && tb.nb <= 4) {
+        // (path 1: the register-row warp kernel for <= 256 references)
+        switch (tb.nb) {
+            case 1: emu::launch(dim3(grid), dim3(block), 0, [=] { classify_memo_warp_kernel<2>(sb, s, mm, tb, predo, pcount, out); }); break;
+            case 2: emu::launch(dim3(grid), dim3(block), 0, [=] { classify_memo_warp_kernel<4>(sb, s, mm, tb, predo, pcount, out); }); break;
+            case 3: emu::launch(dim3(grid), dim3(block), 0, [=] { classify_memo_warp_kernel<6>(sb, s, mm, tb, predo, pcount, out); }); break;
+            default: emu::launch(dim3(grid), dim3(block), 0, [=] { classify_memo_warp_kernel<8>(sb, s, mm, tb, predo, pcount, out); }); break;
+        }
+    } else if (path >= 1) {       // path 2 forces the wide (shared-memory counter) kernel
         const int rwords = (nrefs + 1) / 2;
         size_t smem = (size_t)(block / 32) * (sizeof(MemoWarpSmem) + (size_t)rwords * 4);
-        emu::launch(dim3(grid), dim3(block), smem, [=] { classify_memo_warp_kernel(sb, s, mm, tb, rwords, predo, pcount, out); });
+        emu::launch(dim3(grid), dim3(block), smem, [=] { classify_memo_wide_kernel(sb, s, mm, tb, rwords, predo, pcount, out); });
     }
     if (redo_count_out) *redo_count_out = redo_count;
     {
@@ -304,7 +321,7 @@ int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, con
         size_t smem = 4 * ((size_t)vcap + MEMO_BINS + 2 * (size_t)hs_cap + rpad);
         std::vector<u32> scratch((size_t)grid * (size_t)stride + 8);
         u32* ps = scratch.data();
-        const int* list = (path == 1) ? predo : nullptr;
+        const int* list = (path >= 1) ? predo : nullptr;
         emu::launch(dim3(grid), dim3(block), smem, [=] {
             classify_memo_block_kernel(sb, s, mm, tb, list, pcount, nreads, vcap, hs_cap, rpad, ps, stride, out);
         });

@@ -116,7 +116,8 @@ def _memo_case(emu, oracle, refs, reads, k, s, counts=None, min_occ=-1, **kw):
     return redo
 
 
-@pytest.mark.parametrize("kw", [dict(path=0), dict(path=1), dict(path=0, vcap_limit=16), dict(path=1, block=128)])
+@pytest.mark.parametrize("kw", [dict(path=0), dict(path=1), dict(path=2), dict(path=3), dict(path=0, vcap_limit=16),
+                                dict(path=1, block=128)])
 def test_memo_classify_awkward(emu, oracle, kw):
     _, refs, _ = load_sequences([data_path("awkward_refs.fa.gz")])
     _, reads, _ = load_sequences([data_path("awkward_reads.fq.gz")])
@@ -132,6 +133,7 @@ def test_memo_classify_fixtures(emu, oracle):
     assert _memo_case(emu, oracle, refs, reads[:3], 8, 300, path=1) == 3        # long reads: all through the block kernel
     _, short, _ = load_sequences([data_path("z1.fq.gz")])
     assert _memo_case(emu, oracle, refs, short[:40], 8, 1000, path=1) == 0
+    assert _memo_case(emu, oracle, refs, short[:500] + reads[:1], 8, 1000, path=3) == 1   # tile kernel: two runs of reads + a long read
 
 
 def test_memo_count_and_min_occ(emu, oracle):
@@ -151,5 +153,5 @@ def test_memo_count_and_min_occ(emu, oracle):
     c = np.zeros(size, np.int32)
     oracle.count_batch(reads, [8], c)
     for m in (1, 30, 200):
-        for path in (0, 1):
+        for path in (0, 1, 3):
             _memo_case(emu, oracle, refs[:4], reads, 8, 200, counts=c, min_occ=m, path=path)

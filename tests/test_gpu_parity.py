@@ -271,7 +271,8 @@ def test_full_size_properties(gpu, oracle):
     assert np.array_equal(_fields(hits[idx]), _fields(exp))
 
 
-def test_memo_path_is_taken_and_matches_murmur(oracle):
+@pytest.mark.parametrize("tile", [False, True])
+def test_memo_path_is_taken_and_matches_murmur(oracle, tile, monkeypatch):
     """The memoised kernels run for a single k <= 12 and give the same records as the Murmur kernels: short reads
     (warp kernel), long reads (block kernel, bottom-s by rank), with and without -M."""
     import rkmh_b200
@@ -282,6 +283,8 @@ def test_memo_path_is_taken_and_matches_murmur(oracle):
     sb, so = _synthetic_reads(rng, rs, 20000, 150)
     lb, lo = ont_reads(rng, hpv, 300, 10000)
     res = {}
+    monkeypatch.setenv("RKMH_TILE", "1" if tile else "0")      # the thread-per-read variant of the short-read kernel
+    short_kernel = "classify_memo_tile_kernel" if tile else "classify_memo_warp_kernel"
     for memo in (True, False):
         with rkmh_b200.RkmhGpu(0) as g:
             g.set_memo(memo)
@@ -300,7 +303,7 @@ def test_memo_path_is_taken_and_matches_murmur(oracle):
                 out.append(_fields(g.classify_batch(sb, so, min_occ=m)))
             out.append(_fields(g.classify_batch(sb, so)))          # -M off again: FAILM flags cleared
             names = set(g.profile_read())
-            assert ("classify_memo_warp_kernel" in names) == memo and ("classify_group_kernel" in names) == (not memo)
+            assert (short_kernel in names) == memo and ("classify_group_kernel" in names) == (not memo)
             assert ("count_memo_kernel" in names) == memo
             res[memo] = out
     for a, b in zip(res[True], res[False]):
