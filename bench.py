@@ -27,6 +27,9 @@ sys.path.insert(0, ROOT)
 DATA = os.path.join(ROOT, "tests", "golden", "data")
 K, S, READ_LEN = 12, 1000, 150
 METRIC = "classify reads/s (rkmh stream, k=12, s=1000, 182 refs, 150 bp reads)"
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one `ncu --set full` capture, scaled to the
+# default 10 M reads per launch; see profiles/README.md for the capture each figure comes from.  None = not captured.
+TRAFFIC = {}
 
 
 def parse_args():
@@ -303,10 +306,19 @@ def main_ours(args, rank, world, local_rank):
         # dominant kernel = the one with the largest share of the timed region
         dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else ("none", {"ms": 0.0, "launches": 1})
         dom_ms = dom[1]["ms"] / max(dom[1]["launches"], 1)
-        # algorithmic bytes of the fused hash+sketch+probe kernel per read:
-        # packed bases 2 bit + mask 1 bit per base, one 8 B offset, one 16 B hit record
-        alg_bytes = n * (READ_LEN * 3 / 8 + 8 + 16)
+        # ALGORITHMIC bytes per read of the dominant kernel.  Memoised kernels (single k <= 12)
+        # read the ASCII bases as parsed -- ingest is fused -- : 150 B bases + 8 B offset + 16 B hit record.  The Murmur
+        # group kernel reads the packed batch: 2-bit codes + 1-bit mask per base + offset + hit record.
+        memo_path = dom[0].startswith("classify_memo")
+        bytes_per_read = (READ_LEN + 8 + 16) if memo_path else (READ_LEN * 3 / 8 + 8 + 16)
+        alg_bytes = n * bytes_per_read
         achieved = alg_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+        if memo_path:
+            note = ("memoised path: every window is one lookup (shared-memory sieve, then L2-resident code map and bitset "
+                    "rows); the kernel is issue/latency bound, not HBM bound -- ncu counters in profiles/, DESIGN.md section 5")
+        else:
+            note = ("the kernel is INT-pipe bound (2 x MurmurHash3_x64_128 per k-mer), not HBM bound; see DESIGN.md "
+                    "section 5")
         line = {
             "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
@@ -324,11 +336,10 @@ def main_ours(args, rank, world, local_rank):
             "kernels": {k: {"launches": v["launches"], "ms_per_launch": v["ms"] / max(v["launches"], 1),
                             "share": v["ms"] / max(sum(x["ms"] for x in prof.values()), 1e-9)} for k, v in prof.items()},
             "roofline": {"kernel": dom[0], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "note": "the kernel is INT-pipe bound (2 x MurmurHash3_x64_128 per k-mer), not HBM bound; "
-                                 "see int_pipe and DESIGN.md section 5"},
-            "int_pipe": {"kmers_per_s_per_gpu": (n * (READ_LEN - K)) / (dom_ms / 1e3) if dom_ms > 0 else 0.0,
-                         "kernel": dom[0]},
+                         "frac": achieved / hbm_peak, "traffic": TRAFFIC.get(dom[0]), "peak_source": peak_src,
+                         "algorithmic_bytes_per_read": bytes_per_read, "note": note},
+            "dominant_kernel": {"kernel": dom[0], "ms_per_launch": dom_ms,
+                                "kmers_per_s_per_gpu": (n * (READ_LEN - K)) / (dom_ms / 1e3) if dom_ms > 0 else 0.0},
         }
         if not args.no_cpu_baseline and world == 1:
             workdir = tempfile.mkdtemp(prefix="rkmh_cpu_")

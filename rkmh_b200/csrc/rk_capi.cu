@@ -26,13 +26,14 @@ thread_local std::string g_create_error;
 
 enum KernelId { K_INGEST, K_HASH, K_COUNT, K_COUNT_DISTINCT, K_SKETCH, K_MERGE, K_TABLE, K_CLASSIFY_GROUP,
                 K_CLASSIFY_BLOCK, K_MEMO_BUILD, K_MEMO_MAINT, K_COUNT_MEMO, K_CLASSIFY_MEMO_WARP, K_CLASSIFY_MEMO_BLOCK,
-                K_CLASSIFY_MEMO_TILE,
+                K_CLASSIFY_MEMO_TILE, K_CLASSIFY_MEMO_SIEVE,
                 K_NUM };
 const char* const kKernelNames[K_NUM] = {"ingest_kernel", "hash_kernel", "count_kernel", "count_distinct_kernel",
                                          "sketch_kernel", "merge_kernel", "table_build_kernels",
                                          "classify_group_kernel", "classify_block_kernel", "memo_build_kernels",
                                          "memo_fold_apply_kernels", "count_memo_kernel", "classify_memo_warp_kernel",
-                                         "classify_memo_block_kernel", "classify_memo_tile_kernel"};
+                                         "classify_memo_block_kernel", "classify_memo_tile_kernel",
+                                         "classify_memo_sieve_kernel"};
 
 struct DevBuf {
     void* p = nullptr;
@@ -84,8 +85,9 @@ struct rkg_ctx {
     cudaStream_t stream = nullptr;
     rkg_batch* slots[2] = {nullptr, nullptr};   // internal double buffer of rkg_classify_batch / count
     // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
-    bool memo_enabled = true, memo_ready = false, tile_kernel = false;
-    DevBuf memo_tab, memo_tab2, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc;
+    bool memo_enabled = true, memo_ready = false, tile_kernel = false, sieve_enabled = true;
+    DevBuf memo_tab, memo_tab2, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc, memo_sieve, memo_cmap;
+    double sieve_fill = 0.0;             // fraction of the sieve's bits that are set (false-positive rate = fill^2)
     Memo memo{};
     bool memo_pending = false;           // code_counts holds increments not yet folded into the read count table
     int memo_pending_zeros = 0;
@@ -286,6 +288,48 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     CK(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (herr) return RKG_OK;          // a hash bucket larger than the sort capacity: keep the Murmur path (still exact)
+    // sieve + code map of classify_memo_sieve_kernel (rk_memo.cuh).  The sieve takes what a 1024-thread block can
+    // have beside its candidate queues; it is dropped when it would let more than a quarter of all windows through.
+    mm.sieve = nullptr; mm.cmap = nullptr; mm.sieve_words = 0; mm.zero_codes = 0;
+    ctx->sieve_fill = 0.0;
+    const size_t queues = (size_t)32 * SIEVE_QCAP * 4 + 1024;
+    if (ctx->sieve_enabled && ctx->tb.entries != nullptr && ctx->smem_optin > queues + 8192) {
+        const u32 nwords = (u32)std::min<size_t>(SIEVE_MAX_WORDS, (ctx->smem_optin - queues) / 4);
+        CK(ctx->memo_sieve.ensure(sizeof(u32) * (size_t)nwords));
+        CK(cudaMemsetAsync(ctx->memo_sieve.p, 0, sizeof(u32) * (size_t)nwords, st));
+        u32* stats = ctx->memo_misc.as<u32>() + 16;
+        const int grid = (int)std::min<i64>(((i64)ncodes + 255) / 256, (i64)ctx->sm_count * 16);
+        {
+            Timed t(ctx, st, K_MEMO_BUILD);
+            memo_sieve_kernel<<<grid, 256, 0, st>>>(mm, ctx->memo_sieve.as<u32>(), nwords, stats);
+            ctx->launches += 1;
+        }
+        CK(cudaGetLastError());
+        u32 hstats[2] = {0, 0};
+        std::vector<u32> image(nwords);
+        CK(cudaMemcpyAsync(hstats, stats, sizeof(hstats), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(image.data(), ctx->memo_sieve.p, sizeof(u32) * (size_t)nwords, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        size_t set_bits = 0;
+        for (u32 w : image) set_bits += (size_t)__builtin_popcount(w);
+        ctx->sieve_fill = (double)set_bits / (32.0 * nwords);
+        mm.zero_codes = hstats[1];
+        if (ctx->sieve_fill <= 0.5) {
+            const u32 cap = (u32)next_pow2(std::max<i64>(2 * (i64)hstats[0], 1024));
+            int log2cap = 0; while ((1u << log2cap) < cap) ++log2cap;
+            CK(ctx->memo_cmap.ensure(sizeof(u64) * (size_t)cap));
+            CK(cudaMemsetAsync(ctx->memo_cmap.p, 0xFF, sizeof(u64) * (size_t)cap, st));
+            {
+                Timed t(ctx, st, K_MEMO_BUILD);
+                memo_cmap_kernel<<<grid, 256, 0, st>>>(mm, ctx->memo_cmap.as<unsigned long long>(), cap - 1, 32 - log2cap);
+                ctx->launches += 1;
+            }
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(st));
+            mm.sieve = ctx->memo_sieve.as<u32>(); mm.sieve_words = nwords;
+            mm.cmap = ctx->memo_cmap.as<unsigned long long>(); mm.cmap_mask = cap - 1; mm.cmap_shift = 32 - log2cap;
+        }
+    }
     ctx->memo = mm;
     ctx->memo_ready = true;
     ctx->memo_pending = false; ctx->memo_occ_stale = true; ctx->memo_occ = INT_MIN;
@@ -437,6 +481,26 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
                 }
 #undef RK_TILE_LAUNCH
                 CK(cudaGetLastError());
+            } else if (mg.use_warp && ctx->tb.nb <= 4 && ctx->memo.sieve != nullptr && ctx->memo.zero_codes == 0 &&
+                       ctx->memo_occ == INT_MIN) {
+                // <= 256 references, no FAILM flags baked, no zero hash: sketch membership from a shared-memory sieve
+                Timed t(ctx, b->stream, K_CLASSIFY_MEMO_SIEVE);
+                const int grid = ctx->sm_count;
+                const size_t smem = ((size_t)ctx->memo.sieve_words + (size_t)32 * SIEVE_QCAP) * 4;
+#define RK_SIEVE_LAUNCH(NWV)                                                                                             \
+    do {                                                                                                                 \
+        CK(cudaFuncSetAttribute(classify_memo_sieve_kernel<NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        classify_memo_sieve_kernel<NWV><<<grid, 1024, smem, b->stream>>>(sb, ctx->s, ctx->memo, ctx->tb, redo, redo_count, \
+                                                                          hits);                                        \
+    } while (0)
+                switch (ctx->tb.nb) {
+                    case 1: RK_SIEVE_LAUNCH(2); break;
+                    case 2: RK_SIEVE_LAUNCH(4); break;
+                    case 3: RK_SIEVE_LAUNCH(6); break;
+                    default: RK_SIEVE_LAUNCH(8); break;
+                }
+#undef RK_SIEVE_LAUNCH
+                CK(cudaGetLastError());
             } else if (mg.use_warp && ctx->tb.nb <= 4) {     // <= 256 references: bitset rows in registers
                 Timed t(ctx, b->stream, K_CLASSIFY_MEMO_WARP);
                 const int grid = ctx->sm_count;
@@ -585,6 +649,7 @@ int rkg_create(int device, rkg_ctx** out) {
     ctx = new rkg_ctx();
     ctx->device = device;
     { const char* nm = getenv("RKMH_NO_MEMO"); ctx->memo_enabled = !(nm && nm[0] && nm[0] != '0'); }
+    { const char* nm = getenv("RKMH_NO_SIEVE"); ctx->sieve_enabled = !(nm && nm[0] && nm[0] != '0'); }
     { const char* tk = getenv("RKMH_TILE"); ctx->tile_kernel = tk && tk[0] && tk[0] != '0'; }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
@@ -604,7 +669,8 @@ void rkg_destroy(rkg_ctx* ctx) {
     for (int i = 0; i < 2; ++i) batch_release(ctx->slots[i]);
     for (DevBuf* d : {&ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
                       &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
-                      &ctx->memo_tab, &ctx->memo_tab2, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc})
+                      &ctx->memo_tab, &ctx->memo_tab2, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
+                      &ctx->memo_sieve, &ctx->memo_cmap})
         d->release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

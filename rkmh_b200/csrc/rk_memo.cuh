@@ -39,6 +39,12 @@ struct Memo {
     u32 ncodes;
     u32 kmask;                      // (1 << k) - 1
     int k;
+    // sieve kernel (classify_memo_sieve_kernel): shared-memory Bloom filter image and the code -> slot + 1 map
+    const u32* sieve;               // nullptr: not built / too full to be useful
+    const unsigned long long* cmap;
+    u32 sieve_words, cmap_mask;
+    int cmap_shift;
+    u32 zero_codes;                 // codes whose hash is 0 (the sieve kernel needs none)
 };
 
 #ifdef RK_EMU
@@ -558,6 +564,243 @@ classify_memo_warp_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
             __syncwarp();
         }
         if (lane == 0) { Hit hh; hh.ref_id = id; hh.best = best; hh.prev = prev; hh.sketch_len = (int)nz; out[rid] = hh; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// classify_memo_sieve_kernel: the warp-per-read kernel for the common case (no -M mask baked, no k-mer whose hash
+// is 0, at most 256 references).  Same results as classify_memo_warp_kernel; what changes is where the memory
+// traffic goes:
+//
+//   * "is this window a member of some reference sketch?" is answered in SHARED memory by a blocked Bloom filter
+//     (the sieve: one 32-bit word per window, two bits per code, built once per rkg_load_refs and copied into each
+//     block at launch).  Only the windows that pass (the true members plus ~7 % of the others at 182 references)
+//     touch global memory at all; the 64 MB rank table is not read (it only half fits a die's L2: ncu showed 37 % of
+//     its lookups going to HBM);
+//   * those windows are looked up AFTER the read has been streamed, all lanes at once, in a compact open-addressing
+//     map code -> table slot + 1 (8 B entries, ~4 MB at 182 references, L2 resident), which replaces the two dependent
+//     lookups tab[code] -> ref[rank]; the bitset rows follow as before.  A read costs two dependent L2 round trips
+//     instead of seven;
+//   * the number of counted windows (sketch_len) is the number of valid windows: no table value is needed for it
+//     because no code hashes to 0 and no FAILM flag is baked (checked by the host before this kernel is chosen);
+//   * per-reference counts: the 32 x (32 NW) bit matrix (a hit per lane) is transposed in registers (five
+//     shuffle steps per word: PRMT for the 16/8-bit steps, rotate + LOP3 for 4/2/1), after which lane l holds, for
+//     each word w, the rows that contain reference 32 w + l: its count is one POPC.  The scan of
+//     src/rkmh.cpp:874-883 is a warp max over keys (count << 8 | 255 - index) and a second max over the counts in
+//     front of the winner.  The cost does not depend on how many references the hits share;
+//   * the first 64 bases of a warp's NEXT read are requested before the current read's hits are resolved.
+constexpr u32 SIEVE_MUL = 0x9E3779B1u;
+constexpr int SIEVE_QCAP = 64;                  // sieve-positive windows per read the kernel resolves itself
+constexpr u32 SIEVE_MAX_WORDS = 55040;          // 215 KB of the 227 KB a block may use
+
+RK_D u32 sieve_bits(u32 h) { return (1u << ((h >> 3) & 31u)) | (1u << ((h >> 11) & 31u)); }
+
+// stats[0] = codes that are members of a reference sketch, stats[1] = codes whose hash is 0
+__global__ void __launch_bounds__(256)
+memo_sieve_kernel(Memo mm, u32* __restrict__ sieve, u32 nwords, u32* __restrict__ stats) {
+    for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < mm.ncodes; c += gridDim.x * blockDim.x) {
+        const u32 t = mm.tab[c];
+        if (t & MEMO_ZERO) atomicAdd(&stats[1], 1u);
+        else if (t & MEMO_REF) {
+            const u32 h = c * SIEVE_MUL;
+            atomicOr(&sieve[__umulhi(h, nwords)], sieve_bits(h));
+            atomicAdd(&stats[0], 1u);
+        }
+    }
+}
+
+// code -> slot + 1 of its hash in the reference table; entry = slot + 1 in the high word, code in the low word
+__global__ void __launch_bounds__(256)
+memo_cmap_kernel(Memo mm, unsigned long long* __restrict__ cmap, u32 mask, int shift) {
+    for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < mm.ncodes; c += gridDim.x * blockDim.x) {
+        const u32 t = mm.tab[c];
+        if ((t & (MEMO_REF | MEMO_ZERO)) != MEMO_REF) continue;
+        const unsigned long long e = ((unsigned long long)mm.ref[t >> 8] << 32) | c;
+        u32 i = (c * SIEVE_MUL) >> shift;
+        for (;;) {
+            if (atomicCAS(&cmap[i], ~0ULL, e) == ~0ULL) break;
+            i = (i + 1) & mask;
+        }
+    }
+}
+
+// Per-lane constants of the 32 x 32 bit-matrix transpose (lane = row, bit = column).  Step j swaps, inside every
+// 2j x 2j block, the block (rows without bit j, columns with bit j) with (rows with bit j, columns without it).
+struct TrLane { u32 sel16, sel8, rot4, rot2, rot1, keep4, keep2, keep1; };
+
+RK_D TrLane tr_lane(int lane) {
+    TrLane t;
+    t.sel16 = (lane & 16) ? 0x3276u : 0x5410u;
+    t.sel8 = (lane & 8) ? 0x3715u : 0x6240u;
+    t.rot4 = (lane & 4) ? 28u : 4u;  t.keep4 = (lane & 4) ? 0xF0F0F0F0u : 0x0F0F0F0Fu;
+    t.rot2 = (lane & 2) ? 30u : 2u;  t.keep2 = (lane & 2) ? 0xCCCCCCCCu : 0x33333333u;
+    t.rot1 = (lane & 1) ? 31u : 1u;  t.keep1 = (lane & 1) ? 0xAAAAAAAAu : 0x55555555u;
+    return t;
+}
+
+RK_D u32 tr32(u32 x, const TrLane& t) {
+    u32 y = __shfl_xor_sync(0xffffffffu, x, 16); x = __byte_perm(x, y, t.sel16);
+    y = __shfl_xor_sync(0xffffffffu, x, 8);      x = __byte_perm(x, y, t.sel8);
+    y = __shfl_xor_sync(0xffffffffu, x, 4); y = __funnelshift_l(y, y, t.rot4); x = (x & t.keep4) | (y & ~t.keep4);
+    y = __shfl_xor_sync(0xffffffffu, x, 2); y = __funnelshift_l(y, y, t.rot2); x = (x & t.keep2) | (y & ~t.keep2);
+    y = __shfl_xor_sync(0xffffffffu, x, 1); y = __funnelshift_l(y, y, t.rot1); x = (x & t.keep1) | (y & ~t.keep1);
+    return x;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(1024, 1)
+classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
+                           int* __restrict__ redo, int* __restrict__ redo_count, Hit* __restrict__ out) {
+#ifdef RK_EMU
+    unsigned char* dsm = reinterpret_cast<unsigned char*>(EMU_DYN_SMEM());
+#else
+    extern __shared__ __align__(16) unsigned char dsm[];
+#endif
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    u32* sv = reinterpret_cast<u32*>(dsm);
+    const u32 nwords = mm.sieve_words;
+    u32* q = sv + nwords + wib * SIEVE_QCAP;
+    for (u32 i = threadIdx.x; i < nwords; i += blockDim.x) sv[i] = mm.sieve[i];
+    __syncthreads();
+
+    const TrLane tl = tr_lane(lane);
+    const int k = mm.k;
+    const u32 kmask = mm.kmask;
+    const u32 lt = (1u << lane) - 1u;
+    const unsigned long long* __restrict__ cmap = mm.cmap;
+    const u32 cmask = mm.cmap_mask;
+    const int cshift = mm.cmap_shift;
+    const unsigned char* __restrict__ bases = sb.bases;
+
+    auto cmap_find = [&](u32 code) -> u32 {                  // slot + 1, or 0 when the code is no sketch member
+        u32 i = (code * SIEVE_MUL) >> cshift;
+        for (;;) {
+            const unsigned long long e = __ldg(&cmap[i]);
+            if ((u32)e == code) return (u32)(e >> 32);
+            if ((u32)e == 0xFFFFFFFFu) return 0u;
+            i = (i + 1) & cmask;
+        }
+    };
+
+    const i64 nwarps = (i64)gridDim.x * nwb;
+    i64 rid = (i64)blockIdx.x * nwb + wib;
+    i64 beg = 0, len64 = 0;
+    u32 cha = 0, chb = 0;
+    if (rid < sb.nseq) {
+        beg = sb.offs[rid] - sb.base0; len64 = sb.offs[rid + 1] - sb.offs[rid];
+        cha = lane < len64 ? (u32)bases[beg + lane] : 0u;
+        chb = 32 + lane < len64 ? (u32)bases[beg + 32 + lane] : 0u;
+    }
+    while (rid < sb.nseq) {
+        const i64 nrid = rid + nwarps;
+        i64 nbeg = 0, nlen = 0;
+        if (nrid < sb.nseq) { nbeg = sb.offs[nrid] - sb.base0; nlen = sb.offs[nrid + 1] - sb.offs[nrid]; }
+        const i64 n64 = nkmers(len64, k);
+        const bool skip = n64 > s || n64 > MEMO_WARP_MAX_KMERS;      // the sketch is a strict subset: block kernel
+        // ---- stream the windows through the sieve; queue the codes that pass --------------------------------------
+        int nc = 0;
+        u32 nz = 0;
+        if (!skip && n64 > 0) {
+            const unsigned char* __restrict__ p = bases + beg;
+            const int len = (int)len64, n = (int)n64;
+            u32 c0, c1, cv;
+            {
+                const u32 c2 = base_code(cha);
+                c0 = __ballot_sync(0xffffffffu, c2 & 1u); c1 = __ballot_sync(0xffffffffu, c2 & 2u);
+                cv = __ballot_sync(0xffffffffu, memo_base_invalid(cha));
+            }
+            u32 chn = chb;
+            for (int base = 0; base < n; base += 32) {
+                const u32 c2 = base_code(chn);
+                const u32 n0 = __ballot_sync(0xffffffffu, c2 & 1u), n1 = __ballot_sync(0xffffffffu, c2 & 2u);
+                const u32 nv = __ballot_sync(0xffffffffu, memo_base_invalid(chn));
+                chn = base + 64 + lane < len ? (u32)p[base + 64 + lane] : 0u;     // in flight while this round is processed
+                const u32 f0 = __funnelshift_r(c0, n0, (u32)lane) & kmask;
+                const u32 f1 = __funnelshift_r(c1, n1, (u32)lane) & kmask;
+                const u32 fv = __funnelshift_r(cv, nv, (u32)lane) & kmask;
+                const bool valid = base + lane < n && fv == 0u;
+                const u32 code = f0 | (f1 << k);
+                const u32 h = code * SIEVE_MUL;
+                const u32 bits = sieve_bits(h);
+                const bool cand = valid && (sv[__umulhi(h, nwords)] & bits) == bits;
+                nz += valid;
+                const u32 bal = __ballot_sync(0xffffffffu, cand);
+                if (bal) {
+                    const int at = nc + __popc(bal & lt);
+                    if (cand && at < SIEVE_QCAP) q[at] = code;
+                    nc += __popc(bal);
+                }
+                c0 = n0; c1 = n1; cv = nv;
+            }
+        }
+        // ---- the next read's first 64 bases: in flight while this read's hits are resolved -------------------------
+        u32 ncha = 0, nchb = 0;
+        if (nrid < sb.nseq) {
+            ncha = lane < nlen ? (u32)bases[nbeg + lane] : 0u;
+            nchb = 32 + lane < nlen ? (u32)bases[nbeg + 32 + lane] : 0u;
+        }
+        bool give_up = skip || nc > SIEVE_QCAP;
+        int best = 0, id = 0, prev = -1;
+        if (!give_up && nc > 0) {
+            __syncwarp();
+            // ---- codes -> table slots (false positives of the sieve drop out here) --------------------------------
+            u32 key = 0, key1 = 0;
+            if (lane < nc) key = cmap_find(q[lane]);
+            if (32 + lane < nc) key1 = cmap_find(q[32 + lane]);
+            const u32 b1 = __ballot_sync(0xffffffffu, key1 != 0u);
+            if (b1) {                                        // more than 32 candidates: compact the hits into one per lane
+                const u32 b0 = __ballot_sync(0xffffffffu, key != 0u);
+                const int nh0 = __popc(b0), nh = nh0 + __popc(b1);
+                if (nh > 32) give_up = true;
+                else {
+                    __syncwarp();
+                    if (key) q[__popc(b0 & lt)] = key;
+                    if (key1) q[nh0 + __popc(b1 & lt)] = key1;
+                    __syncwarp();
+                    key = lane < nh ? q[lane] : 0u;
+                }
+                __syncwarp();
+            }
+            const u32 active = __ballot_sync(0xffffffffu, key != 0u);
+            if (!give_up && active) {
+                // ---- one hit per lane: its reference bitset row; the copy number of a hash that occurs more than once
+                //      in the read is its position among equal keys (multiset semantics) ---------------------
+                u32 x[NW];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) x[w] = 0;
+                if (key) {
+                    const u32 same = __match_any_sync(active, key);
+                    const u64* row = table_row(tb, (int)key - 1, (u32)__popc(same & lt));
+                    if (row != nullptr) {
+#pragma unroll
+                        for (int w = 0; w < NW / 2; ++w) { const u64 v = __ldg(&row[w]); x[2 * w] = (u32)v; x[2 * w + 1] = (u32)(v >> 32); }
+                    }
+                }
+                // ---- counts per reference (lane l, word w: reference 32 w + l) and the scan of src/rkmh.cpp:874-883 -----
+                u32 cnt[NW];
+                u32 kbest = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    cnt[w] = (u32)__popc(tr32(x[w], tl));
+                    kbest = max(kbest, (cnt[w] << 8) | (255u - (u32)(32 * w + lane)));
+                }
+                kbest = warp_max(kbest);
+                best = (int)(kbest >> 8);
+                id = 255 - (int)(kbest & 255u);
+                u32 p1 = 0;                                  // max of (count + 1) in front of the winner, 0 = none
+#pragma unroll
+                for (int w = 0; w < NW; ++w) if (32 * w + lane < id) p1 = max(p1, cnt[w] + 1u);
+                prev = (int)warp_max(p1) - 1;
+            }
+        }
+        if (give_up) {
+            if (lane == 0) redo[atomicAdd(redo_count, 1)] = (int)rid;
+        } else {
+            nz = warp_sum(nz);
+            if (lane == 0) { Hit hh; hh.ref_id = id; hh.best = best; hh.prev = prev; hh.sketch_len = (int)nz; out[rid] = hh; }
+        }
+        __syncwarp();
+        rid = nrid; beg = nbeg; len64 = nlen; cha = ncha; chb = nchb;
     }
 }
 

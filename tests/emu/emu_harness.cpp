@@ -224,7 +224,9 @@ int emu_classify(const char* ref_bases, const i64* ref_offs, int nrefs, const ch
 
 // ---- memoised path (rk_memo.cuh) -------------------------------------------------------------------------
 struct HostMemo {
-    std::vector<u32> tab, tab2, ref, tmp;
+    std::vector<u32> tab, tab2, ref, tmp, sieve;
+    std::vector<unsigned long long> cmap;
+    u32 stats[2] = {0, 0};
     std::vector<u64> hash;
     std::vector<int> code_counts;
     unsigned long long inval = 0;
@@ -251,6 +253,20 @@ static void build_memo(HostMemo& hm, int k, const RefTable& tb, int block) {
     hm.mm.inval = &hm.inval; hm.mm.ncodes = ncodes; hm.mm.kmask = (1u << k) - 1u; hm.mm.k = k;
     Memo mm = hm.mm;
     emu::launch(dim3(2), dim3(block), 0, [=] { memo_tab2_kernel(mm); });
+    // sieve + code map (classify_memo_sieve_kernel); a small sieve so that false positives do occur in the tests
+    if (tb.entries != nullptr) {
+        const u32 nwords = 257;
+        hm.sieve.assign(nwords, 0);
+        u32* sieve = hm.sieve.data(); u32* stats = hm.stats;
+        emu::launch(dim3(2), dim3(block), 0, [=] { memo_sieve_kernel(mm, sieve, nwords, stats); });
+        const u32 cap = (u32)next_pow2(std::max<i64>(2 * (i64)hm.stats[0], 16));
+        int log2cap = 0; while ((1u << log2cap) < cap) ++log2cap;
+        hm.cmap.assign(cap, ~0ULL);
+        unsigned long long* cmap = hm.cmap.data();
+        emu::launch(dim3(2), dim3(block), 0, [=] { memo_cmap_kernel(mm, cmap, cap - 1, 32 - log2cap); });
+        hm.mm.sieve = sieve; hm.mm.sieve_words = nwords; hm.mm.cmap = cmap; hm.mm.cmap_mask = cap - 1; hm.mm.cmap_shift = 32 - log2cap;
+        hm.mm.zero_codes = hm.stats[1];
+    }
 }
 
 extern "C" {
@@ -298,7 +314,16 @@ int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, con
             case 3: emu::launch(dim3(grid), dim3(TILE_THREADS), TILE_SMEM, [=] { classify_memo_tile_kernel<6>(sb, s, mm, tb, predo, pcount, out); }); break;
             default: emu::launch(dim3(grid), dim3(TILE_THREADS), TILE_SMEM, [=] { classify_memo_tile_kernel<8>(sb, s, mm, tb, predo, pcount, out); }); break;
         }
-    } else if (path == 1 && tb.nb <= 4) {
+    } else if (path == 4 && tb.nb <= 4 && mm.sieve != nullptr && mm.zero_codes == 0 && min_occ < 0) {
+        // (path 4: the sieve kernel; falls through to the warp kernel when its preconditions do not hold)
+        const size_t smem = ((size_t)mm.sieve_words + (size_t)(block / 32) * SIEVE_QCAP) * 4;
+        switch (tb.nb) {
+            case 1: emu::launch(dim3(grid), dim3(block), smem, [=] { classify_memo_sieve_kernel<2>(sb, s, mm, tb, predo, pcount, out); }); break;
+            case 2: emu::launch(dim3(grid), dim3(block), smem, [=] { classify_memo_sieve_kernel<4>(sb, s, mm, tb, predo, pcount, out); }); break;
+            case 3: emu::launch(dim3(grid), dim3(block), smem, [=] { classify_memo_sieve_kernel<6>(sb, s, mm, tb, predo, pcount, out); }); break;
+            default: emu::launch(dim3(grid), dim3(block), smem, [=] { classify_memo_sieve_kernel<8>(sb, s, mm, tb, predo, pcount, out); }); break;
+        }
+    } else if ((path == 1 || path == 4) && tb.nb <= 4) {
         // (path 1: the register-row warp kernel for <= 256 references)
         switch (tb.nb) {
             case 1: emu::launch(dim3(grid), dim3(block), 0, [=] { classify_memo_warp_kernel<2>(sb, s, mm, tb, predo, pcount, out); }); break;

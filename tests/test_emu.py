@@ -117,7 +117,7 @@ def _memo_case(emu, oracle, refs, reads, k, s, counts=None, min_occ=-1, **kw):
 
 
 @pytest.mark.parametrize("kw", [dict(path=0), dict(path=1), dict(path=2), dict(path=3), dict(path=0, vcap_limit=16),
-                                dict(path=1, block=128)])
+                                dict(path=1, block=128), dict(path=4), dict(path=4, block=128)])
 def test_memo_classify_awkward(emu, oracle, kw):
     _, refs, _ = load_sequences([data_path("awkward_refs.fa.gz")])
     _, reads, _ = load_sequences([data_path("awkward_reads.fq.gz")])
@@ -133,6 +133,8 @@ def test_memo_classify_fixtures(emu, oracle):
     assert _memo_case(emu, oracle, refs, reads[:3], 8, 300, path=1) == 3        # long reads: all through the block kernel
     _, short, _ = load_sequences([data_path("z1.fq.gz")])
     assert _memo_case(emu, oracle, refs, short[:40], 8, 1000, path=1) == 0
+    _memo_case(emu, oracle, refs, short[:300] + reads[:1], 8, 1000, path=4)     # sieve kernel (+ its redo list)
+    _memo_case(emu, oracle, refs, short[:120], 6, 1000, path=4)                 # dense sieve: many false positives
     assert _memo_case(emu, oracle, refs, short[:500] + reads[:1], 8, 1000, path=3) == 1   # tile kernel: two runs of reads + a long read
 
 

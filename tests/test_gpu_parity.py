@@ -271,8 +271,8 @@ def test_full_size_properties(gpu, oracle):
     assert np.array_equal(_fields(hits[idx]), _fields(exp))
 
 
-@pytest.mark.parametrize("tile", [False, True])
-def test_memo_path_is_taken_and_matches_murmur(oracle, tile, monkeypatch):
+@pytest.mark.parametrize("variant", ["sieve", "warp", "tile"])
+def test_memo_path_is_taken_and_matches_murmur(oracle, variant, monkeypatch):
     """The memoised kernels run for a single k <= 12 and give the same records as the Murmur kernels: short reads
     (warp kernel), long reads (block kernel, bottom-s by rank), with and without -M."""
     import rkmh_b200
@@ -283,8 +283,10 @@ def test_memo_path_is_taken_and_matches_murmur(oracle, tile, monkeypatch):
     sb, so = _synthetic_reads(rng, rs, 20000, 150)
     lb, lo = ont_reads(rng, hpv, 300, 10000)
     res = {}
-    monkeypatch.setenv("RKMH_TILE", "1" if tile else "0")      # the thread-per-read variant of the short-read kernel
-    short_kernel = "classify_memo_tile_kernel" if tile else "classify_memo_warp_kernel"
+    # the three short-read kernels: shared-memory sieve (default), rank-table warp kernel, thread-per-read tile kernel
+    monkeypatch.setenv("RKMH_TILE", "1" if variant == "tile" else "0")
+    monkeypatch.setenv("RKMH_NO_SIEVE", "0" if variant == "sieve" else "1")
+    short_kernel = f"classify_memo_{variant}_kernel"
     for memo in (True, False):
         with rkmh_b200.RkmhGpu(0) as g:
             g.set_memo(memo)
@@ -304,6 +306,8 @@ def test_memo_path_is_taken_and_matches_murmur(oracle, tile, monkeypatch):
             out.append(_fields(g.classify_batch(sb, so)))          # -M off again: FAILM flags cleared
             names = set(g.profile_read())
             assert (short_kernel in names) == memo and ("classify_group_kernel" in names) == (not memo)
+            if memo and variant == "sieve":                    # -M bakes FAILM flags: those passes take the rank-table kernel
+                assert "classify_memo_warp_kernel" in names
             assert ("count_memo_kernel" in names) == memo
             res[memo] = out
     for a, b in zip(res[True], res[False]):
