@@ -593,6 +593,13 @@ constexpr u32 SIEVE_MUL = 0x9E3779B1u;
 constexpr int SIEVE_QCAP = 64;                  // sieve-positive windows per read the kernel resolves itself
 constexpr u32 SIEVE_MAX_WORDS = 55040;          // 215 KB of the 227 KB a block may use
 
+// the sieve / code-map key of the k-mer with plane code c: base j at bits 2 j (what the kernel assembles from pieces)
+RK_HD u32 memo_il_code(u32 c, int k) {
+    u32 r = 0;
+    for (int j = 0; j < k; ++j) r |= (((c >> j) & 1u) | (((c >> (k + j)) & 1u) << 1)) << (2 * j);
+    return r;
+}
+
 RK_D u32 sieve_bits(u32 h) { return (1u << ((h >> 3) & 31u)) | (1u << ((h >> 11) & 31u)); }
 
 // stats[0] = codes that are members of a reference sketch, stats[1] = codes whose hash is 0
@@ -602,7 +609,7 @@ memo_sieve_kernel(Memo mm, u32* __restrict__ sieve, u32 nwords, u32* __restrict_
         const u32 t = mm.tab[c];
         if (t & MEMO_ZERO) atomicAdd(&stats[1], 1u);
         else if (t & MEMO_REF) {
-            const u32 h = c * SIEVE_MUL;
+            const u32 h = memo_il_code(c, mm.k) * SIEVE_MUL;
             atomicOr(&sieve[__umulhi(h, nwords)], sieve_bits(h));
             atomicAdd(&stats[0], 1u);
         }
@@ -615,8 +622,9 @@ memo_cmap_kernel(Memo mm, unsigned long long* __restrict__ cmap, u32 mask, int s
     for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < mm.ncodes; c += gridDim.x * blockDim.x) {
         const u32 t = mm.tab[c];
         if ((t & (MEMO_REF | MEMO_ZERO)) != MEMO_REF) continue;
-        const unsigned long long e = ((unsigned long long)mm.ref[t >> 8] << 32) | c;
-        u32 i = (c * SIEVE_MUL) >> shift;
+        const u32 il = memo_il_code(c, mm.k);
+        const unsigned long long e = ((unsigned long long)mm.ref[t >> 8] << 32) | il;
+        u32 i = (il * SIEVE_MUL) >> shift;
         for (;;) {
             if (atomicCAS(&cmap[i], ~0ULL, e) == ~0ULL) break;
             i = (i + 1) & mask;
@@ -647,6 +655,20 @@ RK_D u32 tr32(u32 x, const TrLane& t) {
     return x;
 }
 
+// Four bases of the read as one aligned 32-bit load: `piece` = their four 2-bit codes (first base in the low bits),
+// `bad` has a non-zero byte for every base that is not one of ACGTacgt (canonical(), mkmh.hpp:137-152): the letter is
+// rebuilt from its code (A 0x41, C 0x43, T 0x54, G 0x47 for codes 0, 1, 2, 3) and compared with the upper-cased byte.
+RK_D void sv_decode(u32 w, u32& piece, u32& bad) {
+    const u32 x = (w >> 1) & 0x03030303u;
+    piece = (x * 0x01041040u) >> 24;                         // byte i -> bits 2 i (the partial products do not overlap)
+    const u32 lo = x & 0x01010101u, hi = (x >> 1) & 0x01010101u;
+    const u32 e = 0x41414141u + 2u * lo + 0x13u * hi - 0xFu * (lo & hi);
+    bad = (w & 0xDFDFDFDFu) ^ e;
+}
+RK_D u32 sv_bad4(u32 bad) {
+    return ((bad & 0xFFu) ? 1u : 0u) | ((bad & 0xFF00u) ? 2u : 0u) | ((bad & 0xFF0000u) ? 4u : 0u) | ((bad & 0xFF000000u) ? 8u : 0u);
+}
+
 template <int NW>
 __global__ void __launch_bounds__(1024, 1)
 classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
@@ -666,11 +688,17 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
     const TrLane tl = tr_lane(lane);
     const int k = mm.k;
     const u32 kmask = mm.kmask;
+    const u32 cmask2 = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
     const u32 lt = (1u << lane) - 1u;
     const unsigned long long* __restrict__ cmap = mm.cmap;
     const u32 cmask = mm.cmap_mask;
     const int cshift = mm.cmap_shift;
     const unsigned char* __restrict__ bases = sb.bases;
+    // window at position 32 r + lane of a 128-base chunk: pieces 8 r + (lane >> 2) .. + 3, from base (lane & 3) on
+    const int src0 = lane >> 2;
+    const u32 osh = 2u * (u32)(lane & 3), ish = (u32)(lane & 3);
+    // piece j + i of lane j comes from the next chunk when j + i >= 32 (byte 1 of the shuffled pair instead of byte 0)
+    const u32 sel1 = lane >= 31 ? 0x3250u : 0x3240u, sel2 = lane >= 30 ? 0x3510u : 0x3410u, sel3 = lane >= 29 ? 0x5210u : 0x4210u;
 
     auto cmap_find = [&](u32 code) -> u32 {                  // slot + 1, or 0 when the code is no sketch member
         u32 i = (code * SIEVE_MUL) >> cshift;
@@ -681,15 +709,19 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
             i = (i + 1) & cmask;
         }
     };
+    // word `widx` of the read's 4-byte-aligned stream (wp = first word, nbytes = bytes from wp to the end of the read);
+    // words that hold no base of the read are not loaded and decode as valid 'AAAA'
+    auto load_word = [&](const u32* wp, i64 nbytes, i64 widx) -> u32 { return 4 * widx < nbytes ? __ldg(wp + widx) : 0x41414141u; };
 
     const i64 nwarps = (i64)gridDim.x * nwb;
     i64 rid = (i64)blockIdx.x * nwb + wib;
     i64 beg = 0, len64 = 0;
-    u32 cha = 0, chb = 0;
+    u32 wa = 0x41414141u, wb = 0x41414141u;
     if (rid < sb.nseq) {
         beg = sb.offs[rid] - sb.base0; len64 = sb.offs[rid + 1] - sb.offs[rid];
-        cha = lane < len64 ? (u32)bases[beg + lane] : 0u;
-        chb = 32 + lane < len64 ? (u32)bases[beg + 32 + lane] : 0u;
+        const u32* wp = reinterpret_cast<const u32*>(bases + (beg & ~(i64)3));
+        const i64 nbytes = (beg & 3) + len64;
+        wa = load_word(wp, nbytes, lane); wb = load_word(wp, nbytes, 32 + lane);
     }
     while (rid < sb.nseq) {
         const i64 nrid = rid + nwarps;
@@ -699,45 +731,64 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
         const bool skip = n64 > s || n64 > MEMO_WARP_MAX_KMERS;      // the sketch is a strict subset: block kernel
         // ---- stream the windows through the sieve; queue the codes that pass --------------------------------------
         int nc = 0;
-        u32 nz = 0;
+        u32 ninv = 0;                                        // in-range windows that contain an invalid base
         if (!skip && n64 > 0) {
-            const unsigned char* __restrict__ p = bases + beg;
-            const int len = (int)len64, n = (int)n64;
-            u32 c0, c1, cv;
-            {
-                const u32 c2 = base_code(cha);
-                c0 = __ballot_sync(0xffffffffu, c2 & 1u); c1 = __ballot_sync(0xffffffffu, c2 & 2u);
-                cv = __ballot_sync(0xffffffffu, memo_base_invalid(cha));
-            }
-            u32 chn = chb;
-            for (int base = 0; base < n; base += 32) {
-                const u32 c2 = base_code(chn);
-                const u32 n0 = __ballot_sync(0xffffffffu, c2 & 1u), n1 = __ballot_sync(0xffffffffu, c2 & 2u);
-                const u32 nv = __ballot_sync(0xffffffffu, memo_base_invalid(chn));
-                chn = base + 64 + lane < len ? (u32)p[base + 64 + lane] : 0u;     // in flight while this round is processed
-                const u32 f0 = __funnelshift_r(c0, n0, (u32)lane) & kmask;
-                const u32 f1 = __funnelshift_r(c1, n1, (u32)lane) & kmask;
-                const u32 fv = __funnelshift_r(cv, nv, (u32)lane) & kmask;
-                const bool valid = base + lane < n && fv == 0u;
-                const u32 code = f0 | (f1 << k);
-                const u32 h = code * SIEVE_MUL;
-                const u32 bits = sieve_bits(h);
-                const bool cand = valid && (sv[__umulhi(h, nwords)] & bits) == bits;
-                nz += valid;
-                const u32 bal = __ballot_sync(0xffffffffu, cand);
-                if (bal) {
+            const int sh = (int)(beg & 3), n = (int)n64;
+            const u32* __restrict__ wp = reinterpret_cast<const u32*>(bases + (beg & ~(i64)3));
+            const i64 nbytes = sh + len64;
+            const int pend = sh + n;                         // stream positions [sh, pend) start a window
+            u32 pc, bc, wn = wb;
+            sv_decode(wa, pc, bc);
+            for (int c0 = 0; c0 < pend; c0 += 128) {
+                u32 pn, bn;
+                sv_decode(wn, pn, bn);
+                wn = load_word(wp, nbytes, (i64)(c0 >> 2) + 64 + lane);       // in flight while this chunk is processed
+                const bool slow = __any_sync(0xffffffffu, (bc | bn) != 0u);
+                // Q: the 16 bases from piece `lane` on
+                const u32 xq = pc | (pn << 8);
+                u32 Q = xq;
+                Q = __byte_perm(Q, __shfl_sync(0xffffffffu, xq, (lane + 1) & 31), sel1);
+                Q = __byte_perm(Q, __shfl_sync(0xffffffffu, xq, (lane + 2) & 31), sel2);
+                Q = __byte_perm(Q, __shfl_sync(0xffffffffu, xq, (lane + 3) & 31), sel3);
+                u32 IQ = 0;                                  // the same for the invalid flags (one bit per base)
+                if (slow) {
+                    const u32 xi = sv_bad4(bc) | (sv_bad4(bn) << 4);
+                    IQ = xi & 15u;
+#pragma unroll
+                    for (int i = 1; i < 4; ++i) {
+                        const u32 t = __shfl_sync(0xffffffffu, xi, (lane + i) & 31);
+                        IQ |= ((lane + i < 32) ? (t & 15u) : (t >> 4)) << (4 * i);
+                    }
+                }
+                const int wi0 = c0 + lane - sh;              // window index of this lane in round 0
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (c0 + 32 * r >= pend) break;          // warp-uniform
+                    const u32 code = (__shfl_sync(0xffffffffu, Q, src0 + 8 * r) >> osh) & cmask2;
+                    bool ok = (u32)(wi0 + 32 * r) < (u32)n;
+                    if (slow) {
+                        const bool inv = ((__shfl_sync(0xffffffffu, IQ, src0 + 8 * r) >> ish) & kmask) != 0u;
+                        ninv += ok && inv;
+                        ok = ok && !inv;
+                    }
+                    const u32 h = code * SIEVE_MUL;
+                    const u32 bits = sieve_bits(h);
+                    const u32 word = sv[__umulhi(h, nwords)];                  // unconditional: no divergent branch in the loop
+                    const bool cand = ok & ((word & bits) == bits);
+                    const u32 bal = __ballot_sync(0xffffffffu, cand);
                     const int at = nc + __popc(bal & lt);
                     if (cand && at < SIEVE_QCAP) q[at] = code;
                     nc += __popc(bal);
                 }
-                c0 = n0; c1 = n1; cv = nv;
+                pc = pn; bc = bn;
             }
         }
-        // ---- the next read's first 64 bases: in flight while this read's hits are resolved -------------------------
-        u32 ncha = 0, nchb = 0;
+        // ---- the next read's first 256 bases: in flight while this read's hits are resolved ------------------------
+        u32 nwa = 0x41414141u, nwb2 = 0x41414141u;
         if (nrid < sb.nseq) {
-            ncha = lane < nlen ? (u32)bases[nbeg + lane] : 0u;
-            nchb = 32 + lane < nlen ? (u32)bases[nbeg + 32 + lane] : 0u;
+            const u32* nwp = reinterpret_cast<const u32*>(bases + (nbeg & ~(i64)3));
+            const i64 nnb = (nbeg & 3) + nlen;
+            nwa = load_word(nwp, nnb, lane); nwb2 = load_word(nwp, nnb, 32 + lane);
         }
         bool give_up = skip || nc > SIEVE_QCAP;
         int best = 0, id = 0, prev = -1;
@@ -796,11 +847,12 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
         if (give_up) {
             if (lane == 0) redo[atomicAdd(redo_count, 1)] = (int)rid;
         } else {
-            nz = warp_sum(nz);
-            if (lane == 0) { Hit hh; hh.ref_id = id; hh.best = best; hh.prev = prev; hh.sketch_len = (int)nz; out[rid] = hh; }
+            // every window counts unless it holds an invalid base: no code hashes to 0, no FAILM flag is baked
+            const int nz = (int)n64 - (int)warp_sum(ninv);
+            if (lane == 0) { Hit hh; hh.ref_id = id; hh.best = best; hh.prev = prev; hh.sketch_len = nz; out[rid] = hh; }
         }
         __syncwarp();
-        rid = nrid; beg = nbeg; len64 = nlen; cha = ncha; chb = nchb;
+        rid = nrid; beg = nbeg; len64 = nlen; wa = nwa; wb = nwb2;
     }
 }
 
