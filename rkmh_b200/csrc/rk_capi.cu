@@ -86,7 +86,7 @@ struct rkg_ctx {
     rkg_batch* slots[2] = {nullptr, nullptr};   // internal double buffer of rkg_classify_batch / count
     // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
     bool memo_enabled = true, memo_ready = false, tile_kernel = false, sieve_enabled = true;
-    DevBuf memo_tab, memo_tab2, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc, memo_sieve, memo_cmap;
+    DevBuf memo_tab, memo_sieve_t, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc, memo_sieve, memo_cmap;
     double sieve_fill = 0.0;             // fraction of the sieve's bits that are set (false-positive rate = fill^2)
     Memo memo{};
     bool memo_pending = false;           // code_counts holds increments not yet folded into the read count table
@@ -246,7 +246,6 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     const int bucket_bits = std::max(2 * k - 8, 0);
     const u32 nb = 1u << bucket_bits;
     CK(ctx->memo_tab.ensure(sizeof(u32) * (size_t)ncodes));
-    CK(ctx->memo_tab2.ensure(sizeof(u32) * (size_t)ncodes));
     CK(ctx->memo_ref.ensure(sizeof(u32) * (size_t)ncodes));
     CK(ctx->memo_hash.ensure(sizeof(u64) * (size_t)ncodes));
     CK(ctx->memo_tmp.ensure(sizeof(u32) * ((size_t)3 * nb + ncodes)));
@@ -257,7 +256,7 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     CK(cudaMemsetAsync(ctx->memo_ref.p, 0, sizeof(u32) * (size_t)ncodes, st));
     CK(cudaMemsetAsync(ctx->memo_misc.p, 0, 256, st));
     Memo mm{};
-    mm.tab = ctx->memo_tab.as<u32>(); mm.tab2 = ctx->memo_tab2.as<u32>(); mm.ref = ctx->memo_ref.as<u32>(); mm.hash = ctx->memo_hash.as<u64>();
+    mm.tab = ctx->memo_tab.as<u32>(); mm.ref = ctx->memo_ref.as<u32>(); mm.hash = ctx->memo_hash.as<u64>();
     mm.inval = ctx->memo_misc.as<unsigned long long>();
     int* err = ctx->memo_misc.as<int>() + 8;
     mm.ncodes = ncodes; mm.kmask = (1u << k) - 1u; mm.k = k;
@@ -280,8 +279,7 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
         memo_scatter_kernel<<<grid, 256, 0, st>>>(ncodes, hash, bstart, bfill, bcodes, bucket_bits);
         memo_rank_kernel<<<(int)std::min<i64>(nb, (i64)ctx->sm_count * 8), 256, 0, st>>>(hash, bcount, bstart, bcodes, nb, ctx->tb,
                                                                                         mm.tab, mm.ref);
-        memo_tab2_kernel<<<grid, 256, 0, st>>>(mm);
-        ctx->launches += 4;
+        ctx->launches += 3;
     }
     CK(cudaGetLastError());
     int herr = 0;
@@ -290,7 +288,7 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     if (herr) return RKG_OK;          // a hash bucket larger than the sort capacity: keep the Murmur path (still exact)
     // sieve + code map of classify_memo_sieve_kernel (rk_memo.cuh).  The sieve takes what a 1024-thread block can
     // have beside its candidate queues; it is dropped when it would let more than a quarter of all windows through.
-    mm.sieve = nullptr; mm.cmap = nullptr; mm.sieve_words = 0; mm.zero_codes = 0;
+    mm.sieve = nullptr; mm.sieve_t = nullptr; mm.cmap = nullptr; mm.sieve_words = 0; mm.sieve_t_words = 0; mm.zero_codes = 0;
     ctx->sieve_fill = 0.0;
     const size_t queues = (size_t)32 * SIEVE_QCAP * 4 + 1024;
     if (ctx->sieve_enabled && ctx->tb.entries != nullptr && ctx->smem_optin > queues + 8192) {
@@ -315,7 +313,7 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
         ctx->sieve_fill = (double)set_bits / (32.0 * nwords);
         mm.zero_codes = hstats[1];
         if (ctx->sieve_fill <= 0.5) {
-            const u32 cap = (u32)next_pow2(std::max<i64>(2 * (i64)hstats[0], 1024));
+            const u32 cap = (u32)next_pow2(std::max<i64>(8 * (i64)hstats[0], 1024));   // load <= 1/8: one probe, nearly always
             int log2cap = 0; while ((1u << log2cap) < cap) ++log2cap;
             CK(ctx->memo_cmap.ensure(sizeof(u64) * (size_t)cap));
             CK(cudaMemsetAsync(ctx->memo_cmap.p, 0xFF, sizeof(u64) * (size_t)cap, st));
@@ -328,6 +326,24 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
             CK(cudaStreamSynchronize(st));
             mm.sieve = ctx->memo_sieve.as<u32>(); mm.sieve_words = nwords;
             mm.cmap = ctx->memo_cmap.as<unsigned long long>(); mm.cmap_mask = cap - 1; mm.cmap_shift = 32 - log2cap;
+            // the thread-per-read tile kernel shares its block's shared memory with the staged reads: a smaller sieve
+            if (ctx->tile_kernel && ctx->smem_optin > TILE_FIXED_SMEM + 1024 + 16384) {
+                const u32 nwt = (u32)((ctx->smem_optin - TILE_FIXED_SMEM - 1024) / 4);
+                CK(ctx->memo_sieve_t.ensure(sizeof(u32) * (size_t)nwt));
+                CK(cudaMemsetAsync(ctx->memo_sieve_t.p, 0, sizeof(u32) * (size_t)nwt, st));
+                {
+                    Timed t(ctx, st, K_MEMO_BUILD);
+                    memo_sieve_kernel<<<grid, 256, 0, st>>>(mm, ctx->memo_sieve_t.as<u32>(), nwt, stats + 2);
+                    ctx->launches += 1;
+                }
+                CK(cudaGetLastError());
+                std::vector<u32> image_t(nwt);
+                CK(cudaMemcpyAsync(image_t.data(), ctx->memo_sieve_t.p, sizeof(u32) * (size_t)nwt, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                size_t bits_t = 0;
+                for (u32 w : image_t) bits_t += (size_t)__builtin_popcount(w);
+                if ((double)bits_t / (32.0 * nwt) <= 0.5) { mm.sieve_t = ctx->memo_sieve_t.as<u32>(); mm.sieve_t_words = nwt; }
+            }
         }
     }
     ctx->memo = mm;
@@ -440,10 +456,10 @@ MemoGeom memo_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
             const size_t smem = (size_t)(block / 32) * (sizeof(MemoWarpSmem) + (size_t)g.rwords * 4);
             if (smem <= ctx->smem_optin) { g.use_warp = true; g.warp_block = block; g.warp_smem = smem; break; }
         }
-        // thread per read: enough reads per shared-memory tile to fill the block
-        // (experimental, RKMH_TILE=1: measured 2x slower than the warp kernel on config 2 -- latency bound)
-        g.use_tile = ctx->tile_kernel && g.use_warp && ctx->tb.nb <= 4 && b->total / b->nseq <= 400 &&
-                     TILE_SMEM + 2048 <= ctx->smem_optin;
+        // thread per read (opt-in, RKMH_TILE=1: measured 2x slower than the sieve kernel on config 2 -- 12 warps per SM and
+        // divergent per-thread resolve loops): every read of the batch has at most TILE_MAXWIN windows
+        g.use_tile = g.use_warp && ctx->tb.nb <= 4 && ctx->memo.sieve_t != nullptr && ctx->memo.zero_codes == 0 &&
+                     b->max_ntotal <= TILE_MAXWIN;
     }
     return g;
 }
@@ -464,9 +480,10 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
         if (mg.ok) {
             int rc = memo_prepare(ctx, min_occ);
             if (rc) return rc;
-            if (mg.use_tile) {                               // short reads, <= 256 references: a thread per read
+            if (mg.use_tile && ctx->memo_occ == INT_MIN) {   // short reads, <= 256 references, no -M mask: a thread per read
                 Timed t(ctx, b->stream, K_CLASSIFY_MEMO_TILE);
-                const int grid = ctx->sm_count * 2;
+                const int grid = ctx->sm_count;
+                const size_t TILE_SMEM = TILE_FIXED_SMEM + (size_t)ctx->memo.sieve_t_words * 4;
 #define RK_TILE_LAUNCH(NWV)                                                                                              \
     do {                                                                                                                 \
         CK(cudaFuncSetAttribute(classify_memo_tile_kernel<NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM)); \
@@ -669,7 +686,7 @@ void rkg_destroy(rkg_ctx* ctx) {
     for (int i = 0; i < 2; ++i) batch_release(ctx->slots[i]);
     for (DevBuf* d : {&ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
                       &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
-                      &ctx->memo_tab, &ctx->memo_tab2, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
+                      &ctx->memo_tab, &ctx->memo_sieve_t, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
                       &ctx->memo_sieve, &ctx->memo_cmap})
         d->release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -31,7 +31,6 @@ constexpr int MEMO_BINS = 4096;                 // radix-select histogram (12 bi
 
 struct Memo {
     u32* tab;                       // indexed by the plane code (warp-streaming kernels)
-    u32* tab2;                      // the same entries indexed by the rolling code (thread-per-read tile kernel)
     u32* ref;
     const u64* hash;
     int* code_counts;               // nullptr when the context has no read count table
@@ -41,6 +40,8 @@ struct Memo {
     int k;
     // sieve kernel (classify_memo_sieve_kernel): shared-memory Bloom filter image and the code -> slot + 1 map
     const u32* sieve;               // nullptr: not built / too full to be useful
+    const u32* sieve_t;             // the (smaller) sieve of the thread-per-read tile kernel
+    u32 sieve_t_words;
     const unsigned long long* cmap;
     u32 sieve_words, cmap_mask;
     int cmap_shift;
@@ -114,22 +115,6 @@ RK_D u64 memo_code_hash(u32 c, int k) {
     }
     const u64 hf = murmur_kmer<KV>(f, k), hr = murmur_kmer<KV>(r, k);
     return hf < hr ? hf : hr;
-}
-
-// rolling code of the k-mer with plane code c: base j at bits 2 (k-1-j) (the newest base in the low bits)
-RK_HD u32 memo_roll_code(u32 c, int k) {
-    u32 r = 0;
-    for (int j = 0; j < k; ++j) {
-        const u32 c2 = ((c >> j) & 1u) | (((c >> (k + j)) & 1u) << 1);
-        r |= c2 << (2 * (k - 1 - j));
-    }
-    return r;
-}
-
-__global__ void __launch_bounds__(256)
-memo_tab2_kernel(Memo mm) {
-    for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < mm.ncodes; c += gridDim.x * blockDim.x)
-        mm.tab2[memo_roll_code(c, mm.k)] = mm.tab[c];
 }
 
 RK_D u32 memo_bucket(u64 h, int bucket_bits) { return bucket_bits ? (u32)(h >> (64 - bucket_bits)) : 0u; }
@@ -243,7 +228,7 @@ memo_apply_occ_kernel(Memo mm, CountTable ct, int min_occ) {
             if (h != 0 && !(min_occ <= ct.counts[fastmod(h, ct.mod)])) fail = MEMO_FAILM;
         }
         const u32 nt = (t & ~MEMO_FAILM) | fail;
-        if (nt != t) { mm.tab[c] = nt; mm.tab2[memo_roll_code(c, mm.k)] = nt; }
+        if (nt != t) mm.tab[c] = nt;
     }
 }
 
@@ -857,33 +842,39 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
 }
 
 // ------------------------------------------------------------------------------------------------
-// classify_memo_tile_kernel: ONE THREAD PER READ for short reads (the config-2 shape), at most 256 references.
+// classify_memo_tile_kernel: ONE THREAD PER READ for short reads (at most TILE_MAXWIN windows: the config-2 shape),
+// at most 256 references, same preconditions as the sieve kernel (no FAILM flag baked, no code that hashes to 0).
 //
-// A block stages a tile of consecutive reads (their ASCII bases, <= TILE_BYTES) in shared memory with one TMA bulk
-// copy (cp.async.bulk + mbarrier) and then every thread walks its own read:
-//   1. per base: byte -> (2-bit code, invalid flag) through a 256-entry shared-memory table, roll the 2k-bit code,
-//      look the table entry up in L2 (eight lookups in flight per thread); entries that are members of a reference
-//      sketch (REF) go to the thread's candidate list in shared memory;
-//   2. per candidate: table slot (ref[rank]), copy number inside the read (a 64-bit Bloom word decides whether the
-//      earlier candidates have to be compared at all -- multiset semantics), bitset row of the
-//      (hash, copy) pair, added into BIT-SLICED per-reference counters held in registers (plane p of word w = bit p
-//      of the counts of references 32 w .. 32 w + 31);
-//   3. the scan of src/rkmh.cpp:874-883 on the bit-sliced counters: most significant plane first, the set of
-//      references that can still hold the maximum shrinks; its lowest index is the winner, and the same walk over
-//      the references before it gives the previous best.
-// No warp-level cooperation at all: the per-read cost is ~25 thread-instructions per base instead of ~8 warp-
-// instructions.  Reads that do not fit (more k-mers than s, more than TILE_LIST candidates, a count above 31, longer
+// A block stages a tile of consecutive reads (their ASCII bases as parsed, <= TILE_BYTES) in shared memory with one
+// TMA bulk copy (cp.async.bulk + mbarrier); every thread then walks its own read, so nothing in the per-window work
+// is a warp collective:
+//   1. sixteen bases at a time: four aligned shared-memory words are realigned (funnel shift), decoded (sv_decode)
+//      into one 32-bit word of 2-bit codes, and the codes of the 16 windows that start in it -- funnel shifts of two
+//      consecutive code words -- are tested against the shared-memory sieve.  The code words overwrite the read's own
+//      bytes in the tile (4x smaller, always behind the bytes still to be decoded); the 16-bit masks of the windows
+//      that pass go to a small per-thread area;
+//   2. the windows that passed are looked up in the L2-resident code map, four lookups in flight; the table slots of
+//      the true sketch members are kept (for the copy number of a hash that occurs more than once in the read --
+//      multiset semantics, SURVEY F10 -- a 64-bit Bloom word decides whether the earlier ones are compared at all);
+//   3. their reference bitset rows are added, two rows in flight, into BIT-SLICED per-reference counters held in
+//      registers (plane p of word w = bit p of the counts of references 32 w .. 32 w + 31);
+//   4. the scan of src/rkmh.cpp:874-883 on the bit-sliced counters: most significant plane first, the set of
+//      references that can still hold the maximum shrinks; its lowest index is the winner, and the same walk over the
+//      references in front of it gives the previous best.
+// ~20 thread-instructions per window instead of ~5 warp-instructions.  Reads that do not fit (more windows than s or
+// TILE_MAXWIN, more hits than the key area holds, a count above 31, too short to hold their own code words, longer
 // than a tile) are handed to the block kernel through `redo`.
 constexpr int TILE_THREADS = 384;
 constexpr int TILE_BYTES = 61440;
-constexpr int TILE_LIST = 32;
+constexpr int TILE_MAXWIN = 160;                // candidate masks: ten 16-bit groups
+constexpr int TILE_XWORDS = 16;                 // per-thread extra words: 5 of candidate masks + 11 hit slots
 constexpr int TILE_PLANES = 5;
-constexpr size_t TILE_SMEM = (size_t)TILE_BYTES + (size_t)TILE_LIST * TILE_THREADS * 4;
+constexpr size_t TILE_FIXED_SMEM = (size_t)TILE_BYTES + (size_t)TILE_XWORDS * TILE_THREADS * 4;
 
 struct TileCtl { i64 b0; int m; int skip; };
 
 template <int NW>
-__global__ void __launch_bounds__(TILE_THREADS, 2)
+__global__ void __launch_bounds__(TILE_THREADS, 1)
 classify_memo_tile_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
                           int* __restrict__ redo, int* __restrict__ redo_count, Hit* __restrict__ out) {
 #ifdef RK_EMU
@@ -891,17 +882,23 @@ classify_memo_tile_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
 #else
     extern __shared__ __align__(128) unsigned char dsm[];
 #endif
-    __shared__ u32 lut[256];
     __shared__ TileCtl ctl;
     __shared__ __align__(8) unsigned long long bar;
+    // dynamic shared memory: [tile bytes][per-thread extra words][sieve]
     unsigned char* rd = dsm;
-    u32* lists = reinterpret_cast<u32*>(dsm + TILE_BYTES);
+    u32* tw = reinterpret_cast<u32*>(dsm);
+    u32* xw = reinterpret_cast<u32*>(dsm + TILE_BYTES);
+    u32* sv = xw + TILE_XWORDS * TILE_THREADS;
+    const u32 nwords = mm.sieve_t_words;
     const int t = threadIdx.x;
     const int k = mm.k;
-    const u32 cmask = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
-    const u32* __restrict__ tab2 = mm.tab2;
+    const u32 kmask = mm.kmask;
+    const u32 cmask2 = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+    const unsigned long long* __restrict__ cmap = mm.cmap;
+    const u32 cmask = mm.cmap_mask;
+    const int cshift = mm.cmap_shift;
 
-    for (int b = t; b < 256; b += TILE_THREADS) lut[b] = base_code((u32)b) | (memo_base_invalid((u32)b) ? 0x80000000u : 0u);
+    for (u32 i = (u32)t; i < nwords; i += TILE_THREADS) sv[i] = mm.sieve_t[i];
 #ifndef RK_EMU
     const u32 bar_addr = (u32)__cvta_generic_to_shared(&bar);
     if (t == 0) {
@@ -919,7 +916,7 @@ classify_memo_tile_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
             // ---- the next run of reads that fits in the tile ----------------------------------------------------
             if (t == 0) {
                 const i64 b0 = sb.offs[r];
-                const i64 lim = (i64)TILE_BYTES - 32;
+                const i64 lim = (i64)TILE_BYTES - 64;
                 int lo = 1, hi = (int)(rend - r), m = 0;
                 while (lo <= hi) {                           // largest m with offs[r + m] - b0 <= lim
                     const int mid = (lo + hi) >> 1;
@@ -942,7 +939,7 @@ classify_memo_tile_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
 #else
             if (t == 0) {
                 const u32 dst = (u32)__cvta_generic_to_shared(rd);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the previous tile was read through the generic proxy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the previous tile was accessed through the generic proxy
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_addr), "r"(copy_bytes) : "memory");
                 asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              :: "r"(dst), "l"(sb.bases + ga), "r"(copy_bytes), "r"(bar_addr) : "memory");
@@ -959,150 +956,191 @@ classify_memo_tile_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
             if (t < m) {
                 const i64 rid = r + t;
                 const i64 o0 = sb.offs[rid], o1 = sb.offs[rid + 1];
-                const unsigned char* rp = rd + shift + (int)(o0 - ctl.b0);
                 const int len = (int)(o1 - o0);
                 const int n = len - k > 0 ? len - k : 0;
-                u32* mylist = lists + t;
-                bool give_up = n > s;
-                int nc = 0;
-                u32 nz = 0;
-                if (!give_up) {
-                    // ---- 1: walk the read; window ending at base i starts at i - k + 1 and counts iff i < len - 1 --------
-                    const int lim = len - 1;
-                    u32 c = 0;
-                    int lastinv = -1;
-                    for (int i0 = 0; i0 < lim; i0 += 8) {
-                        u32 mv[8];
-                        if (i0 + 8 <= lim) {
+                const u32 addr = (u32)(shift + (int)(o0 - ctl.b0));          // first byte of the read in the tile
+                const u32 aw = addr >> 2, sh8 = 8u * (addr & 3u);
+                const int ng = (n + 15) >> 4;                                // groups of 16 windows
+                const int nsw = ng + 1;                                      // code words kept for step 2
+                u32* privw = tw + ((addr + 3u) >> 2);                        // the words that lie wholly inside the read
+                const int privn = (int)((addr + (u32)len) >> 2) - (int)((addr + 3u) >> 2);
+                const int kcap0 = privn - nsw;                               // hit slots inside the read's own bytes
+                u32* myx = xw + t;                                           // extra words, strided by TILE_THREADS
+                bool give_up = n > s || n > TILE_MAXWIN || kcap0 < 0;
+                int best = 0, id = 0, prev = -1, ninv = 0;
+                if (!give_up && n > 0) {
+                    // ---- 1: decode, sieve ---------------------------------------------------------------------------
+                    auto decode = [&](int g, u32& cw, u32& bw) {
+                        const u32* w = tw + aw + 4 * g;
+                        const u32 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+                        u32 p0, p1, p2, p3, b0, b1, b2, b3;
+                        sv_decode(__funnelshift_r(w0, w1, sh8), p0, b0);
+                        sv_decode(__funnelshift_r(w1, w2, sh8), p1, b1);
+                        sv_decode(__funnelshift_r(w2, w3, sh8), p2, b2);
+                        sv_decode(__funnelshift_r(w3, w4, sh8), p3, b3);
+                        cw = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+                        bw = 0;
+                        if (b0 | b1 | b2 | b3) bw = sv_bad4(b0) | (sv_bad4(b1) << 4) | (sv_bad4(b2) << 8) | (sv_bad4(b3) << 12);
+                    };
+                    u32 cw_cur, bw_cur, gm_lo = 0;
+                    decode(0, cw_cur, bw_cur);
+                    for (int g = 0; g < ng; ++g) {
+                        u32 cw_next, bw_next;
+                        decode(g + 1, cw_next, bw_next);
+                        privw[g] = cw_cur;                   // bases 4 g .. 4 g + 6 of the read: decoded long ago
+                        u32 gm = 0;
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const int i = i0 + u;
-                                const u32 e = lut[rp[i]];
-                                c = ((c << 2) | e) & cmask;
-                                if ((int)e < 0) lastinv = i;
-                                mv[u] = MEMO_ZERO;
-                                if (i - lastinv >= k) mv[u] = __ldg(&tab2[c]);
+                        for (int j = 0; j < 16; ++j) {
+                            const u32 code = (j ? __funnelshift_r(cw_cur, cw_next, 2 * j) : cw_cur) & cmask2;
+                            const u32 h = code * SIEVE_MUL;
+                            const u32 bits = sieve_bits(h);
+                            if ((sv[__umulhi(h, nwords)] & bits) == bits) gm |= 1u << j;
+                        }
+                        const int rem = n - 16 * g;
+                        const u32 inr = rem < 16 ? ((1u << rem) - 1u) : 0xFFFFu;
+                        gm &= inr;
+                        const u32 bb = bw_cur | (bw_next << 16);
+                        if (bb) {                            // some base near these windows is not ACGTacgt (rare)
+                            u32 invm = 0;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) if ((bb >> j) & kmask) invm |= 1u << j;
+                            invm &= inr;
+                            ninv += __popc(invm);
+                            gm &= ~invm;
+                        }
+                        if (g & 1) myx[(g >> 1) * TILE_THREADS] = gm_lo | (gm << 16); else gm_lo = gm;
+                        cw_cur = cw_next; bw_cur = bw_next;
+                    }
+                    privw[ng] = cw_cur;
+                    if (ng & 1) myx[(ng >> 1) * TILE_THREADS] = gm_lo;
+                    // ---- 2: windows that passed -> table slots of the true sketch members -----------------------------
+                    const int kcap = kcap0 + (TILE_XWORDS - 5);
+                    auto key_ref = [&](int i) -> u32& { return i < kcap0 ? privw[nsw + i] : myx[(5 + i - kcap0) * TILE_THREADS]; };
+                    int nk = 0;
+                    for (int gi = 0; gi < (ng + 1) / 2 && !give_up; ++gi) {
+                        u32 mbits = myx[gi * TILE_THREADS];
+                        while (mbits) {
+                            u32 code[4], idx[4];
+                            unsigned long long e[4];
+                            int cnt = 0;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                code[u] = 0xFFFFFFFFu; idx[u] = 0; e[u] = ~0ULL;
+                                if (mbits) {
+                                    const int p = 32 * gi + __ffs((int)mbits) - 1;
+                                    mbits &= mbits - 1;
+                                    code[u] = __funnelshift_r(privw[p >> 4], privw[(p >> 4) + 1], 2 * (p & 15)) & cmask2;
+                                    idx[u] = (code[u] * SIEVE_MUL) >> cshift;
+                                    e[u] = __ldg(&cmap[idx[u]]);
+                                    cnt = u + 1;
+                                }
                             }
-                        } else {
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const int i = i0 + u;
-                                mv[u] = MEMO_ZERO;
-                                if (i < lim) {
-                                    const u32 e = lut[rp[i]];
-                                    c = ((c << 2) | e) & cmask;
-                                    if ((int)e < 0) lastinv = i;
-                                    if (i - lastinv >= k) mv[u] = __ldg(&tab2[c]);
+                            for (int u = 0; u < 4; ++u) {
+                                if (u >= cnt) break;
+                                while ((u32)e[u] != code[u] && (u32)e[u] != 0xFFFFFFFFu) { idx[u] = (idx[u] + 1) & cmask; e[u] = __ldg(&cmap[idx[u]]); }
+                                if ((u32)e[u] == code[u]) {
+                                    if (nk < kcap) key_ref(nk) = (u32)(e[u] >> 32);
+                                    ++nk;
                                 }
                             }
                         }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const u32 mval = mv[u];
-                            nz += !(mval & (MEMO_ZERO | MEMO_FAILM));
-                            if ((mval & (MEMO_REF | MEMO_ZERO | MEMO_FAILM)) == MEMO_REF) {
-                                if (nc < TILE_LIST) mylist[nc * TILE_THREADS] = mval >> 8;
-                                ++nc;
-                            }
-                        }
                     }
-                    if (nc > TILE_LIST) give_up = true;
-                }
-                int best = 0, id = 0, prev = -1;
-                if (!give_up && nc > 0) {
-                    // ---- 2: candidates -> table slots -> bitset rows -> bit-sliced counters --------------------------------
-                    for (int j = 0; j < nc; ++j) mylist[j * TILE_THREADS] = __ldg(&mm.ref[mylist[j * TILE_THREADS]]);   // slot + 1
-                    u32 P[TILE_PLANES][NW];
+                    if (nk > kcap) give_up = true;
+                    // ---- 3: bitset rows -> bit-sliced counters ----------------------------------------------------------
+                    if (!give_up && nk > 0) {
+                        u32 P[TILE_PLANES][NW];
 #pragma unroll
-                    for (int pl = 0; pl < TILE_PLANES; ++pl)
+                        for (int pl = 0; pl < TILE_PLANES; ++pl)
 #pragma unroll
-                        for (int w = 0; w < NW; ++w) P[pl][w] = 0;
-                    unsigned long long bloom = 0;
-                    u32 carry_out = 0;
-                    for (int j0 = 0; j0 < nc; j0 += 2) {
-                        const u64* rowp[2];
+                            for (int w = 0; w < NW; ++w) P[pl][w] = 0;
+                        unsigned long long bloom = 0;
+                        u32 carry_out = 0;
+                        for (int j0 = 0; j0 < nk; j0 += 2) {
+                            const u64* rowp[2];
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            rowp[u] = nullptr;
-                            const int j = j0 + u;
-                            if (j < nc) {
-                                const u32 key = mylist[j * TILE_THREADS];
-                                const unsigned long long bit = 1ULL << ((key * 0x9E3779B1u) >> 26);
-                                u32 copy = 0;
-                                if (bloom & bit) for (int jj = 0; jj < j; ++jj) copy += mylist[jj * TILE_THREADS] == key;
-                                bloom |= bit;
-                                rowp[u] = table_row(tb, (int)key - 1, copy);
-                            }
-                        }
-                        u32 x[2][NW];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u)
-#pragma unroll
-                            for (int w = 0; w < NW / 2; ++w) {
-                                const u64 v = rowp[u] ? __ldg(&rowp[u][w]) : 0ULL;
-                                x[u][2 * w] = (u32)v; x[u][2 * w + 1] = (u32)(v >> 32);
-                            }
-#pragma unroll
-                        for (int u = 0; u < 2; ++u)
-#pragma unroll
-                            for (int w = 0; w < NW; ++w) {
-                                u32 cy = x[u][w];
-                                if (cy) {
-#pragma unroll
-                                    for (int pl = 0; pl < TILE_PLANES; ++pl) { const u32 tt = P[pl][w] & cy; P[pl][w] ^= cy; cy = tt; }
-                                    carry_out |= cy;
+                            for (int u = 0; u < 2; ++u) {
+                                rowp[u] = nullptr;
+                                const int j = j0 + u;
+                                if (j < nk) {
+                                    const u32 key = key_ref(j);
+                                    const unsigned long long bit = 1ULL << ((key * 0x9E3779B1u) >> 26);
+                                    u32 copy = 0;
+                                    if (bloom & bit) for (int jj = 0; jj < j; ++jj) copy += key_ref(jj) == key;
+                                    bloom |= bit;
+                                    rowp[u] = table_row(tb, (int)key - 1, copy);
                                 }
                             }
-                    }
-                    if (carry_out) give_up = true;           // some count reached 2^TILE_PLANES
-                    else {
-                        // ---- 3: first index of the maximum, and the maximum before it ------------------------------------
-                        u32 cand[NW];
+                            u32 x[2][NW];
 #pragma unroll
-                        for (int w = 0; w < NW; ++w) cand[w] = 0xFFFFFFFFu;
+                            for (int u = 0; u < 2; ++u)
 #pragma unroll
-                        for (int pl = TILE_PLANES - 1; pl >= 0; --pl) {
-                            u32 tsel[NW], any = 0;
+                                for (int w = 0; w < NW / 2; ++w) {
+                                    const u64 v = rowp[u] ? __ldg(&rowp[u][w]) : 0ULL;
+                                    x[u][2 * w] = (u32)v; x[u][2 * w + 1] = (u32)(v >> 32);
+                                }
 #pragma unroll
-                            for (int w = 0; w < NW; ++w) { tsel[w] = cand[w] & P[pl][w]; any |= tsel[w]; }
-                            if (any) {
-                                best |= 1 << pl;
+                            for (int u = 0; u < 2; ++u)
 #pragma unroll
-                                for (int w = 0; w < NW; ++w) cand[w] = tsel[w];
-                            }
-                        }
-                        if (best > 0) {
-                            int idw = 0;
+                                for (int w = 0; w < NW; ++w) {
+                                    u32 cy = x[u][w];
+                                    if (cy) {
 #pragma unroll
-                            for (int w = NW - 1; w >= 0; --w) if (cand[w]) idw = w;
-                            u32 cw = 0;
-#pragma unroll
-                            for (int w = 0; w < NW; ++w) if (w == idw) cw = cand[w];
-                            const int idb = __ffs((int)cw) - 1;
-                            id = 32 * idw + idb;
-                            if (id > 0) {
-                                u32 below[NW];
-#pragma unroll
-                                for (int w = 0; w < NW; ++w) below[w] = w < idw ? 0xFFFFFFFFu : (w == idw ? ((1u << idb) - 1u) : 0u);
-                                int pbest = 0;
-#pragma unroll
-                                for (int pl = TILE_PLANES - 1; pl >= 0; --pl) {
-                                    u32 tsel[NW], any = 0;
-#pragma unroll
-                                    for (int w = 0; w < NW; ++w) { tsel[w] = below[w] & P[pl][w]; any |= tsel[w]; }
-                                    if (any) {
-                                        pbest |= 1 << pl;
-#pragma unroll
-                                        for (int w = 0; w < NW; ++w) below[w] = tsel[w];
+                                        for (int pl = 0; pl < TILE_PLANES; ++pl) { const u32 tt = P[pl][w] & cy; P[pl][w] ^= cy; cy = tt; }
+                                        carry_out |= cy;
                                     }
                                 }
-                                prev = pbest;
+                        }
+                        if (carry_out) give_up = true;           // some count reached 2^TILE_PLANES
+                        else {
+                            // ---- 4: first index of the maximum, and the maximum before it --------------------------------
+                            u32 cand[NW];
+#pragma unroll
+                            for (int w = 0; w < NW; ++w) cand[w] = 0xFFFFFFFFu;
+#pragma unroll
+                            for (int pl = TILE_PLANES - 1; pl >= 0; --pl) {
+                                u32 tsel[NW], any = 0;
+#pragma unroll
+                                for (int w = 0; w < NW; ++w) { tsel[w] = cand[w] & P[pl][w]; any |= tsel[w]; }
+                                if (any) {
+                                    best |= 1 << pl;
+#pragma unroll
+                                    for (int w = 0; w < NW; ++w) cand[w] = tsel[w];
+                                }
+                            }
+                            if (best > 0) {
+                                int idw = 0;
+#pragma unroll
+                                for (int w = NW - 1; w >= 0; --w) if (cand[w]) idw = w;
+                                u32 cw = 0;
+#pragma unroll
+                                for (int w = 0; w < NW; ++w) if (w == idw) cw = cand[w];
+                                const int idb = __ffs((int)cw) - 1;
+                                id = 32 * idw + idb;
+                                if (id > 0) {
+                                    u32 below[NW];
+#pragma unroll
+                                    for (int w = 0; w < NW; ++w) below[w] = w < idw ? 0xFFFFFFFFu : (w == idw ? ((1u << idb) - 1u) : 0u);
+                                    int pbest = 0;
+#pragma unroll
+                                    for (int pl = TILE_PLANES - 1; pl >= 0; --pl) {
+                                        u32 tsel[NW], any = 0;
+#pragma unroll
+                                        for (int w = 0; w < NW; ++w) { tsel[w] = below[w] & P[pl][w]; any |= tsel[w]; }
+                                        if (any) {
+                                            pbest |= 1 << pl;
+#pragma unroll
+                                            for (int w = 0; w < NW; ++w) below[w] = tsel[w];
+                                        }
+                                    }
+                                    prev = pbest;
+                                }
                             }
                         }
                     }
                 }
                 if (give_up) redo[atomicAdd(redo_count, 1)] = (int)rid;
-                else { Hit hh; hh.ref_id = id; hh.best = best; hh.prev = prev; hh.sketch_len = (int)nz; out[rid] = hh; }
+                else { Hit hh; hh.ref_id = id; hh.best = best; hh.prev = prev; hh.sketch_len = n - ninv; out[rid] = hh; }
             }
             __syncthreads();                                 // the tile is reused by the next run
             r += m;

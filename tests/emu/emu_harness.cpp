@@ -224,9 +224,9 @@ int emu_classify(const char* ref_bases, const i64* ref_offs, int nrefs, const ch
 
 // ---- memoised path (rk_memo.cuh) -------------------------------------------------------------------------
 struct HostMemo {
-    std::vector<u32> tab, tab2, ref, tmp, sieve;
+    std::vector<u32> tab, ref, tmp, sieve, sieve_t;
     std::vector<unsigned long long> cmap;
-    u32 stats[2] = {0, 0};
+    u32 stats[2] = {0, 0}, stats_t[2] = {0, 0};
     std::vector<u64> hash;
     std::vector<int> code_counts;
     unsigned long long inval = 0;
@@ -238,7 +238,7 @@ static void build_memo(HostMemo& hm, int k, const RefTable& tb, int block) {
     const u32 ncodes = 1u << (2 * k);
     const int bucket_bits = std::max(2 * k - 8, 0);
     const u32 nb = 1u << bucket_bits;
-    hm.tab.assign(ncodes, 0); hm.tab2.assign(ncodes, 0); hm.ref.assign(ncodes, 0); hm.hash.assign(ncodes, 0); hm.code_counts.assign(ncodes, 0);
+    hm.tab.assign(ncodes, 0); hm.ref.assign(ncodes, 0); hm.hash.assign(ncodes, 0); hm.code_counts.assign(ncodes, 0);
     hm.tmp.assign((size_t)3 * nb + ncodes, 0);
     u32* bcount = hm.tmp.data(); u32* bstart = bcount + nb; u32* bfill = bstart + nb; u32* bcodes = bfill + nb;
     u64* hash = hm.hash.data(); u32* tab = hm.tab.data(); u32* ref = hm.ref.data(); int* err = &hm.err;
@@ -249,10 +249,9 @@ static void build_memo(HostMemo& hm, int k, const RefTable& tb, int block) {
     emu::launch(dim3(1), dim3(1024), 0, [=] { memo_scan_kernel(bcount, bstart, bfill, nb, err); });
     emu::launch(dim3(2), dim3(block), 0, [=] { memo_scatter_kernel(ncodes, hash, bstart, bfill, bcodes, bucket_bits); });
     emu::launch(dim3(2), dim3(block), 0, [=] { memo_rank_kernel(hash, bcount, bstart, bcodes, nb, tb, tab, ref); });
-    hm.mm.tab = tab; hm.mm.tab2 = hm.tab2.data(); hm.mm.ref = ref; hm.mm.hash = hash; hm.mm.code_counts = hm.code_counts.data();
+    hm.mm.tab = tab; hm.mm.ref = ref; hm.mm.hash = hash; hm.mm.code_counts = hm.code_counts.data();
     hm.mm.inval = &hm.inval; hm.mm.ncodes = ncodes; hm.mm.kmask = (1u << k) - 1u; hm.mm.k = k;
     Memo mm = hm.mm;
-    emu::launch(dim3(2), dim3(block), 0, [=] { memo_tab2_kernel(mm); });
     // sieve + code map (classify_memo_sieve_kernel); a small sieve so that false positives do occur in the tests
     if (tb.entries != nullptr) {
         const u32 nwords = 257;
@@ -266,6 +265,11 @@ static void build_memo(HostMemo& hm, int k, const RefTable& tb, int block) {
         emu::launch(dim3(2), dim3(block), 0, [=] { memo_cmap_kernel(mm, cmap, cap - 1, 32 - log2cap); });
         hm.mm.sieve = sieve; hm.mm.sieve_words = nwords; hm.mm.cmap = cmap; hm.mm.cmap_mask = cap - 1; hm.mm.cmap_shift = 32 - log2cap;
         hm.mm.zero_codes = hm.stats[1];
+        const u32 nwt = 193;
+        hm.sieve_t.assign(nwt, 0);
+        u32* sieve_t = hm.sieve_t.data(); u32* stats_t = hm.stats_t;
+        emu::launch(dim3(2), dim3(block), 0, [=] { memo_sieve_kernel(mm, sieve_t, nwt, stats_t); });
+        hm.mm.sieve_t = sieve_t; hm.mm.sieve_t_words = nwt;
     }
 }
 
@@ -307,7 +311,8 @@ int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, con
     std::vector<int> redo((size_t)std::max<i64>(nreads, 1)); int redo_count = 0;
     int* predo = redo.data(); int* pcount = &redo_count;
     const int grid = 2;
-    if (path == 3 && tb.nb <= 4) {       // thread per read (tile kernel)
+    if (path == 3 && tb.nb <= 4 && mm.sieve_t != nullptr && mm.zero_codes == 0 && min_occ < 0) {       // thread per read (tile kernel)
+        const size_t TILE_SMEM = TILE_FIXED_SMEM + (size_t)mm.sieve_t_words * 4;
         switch (tb.nb) {
             case 1: emu::launch(dim3(grid), dim3(TILE_THREADS), TILE_SMEM, [=] { classify_memo_tile_kernel<2>(sb, s, mm, tb, predo, pcount, out); }); break;
             case 2: emu::launch(dim3(grid), dim3(TILE_THREADS), TILE_SMEM, [=] { classify_memo_tile_kernel<4>(sb, s, mm, tb, predo, pcount, out); }); break;
@@ -323,7 +328,7 @@ int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, con
             case 3: emu::launch(dim3(grid), dim3(block), smem, [=] { classify_memo_sieve_kernel<6>(sb, s, mm, tb, predo, pcount, out); }); break;
             default: emu::launch(dim3(grid), dim3(block), smem, [=] { classify_memo_sieve_kernel<8>(sb, s, mm, tb, predo, pcount, out); }); break;
         }
-    } else if ((path == 1 || path == 4) && tb.nb <= 4) {
+    } else if ((path == 1 || path == 4 || path == 3) && tb.nb <= 4) {
         // (path 1: the register-row warp kernel for <= 256 references)
         switch (tb.nb) {
             case 1: emu::launch(dim3(grid), dim3(block), 0, [=] { classify_memo_warp_kernel<2>(sb, s, mm, tb, predo, pcount, out); }); break;

@@ -285,7 +285,7 @@ def test_memo_path_is_taken_and_matches_murmur(oracle, variant, monkeypatch):
     res = {}
     # the three short-read kernels: shared-memory sieve (default), rank-table warp kernel, thread-per-read tile kernel
     monkeypatch.setenv("RKMH_TILE", "1" if variant == "tile" else "0")
-    monkeypatch.setenv("RKMH_NO_SIEVE", "0" if variant == "sieve" else "1")
+    monkeypatch.setenv("RKMH_NO_SIEVE", "1" if variant == "warp" else "0")
     short_kernel = f"classify_memo_{variant}_kernel"
     for memo in (True, False):
         with rkmh_b200.RkmhGpu(0) as g:
@@ -306,7 +306,7 @@ def test_memo_path_is_taken_and_matches_murmur(oracle, variant, monkeypatch):
             out.append(_fields(g.classify_batch(sb, so)))          # -M off again: FAILM flags cleared
             names = set(g.profile_read())
             assert (short_kernel in names) == memo and ("classify_group_kernel" in names) == (not memo)
-            if memo and variant == "sieve":                    # -M bakes FAILM flags: those passes take the rank-table kernel
+            if memo and variant != "warp":                     # -M bakes FAILM flags: those passes take the rank-table kernel
                 assert "classify_memo_warp_kernel" in names
             assert ("count_memo_kernel" in names) == memo
             res[memo] = out
