@@ -738,7 +738,7 @@ int rkg_set_params(rkg_ctx* ctx, const int* ks, int nk, int sketch_size, uint64_
 int rkg_host_alloc(rkg_ctx* ctx, size_t bytes, void** ptr) {
     if (!ctx || !ptr) return RKG_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    CK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
     return RKG_OK;
 }
 

@@ -23,7 +23,11 @@ namespace rkhost {
 
 class ByteStream {
   public:
-    explicit ByteStream(const char* path) : buf_(1 << 20) { fp_ = gzopen(path, "r"); if (fp_) gzbuffer(fp_, 1 << 20); }
+    // "-" reads standard input (gzip or plain, like any other path)
+    explicit ByteStream(const char* path) : buf_(1 << 20) {
+        fp_ = (path[0] == '-' && path[1] == 0) ? gzdopen(0, "r") : gzopen(path, "r");
+        if (fp_) gzbuffer(fp_, 1 << 20);
+    }
     ~ByteStream() { if (fp_) gzclose(fp_); }
     bool ok() const { return fp_ != nullptr; }
     int get() {
@@ -52,46 +56,58 @@ struct SeqSet {
     size_t size() const { return names.size(); }
 };
 
+// One record at a time; the state machine of the header comment above.  `next` returns false at the end of the file
+// (or at a truncated quality string, where the reference stops too).
+class FastxReader {
+  public:
+    explicit FastxReader(const char* path) : in_(path) {
+        if (!in_.ok()) return;
+        c_ = in_.get();
+        while (c_ != -1 && c_ != '>' && c_ != '@') c_ = in_.get();
+    }
+    bool ok() const { return in_.ok(); }
+    bool next(std::string& name, std::string& seq, std::string& qual) {
+        if (c_ == -1) return false;                      // c_ is the header byte of the current record
+        name.clear(); seq.clear(); qual.clear();
+        int c = in_.get();
+        while (c != -1 && !isspace(c)) { name.push_back((char)c); c = in_.get(); }
+        while (c != -1 && c != '\n') c = in_.get();      // comment
+        c = in_.get();
+        while (c != -1 && c != '>' && c != '+' && c != '@') {
+            if (isgraph(c)) seq.push_back((char)c);
+            c = in_.get();
+        }
+        if (c == '+') {
+            c = in_.get();
+            while (c != -1 && c != '\n') c = in_.get();  // rest of the '+' line
+            if (c == -1) { c_ = -1; return false; }
+            c = in_.get();
+            while (c != -1 && qual.size() < seq.size()) {
+                if (c >= 33 && c <= 127) qual.push_back((char)c);
+                c = in_.get();                           // note: one byte past the last quality byte is consumed
+            }
+            if (qual.size() != seq.size()) { c_ = -1; return false; }
+            c = in_.get();                               // the byte after the quality string is dropped unseen
+            while (c != -1 && c != '>' && c != '@') c = in_.get();
+        }
+        c_ = c;
+        return true;
+    }
+  private:
+    ByteStream in_;
+    int c_ = -1;
+};
+
 // Appends every record of `path` to `out`.  Returns false when the file cannot be opened.
 inline bool read_fastx(const char* path, SeqSet& out, bool keep_qual) {
-    ByteStream in(path);
-    if (!in.ok()) return false;
-    int c = in.get();
-    while (c != -1 && c != '>' && c != '@') c = in.get();
-    std::string name, qual;
-    while (c != -1) {                                   // c is the header byte of the current record
-        name.clear();
-        c = in.get();
-        while (c != -1 && !isspace(c)) { name.push_back((char)c); c = in.get(); }
-        while (c != -1 && c != '\n') c = in.get();       // comment
-        const size_t start = out.bases.size();
-        c = in.get();
-        while (c != -1 && c != '>' && c != '+' && c != '@') {
-            if (isgraph(c)) out.bases.push_back((char)c);
-            c = in.get();
-        }
-        const size_t len = out.bases.size() - start;
-        if (c == '+') {
-            c = in.get();
-            while (c != -1 && c != '\n') c = in.get();   // rest of the '+' line
-            if (c == -1) { out.bases.resize(start); return true; }
-            qual.clear();
-            c = in.get();
-            while (c != -1 && qual.size() < len) {
-                if (c >= 33 && c <= 127) qual.push_back((char)c);
-                c = in.get();                            // note: one byte past the last quality byte is consumed
-            }
-            if (qual.size() != len) { out.bases.resize(start); return true; }
-            out.names.push_back(name);
-            out.offs.push_back((int64_t)out.bases.size());
-            if (keep_qual) out.quals.push_back(qual);
-            c = in.get();                                // the byte after the quality string is dropped unseen
-            while (c != -1 && c != '>' && c != '@') c = in.get();
-        } else {
-            out.names.push_back(name);
-            out.offs.push_back((int64_t)out.bases.size());
-            if (keep_qual) out.quals.emplace_back();
-        }
+    FastxReader rd(path);
+    if (!rd.ok()) return false;
+    std::string name, seq, qual;
+    while (rd.next(name, seq, qual)) {
+        out.bases.insert(out.bases.end(), seq.begin(), seq.end());
+        out.offs.push_back((int64_t)out.bases.size());
+        out.names.push_back(name);
+        if (keep_qual) out.quals.push_back(qual);
     }
     return true;
 }

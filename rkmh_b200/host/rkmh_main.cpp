@@ -4,13 +4,25 @@
 // sharding of read chunks over the GPUs of the box, and formatting of the reference's exact output lines.
 // Every arithmetic step of the hot path runs in the CUDA library; there is no CPU fallback.
 //
+// Reads are STREAMED: a parser thread fills chunks of pinned host memory (RKMH_CHUNK_MB, default 64 MB of bases each),
+// one worker thread per GPU pushes chunks through rkg_count_batch / rkg_classify_batch, and the main thread writes
+// the results in input order, so host memory stays bounded whatever the input size (the reference loads every read
+// first, src/rkmh.cpp:238-292).  `-f -` reads standard input.  With -M the read files are streamed twice (pass 1
+// counts, pass 2 classifies); only when a read file is standard input are the reads buffered instead.
+//
 // Extra, non-reference option: -g/--gpus N (default: RKMH_GPUS or 1) shards reads over N GPUs.  -t is accepted
 // and ignored (the reference's OpenMP thread count).
 #include <getopt.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
+#include <functional>
+#include <map>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -211,6 +223,170 @@ std::vector<rkg_hit> classify_all(Fleet& fl, const Options& o, const SeqSet& rea
     return hits;
 }
 
+// ---- streaming pipeline -----------------------------------------------------------------------------------
+// One chunk of reads in pinned host memory, in the layout the C ABI takes.
+struct Chunk {
+    char* bases = nullptr; int64_t* offs = nullptr; rkg_hit* hits = nullptr;
+    size_t cap_bases = 0, cap_reads = 0, nreads = 0;
+    std::vector<char> big;                 // a single record larger than cap_bases goes here (pageable)
+    std::vector<std::string> names, quals;
+    uint64_t seq = 0;                      // position of the chunk in the input order
+    std::string out;                       // formatted result lines
+    const char* data() const { return big.empty() ? bases : big.data(); }
+    void reset(uint64_t s) { nreads = 0; offs[0] = 0; big.clear(); big.shrink_to_fit(); names.clear(); quals.clear(); out.clear(); seq = s; }
+};
+
+template <typename T> class Channel {      // unbounded MPMC queue; the chunk pool bounds what is in flight
+  public:
+    void push(T v) { { std::lock_guard<std::mutex> g(m_); q_.push_back(v); } cv_.notify_one(); }
+    T pop() { std::unique_lock<std::mutex> g(m_); cv_.wait(g, [&] { return !q_.empty(); }); T v = q_.front(); q_.pop_front(); return v; }
+  private:
+    std::mutex m_; std::condition_variable cv_; std::deque<T> q_;
+};
+
+struct ChunkPool {
+    rkg_ctx* owner = nullptr;
+    std::vector<Chunk*> all;
+    Channel<Chunk*> free_q;
+    void open(rkg_ctx* ctx, int n, size_t cap_bases) {
+        owner = ctx;
+        const size_t cap_reads = std::max<size_t>(cap_bases / 32, 1024);
+        for (int i = 0; i < n; ++i) {
+            Chunk* c = new Chunk();
+            void *pb = nullptr, *po = nullptr, *ph = nullptr;
+            RK(ctx, rkg_host_alloc(ctx, cap_bases, &pb));
+            RK(ctx, rkg_host_alloc(ctx, sizeof(int64_t) * (cap_reads + 1), &po));
+            RK(ctx, rkg_host_alloc(ctx, sizeof(rkg_hit) * cap_reads, &ph));
+            c->bases = (char*)pb; c->offs = (int64_t*)po; c->hits = (rkg_hit*)ph;
+            c->cap_bases = cap_bases; c->cap_reads = cap_reads;
+            all.push_back(c);
+            free_q.push(c);
+        }
+    }
+    ~ChunkPool() {
+        for (Chunk* c : all) { rkg_host_free(owner, c->bases); rkg_host_free(owner, c->offs); rkg_host_free(owner, c->hits); delete c; }
+    }
+};
+
+size_t chunk_bytes() {
+    if (const char* b = getenv("RKMH_CHUNK_BYTES")) return (size_t)std::max<long>(atol(b), 64);   // testing knob
+    const char* e = getenv("RKMH_CHUNK_MB");
+    const long mb = e ? atol(e) : 64;
+    return (size_t)std::max<long>(mb, 1) << 20;
+}
+
+// Streams every record of `files` through `work` (called on one worker thread per GPU, any order) and then through
+// `emit` (called on the calling thread, in input order).  Returns the number of records.
+uint64_t stream_reads(Fleet& fl, ChunkPool& pool, const std::vector<const char*>& files, bool keep_qual,
+                      const std::function<void(int, rkg_ctx*, Chunk&)>& work, const std::function<void(Chunk&)>& emit) {
+    Channel<Chunk*> work_q;
+    std::mutex dm; std::condition_variable dcv; std::map<uint64_t, Chunk*> done;
+    std::atomic<int64_t> total_chunks{-1};
+    uint64_t nrecords = 0;
+    std::thread reader([&] {
+        uint64_t seq = 0;
+        Chunk* cur = nullptr;
+        std::string name, sq, qual;
+        for (const char* f : files) {
+            rkhost::FastxReader rd(f);
+            if (!rd.ok()) { fprintf(stderr, "rkmh: cannot open %s\n", f); exit(2); }
+            while (rd.next(name, sq, qual)) {
+                ++nrecords;
+                if (cur && (cur->nreads >= cur->cap_reads || !cur->big.empty() ||
+                            (size_t)cur->offs[cur->nreads] + sq.size() > cur->cap_bases)) { work_q.push(cur); cur = nullptr; }
+                if (!cur) { cur = pool.free_q.pop(); cur->reset(seq++); }
+                const size_t at = (size_t)cur->offs[cur->nreads];
+                if (sq.size() > cur->cap_bases) cur->big.assign(sq.begin(), sq.end());      // alone in its chunk
+                else memcpy(cur->bases + at, sq.data(), sq.size());
+                cur->offs[++cur->nreads] = (int64_t)(at + sq.size());
+                cur->names.push_back(name);
+                if (keep_qual) cur->quals.push_back(qual);
+            }
+        }
+        if (cur) work_q.push(cur);
+        total_chunks = (int64_t)seq;
+        for (size_t d = 0; d < fl.ctx.size(); ++d) work_q.push(nullptr);
+        dcv.notify_all();
+    });
+    std::vector<std::thread> workers;
+    for (size_t d = 0; d < fl.ctx.size(); ++d)
+        workers.emplace_back([&, d] {
+            for (;;) {
+                Chunk* c = work_q.pop();
+                if (!c) break;
+                work((int)d, fl.ctx[d], *c);
+                { std::lock_guard<std::mutex> g(dm); done[c->seq] = c; }
+                dcv.notify_all();
+            }
+        });
+    for (uint64_t next = 0;; ++next) {
+        Chunk* c = nullptr;
+        {
+            std::unique_lock<std::mutex> g(dm);
+            dcv.wait(g, [&] { return done.count(next) || (total_chunks >= 0 && (int64_t)next >= total_chunks); });
+            auto it = done.find(next);
+            if (it == done.end()) break;
+            c = it->second; done.erase(it);
+        }
+        emit(*c);
+        pool.free_q.push(c);
+    }
+    reader.join();
+    for (auto& w : workers) w.join();
+    return nrecords;
+}
+
+bool any_stdin(const std::vector<const char*>& files) {
+    for (const char* f : files) if (f[0] == '-' && f[1] == 0) return true;
+    return false;
+}
+
+// The classification of every read of `files`, streamed; `format` turns a classified chunk into output lines.
+void run_streamed(Fleet& fl, const Options& o, bool keep_qual, bool count_zeros,
+                  const std::function<void(Chunk&)>& format) {
+    ChunkPool pool;
+    pool.open(fl.ctx[0], 2 * (int)fl.ctx.size() + 2, chunk_bytes());
+    const auto write_out = [](Chunk& c) { fwrite(c.out.data(), 1, c.out.size(), stdout); };
+    if (o.do_read_depth) {                              // pass 1: global k-mer count table (src/rkmh.cpp:904-910)
+        fl.each([&](int, rkg_ctx* c) { RK(c, rkg_count_reset(c)); });
+        stream_reads(fl, pool, o.reads, false,
+                     [&](int, rkg_ctx* c, Chunk& ch) { RK(c, rkg_count_batch(c, ch.data(), ch.offs, (int64_t)ch.nreads, count_zeros)); },
+                     [](Chunk&) {});
+        allreduce_counts(fl);
+    }
+    stream_reads(fl, pool, o.reads, keep_qual,
+                 [&](int, rkg_ctx* c, Chunk& ch) {
+                     RK(c, rkg_classify_batch(c, ch.data(), ch.offs, (int64_t)ch.nreads, o.do_read_depth ? o.min_occ : -1, ch.hits));
+                     format(ch);
+                 },
+                 write_out);
+}
+
+// result line of stream / classify: src/rkmh.cpp:884-893
+void format_stream_line(std::string& out, const Options& o, const SeqSet& refs, const std::string& read_name, const rkg_hit& h) {
+    const int diff = h.best - h.prev;
+    const bool depth_fail = h.sketch_len <= o.min_matches, match_fail = h.best < o.min_matches, diff_ok = diff > o.min_diff;
+    out += refs.names[h.ref_id]; out += '\t'; out += read_name; out += '\t';
+    append_int(out, h.best); out += '\t'; append_int(out, o.sketch);
+    if (depth_fail) out += "FAIL:DEPTH";
+    out += '\t'; if (match_fail) out += "FAIL:MATCHES";
+    out += '\t'; if (!diff_ok) out += "FAIL:DIFF";
+    out += '\n';
+}
+
+// record of filter: src/rkmh.cpp:1289-1309, src/equiv.hpp:328-352
+void format_filter_record(std::string& out, const Options& o, const std::string& name, const char* s, int64_t L,
+                          const std::string& qual, const rkg_hit& h) {
+    const int best = std::max(h.best, 0), prev = std::max(h.prev, 0);
+    if (!(h.sketch_len > 0) || best < o.min_matches || !(best - prev > o.min_diff)) return;
+    out += '>'; out += name; out += '\n';
+    for (int64_t j = 0; j < L; ++j) {
+        signed char ch = (signed char)s[j];
+        out += (char)((int)ch - 91 > 0 ? ch - 32 : ch);          // to_upper, mkmh.hpp:231-236
+    }
+    out += "\n+\n"; out += qual; out += '\n';
+}
+
 // ---- stream / classify: src/rkmh.cpp:584-989 ------------------------------------------------------------
 int main_stream(int argc, char** argv) {
     if (argc <= 2) { usage(argv[0]); exit(1); }
@@ -218,25 +394,24 @@ int main_stream(int argc, char** argv) {
     const char* env = getenv("RKMH_GPUS");
     if (env) o.gpus = atoi(env);
     parse_common(argc, argv, o, "zmhdk:f:r:s:S:t:M:N:I:R:F:p:q:iD:g:");
-    SeqSet refs, reads;
+    SeqSet refs;
     load_all(o.refs, refs, false);
-    load_all(o.reads, reads, false);
     if (refs.size() == 0) { fprintf(stderr, "rkmh: no reference sequences (the reference binary is undefined here)\n"); return 2; }
     Fleet fl; fl.open(std::max(1, o.gpus));
     setup_refs(fl, o, refs, STREAM_TABLE, false);
+    if (!(o.do_read_depth && any_stdin(o.reads))) {
+        run_streamed(fl, o, false, false, [&](Chunk& c) {
+            for (size_t i = 0; i < c.nreads; ++i) format_stream_line(c.out, o, refs, c.names[i], c.hits[i]);
+        });
+        return 0;
+    }
+    SeqSet reads;                                        // -M on standard input: two passes need the reads twice
+    load_all(o.reads, reads, false);
     std::vector<rkg_hit> hits = classify_all(fl, o, reads, false);
     std::string out;
     out.reserve(1 << 22);
-    for (size_t i = 0; i < reads.size(); ++i) {          // src/rkmh.cpp:884-893
-        const rkg_hit& h = hits[i];
-        const int diff = h.best - h.prev;
-        const bool depth_fail = h.sketch_len <= o.min_matches, match_fail = h.best < o.min_matches, diff_ok = diff > o.min_diff;
-        out += refs.names[h.ref_id]; out += '\t'; out += reads.names[i]; out += '\t';
-        append_int(out, h.best); out += '\t'; append_int(out, o.sketch);
-        if (depth_fail) out += "FAIL:DEPTH";
-        out += '\t'; if (match_fail) out += "FAIL:MATCHES";
-        out += '\t'; if (!diff_ok) out += "FAIL:DIFF";
-        out += '\n';
+    for (size_t i = 0; i < reads.size(); ++i) {
+        format_stream_line(out, o, refs, reads.names[i], hits[i]);
         if (out.size() > (1 << 22) - 4096) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
     }
     fwrite(out.data(), 1, out.size(), stdout);
@@ -250,25 +425,25 @@ int main_filter(int argc, char** argv) {
     const char* env = getenv("RKMH_GPUS");
     if (env) o.gpus = atoi(env);
     parse_common(argc, argv, o, "hdk:f:r:s:S:t:M:N:I:R:F:p:q:iD:g:");
-    SeqSet refs, reads;
+    SeqSet refs;
     load_all(o.refs, refs, false);
-    load_all(o.reads, reads, true);
     if (refs.size() == 0) { fprintf(stderr, "rkmh: no reference sequences\n"); return 2; }
     Fleet fl; fl.open(std::max(1, o.gpus));
     setup_refs(fl, o, refs, FILTER_TABLE, true);
+    if (!(o.do_read_depth && any_stdin(o.reads))) {
+        run_streamed(fl, o, true, true, [&](Chunk& c) {
+            for (size_t i = 0; i < c.nreads; ++i)
+                format_filter_record(c.out, o, c.names[i], c.data() + c.offs[i], c.offs[i + 1] - c.offs[i], c.quals[i], c.hits[i]);
+        });
+        return 0;
+    }
+    SeqSet reads;
+    load_all(o.reads, reads, true);
     std::vector<rkg_hit> hits = classify_all(fl, o, reads, true);
     std::string out;
-    for (size_t i = 0; i < reads.size(); ++i) {          // src/rkmh.cpp:1289-1309, src/equiv.hpp:328-352
-        const rkg_hit& h = hits[i];
-        const int best = std::max(h.best, 0), prev = std::max(h.prev, 0);
-        if (!(h.sketch_len > 0) || best < o.min_matches || !(best - prev > o.min_diff)) continue;
-        out += '>'; out += reads.names[i]; out += '\n';
-        const char* s = reads.bases.data() + reads.offs[i];
-        for (int64_t j = 0, L = reads.offs[i + 1] - reads.offs[i]; j < L; ++j) {
-            signed char ch = (signed char)s[j];
-            out += (char)((int)ch - 91 > 0 ? ch - 32 : ch);      // to_upper, mkmh.hpp:231-236
-        }
-        out += "\n+\n"; out += reads.quals[i]; out += '\n';
+    for (size_t i = 0; i < reads.size(); ++i) {
+        format_filter_record(out, o, reads.names[i], reads.bases.data() + reads.offs[i], reads.offs[i + 1] - reads.offs[i],
+                             reads.quals[i], hits[i]);
         if (out.size() > (1 << 22)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
     }
     fwrite(out.data(), 1, out.size(), stdout);

@@ -108,3 +108,33 @@ def test_two_gpus_same_output(rkmh_bin, cli_manifest):
         res = subprocess.run([rkmh_bin] + argv + ["-g", "2"], cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         assert res.returncode == 0, res.stderr.decode()[-400:]
         assert hashlib.md5(res.stdout).hexdigest() == cli_manifest[name]["md5"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["pave_mix2k_k12_s100", "newrefs_mix2k_M20_N10", "filter_viral4_z1_M2_D2", "pave_minion_k12",
+                                  "awkward_k8"])
+def test_streaming_chunks_do_not_change_stdout(rkmh_bin, cli_manifest, name):
+    """The reads are streamed through small pinned chunks (here 20 kB: hundreds of chunks, records larger than a
+    chunk, two passes over the files with -M) and written in input order: stdout is the reference's, byte for byte."""
+    _, argv = CLI_CASES[name]
+    env = dict(os.environ, RKMH_CHUNK_BYTES="20000")
+    res = subprocess.run([rkmh_bin] + argv, cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    assert res.returncode == 0, res.stderr.decode()[-400:]
+    assert hashlib.md5(res.stdout).hexdigest() == cli_manifest[name]["md5"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["pave_z1_k12", "filter_zika_z1_N5", "hpv16_minion_M2_N10"])
+def test_reads_from_standard_input(rkmh_bin, cli_manifest, name):
+    """`-f -` streams the reads from standard input (gzip or plain); with -M they are buffered for the second pass."""
+    _, argv = CLI_CASES[name]
+    i = argv.index("-f")
+    reads = os.path.join(DATA, argv[i + 1])
+    argv = argv[:i + 1] + ["-"] + argv[i + 2:]
+    with open(reads, "rb") as fh:
+        res = subprocess.run([rkmh_bin] + argv, cwd=DATA, stdin=fh, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert res.returncode == 0, res.stderr.decode()[-400:]
+    assert hashlib.md5(res.stdout).hexdigest() == cli_manifest[name]["md5"]
+    plain = gzip.open(reads, "rb").read()
+    res = subprocess.run([rkmh_bin] + argv, cwd=DATA, input=plain, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert res.returncode == 0 and hashlib.md5(res.stdout).hexdigest() == cli_manifest[name]["md5"]
