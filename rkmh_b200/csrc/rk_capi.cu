@@ -440,7 +440,7 @@ MemoGeom memo_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
     // block kernel: [vcap values][MEMO_BINS histogram][2 hs_cap hit set][rpad counters] in u32, two blocks per SM
     g.hs_cap = next_pow2(2 * (i64)std::min<i64>(ctx->s, std::max<i64>(b->max_ntotal, 1)));
     g.rpad = (ctx->nrefs + 63) / 64 * 64;
-    const size_t budget = ctx->smem_optin / 2 - 2048;
+    const size_t budget = ctx->smem_optin / 2 - 4608;      // two blocks per SM: static scratch + hit rings + the 1 KB reserve
     const size_t fixed = 4 * ((size_t)MEMO_BINS + 2 * (size_t)g.hs_cap + (size_t)g.rpad);
     if (fixed + 4096 > budget) return g;
     const i64 room = (i64)((budget - fixed) / 4);

@@ -27,7 +27,8 @@ constexpr int MEMO_MAX_K = 12;
 constexpr u32 MEMO_REF = 1u, MEMO_ZERO = 2u, MEMO_FAILM = 4u;
 constexpr u32 MEMO_SKIP = 0xFFFFFFFFu;          // "window does not count": never a real entry (5 flag bits unused)
 constexpr int MEMO_BUCKET_CAP = 1024;           // rank build: largest hash bucket that is sorted in shared memory
-constexpr int MEMO_BINS = 4096;                 // radix-select histogram (12 bits of the 24-bit rank per level)
+constexpr int MEMO_BINS = 4096;
+constexpr int MEMO_RING = 64;                   // block kernel: per-warp ring of sketch members waiting for their rows                 // radix-select histogram (12 bits of the 24-bit rank per level)
 
 struct Memo {
     u32* tab;                       // indexed by the plane code (warp-streaming kernels)
@@ -817,7 +818,8 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
                 u32 kbest = 0;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) {
-                    cnt[w] = (u32)__popc(tr32(x[w], tl));
+                    cnt[w] = 0;                              // a word no hit touches (warp-uniform test) needs no transpose
+                    if (__any_sync(0xffffffffu, x[w] != 0u)) cnt[w] = (u32)__popc(tr32(x[w], tl));
                     kbest = max(kbest, (cnt[w] << 8) | (255u - (u32)(32 * w + lane)));
                 }
                 kbest = warp_max(kbest);
@@ -1191,6 +1193,7 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
     extern __shared__ __align__(16) unsigned char dsm[];
 #endif
     __shared__ MemoBlockScratch bs;
+    __shared__ u32 wq[8][MEMO_RING];                         // per-warp ring of hit ranks (blocks of 256 threads)
     u32* vals_smem = reinterpret_cast<u32*>(dsm);
     u32* hist = vals_smem + vcap;
     u32* hs_keys = hist + MEMO_BINS;
@@ -1263,27 +1266,28 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
 #pragma unroll
             for (int pl = 0; pl < 5; ++pl) { vp[pl][0] = 0; vp[pl][1] = 0; }
         };
-        for (i64 i0 = (i64)wib * 32; i0 < n; i0 += (i64)nwb * 32) {
-            const i64 i = i0 + lane;
-            const u32 m = i < n ? V[i] : MEMO_SKIP;
+        // The scan over the read's windows only picks the REF members of the sketch (a few per cent of the windows of a
+        // long read) and compacts their ranks into a per-warp ring; rows are resolved 32 hits at a time, all lanes busy.
+        u32* ring = wq[wib];
+        int qhead = 0, qn = 0;
+        const u32 ltm = (1u << lane) - 1u;
+        auto drain = [&](int cnt) {                          // resolve the first cnt (<= 32) queued ranks
             const u64* row = nullptr;
-            if (m != MEMO_SKIP) {
-                const u32 rank = m >> 8;
-                const bool member = rank < T || (rank == T && atomicAdd(&bs.take, 1) < need);
-                if (member && (m & MEMO_REF)) {
-                    const u32 key = mm.ref[rank];                // slot + 1
-                    u32 p = (key * 0x9E3779B1u) & hs_mask;
-                    for (;;) {
-                        const u32 old = atomicCAS(&hs_keys[p], 0u, key);
-                        if (old == 0u || old == key) break;
-                        p = (p + 1) & hs_mask;
-                    }
-                    row = table_row(tb, (int)key - 1, atomicAdd(&hs_cnt[p], 1u));
+            if (lane < cnt) {
+                const u32 key = mm.ref[ring[(qhead + lane) & (MEMO_RING - 1)]];          // slot + 1
+                u32 p = (key * 0x9E3779B1u) & hs_mask;
+                for (;;) {
+                    const u32 old = atomicCAS(&hs_keys[p], 0u, key);
+                    if (old == 0u || old == key) break;
+                    p = (p + 1) & hs_mask;
                 }
+                row = table_row(tb, (int)key - 1, atomicAdd(&hs_cnt[p], 1u));
             }
+            qhead = (qhead + cnt) & (MEMO_RING - 1);
+            qn -= cnt;
             if (small) {
                 // <= 64 references: every lane adds its row into private bit-sliced counters (plane p = bit p of the
-                // per-reference counts), flushed to the shared counters every 31 steps and at the end of the read
+                // per-reference counts), flushed to the shared counters every 31 batches and at the end of the read
                 if (row != nullptr) {
                     const u64 v = row[0];
                     u32 cy0 = (u32)v, cy1 = (u32)(v >> 32);
@@ -1295,10 +1299,10 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
                     }
                 }
                 if (++vsteps == 31) { flush_planes(); vsteps = 0; }
-                continue;
+                return;
             }
-            if (!__any_sync(0xffffffffu, row != nullptr)) continue;
-            // column sums of this step's rows: one shared-memory add per reference that occurs, not per set bit
+            if (!__any_sync(0xffffffffu, row != nullptr)) return;
+            // column sums of this batch's rows: one shared-memory add per reference that occurs, not per set bit
             const u32* r32 = reinterpret_cast<const u32*>(row);
             for (u32 w = 0; w < 2u * tb.nb; ++w) {
                 const u32 xw = row ? r32[w] : 0u;
@@ -1310,7 +1314,25 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
                     if (lane == 0) atomicAdd(&counts[32u * w + (u32)__ffs((int)low) - 1u], c);
                 }
             }
+        };
+        for (i64 i0 = (i64)wib * 32; i0 < n; i0 += (i64)nwb * 32) {
+            const i64 i = i0 + lane;
+            const u32 m = i < n ? V[i] : MEMO_SKIP;
+            bool hit = false;
+            if (m != MEMO_SKIP) {
+                const u32 rank = m >> 8;
+                const bool member = rank < T || (rank == T && atomicAdd(&bs.take, 1) < need);
+                hit = member && (m & MEMO_REF);
+            }
+            const u32 bal = __ballot_sync(0xffffffffu, hit);
+            if (bal) {
+                if (hit) ring[(qhead + qn + __popc(bal & ltm)) & (MEMO_RING - 1)] = m >> 8;
+                qn += __popc(bal);
+                __syncwarp();
+                if (qn >= 32) { drain(32); __syncwarp(); }
+            }
         }
+        if (qn > 0) { __syncwarp(); drain(qn); }
         if (small && vsteps) flush_planes();
         __syncthreads();
         block_argmax(counts, (int)tb.nrefs, &bs.as, &out[rid], L);
