@@ -216,7 +216,20 @@ def main_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        # NCCL may print its version banner on stdout while the communicator is built; stdout carries exactly one JSON
+        # line, so anything printed during initialisation goes to stderr instead
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+            warm = torch.zeros(1, device=f"cuda:{local_rank}")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
 

@@ -818,8 +818,7 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
                 u32 kbest = 0;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) {
-                    cnt[w] = 0;                              // a word no hit touches (warp-uniform test) needs no transpose
-                    if (__any_sync(0xffffffffu, x[w] != 0u)) cnt[w] = (u32)__popc(tr32(x[w], tl));
+                    cnt[w] = (u32)__popc(tr32(x[w], tl));
                     kbest = max(kbest, (cnt[w] << 8) | (255u - (u32)(32 * w + lane)));
                 }
                 kbest = warp_max(kbest);
