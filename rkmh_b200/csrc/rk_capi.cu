@@ -1122,46 +1122,61 @@ int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t km
     if (!ctx || !bases || !sketch || !len) return RKG_ERR_ARG;
     if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_sketch_shard before rkg_set_params");
     if (ctx->kl.nk != 1) return fail(ctx, RKG_ERR_ARG, "rkg_sketch_shard: exactly one k-mer size");
-    // The shard is cut into pieces of PIECE k-mer starts; each piece is an ordinary record whose last
-    // k-mer would be dropped by the len-k rule, so a piece carries k bases of right context, except the
-    // piece that holds the true end of the record.
+    // The shard is ONE device-resident record: its windows are hashed twice (histogram of the top 16 hash bits, then
+    // the hashes at or below the bin that holds the s-th smallest are kept and sorted).  Nothing of size n is ever
+    // materialised and nothing but the sketch comes back to the host.
     const int k = ctx->kl.k[0];
     const i64 last_start = record_len - k;            // k-mer starts [0, record_len - k) exist
     kmer_end = std::min<i64>(kmer_end, last_start);
     *len = 0;
     if (kmer_end <= kmer_begin) return RKG_OK;
-    const i64 PIECE = 1 << 20;
-    std::vector<int64_t> offs;
-    std::vector<char> buf;
-    // pieces overlap, so they are materialised into a staging buffer (k bytes of overlap per MiB)
-    for (i64 p0 = kmer_begin; p0 < kmer_end; p0 += PIECE) {
-        i64 p1 = std::min<i64>(p0 + PIECE, kmer_end);
-        i64 b0 = p0 - kmer_begin, b1 = (p1 - kmer_begin) + k;     // bytes [b0, b1): p1 - p0 starts + k
-        if (b1 > nbytes) return fail(ctx, RKG_ERR_ARG, "rkg_sketch_shard: shard buffer too short");
-        offs.push_back((int64_t)buf.size());
-        buf.insert(buf.end(), bases + b0, bases + b1);
-    }
-    offs.push_back((int64_t)buf.size());
-    const int nparts = (int)offs.size() - 1;
-    std::vector<uint64_t> parts((size_t)nparts * ctx->s);
-    std::vector<int32_t> lens(nparts);
-    int rc = rkg_sketch_batch(ctx, buf.data(), offs.data(), nparts, -1, parts.data(), lens.data());
+    const i64 n = kmer_end - kmer_begin;               // windows of this shard
+    if (n + k > nbytes) return fail(ctx, RKG_ERR_ARG, "rkg_sketch_shard: shard buffer too short");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_slots(ctx);
     if (rc) return rc;
-    // merge in groups so that one launch never holds more than 64 parts
-    while ((int)lens.size() > 1) {
-        std::vector<uint64_t> np; std::vector<int32_t> nl;
-        for (size_t i = 0; i < lens.size(); i += 64) {
-            int cnt = (int)std::min<size_t>(64, lens.size() - i);
-            std::vector<uint64_t> o(ctx->s); int32_t ol = 0;
-            rc = rkg_merge_sketches(ctx, parts.data() + i * ctx->s, lens.data() + i, cnt, o.data(), &ol);
-            if (rc) return rc;
-            np.insert(np.end(), o.begin(), o.end()); nl.push_back(ol);
+    rkg_batch* b = ctx->slots[0];
+    CK(cudaStreamSynchronize(b->stream));
+    const int64_t one[2] = {0, n + k};
+    if ((rc = batch_fill(ctx, b, bases, one, 0, 1))) return rc;
+    if ((rc = ensure_packed(ctx, b))) return rc;
+    DevBuf d_hist, d_pick, d_cand;
+    rc = RKG_OK;
+    do {
+        if (d_hist.ensure(sizeof(u32) * SHARD_BINS) || d_pick.ensure(64)) { rc = fail(ctx, RKG_ERR_NOMEM, "rkg_sketch_shard: device allocation failed"); break; }
+        cudaMemsetAsync(d_hist.p, 0, sizeof(u32) * SHARD_BINS, b->stream);
+        cudaMemsetAsync(d_pick.p, 0, 64, b->stream);
+        const int grid = ctx->sm_count * 8;
+        u64 hpick[2] = {0, 0};
+        {
+            Timed t(ctx, b->stream, K_SKETCH);
+            DISPATCH_KCSEL(ctx->kcsel, (shard_hist_kernel<KS><<<grid, 256, 0, b->stream>>>(b->codes.as<u32>(), b->nmask.as<u32>(), n, ctx->kl,
+                                                                                         d_hist.as<u32>())));
+            shard_pick_kernel<<<1, 1024, 0, b->stream>>>(d_hist.as<u32>(), (u64)ctx->s, d_pick.as<u64>());
+            ctx->launches += 2;
         }
-        parts.swap(np); lens.swap(nl);
-    }
-    *len = lens[0];
-    std::memcpy(sketch, parts.data(), sizeof(uint64_t) * (size_t)lens[0]);
-    return RKG_OK;
+        cudaMemcpyAsync(hpick, d_pick.p, sizeof(hpick), cudaMemcpyDeviceToHost, b->stream);
+        if (cudaStreamSynchronize(b->stream) != cudaSuccess) { rc = fail(ctx, RKG_ERR_CUDA, "rkg_sketch_shard: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        const u64 kept = hpick[1];
+        if (kept == 0) break;                          // no valid window
+        if (kept > (1ULL << 30)) { rc = fail(ctx, RKG_ERR_ARG, "rkg_sketch_shard: more than 2^30 hashes share the boundary bin"); break; }
+        const int P = next_pow2((i64)std::max<u64>(kept, 2));
+        if (d_cand.ensure(sizeof(u64) * (size_t)P)) { rc = fail(ctx, RKG_ERR_NOMEM, "rkg_sketch_shard: device allocation failed"); break; }
+        unsigned long long* ncand = d_pick.as<unsigned long long>() + 4;
+        {
+            Timed t(ctx, b->stream, K_SKETCH);
+            DISPATCH_KCSEL(ctx->kcsel, (shard_emit_kernel<KS><<<grid, 256, 0, b->stream>>>(b->codes.as<u32>(), b->nmask.as<u32>(), n, ctx->kl,
+                                                                                         d_pick.as<u64>(), d_cand.as<u64>(), ncand, kept)));
+            shard_sort_kernel<<<1, 1024, 0, b->stream>>>(d_cand.as<u64>(), (int)kept, P);
+            ctx->launches += 2;
+        }
+        const int out_n = (int)std::min<u64>(kept, (u64)ctx->s);
+        cudaMemcpyAsync(sketch, d_cand.p, sizeof(u64) * (size_t)out_n, cudaMemcpyDeviceToHost, b->stream);
+        if (cudaStreamSynchronize(b->stream) != cudaSuccess) { rc = fail(ctx, RKG_ERR_CUDA, "rkg_sketch_shard: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        *len = out_n;
+    } while (0);
+    d_hist.release(); d_pick.release(); d_cand.release();
+    return rc;
 }
 
 int rkg_set_memo(rkg_ctx* ctx, int enable) {

@@ -410,6 +410,80 @@ sketch_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int filter_mode, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Bottom-s sketch of ONE long record (a shard of it) without materialising its hashes: `rkmh hash` on a
+// chromosome-scale sequence (minhashes(calc_hashes()), mkmh.hpp:505-532, 931-950).
+//   shard_hist_kernel   hash every window, histogram of the top 16 hash bits (non-zero hashes only)
+//   shard_pick_kernel   the bin in which the running count reaches s, and the count through that bin
+//   shard_emit_kernel   hash again, keep the hashes whose top 16 bits are <= that bin (s plus one bin's worth)
+//   shard_sort_kernel   bitonic sort of the kept hashes; the first min(s, kept) are the sketch (duplicates kept)
+constexpr int SHARD_BINS = 65536;
+constexpr i64 SHARD_SEG = 4096;                 // windows per warp task
+
+template <int KCSEL>
+__global__ void __launch_bounds__(256)
+shard_hist_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, i64 n, KList kl, u32* __restrict__ hist) {
+    const int lane = threadIdx.x & 31, k = kl.k[0];
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 w0 = warp * SHARD_SEG; w0 < n; w0 += nwarps * SHARD_SEG) {
+        const i64 cnt = min(SHARD_SEG, n - w0);
+        team_hash_k<KCSEL>(kl.kv[0], codes, nmask, w0, cnt, k, lane, 32, 8,
+                           [&](i64, u64 h) { if (h) atomicAdd(&hist[(u32)(h >> 48)], 1u); });
+    }
+}
+
+// out[0] = bin, out[1] = number of non-zero hashes with top 16 bits <= bin (all of them when fewer than s exist)
+__global__ void __launch_bounds__(1024)
+shard_pick_kernel(const u32* __restrict__ hist, u64 s, u64* __restrict__ out) {
+    __shared__ u64 part[1024];
+    const int per = SHARD_BINS / 1024, b0 = (int)threadIdx.x * per;
+    u64 sum = 0;
+    for (int i = 0; i < per; ++i) sum += hist[b0 + i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const u64 v = ((int)threadIdx.x >= d) ? part[threadIdx.x - d] : 0ULL;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const u64 incl = part[threadIdx.x], excl = incl - sum, total = part[1023];
+    if (total < s) { if (threadIdx.x == 0) { out[0] = SHARD_BINS - 1; out[1] = total; } return; }
+    if (excl < s && s <= incl) {
+        u64 run = excl;
+        for (int i = 0; i < per; ++i) {
+            run += hist[b0 + i];
+            if (run >= s) { out[0] = (u64)(b0 + i); out[1] = run; break; }
+        }
+    }
+}
+
+template <int KCSEL>
+__global__ void __launch_bounds__(256)
+shard_emit_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, i64 n, KList kl, const u64* __restrict__ pick,
+                  u64* __restrict__ cand, unsigned long long* __restrict__ ncand, u64 cap) {
+    const int lane = threadIdx.x & 31, k = kl.k[0];
+    const u32 bin = (u32)pick[0];
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 w0 = warp * SHARD_SEG; w0 < n; w0 += nwarps * SHARD_SEG) {
+        const i64 cnt = min(SHARD_SEG, n - w0);
+        team_hash_k<KCSEL>(kl.kv[0], codes, nmask, w0, cnt, k, lane, 32, 8, [&](i64, u64 h) {
+            if (h && (u32)(h >> 48) <= bin) {
+                const unsigned long long at = atomicAdd(ncand, 1ULL);
+                if (at < cap) cand[at] = h;
+            }
+        });
+    }
+}
+
+// a[0, m) are the kept hashes, a has room for P = 2^j >= m values
+__global__ void __launch_bounds__(1024)
+shard_sort_kernel(u64* __restrict__ a, int m, int P) {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) if (i >= m) a[i] = ~0ULL;
+    __syncthreads();
+    block_bitonic_sort(a, P);
+}
+
 // merge_kernel: one block merges `nparts` sorted sketches (rows of `parts`, row stride s) into the
 // first s of their multiset union.  P = 2^m >= s; smem holds P u64.
 __global__ void __launch_bounds__(512)

@@ -245,6 +245,21 @@ def test_sharded_sketch_equals_whole(gpu, oracle):
     ref = oracle.minhashes(oracle.calc_hashes(seq[:400_000].tobytes(), [k]), s)
     part, pl = gpu.sketch_batch(seq[:400_000], np.array([0, 400_000], np.int64))
     assert np.array_equal(part[0, :pl[0]], ref)
+    # the shard path itself against the oracle: a whole record as one shard, a middle shard, fewer windows than s,
+    # a record of invalid bases only, and a period-4 repeat (a handful of distinct hashes, thousands of copies each)
+    assert np.array_equal(gpu.sketch_shard(seq[:400_000], 0, 400_000 - k, 400_000), ref)
+    mid = oracle.minhashes(oracle.calc_hashes(seq[100_000:250_000 + k].tobytes(), [k]), s)     # windows [100000, 250000)
+    assert np.array_equal(gpu.sketch_shard(seq[100_000:250_000 + k], 100_000, 250_000, seq.size), mid)
+    tiny = seq[:3000]
+    assert np.array_equal(gpu.sketch_shard(tiny, 0, tiny.size - k, tiny.size), oracle.minhashes(oracle.calc_hashes(tiny.tobytes(), [k]), s))
+    allN = np.full(5000, ord("N"), np.uint8)
+    assert len(gpu.sketch_shard(allN, 0, allN.size - k, allN.size)) == 0
+    rep = np.frombuffer(b"ACGT" * 50_000, np.uint8)
+    gpu.set_params([k], 1000)
+    assert np.array_equal(gpu.sketch_shard(rep, 0, rep.size - k, rep.size), oracle.minhashes(oracle.calc_hashes(rep.tobytes(), [k]), 1000))
+    gpu.set_params([12], 777)                      # a memoisable k goes through the same kernels (Murmur hashing)
+    m12 = oracle.minhashes(oracle.calc_hashes(seq[:300_000].tobytes(), [12]), 777)
+    assert np.array_equal(gpu.sketch_shard(seq[:300_000], 0, 300_000 - 12, 300_000), m12)
 
 
 def test_full_size_properties(gpu, oracle):

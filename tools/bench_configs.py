@@ -101,16 +101,28 @@ def config5(args, gpu):
     from rkmh_b200.synth import random_genome
     nb, k, s = args.bases or 400_000_000, 21, 10_000
     seq = random_genome(np.random.default_rng(5), nb)
+    from rkmh_b200.api import PinnedBuffer
     gpu.set_params([k], s)
     gpu.sketch_shard(seq[:5_000_000], 0, 5_000_000 - k, nb)     # warm-up
+    gpu.sketch_shard(seq, 0, nb - k, nb)                         # sizes the device buffers
     gpu.profile_enable(True); gpu.profile_read(reset=True)
     t0 = time.perf_counter()
     sk = gpu.sketch_shard(seq, 0, nb - k, nb)
     ms = 1e3 * (time.perf_counter() - t0)
     kk = kernels(gpu)
+    pin = PinnedBuffer(gpu, nb)
+    pv = pin.view(np.uint8, nb)
+    pv[:] = seq
+    gpu.profile_read(reset=True)
+    t0 = time.perf_counter()
+    sk2 = gpu.sketch_shard(pv, 0, nb - k, nb)
+    ms_pinned = 1e3 * (time.perf_counter() - t0)
+    same = bool(np.array_equal(sk, sk2))
+    pin.free()
     gpu.profile_enable(False)
-    return {"config": 5, "bases": nb, "k": k, "s": s, "shard_ms_host_buffers": ms, "kmers_per_s": (nb - k) / (ms / 1e3),
-            "kernels": kk, "sketch_len": int(len(sk)), "sketch_head": [int(x) for x in sk[:3]]}
+    return {"config": 5, "bases": nb, "k": k, "s": s, "shard_ms_pageable_host_buffer": ms, "shard_ms_pinned_host_buffer": ms_pinned,
+            "kmers_per_s_pinned": (nb - k) / (ms_pinned / 1e3), "kernels": kk, "sketch_len": int(len(sk)), "same": same,
+            "sketch_head": [int(x) for x in sk[:3]]}
 
 
 def main():
