@@ -462,19 +462,46 @@ int main_hash(int argc, char** argv) {
     SeqSet seqs;
     load_all(o.refs, seqs, false);                        // -r is accepted here (HEAD aborts on it)
     load_all(o.reads, seqs, false);
-    Fleet fl; fl.open(1);
+    Fleet fl; fl.open(std::max(1, o.gpus));
     rkg_ctx* c = fl.ctx[0];
     const bool sketch_mode = o.sketch > 0;
-    RK(c, rkg_set_params(c, o.ks.data(), (int)o.ks.size(), sketch_mode ? o.sketch : 1, 0, 0));
+    fl.each([&](int, rkg_ctx* cc) { RK(cc, rkg_set_params(cc, o.ks.data(), (int)o.ks.size(), sketch_mode ? o.sketch : 1, 0, 0)); });
     std::string out;
     const size_t n = seqs.size();
     if (sketch_mode) {
+        // Records of at least RKMH_SHARD_MIN bases (default 16 Mi; single k only) are sketched as ONE device-resident
+        // record by rkg_sketch_shard, their windows split over the GPUs of the fleet and the partial bottom-s sketches
+        // merged; runs of shorter records go through rkg_sketch_batch on the first GPU.
+        const char* sm = getenv("RKMH_SHARD_MIN");
+        const int64_t shard_min = sm ? std::max<long long>(atoll(sm), 1) : (int64_t)1 << 24;
+        const int G = (int)fl.ctx.size(), k0 = o.ks[0];
         std::vector<uint64_t> sk(n * (size_t)o.sketch);
         std::vector<int32_t> lens(n);
-        if (n) RK(c, rkg_sketch_batch(c, seqs.bases.data(), seqs.offs.data(), (int64_t)n, -1, sk.data(), lens.data()));
-        for (size_t i = 0; i < n; ++i) {                  // print_hashes format, mkmh.hpp:1438-1449
-            out += seqs.names[i]; out += '\t';
-            for (int j = 0; j < lens[i]; ++j) { if (j) out += '\t'; char b[24]; out.append(b, snprintf(b, sizeof b, "%llu", (unsigned long long)sk[i * o.sketch + j])); }
+        auto is_big = [&](size_t i) { return o.ks.size() == 1 && seqs.offs[i + 1] - seqs.offs[i] >= shard_min; };
+        size_t i = 0;
+        while (i < n) {
+            if (!is_big(i)) {
+                size_t j = i;
+                while (j < n && !is_big(j)) ++j;
+                RK(c, rkg_sketch_batch(c, seqs.bases.data(), seqs.offs.data() + i, (int64_t)(j - i), -1, sk.data() + i * o.sketch, lens.data() + i));
+                i = j;
+                continue;
+            }
+            const int64_t L = seqs.offs[i + 1] - seqs.offs[i], nk = std::max<int64_t>(L - k0, 0);
+            const char* rec = seqs.bases.data() + seqs.offs[i];
+            std::vector<uint64_t> parts((size_t)G * o.sketch, 0);
+            std::vector<int32_t> plens(G, 0);
+            fl.each([&](int d, rkg_ctx* cc) {
+                const int64_t b = nk * d / G, e = nk * (d + 1) / G;
+                if (e > b) RK(cc, rkg_sketch_shard(cc, rec + b, std::min<int64_t>(e + k0, L) - b, b, e, L, parts.data() + (size_t)d * o.sketch, &plens[d]));
+            });
+            if (G == 1) { lens[i] = plens[0]; std::copy(parts.begin(), parts.begin() + plens[0], sk.begin() + i * o.sketch); }
+            else RK(c, rkg_merge_sketches(c, parts.data(), plens.data(), G, sk.data() + i * o.sketch, &lens[i]));
+            ++i;
+        }
+        for (size_t i2 = 0; i2 < n; ++i2) {               // print_hashes format, mkmh.hpp:1438-1449
+            out += seqs.names[i2]; out += '\t';
+            for (int j = 0; j < lens[i2]; ++j) { if (j) out += '\t'; char b[24]; out.append(b, snprintf(b, sizeof b, "%llu", (unsigned long long)sk[i2 * o.sketch + j])); }
             out += '\n';
             if (out.size() > (1 << 22)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
         }

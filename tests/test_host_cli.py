@@ -138,3 +138,19 @@ def test_reads_from_standard_input(rkmh_bin, cli_manifest, name):
     plain = gzip.open(reads, "rb").read()
     res = subprocess.run([rkmh_bin] + argv, cwd=DATA, input=plain, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert res.returncode == 0 and hashlib.md5(res.stdout).hexdigest() == cli_manifest[name]["md5"]
+
+
+@pytest.mark.gpu
+def test_hash_command_sharded_records(rkmh_bin):
+    """Records above RKMH_SHARD_MIN go through rkg_sketch_shard (split over the GPUs with -g, partial sketches merged):
+    stdout does not change."""
+    import torch
+    path = os.path.join(DATA, "hpv_16_allFasta.fa.gz")
+    base = subprocess.run([rkmh_bin, "hash", "-f", path, "-k", "21", "-s", "300"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+    assert len(base.splitlines()) == 10
+    env = dict(os.environ, RKMH_SHARD_MIN="1000")
+    for g in ([1, 2] if torch.cuda.device_count() >= 2 else [1]):
+        res = subprocess.run([rkmh_bin, "hash", "-f", path, "-k", "21", "-s", "300", "-g", str(g)], stdout=subprocess.PIPE,
+                             stderr=subprocess.PIPE, env=env)
+        assert res.returncode == 0, res.stderr.decode()[-400:]
+        assert res.stdout == base, g
