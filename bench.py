@@ -27,9 +27,13 @@ sys.path.insert(0, ROOT)
 DATA = os.path.join(ROOT, "tests", "golden", "data")
 K, S, READ_LEN = 12, 1000, 150
 METRIC = "classify reads/s (rkmh stream, k=12, s=1000, 182 refs, 150 bp reads)"
-# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one `ncu --set full` capture, scaled to the
-# default 10 M reads per launch; see profiles/README.md for the capture each figure comes from.  None = not captured.
-TRAFFIC = {}
+WORKLOAD = ("BASELINE config 2: rkmh stream -r all_pave_ref.fa -k 12 -s 1000, synthetic 150 bp Illumina-like reads "
+            "(90% sampled from the 182 refs, 0.5% subs, 0.1% N; 10% random)")
+# DRAM bytes per read (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of a 2 M-read launch,
+# divided by the reads); `roofline.traffic` scales it to the reads of one launch.  Kernels without a capture report null.
+TRAFFIC_PER_READ = {"classify_memo_sieve_kernel": 188.6,      # profiles/r01_sieve_final_ncu_raw.json (377.2 MB / 2 M reads)
+                    "classify_memo_warp_kernel": 1831.4,      # profiles/r01_memo_warp_ncu_raw.json
+                    "classify_group_kernel": 91.0}            # profiles/r01_group_kernel_ncu_raw.json
 
 
 def parse_args():
@@ -197,8 +201,9 @@ def main_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: rkmh stream -r all_pave_ref.fa -k 12 -s 1000, 150 bp reads",
-                       "reads_per_step": sample, "k": K, "s": S, "refs": len(refs)},
+            "config": {"workload": WORKLOAD, "reads_per_gpu_per_step": args.reads, "k": K, "s": S, "refs": len(refs),
+                       "parallelism": "host cores of rank 0", "sample_reads_per_step": sample,
+                       "note": "each step is a bounded sample of the workload through the reference's own CPU implementation"},
             "kmers_per_s": value * (READ_LEN - K),
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind,
                              "sample": f"{sample} reads per step, wall clock of the CLI minus a refs-only run"},
@@ -336,8 +341,7 @@ def main_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: rkmh stream -r all_pave_ref.fa -k 12 -s 1000, synthetic 150 bp "
-                                   "Illumina-like reads (90% sampled from the 182 refs, 0.5% subs, 0.1% N; 10% random)",
+            "config": {"workload": WORKLOAD,
                        "reads_per_gpu_per_step": n, "k": K, "s": S, "refs": len(refs), "parallelism": f"reads sharded x{world}",
                        "l2": "inputs (1.5 GB of bases per step) are larger than L2; no flush needed"},
             "kmers_per_s": value * (READ_LEN - K),
@@ -349,7 +353,7 @@ def main_ours(args, rank, world, local_rank):
             "kernels": {k: {"launches": v["launches"], "ms_per_launch": v["ms"] / max(v["launches"], 1),
                             "share": v["ms"] / max(sum(x["ms"] for x in prof.values()), 1e-9)} for k, v in prof.items()},
             "roofline": {"kernel": dom[0], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": TRAFFIC.get(dom[0]), "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": (TRAFFIC_PER_READ[dom[0]] * n if dom[0] in TRAFFIC_PER_READ else None), "peak_source": peak_src,
                          "algorithmic_bytes_per_read": bytes_per_read, "note": note},
             "dominant_kernel": {"kernel": dom[0], "ms_per_launch": dom_ms,
                                 "kmers_per_s_per_gpu": (n * (READ_LEN - K)) / (dom_ms / 1e3) if dom_ms > 0 else 0.0},
