@@ -286,21 +286,21 @@ uint64_t stream_reads(Fleet& fl, ChunkPool& pool, const std::vector<const char*>
     std::thread reader([&] {
         uint64_t seq = 0;
         Chunk* cur = nullptr;
-        std::string name, sq, qual;
+        rkhost::Record rec;
         for (const char* f : files) {
             rkhost::FastxReader rd(f);
             if (!rd.ok()) { fprintf(stderr, "rkmh: cannot open %s\n", f); exit(2); }
-            while (rd.next(name, sq, qual)) {
+            while (rd.next(rec)) {
                 ++nrecords;
                 if (cur && (cur->nreads >= cur->cap_reads || !cur->big.empty() ||
-                            (size_t)cur->offs[cur->nreads] + sq.size() > cur->cap_bases)) { work_q.push(cur); cur = nullptr; }
+                            (size_t)cur->offs[cur->nreads] + rec.seq_len > cur->cap_bases)) { work_q.push(cur); cur = nullptr; }
                 if (!cur) { cur = pool.free_q.pop(); cur->reset(seq++); }
                 const size_t at = (size_t)cur->offs[cur->nreads];
-                if (sq.size() > cur->cap_bases) cur->big.assign(sq.begin(), sq.end());      // alone in its chunk
-                else memcpy(cur->bases + at, sq.data(), sq.size());
-                cur->offs[++cur->nreads] = (int64_t)(at + sq.size());
-                cur->names.push_back(name);
-                if (keep_qual) cur->quals.push_back(qual);
+                if (rec.seq_len > cur->cap_bases) cur->big.assign(rec.seq, rec.seq + rec.seq_len);      // alone in its chunk
+                else memcpy(cur->bases + at, rec.seq, rec.seq_len);
+                cur->offs[++cur->nreads] = (int64_t)(at + rec.seq_len);
+                cur->names.emplace_back(rec.name, rec.name_len);
+                if (keep_qual) cur->quals.emplace_back(rec.qual, rec.qual_len);
             }
         }
         if (cur) work_q.push(cur);
