@@ -229,11 +229,28 @@ struct Chunk {
     char* bases = nullptr; int64_t* offs = nullptr; rkg_hit* hits = nullptr;
     size_t cap_bases = 0, cap_reads = 0, nreads = 0;
     std::vector<char> big;                 // a single record larger than cap_bases goes here (pageable)
-    std::vector<std::string> names, quals;
+    std::vector<char> text;                // names (and quality strings) of the chunk's reads, back to back
+    std::vector<uint64_t> name_at, qual_at; // name i = text[name_at[i], name_at[i + 1]); qualities likewise when kept
     uint64_t seq = 0;                      // position of the chunk in the input order
     std::string out;                       // formatted result lines
     const char* data() const { return big.empty() ? bases : big.data(); }
-    void reset(uint64_t s) { nreads = 0; offs[0] = 0; big.clear(); big.shrink_to_fit(); names.clear(); quals.clear(); out.clear(); seq = s; }
+    void reset(uint64_t s) {
+        nreads = 0; offs[0] = 0; big.clear(); big.shrink_to_fit(); text.clear(); name_at.clear(); qual_at.clear(); out.clear(); seq = s;
+    }
+    void add_text(const rkhost::Record& r, bool keep_qual) {
+        name_at.push_back(text.size());
+        text.insert(text.end(), r.name, r.name + r.name_len);
+        if (keep_qual) { qual_at.push_back(text.size()); text.insert(text.end(), r.qual, r.qual + r.qual_len); }
+    }
+    // (pointer, length) of read i's name / quality string; valid once the chunk is complete
+    std::pair<const char*, size_t> name(size_t i) const {
+        const uint64_t e = !qual_at.empty() ? qual_at[i] : (i + 1 < name_at.size() ? name_at[i + 1] : text.size());
+        return {text.data() + name_at[i], (size_t)(e - name_at[i])};
+    }
+    std::pair<const char*, size_t> qual(size_t i) const {
+        const uint64_t e = i + 1 < name_at.size() ? name_at[i + 1] : text.size();
+        return {text.data() + qual_at[i], (size_t)(e - qual_at[i])};
+    }
 };
 
 template <typename T> class Channel {      // unbounded MPMC queue; the chunk pool bounds what is in flight
@@ -299,8 +316,7 @@ uint64_t stream_reads(Fleet& fl, ChunkPool& pool, const std::vector<const char*>
                 if (rec.seq_len > cur->cap_bases) cur->big.assign(rec.seq, rec.seq + rec.seq_len);      // alone in its chunk
                 else memcpy(cur->bases + at, rec.seq, rec.seq_len);
                 cur->offs[++cur->nreads] = (int64_t)(at + rec.seq_len);
-                cur->names.emplace_back(rec.name, rec.name_len);
-                if (keep_qual) cur->quals.emplace_back(rec.qual, rec.qual_len);
+                cur->add_text(rec, keep_qual);
             }
         }
         if (cur) work_q.push(cur);
@@ -363,10 +379,11 @@ void run_streamed(Fleet& fl, const Options& o, bool keep_qual, bool count_zeros,
 }
 
 // result line of stream / classify: src/rkmh.cpp:884-893
-void format_stream_line(std::string& out, const Options& o, const SeqSet& refs, const std::string& read_name, const rkg_hit& h) {
+void format_stream_line(std::string& out, const Options& o, const SeqSet& refs, const char* read_name, size_t read_name_len,
+                        const rkg_hit& h) {
     const int diff = h.best - h.prev;
     const bool depth_fail = h.sketch_len <= o.min_matches, match_fail = h.best < o.min_matches, diff_ok = diff > o.min_diff;
-    out += refs.names[h.ref_id]; out += '\t'; out += read_name; out += '\t';
+    out += refs.names[h.ref_id]; out += '\t'; out.append(read_name, read_name_len); out += '\t';
     append_int(out, h.best); out += '\t'; append_int(out, o.sketch);
     if (depth_fail) out += "FAIL:DEPTH";
     out += '\t'; if (match_fail) out += "FAIL:MATCHES";
@@ -375,16 +392,16 @@ void format_stream_line(std::string& out, const Options& o, const SeqSet& refs, 
 }
 
 // record of filter: src/rkmh.cpp:1289-1309, src/equiv.hpp:328-352
-void format_filter_record(std::string& out, const Options& o, const std::string& name, const char* s, int64_t L,
-                          const std::string& qual, const rkg_hit& h) {
+void format_filter_record(std::string& out, const Options& o, const char* name, size_t name_len, const char* s, int64_t L,
+                          const char* qual, size_t qual_len, const rkg_hit& h) {
     const int best = std::max(h.best, 0), prev = std::max(h.prev, 0);
     if (!(h.sketch_len > 0) || best < o.min_matches || !(best - prev > o.min_diff)) return;
-    out += '>'; out += name; out += '\n';
+    out += '>'; out.append(name, name_len); out += '\n';
     for (int64_t j = 0; j < L; ++j) {
         signed char ch = (signed char)s[j];
         out += (char)((int)ch - 91 > 0 ? ch - 32 : ch);          // to_upper, mkmh.hpp:231-236
     }
-    out += "\n+\n"; out += qual; out += '\n';
+    out += "\n+\n"; out.append(qual, qual_len); out += '\n';
 }
 
 // ---- stream / classify: src/rkmh.cpp:584-989 ------------------------------------------------------------
@@ -401,7 +418,8 @@ int main_stream(int argc, char** argv) {
     setup_refs(fl, o, refs, STREAM_TABLE, false);
     if (!(o.do_read_depth && any_stdin(o.reads))) {
         run_streamed(fl, o, false, false, [&](Chunk& c) {
-            for (size_t i = 0; i < c.nreads; ++i) format_stream_line(c.out, o, refs, c.names[i], c.hits[i]);
+            c.out.reserve(c.nreads * 64);
+            for (size_t i = 0; i < c.nreads; ++i) { const auto nm = c.name(i); format_stream_line(c.out, o, refs, nm.first, nm.second, c.hits[i]); }
         });
         return 0;
     }
@@ -411,7 +429,7 @@ int main_stream(int argc, char** argv) {
     std::string out;
     out.reserve(1 << 22);
     for (size_t i = 0; i < reads.size(); ++i) {
-        format_stream_line(out, o, refs, reads.names[i], hits[i]);
+        format_stream_line(out, o, refs, reads.names[i].data(), reads.names[i].size(), hits[i]);
         if (out.size() > (1 << 22) - 4096) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
     }
     fwrite(out.data(), 1, out.size(), stdout);
@@ -432,8 +450,10 @@ int main_filter(int argc, char** argv) {
     setup_refs(fl, o, refs, FILTER_TABLE, true);
     if (!(o.do_read_depth && any_stdin(o.reads))) {
         run_streamed(fl, o, true, true, [&](Chunk& c) {
-            for (size_t i = 0; i < c.nreads; ++i)
-                format_filter_record(c.out, o, c.names[i], c.data() + c.offs[i], c.offs[i + 1] - c.offs[i], c.quals[i], c.hits[i]);
+            for (size_t i = 0; i < c.nreads; ++i) {
+                const auto nm = c.name(i), ql = c.qual(i);
+                format_filter_record(c.out, o, nm.first, nm.second, c.data() + c.offs[i], c.offs[i + 1] - c.offs[i], ql.first, ql.second, c.hits[i]);
+            }
         });
         return 0;
     }
@@ -442,8 +462,8 @@ int main_filter(int argc, char** argv) {
     std::vector<rkg_hit> hits = classify_all(fl, o, reads, true);
     std::string out;
     for (size_t i = 0; i < reads.size(); ++i) {
-        format_filter_record(out, o, reads.names[i], reads.bases.data() + reads.offs[i], reads.offs[i + 1] - reads.offs[i],
-                             reads.quals[i], hits[i]);
+        format_filter_record(out, o, reads.names[i].data(), reads.names[i].size(), reads.bases.data() + reads.offs[i],
+                             reads.offs[i + 1] - reads.offs[i], reads.quals[i].data(), reads.quals[i].size(), hits[i]);
         if (out.size() > (1 << 22)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
     }
     fwrite(out.data(), 1, out.size(), stdout);
