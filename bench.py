@@ -238,6 +238,9 @@ def main_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
 
+    # each rank sits on its GPU's NUMA node before it allocates pinned memory (matters from 4 ranks up: the reads of
+    # one step are 1.6 GB per GPU, and crossing sockets halves the host-to-device rate)
+    numa_cpus = rkmh_b200.bind_host_thread_to_gpu(local_rank) if world > 1 else None
     ref_names, refs = load_refs()
     gpu = rkmh_b200.RkmhGpu(local_rank)
     gpu.set_params([K], S)
@@ -343,6 +346,7 @@ def main_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "reads_per_gpu_per_step": n, "k": K, "s": S, "refs": len(refs), "parallelism": f"reads sharded x{world}",
+                       "host_numa_binding": (f"{len(numa_cpus)} local cores per rank" if numa_cpus else "none"),
                        "l2": "inputs (1.5 GB of bases per step) are larger than L2; no flush needed"},
             "kmers_per_s": value * (READ_LEN - K),
             "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e2e_ms,

@@ -4,4 +4,4 @@ Only what the path needs lives here: csrc/ (sm_100a kernels + the C ABI), host/ 
 and a thin Python mirror of the call sequence for tests and bench.py.
 """
 from .api import (FILTER_TABLE_SIZE, HIT_DTYPE, STREAM_TABLE_SIZE, RkmhError, RkmhGpu, filter_pass,  # noqa: F401
-                  pack_sequences, stream_line)
+                  bind_host_thread_to_gpu, pack_sequences, stream_line)

@@ -327,3 +327,35 @@ def run_filter(ref_files, read_files, ks, sketch_size=1000, min_kmer_occ=-1, min
     finally:
         if own:
             ctx.close()
+
+
+def bind_host_thread_to_gpu(device):
+    """Pin the calling process to the CPU cores that are local to CUDA device `device` (NVML's ideal CPU set), so that
+    the pinned host buffers allocated afterwards -- and the threads that fill them -- sit on the GPU's own NUMA node.
+    On an 8-GPU box every rank otherwise pulls its reads across the socket interconnect.  Returns the CPU list, or
+    None when NVML or the topology information is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device)
+        handle = None
+        if all(hasattr(props, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                handle = None
+        if handle is None:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
