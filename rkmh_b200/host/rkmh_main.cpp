@@ -4,7 +4,7 @@
 // sharding of read chunks over the GPUs of the box, and formatting of the reference's exact output lines.
 // Every arithmetic step of the hot path runs in the CUDA library; there is no CPU fallback.
 //
-// Reads are STREAMED: a parser thread fills chunks of pinned host memory (RKMH_CHUNK_MB, default 64 MB of bases each),
+// Reads are STREAMED: a parser thread fills chunks of pinned host memory (RKMH_CHUNK_MB, default 32 MB of bases each, pinned on demand),
 // one worker thread per GPU pushes chunks through rkg_count_batch / rkg_classify_batch, four threads format the result
 // lines, and the main thread writes them in input order, so host memory stays bounded whatever the input size (the reference loads every read
 // first, src/rkmh.cpp:238-292).  `-f -` reads standard input.  With -M the read files are streamed twice (pass 1
@@ -263,34 +263,53 @@ template <typename T> class Channel {      // unbounded MPMC queue; the chunk po
     std::mutex m_; std::condition_variable cv_; std::deque<T> q_;
 };
 
+// Chunks are pinned on demand (page-locking costs ~0.5 s per GB: a small input should not pay for the whole pool) up to
+// `max_chunks`; after that the parser waits for the writer to hand one back.
 struct ChunkPool {
     rkg_ctx* owner = nullptr;
     std::vector<Chunk*> all;
-    Channel<Chunk*> free_q;
-    void open(rkg_ctx* ctx, int n, size_t cap_bases) {
-        owner = ctx;
+    std::deque<Chunk*> free_list;
+    std::mutex m; std::condition_variable cv;
+    int max_chunks = 0;
+    size_t cap_bases = 0;
+    void open(rkg_ctx* ctx, int n, size_t cap) { owner = ctx; max_chunks = n; cap_bases = cap; }
+    Chunk* make() {
         const size_t cap_reads = std::max<size_t>(cap_bases / 32, 1024);
-        for (int i = 0; i < n; ++i) {
-            Chunk* c = new Chunk();
-            void *pb = nullptr, *po = nullptr, *ph = nullptr;
-            RK(ctx, rkg_host_alloc(ctx, cap_bases, &pb));
-            RK(ctx, rkg_host_alloc(ctx, sizeof(int64_t) * (cap_reads + 1), &po));
-            RK(ctx, rkg_host_alloc(ctx, sizeof(rkg_hit) * cap_reads, &ph));
-            c->bases = (char*)pb; c->offs = (int64_t*)po; c->hits = (rkg_hit*)ph;
-            c->cap_bases = cap_bases; c->cap_reads = cap_reads;
-            all.push_back(c);
-            free_q.push(c);
+        Chunk* c = new Chunk();
+        void *pb = nullptr, *po = nullptr, *ph = nullptr;
+        RK(owner, rkg_host_alloc(owner, cap_bases, &pb));
+        RK(owner, rkg_host_alloc(owner, sizeof(int64_t) * (cap_reads + 1), &po));
+        RK(owner, rkg_host_alloc(owner, sizeof(rkg_hit) * cap_reads, &ph));
+        c->bases = (char*)pb; c->offs = (int64_t*)po; c->hits = (rkg_hit*)ph;
+        c->cap_bases = cap_bases; c->cap_reads = cap_reads;
+        return c;
+    }
+    Chunk* acquire() {
+        std::unique_lock<std::mutex> g(m);
+        for (;;) {
+            if (!free_list.empty()) { Chunk* c = free_list.front(); free_list.pop_front(); return c; }
+            if ((int)all.size() < max_chunks) {
+                all.push_back(nullptr);
+                const size_t slot = all.size() - 1;
+                g.unlock();
+                Chunk* c = make();
+                g.lock();
+                all[slot] = c;
+                return c;
+            }
+            cv.wait(g);
         }
     }
+    void release(Chunk* c) { { std::lock_guard<std::mutex> g(m); free_list.push_back(c); } cv.notify_one(); }
     ~ChunkPool() {
-        for (Chunk* c : all) { rkg_host_free(owner, c->bases); rkg_host_free(owner, c->offs); rkg_host_free(owner, c->hits); delete c; }
+        for (Chunk* c : all) if (c) { rkg_host_free(owner, c->bases); rkg_host_free(owner, c->offs); rkg_host_free(owner, c->hits); delete c; }
     }
 };
 
 size_t chunk_bytes() {
     if (const char* b = getenv("RKMH_CHUNK_BYTES")) return (size_t)std::max<long>(atol(b), 64);   // testing knob
     const char* e = getenv("RKMH_CHUNK_MB");
-    const long mb = e ? atol(e) : 64;
+    const long mb = e ? atol(e) : 32;
     return (size_t)std::max<long>(mb, 1) << 20;
 }
 
@@ -315,7 +334,7 @@ uint64_t stream_reads(Fleet& fl, ChunkPool& pool, const std::vector<const char*>
                 ++nrecords;
                 if (cur && (cur->nreads >= cur->cap_reads || !cur->big.empty() ||
                             (size_t)cur->offs[cur->nreads] + rec.seq_len > cur->cap_bases)) { work_q.push(cur); cur = nullptr; }
-                if (!cur) { cur = pool.free_q.pop(); cur->reset(seq++); }
+                if (!cur) { cur = pool.acquire(); cur->reset(seq++); }
                 const size_t at = (size_t)cur->offs[cur->nreads];
                 if (rec.seq_len > cur->cap_bases) cur->big.assign(rec.seq, rec.seq + rec.seq_len);      // alone in its chunk
                 else memcpy(cur->bases + at, rec.seq, rec.seq_len);
@@ -361,7 +380,7 @@ uint64_t stream_reads(Fleet& fl, ChunkPool& pool, const std::vector<const char*>
             c = it->second; done.erase(it);
         }
         emit(*c);
-        pool.free_q.push(c);
+        pool.release(c);
     }
     reader.join();
     for (auto& w : workers) w.join();
