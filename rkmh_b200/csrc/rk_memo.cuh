@@ -961,6 +961,7 @@ classify_memo_tile_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
                 const int n = len - k > 0 ? len - k : 0;
                 const u32 addr = (u32)(shift + (int)(o0 - ctl.b0));          // first byte of the read in the tile
                 const u32 aw = addr >> 2, sh8 = 8u * (addr & 3u);
+                const u32 last_w = (addr + (u32)(len > 0 ? len - 1 : 0)) >> 2;   // the word that holds the read's last base
                 const int ng = (n + 15) >> 4;                                // groups of 16 windows
                 const int nsw = ng + 1;                                      // code words kept for step 2
                 u32* privw = tw + ((addr + 3u) >> 2);                        // the words that lie wholly inside the read
@@ -972,8 +973,12 @@ classify_memo_tile_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
                 if (!give_up && n > 0) {
                     // ---- 1: decode, sieve ---------------------------------------------------------------------------
                     auto decode = [&](int g, u32& cw, u32& bw) {
+                        // words past the read's last one belong to the next read's thread, which overwrites them: not read
                         const u32* w = tw + aw + 4 * g;
-                        const u32 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+                        const int left = (int)last_w - (int)(aw + 4 * g);            // index of the last readable word of w[]
+                        const u32 w0 = left >= 0 ? w[0] : 0x41414141u, w1 = left >= 1 ? w[1] : 0x41414141u,
+                                  w2 = left >= 2 ? w[2] : 0x41414141u, w3 = left >= 3 ? w[3] : 0x41414141u,
+                                  w4 = left >= 4 ? w[4] : 0x41414141u;
                         u32 p0, p1, p2, p3, b0, b1, b2, b3;
                         sv_decode(__funnelshift_r(w0, w1, sh8), p0, b0);
                         sv_decode(__funnelshift_r(w1, w2, sh8), p1, b1);
