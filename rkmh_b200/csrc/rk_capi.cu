@@ -535,10 +535,12 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
                     sb, ctx->s, ctx->memo, ctx->tb, mg.rwords, redo, redo_count, hits);
                 CK(cudaGetLastError());
             }
-            const int grid = ctx->sm_count * 2;
+            CK(cudaFuncSetAttribute(classify_memo_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg.block_smem));
+            int per_sm = 2;                                  // as many resident blocks as registers and shared memory allow
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, classify_memo_block_kernel, 256, mg.block_smem));
+            const int grid = ctx->sm_count * std::max(1, std::min(per_sm, 8));
             CK(b->scratch.ensure(sizeof(u32) * (size_t)grid * (size_t)mg.scratch_stride + 64));
             Timed t(ctx, b->stream, K_CLASSIFY_MEMO_BLOCK);
-            CK(cudaFuncSetAttribute(classify_memo_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg.block_smem));
             classify_memo_block_kernel<<<grid, 256, mg.block_smem, b->stream>>>(
                 sb, ctx->s, ctx->memo, ctx->tb, mg.use_warp ? redo : nullptr, mg.use_warp ? redo_count : nullptr, b->nseq,
                 mg.vcap, mg.hs_cap, mg.rpad, b->scratch.as<u32>(), mg.scratch_stride, hits);

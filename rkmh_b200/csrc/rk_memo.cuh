@@ -78,12 +78,16 @@ RK_D void memo_stream(const unsigned char* __restrict__ p, i64 len, int k, u32 k
         c0 = __ballot_sync(0xffffffffu, c2 & 1u); c1 = __ballot_sync(0xffffffffu, c2 & 2u);
         cv = __ballot_sync(0xffffffffu, memo_base_invalid(ch));
     }
-    u32 chn = load(s0 + 32);
+    // the bases are requested four rounds ahead: a warp streams a long read straight from HBM, and one 32-byte request
+    // in flight per warp (the first version) left it waiting ~500 cycles per round
+    u32 q0 = load(s0 + 32), q1 = load(s0 + 64), q2 = load(s0 + 96), q3 = load(s0 + 128);
+#pragma unroll 4
     for (i64 base = s0; base < s1; base += 32) {
+        const u32 chn = q0;
+        q0 = q1; q1 = q2; q2 = q3; q3 = load(base + 160);
         const u32 c2 = base_code(chn);
         const u32 n0 = __ballot_sync(0xffffffffu, c2 & 1u), n1 = __ballot_sync(0xffffffffu, c2 & 2u);
         const u32 nv = __ballot_sync(0xffffffffu, memo_base_invalid(chn));
-        chn = load(base + 64);                                  // in flight while this round is processed
         const u32 f0 = __funnelshift_r(c0, n0, (u32)lane) & kmask;
         const u32 f1 = __funnelshift_r(c1, n1, (u32)lane) & kmask;
         const u32 fv = __funnelshift_r(cv, nv, (u32)lane) & kmask;
@@ -1223,12 +1227,25 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
             const i64 per = ((((n + 31) >> 5) + nwb - 1) / nwb) << 5;
             const i64 s0 = (i64)wib * per, s1 = min(n, s0 + per);
             u32 local_nz = 0;
-            memo_stream(sb.bases + beg, len, k, mm.kmask, s0, s1, lane, [&](i64 pos, u32 code, bool in, bool valid) {
-                u32 m = MEMO_SKIP;
-                if (valid) { m = __ldg(&mm.tab[code]); if (m & (MEMO_ZERO | MEMO_FAILM)) m = MEMO_SKIP; }
+            // the table value of a window is consumed two rounds after its lookup was issued: three lookups of a warp
+            // are in flight (the 64 MB table does not fit one die's L2: a tenth of them go to HBM)
+            u32 m1 = MEMO_SKIP, m2 = MEMO_SKIP;
+            i64 p1 = 0, p2 = 0;
+            bool in1 = false, in2 = false;
+            auto consume = [&](i64 pos, bool in, u32 m) {
+                if (m != MEMO_SKIP && (m & (MEMO_ZERO | MEMO_FAILM))) m = MEMO_SKIP;
                 if (in) V[pos] = m;
                 if (m != MEMO_SKIP) { ++local_nz; atomicAdd(&hist[m >> 20], 1u); }
+            };
+            memo_stream(sb.bases + beg, len, k, mm.kmask, s0, s1, lane, [&](i64 pos, u32 code, bool in, bool valid) {
+                u32 m = MEMO_SKIP;
+                if (valid) m = __ldg(&mm.tab[code]);
+                consume(p2, in2, m2);
+                m2 = m1; p2 = p1; in2 = in1;
+                m1 = m; p1 = pos; in1 = in;
             });
+            consume(p2, in2, m2);
+            consume(p1, in1, m1);
             local_nz = warp_sum(local_nz);
             if (lane == 0 && local_nz) atomicAdd(&bs.nz, (int)local_nz);
         }
