@@ -751,9 +751,7 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
                     }
                 }
                 const int wi0 = c0 + lane - sh;              // window index of this lane in round 0
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    if (c0 + 32 * r >= pend) break;          // warp-uniform
+                auto round = [&](int r) {
                     const u32 code = (__shfl_sync(0xffffffffu, Q, src0 + 8 * r) >> osh) & cmask2;
                     bool ok = (u32)(wi0 + 32 * r) < (u32)n;
                     if (slow) {
@@ -769,6 +767,11 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
                     const int at = nc + __popc(bal & lt);
                     if (cand && at < SIEVE_QCAP) q[at] = code;
                     nc += __popc(bal);
+                };
+                if (c0 + 96 < pend) {                        // four full rounds, straight-line: their chains interleave
+                    round(0); round(1); round(2); round(3);
+                } else {
+                    for (int r = 0; c0 + 32 * r < pend; ++r) round(r);
                 }
                 pc = pn; bc = bn;
             }
