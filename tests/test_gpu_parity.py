@@ -332,3 +332,37 @@ def test_memo_path_is_taken_and_matches_murmur(oracle, variant, monkeypatch):
     reads = [lb[lo[i]:lo[i + 1]].tobytes() for i in range(12)]
     exp = oracle.classify_batch(reads, [12], 1000, sk, ln)
     assert np.array_equal(res[True][1][:12], _fields(exp))
+
+
+@pytest.mark.parametrize("nrefs", [40, 100, 182, 250, 300])
+def test_reference_count_variants(oracle, nrefs):
+    """Every width of the per-reference bitset rows: <= 64 references (2 words), <= 128 (4), <= 192 (6), <= 256 (8:
+    the widest register-row kernels) and more than 256 (shared-memory counters), each against the oracle and against
+    the Murmur path.  References beyond the 182 fixture sequences are mutated copies, so that hits are shared by many."""
+    import rkmh_b200
+    _, rs, _ = load_sequences([data_path("all_pave_ref.fa.gz")])
+    rng = np.random.default_rng(nrefs)
+    refs = list(rs[:min(nrefs, len(rs))])
+    while len(refs) < nrefs:
+        src = np.frombuffer(rs[int(rng.integers(len(rs)))], np.uint8).copy()
+        pos = rng.random(src.size) < 0.03
+        src[pos] = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(pos.sum()))
+        refs.append(src.tobytes())
+    bases, offs = _synthetic_reads(rng, refs, 4000, 150)
+    res = {}
+    for memo in (True, False):
+        with rkmh_b200.RkmhGpu(0) as g:
+            g.set_memo(memo)
+            g.set_params([12], 1000)
+            g.load_refs(*_pack(refs))
+            g.profile_enable(True)
+            res[memo] = _fields(g.classify_batch(bases, offs))
+            names = set(g.profile_read())
+            if memo:
+                assert ("classify_memo_sieve_kernel" in names) == (nrefs <= 256), names
+    assert np.array_equal(res[True], res[False])
+    sk, ln = oracle.sketch_batch(refs, [12], 1000)
+    idx = rng.choice(4000, size=250, replace=False)
+    reads = [bases[offs[i]:offs[i + 1]].tobytes() for i in idx]
+    exp = oracle.classify_batch(reads, [12], 1000, sk, ln)
+    assert np.array_equal(res[True][idx], _fields(exp))
