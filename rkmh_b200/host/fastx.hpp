@@ -27,10 +27,11 @@ namespace rkhost {
 class ByteStream {
   public:
     // "-" reads standard input (gzip or plain, like any other path)
-    explicit ByteStream(const char* path) : buf_(1 << 22) {
+    explicit ByteStream(const char* path, long long offset = 0) : buf_(1 << 22) {
         if (const char* e = getenv("RKMH_PARSE_BUF")) buf_.resize((size_t)std::max<long>(atol(e), 16));   // testing knob
         fp_ = (path[0] == '-' && path[1] == 0) ? gzdopen(0, "r") : gzopen(path, "r");
         if (fp_) gzbuffer(fp_, 1 << 20);
+        if (fp_ && offset > 0 && gzseek(fp_, (z_off_t)offset, SEEK_SET) < 0) { gzclose(fp_); fp_ = nullptr; }
     }
     ~ByteStream() { if (fp_) gzclose(fp_); }
     bool ok() const { return fp_ != nullptr; }
@@ -73,6 +74,48 @@ struct SeqSet {
 // A record as views into the reader's buffers: valid until the next call of FastxReader::next.
 struct Record { const char* name; size_t name_len; const char* seq; size_t seq_len; const char* qual; size_t qual_len; };
 
+// The fast path on a memory range: p points just AFTER the '@' of a header, [p, end) is what is buffered, `eof` says
+// that `end` is the end of the input.  Returns 1 and fills r / consumed / next_header when [p, ...) starts a
+// well-formed four-line record (name line, one line of letters only, '+' line, as many quality bytes in [33, 127],
+// newline, and then the next header byte '@' or '>' or the end of the input); 0 when the record is not of that form
+// (the state machine must parse it); -1 when more bytes are needed to decide.  `consumed` counts from p up to and
+// including the next record's header byte (or to the end of the input, next_header = -1).
+inline bool fastx_all_letters(const char* p, size_t n) {
+    unsigned bad = 0;
+    for (size_t i = 0; i < n; ++i) bad |= (unsigned)((unsigned char)((p[i] | 0x20) - 'a') > 25);
+    return bad == 0;
+}
+inline bool fastx_all_quality(const char* p, size_t n) {
+    unsigned bad = 0;
+    for (size_t i = 0; i < n; ++i) bad |= (unsigned)((unsigned char)(p[i] - 33) > 94);
+    return bad == 0;
+}
+inline int fastx_fast_record(const char* p, const char* end, bool eof, Record& r, size_t& consumed, int& next_header) {
+    const size_t avail = (size_t)(end - p);
+    const char* e1 = (const char*)memchr(p, '\n', avail);
+    const char* e2 = e1 ? (const char*)memchr(e1 + 1, '\n', (size_t)(end - (e1 + 1))) : nullptr;
+    if (!e2) return eof ? 0 : -1;
+    if (e2 + 1 >= end) return eof ? 0 : -1;
+    if (e2[1] != '+') return 0;
+    const char* e3 = (const char*)memchr(e2 + 1, '\n', (size_t)(end - (e2 + 1)));
+    if (!e3) return eof ? 0 : -1;
+    const char* sq = e1 + 1;
+    const size_t L = (size_t)(e2 - sq);
+    const char* q = e3 + 1;
+    if (L == 0) return 0;
+    const bool last = eof && q + L + 1 == end;
+    if (!(q + L + 2 <= end || last)) return eof ? 0 : -1;
+    if (q[L] != '\n') return 0;
+    if (!last && q[L + 1] != '@' && q[L + 1] != '>') return 0;
+    if (!fastx_all_letters(sq, L) || !fastx_all_quality(q, L)) return 0;
+    size_t nl = 0;
+    while (p + nl < e1 && !isspace((unsigned char)p[nl])) ++nl;
+    r = Record{p, nl, sq, L, q, L};
+    if (last) { consumed = (size_t)(q + L + 1 - p); next_header = -1; }
+    else { consumed = (size_t)(q + L + 2 - p); next_header = (unsigned char)q[L + 1]; }
+    return 1;
+}
+
 // One record at a time.  The general path is the byte-wise state machine of the header comment above.  Well-formed
 // four-line FASTQ records ("@name...\n" + one line of letters + "+...\n" + as many quality bytes + "\n", followed by
 // the next header or the end of the input) take a fast path that finds the four line ends with memchr and hands out
@@ -82,7 +125,7 @@ struct Record { const char* name; size_t name_len; const char* seq; size_t seq_l
 // reference stops too).
 class FastxReader {
   public:
-    explicit FastxReader(const char* path) : in_(path) {
+    explicit FastxReader(const char* path, long long offset = 0) : in_(path, offset) {
         if (!in_.ok()) return;
         c_ = in_.get();
         while (c_ != -1 && c_ != '>' && c_ != '@') c_ = in_.get();
@@ -102,49 +145,16 @@ class FastxReader {
         return true;
     }
   private:
-    static bool all_letters(const char* p, size_t n) {
-        unsigned bad = 0;
-        for (size_t i = 0; i < n; ++i) bad |= (unsigned)((unsigned char)((p[i] | 0x20) - 'a') > 25);
-        return bad == 0;
-    }
-    static bool all_quality(const char* p, size_t n) {
-        unsigned bad = 0;
-        for (size_t i = 0; i < n; ++i) bad |= (unsigned)((unsigned char)(p[i] - 33) > 94);
-        return bad == 0;
-    }
     bool fast(Record& r) {                               // nothing is consumed unless the record is accepted
         size_t need = 1024;
         for (;;) {
             const size_t avail = in_.fill(need);
             const char* p = in_.ptr();
-            const char* end = p + avail;
-            const bool eof = in_.at_eof();
-            const char* e1 = (const char*)memchr(p, '\n', avail);
-            const char* e2 = e1 ? (const char*)memchr(e1 + 1, '\n', (size_t)(end - (e1 + 1))) : nullptr;
-            const char* e3 = nullptr;
-            if (e2) {
-                if (e2 + 1 >= end) { if (eof) return false; } else if (e2[1] != '+') return false;
-                else e3 = (const char*)memchr(e2 + 1, '\n', (size_t)(end - (e2 + 1)));
-            }
-            if (e3) {
-                const char* sq = e1 + 1;
-                const size_t L = (size_t)(e2 - sq);
-                const char* q = e3 + 1;
-                if (L == 0) return false;
-                if (q + L + 2 <= end || (eof && q + L + 1 == end)) {
-                    if (q[L] != '\n') return false;
-                    const bool last = q + L + 1 == end;
-                    if (!last && q[L + 1] != '@' && q[L + 1] != '>') return false;
-                    if (!all_letters(sq, L) || !all_quality(q, L)) return false;
-                    size_t nl = 0;
-                    while (p + nl < e1 && !isspace((unsigned char)p[nl])) ++nl;
-                    r = Record{p, nl, sq, L, q, L};
-                    if (last) { in_.skip((size_t)(q + L + 1 - p)); c_ = -1; }
-                    else { c_ = (unsigned char)q[L + 1]; in_.skip((size_t)(q + L + 2 - p)); }
-                    return true;
-                }
-            }
-            if (eof) return false;                       // the tail of the input: the state machine decides
+            size_t consumed = 0;
+            int nh = -1;
+            const int rc = fastx_fast_record(p, p + avail, in_.at_eof(), r, consumed, nh);
+            if (rc == 0) return false;
+            if (rc == 1) { in_.skip(consumed); c_ = nh; return true; }
             need = std::max<size_t>(2 * need, 2 * avail);
         }
     }

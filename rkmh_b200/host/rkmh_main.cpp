@@ -12,7 +12,10 @@
 //
 // Extra, non-reference option: -g/--gpus N (default: RKMH_GPUS or 1) shards reads over N GPUs.  -t is accepted
 // and ignored (the reference's OpenMP thread count).
+#include <fcntl.h>
 #include <getopt.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -277,9 +280,13 @@ struct ChunkPool {
         const size_t cap_reads = std::max<size_t>(cap_bases / 32, 1024);
         Chunk* c = new Chunk();
         void *pb = nullptr, *po = nullptr, *ph = nullptr;
-        RK(owner, rkg_host_alloc(owner, cap_bases, &pb));
-        RK(owner, rkg_host_alloc(owner, sizeof(int64_t) * (cap_reads + 1), &po));
-        RK(owner, rkg_host_alloc(owner, sizeof(rkg_hit) * cap_reads, &ph));
+        if (owner) {
+            RK(owner, rkg_host_alloc(owner, cap_bases, &pb));
+            RK(owner, rkg_host_alloc(owner, sizeof(int64_t) * (cap_reads + 1), &po));
+            RK(owner, rkg_host_alloc(owner, sizeof(rkg_hit) * cap_reads, &ph));
+        } else {                                         // `rkmh parse` (no GPU): ordinary memory
+            pb = malloc(cap_bases); po = malloc(sizeof(int64_t) * (cap_reads + 1)); ph = malloc(sizeof(rkg_hit) * cap_reads);
+        }
         c->bases = (char*)pb; c->offs = (int64_t*)po; c->hits = (rkg_hit*)ph;
         c->cap_bases = cap_bases; c->cap_reads = cap_reads;
         return c;
@@ -302,7 +309,11 @@ struct ChunkPool {
     }
     void release(Chunk* c) { { std::lock_guard<std::mutex> g(m); free_list.push_back(c); } cv.notify_one(); }
     ~ChunkPool() {
-        for (Chunk* c : all) if (c) { rkg_host_free(owner, c->bases); rkg_host_free(owner, c->offs); rkg_host_free(owner, c->hits); delete c; }
+        for (Chunk* c : all) if (c) {
+            if (owner) { rkg_host_free(owner, c->bases); rkg_host_free(owner, c->offs); rkg_host_free(owner, c->hits); }
+            else { free(c->bases); free(c->offs); free(c->hits); }
+            delete c;
+        }
     }
 };
 
@@ -313,8 +324,185 @@ size_t chunk_bytes() {
     return (size_t)std::max<long>(mb, 1) << 20;
 }
 
-// Streams every record of `files` through `work` (called on one worker thread per GPU, any order) and then through
-// `emit` (called on the calling thread, in input order).  Returns the number of records.
+int parse_threads() {                                  // RKMH_PARSE_THREADS (default: up to 4, half the host's cores)
+    if (const char* e = getenv("RKMH_PARSE_THREADS")) return std::min(std::max(atoi(e), 1), 16);
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(4u, hw / 2));
+}
+
+size_t parse_segment_bytes(size_t cap_bases) {          // about one chunk of bases per segment of FASTQ text
+    if (const char* e = getenv("RKMH_PARSE_SEG")) return (size_t)std::max<long>(atol(e), 256);   // testing knob
+    return 2 * cap_bases;
+}
+
+// A plain (uncompressed, regular) FASTQ file mapped into memory for the parallel parser.
+struct MappedFile {
+    const char* data = nullptr; size_t size = 0; int fd = -1;
+    bool open(const char* path) {
+        if (path[0] == '-' && path[1] == 0) return false;
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 4) return false;
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return false;
+        data = (const char*)m; size = (size_t)st.st_size;
+        if ((unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b) return false;    // gzip: sequential reader
+        madvise(m, size, MADV_SEQUENTIAL);
+        return true;
+    }
+    ~MappedFile() { if (data) munmap((void*)data, size); if (fd >= 0) ::close(fd); }
+};
+
+// Appends a record to the chunk being filled, closing it (-> `full`) and taking a new one from the pool when needed.
+struct ChunkFiller {
+    ChunkPool& pool; bool keep_qual; std::function<void(Chunk*)> full;
+    Chunk* cur = nullptr;
+    void add(const rkhost::Record& rec) {
+        if (cur && (cur->nreads >= cur->cap_reads || !cur->big.empty() ||
+                    (size_t)cur->offs[cur->nreads] + rec.seq_len > cur->cap_bases)) flush();
+        if (!cur) { cur = pool.acquire(); cur->reset(0); }
+        const size_t at = (size_t)cur->offs[cur->nreads];
+        if (rec.seq_len > cur->cap_bases) cur->big.assign(rec.seq, rec.seq + rec.seq_len);      // alone in its chunk
+        else memcpy(cur->bases + at, rec.seq, rec.seq_len);
+        cur->offs[++cur->nreads] = (int64_t)(at + rec.seq_len);
+        cur->add_text(rec, keep_qual);
+    }
+    void flush() { if (cur) { full(cur); cur = nullptr; } }
+};
+
+// Parallel parse of the well-formed prefix of a plain four-line FASTQ file.  The file is cut into segments; a team of
+// threads parses them with the fast path only (fastx.hpp), each starting at the first line-initial '@' of its segment
+// from which two well-formed records follow.  The calling thread then walks the segments IN ORDER and accepts one only
+// if it starts exactly where the previous one ended: by induction every accepted record is what the sequential
+// state machine would have produced, because on well-formed records both paths agree and the chain starts at the
+// file's first header.  At the first segment that does not chain, or the first record that is not well-formed, the
+// function stops and returns the byte offset at which the sequential reader must take over (the file size when
+// everything was parsed here, 0 when nothing was).
+size_t parse_parallel_prefix(const char* path, ChunkPool& pool, bool keep_qual, int threads, size_t seg_bytes,
+                             const std::function<void(Chunk*)>& emit_chunk, uint64_t& nrecords) {
+    MappedFile mf;
+    if (threads < 2 || !mf.open(path) || mf.size < 2 * seg_bytes) return 0;
+    const char* d = mf.data;
+    const size_t size = mf.size, npos = (size_t)-1;
+    size_t start0 = 0;
+    while (start0 < size && d[start0] != '>' && d[start0] != '@') ++start0;
+    if (start0 >= size || d[start0] != '@') return 0;
+    struct Seg { size_t first = (size_t)-1, end = (size_t)-1; bool anomaly = false, done = false; std::vector<Chunk*> chunks; uint64_t nrec = 0; };
+    const size_t nseg = (size + seg_bytes - 1) / seg_bytes;
+    std::vector<Seg> segs(nseg);
+    std::mutex m; std::condition_variable cv;
+    size_t next_seg = 0, verified = 0;
+    std::atomic<bool> abort_all{false};
+    auto well_formed_at = [&](size_t pos, rkhost::Record& r, size_t& next) -> bool {     // d[pos] == '@'
+        size_t consumed = 0; int nh = -1;
+        if (rkhost::fastx_fast_record(d + pos + 1, d + size, true, r, consumed, nh) != 1) return false;
+        next = nh == -1 ? size : pos + consumed;
+        return true;
+    };
+    auto parse_segment = [&](size_t i) {
+        Seg& sg = segs[i];
+        const size_t lo = i * seg_bytes, hi = std::min(size, lo + seg_bytes);
+        rkhost::Record r; size_t nx = 0, nx2 = 0;
+        size_t pos = npos;
+        if (i == 0) pos = start0;
+        else
+            for (size_t p = std::max<size_t>(lo, 1); p < hi; ++p) {
+                const char* hit = (const char*)memchr(d + p, '@', hi - p);
+                if (!hit) break;
+                p = (size_t)(hit - d);
+                if (d[p - 1] != '\n') continue;
+                if (well_formed_at(p, r, nx) && (nx >= size || (d[nx] == '@' && well_formed_at(nx, r, nx2)))) { pos = p; break; }
+            }
+        sg.first = pos;
+        if (pos == npos) return;
+        ChunkFiller filler{pool, keep_qual, [&](Chunk* c) { sg.chunks.push_back(c); }};
+        while (pos < hi) {
+            if (abort_all.load(std::memory_order_relaxed)) break;
+            // anything the fast path does not take, a record larger than a chunk, or a fourth chunk for one segment
+            // (the pool is sized for three per segment in flight) ends the parallel prefix here
+            if (d[pos] != '@' || !well_formed_at(pos, r, nx) || r.seq_len > pool.cap_bases ||
+                (sg.chunks.size() >= 2 && filler.cur && ((size_t)filler.cur->offs[filler.cur->nreads] + r.seq_len > filler.cur->cap_bases ||
+                                                         filler.cur->nreads >= filler.cur->cap_reads))) { sg.anomaly = true; break; }
+            filler.add(r);
+            ++sg.nrec;
+            pos = nx;
+        }
+        filler.flush();
+        sg.end = pos;
+    };
+    std::vector<std::thread> team;
+    for (int t = 0; t < threads; ++t)
+        team.emplace_back([&] {
+            for (;;) {
+                size_t i;
+                {
+                    std::unique_lock<std::mutex> g(m);
+                    cv.wait(g, [&] { return abort_all || next_seg >= nseg || next_seg < verified + (size_t)threads; });
+                    if (abort_all || next_seg >= nseg) return;
+                    i = next_seg++;
+                }
+                parse_segment(i);
+                { std::lock_guard<std::mutex> g(m); segs[i].done = true; }
+                cv.notify_all();
+            }
+        });
+    size_t expected = start0;
+    for (size_t i = 0; i < nseg; ++i) {
+        { std::unique_lock<std::mutex> g(m); cv.wait(g, [&] { return segs[i].done; }); }
+        Seg& sg = segs[i];
+        bool stop = false;
+        if (sg.first != npos) {
+            if (sg.first != expected) stop = true;                   // does not chain: the sequential reader decides
+            else {
+                for (Chunk* c : sg.chunks) emit_chunk(c);
+                sg.chunks.clear();
+                nrecords += sg.nrec;
+                expected = sg.end;
+                stop = sg.anomaly;
+            }
+        }
+        if (stop) break;
+        { std::lock_guard<std::mutex> g(m); verified = i + 1; }
+        cv.notify_all();
+    }
+    // segments that were parsed ahead but not accepted give their chunks back (first the finished ones, so that a
+    // thread still waiting for a chunk can see the abort flag and leave)
+    std::vector<Chunk*> back;
+    {
+        std::lock_guard<std::mutex> g(m);
+        abort_all = true;
+        for (Seg& sg : segs) if (sg.done) { back.insert(back.end(), sg.chunks.begin(), sg.chunks.end()); sg.chunks.clear(); }
+    }
+    cv.notify_all();
+    for (Chunk* c : back) pool.release(c);
+    for (auto& t : team) t.join();
+    for (Seg& sg : segs) for (Chunk* c : sg.chunks) pool.release(c);
+    return std::min(expected, size);
+}
+
+// Every record of `files`, in order, as chunks handed to `emit_chunk` (called on this thread).
+uint64_t parse_files(const std::vector<const char*>& files, ChunkPool& pool, bool keep_qual,
+                     const std::function<void(Chunk*)>& emit_chunk) {
+    uint64_t nrecords = 0;
+    ChunkFiller filler{pool, keep_qual, emit_chunk};
+    rkhost::Record rec;
+    const int pthreads = parse_threads();
+    for (const char* f : files) {
+        filler.flush();                                  // chunks of the parallel parser must follow what came before
+        const size_t resume = parse_parallel_prefix(f, pool, keep_qual, pthreads, parse_segment_bytes(pool.cap_bases),
+                                                    emit_chunk, nrecords);
+        if (getenv("RKMH_PARSE_DEBUG")) fprintf(stderr, "rkmh: %s: %llu records from the parallel parser, sequential from byte %zu\n", f, (unsigned long long)nrecords, resume);
+        rkhost::FastxReader rd(f, (long long)resume);
+        if (!rd.ok()) { fprintf(stderr, "rkmh: cannot open %s\n", f); exit(2); }
+        while (rd.next(rec)) { ++nrecords; filler.add(rec); }
+    }
+    filler.flush();
+    return nrecords;
+}
+
+// Streams every record of `files` through `work` (called on one worker thread per GPU, any order), `format` (a small
+// thread pool) and then through `emit` (called on the calling thread, in input order).  Returns the number of records.
 uint64_t stream_reads(Fleet& fl, ChunkPool& pool, const std::vector<const char*>& files, bool keep_qual,
                       const std::function<void(int, rkg_ctx*, Chunk&)>& work, const std::function<void(Chunk&)>& format,
                       const std::function<void(Chunk&)>& emit) {
@@ -325,24 +513,7 @@ uint64_t stream_reads(Fleet& fl, ChunkPool& pool, const std::vector<const char*>
     uint64_t nrecords = 0;
     std::thread reader([&] {
         uint64_t seq = 0;
-        Chunk* cur = nullptr;
-        rkhost::Record rec;
-        for (const char* f : files) {
-            rkhost::FastxReader rd(f);
-            if (!rd.ok()) { fprintf(stderr, "rkmh: cannot open %s\n", f); exit(2); }
-            while (rd.next(rec)) {
-                ++nrecords;
-                if (cur && (cur->nreads >= cur->cap_reads || !cur->big.empty() ||
-                            (size_t)cur->offs[cur->nreads] + rec.seq_len > cur->cap_bases)) { work_q.push(cur); cur = nullptr; }
-                if (!cur) { cur = pool.acquire(); cur->reset(seq++); }
-                const size_t at = (size_t)cur->offs[cur->nreads];
-                if (rec.seq_len > cur->cap_bases) cur->big.assign(rec.seq, rec.seq + rec.seq_len);      // alone in its chunk
-                else memcpy(cur->bases + at, rec.seq, rec.seq_len);
-                cur->offs[++cur->nreads] = (int64_t)(at + rec.seq_len);
-                cur->add_text(rec, keep_qual);
-            }
-        }
-        if (cur) work_q.push(cur);
+        nrecords = parse_files(files, pool, keep_qual, [&](Chunk* c) { c->seq = seq++; work_q.push(c); });
         total_chunks = (int64_t)seq;
         for (size_t d = 0; d < fl.ctx.size(); ++d) work_q.push(nullptr);
         dcv.notify_all();
@@ -398,7 +569,7 @@ bool any_stdin(const std::vector<const char*>& files) {
 void run_streamed(Fleet& fl, const Options& o, bool keep_qual, bool count_zeros,
                   const std::function<void(Chunk&)>& format) {
     ChunkPool pool;
-    pool.open(fl.ctx[0], 2 * (int)fl.ctx.size() + 6, chunk_bytes());
+    pool.open(fl.ctx[0], 2 * (int)fl.ctx.size() + 6 + 3 * parse_threads(), chunk_bytes());
     const auto write_out = [](Chunk& c) { fwrite(c.out.data(), 1, c.out.size(), stdout); };
     if (o.do_read_depth) {                              // pass 1: global k-mer count table (src/rkmh.cpp:904-910)
         fl.each([&](int, rkg_ctx* c) { RK(c, rkg_count_reset(c)); });
@@ -591,6 +762,21 @@ int main(int argc, char** argv) {
     if (cmd == "stream") return main_stream(argc, argv);
     if (cmd == "filter") return main_filter(argc, argv);
     if (cmd == "hash") return main_hash(argc, argv);
+    if (cmd == "parse-stream") {     // host-only: the records as the streaming front-end chunks them (parallel parser included)
+        std::vector<const char*> files(argv + 2, argv + argc);
+        ChunkPool pool;
+        pool.open(nullptr, 6 + 3 * parse_threads(), chunk_bytes());
+        parse_files(files, pool, true, [&](Chunk* c) {
+            for (size_t r = 0; r < c->nreads; ++r) {
+                const auto nm = c->name(r), ql = c->qual(r);
+                fwrite(nm.first, 1, nm.second, stdout); fputc('\t', stdout);
+                fwrite(c->data() + c->offs[r], 1, (size_t)(c->offs[r + 1] - c->offs[r]), stdout); fputc('\t', stdout);
+                fwrite(ql.first, 1, ql.second, stdout); fputc('\n', stdout);
+            }
+            pool.release(c);
+        });
+        return 0;
+    }
     if (cmd == "parse") {            // host-only debugging aid: dump the records the parser sees (no GPU needed)
         for (int i = 2; i < argc; ++i) {
             SeqSet set;

@@ -90,6 +90,25 @@ def test_parser_fast_path_fuzz(rkmh_bin, tmp_path):
             out = subprocess.run([rkmh_bin, "parse", str(f)], stdout=subprocess.PIPE, check=True,
                                  env=dict(os.environ, RKMH_PARSE_BUF=buf)).stdout
             assert out == exp, (case, buf)
+        # the streaming front-end's chunking with the parallel segment parser (tiny segments and chunks: segments that
+        # do not chain, records that are not well-formed and records larger than a chunk all hand over to the state machine)
+        for seg, chunk, thr in (("300", "2000", "4"), ("5000", "1500", "3"), ("700", "100000", "8")):
+            env = dict(os.environ, RKMH_PARSE_SEG=seg, RKMH_CHUNK_BYTES=chunk, RKMH_PARSE_THREADS=thr)
+            out = subprocess.run([rkmh_bin, "parse-stream", str(f)], stdout=subprocess.PIPE, check=True, env=env, timeout=60).stdout
+            assert out == exp, (case, seg, chunk, thr)
+
+
+def test_parallel_parser_on_fixtures(rkmh_bin, tmp_path):
+    """plain-text copies of the FASTQ fixtures through the parallel segment parser == the sequential parser"""
+    for name in ("z1.fq.gz", "mix2k.fq.gz", "minION25.fq.gz", "awkward_reads.fq.gz"):
+        plain = tmp_path / name[:-3]
+        plain.write_bytes(gzip.open(os.path.join(DATA, name), "rb").read())
+        exp = subprocess.run([rkmh_bin, "parse", str(plain)], stdout=subprocess.PIPE, check=True).stdout
+        for seg, chunk in (("4096", "30000"), ("20000", "8000"), ("100000", "1000000")):
+            env = dict(os.environ, RKMH_PARSE_SEG=seg, RKMH_CHUNK_BYTES=chunk, RKMH_PARSE_THREADS="4")
+            out = subprocess.run([rkmh_bin, "parse-stream", str(plain), os.path.join(DATA, name)], stdout=subprocess.PIPE,
+                                 check=True, env=env, timeout=120).stdout
+            assert out == exp + exp, (name, seg, chunk)
 
 
 def test_usage_and_exit_codes(rkmh_bin):
