@@ -1,0 +1,33 @@
+#!/bin/bash
+# Wall clock of `rkmh stream` on one synthetic config-2 FASTQ for several parser thread counts (best of 3 each).
+# usage: tools/cli_parse_scaling.sh [reads]
+set -e
+cd "$(dirname "$0")/.."
+N=${1:-8000000}
+W=$(mktemp -d)
+python - "$N" "$W" <<'PY'
+import sys, gzip, shutil, os
+import numpy as np
+sys.path.insert(0, os.getcwd())
+from rkmh_b200.fastx import load_sequences
+from rkmh_b200.synth import sample_reads, write_fastq
+n, w = int(sys.argv[1]), sys.argv[2]
+_, refs, _ = load_sequences(["tests/golden/data/all_pave_ref.fa.gz"])
+b, o = sample_reads(np.random.default_rng(2), refs, n, 150)
+write_fastq(os.path.join(w, "reads.fq"), b, o)
+with gzip.open("tests/golden/data/all_pave_ref.fa.gz", "rb") as fi, open(os.path.join(w, "refs.fa"), "wb") as fo:
+    shutil.copyfileobj(fi, fo)
+PY
+cat "$W/reads.fq" > /dev/null
+for t in 1 2 4 8; do
+  best=999
+  for rep in 1 2 3; do
+    s=$(date +%s.%N)
+    RKMH_PARSE_THREADS=$t rkmh_b200/bin/rkmh stream -r "$W/refs.fa" -f "$W/reads.fq" -k 12 -s 1000 > "$W/out.txt" 2>/dev/null
+    e=$(date +%s.%N)
+    d=$(python -c "print(round($e-$s,3))")
+    best=$(python -c "print(min($best,$d))")
+  done
+  echo "parse_threads=$t best_of_3_seconds=$best reads=$N md5=$(md5sum < "$W/out.txt" | cut -c1-12)"
+done
+rm -rf "$W"
