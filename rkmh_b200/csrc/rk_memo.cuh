@@ -503,12 +503,16 @@ classify_memo_warp_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
                 c0 = __ballot_sync(0xffffffffu, c2 & 1u); c1 = __ballot_sync(0xffffffffu, c2 & 2u);
                 cv = __ballot_sync(0xffffffffu, memo_base_invalid(ch));
             }
-            u32 chn = 32 + lane < len ? (u32)p[32 + lane] : 0u;
+            // four rounds of bases in flight (a 150-base read is requested whole before its first window is looked up)
+            auto loadb = [&](int at) -> u32 { return at + lane < len ? (u32)p[at + lane] : 0u; };
+            u32 q0 = loadb(32), q1 = loadb(64), q2 = loadb(96), q3 = loadb(128);
+#pragma unroll 4
             for (int base = 0; base < n; base += 32) {
+                const u32 chn = q0;
+                q0 = q1; q1 = q2; q2 = q3; q3 = loadb(base + 160);
                 const u32 c2 = base_code(chn);
                 const u32 n0 = __ballot_sync(0xffffffffu, c2 & 1u), n1 = __ballot_sync(0xffffffffu, c2 & 2u);
                 const u32 nv = __ballot_sync(0xffffffffu, memo_base_invalid(chn));
-                chn = base + 64 + lane < len ? (u32)p[base + 64 + lane] : 0u;     // in flight while this round is processed
                 const u32 f0 = __funnelshift_r(c0, n0, (u32)lane) & kmask;
                 const u32 f1 = __funnelshift_r(c1, n1, (u32)lane) & kmask;
                 const u32 fv = __funnelshift_r(cv, nv, (u32)lane) & kmask;
