@@ -33,6 +33,7 @@ class Emu:
         lib.emu_count.argtypes = [P, P, L, P, I, P, U, I, I]
         lib.emu_sketch.argtypes = [P, P, L, P, I, I, P, U, I, I, P, P, I, I]
         lib.emu_merge.argtypes = [P, P, I, I, P, P, I, I]
+        lib.emu_sketch_shard.argtypes = [P, L, L, I, I, P, P, I]
         lib.emu_classify.argtypes = [P, P, I, P, P, L, P, I, I, P, U, I, I, I, I, I, I, P, P, P, P]
         lib.emu_count_memo.argtypes = [P, P, L, I, P, U, I, I, I]
         lib.emu_classify_memo.argtypes = [P, P, I, P, P, L, I, I, P, U, I, I, I, I, P, P]
@@ -63,6 +64,15 @@ class Emu:
                             C.c_uint64(counts.size if counts is not None else 0), mode, occ,
                             sk.ctypes.data, lens.ctypes.data, block, int(force_global_sort))
         return sk, lens
+
+    def sketch_shard(self, seq, n, k, s, block=64):
+        seq = np.ascontiguousarray(np.frombuffer(seq, np.uint8))
+        out = np.zeros(s, np.uint64)
+        m = np.zeros(1, np.int32)
+        rc = self.lib.emu_sketch_shard(seq.ctypes.data, C.c_int64(seq.size), C.c_int64(n), int(k), int(s), out.ctypes.data,
+                                       m.ctypes.data, block)
+        assert rc == 0, rc
+        return out[:m[0]]
 
     def merge(self, parts, lens, s, block=64, in_smem=True):
         parts = np.ascontiguousarray(parts, np.uint64)

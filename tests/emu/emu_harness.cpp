@@ -159,6 +159,38 @@ int emu_sketch(const char* bases, const i64* offs, i64 nseq, const int* ks, int 
     return 0;
 }
 
+// rkg_sketch_shard's kernels (histogram of the top 16 hash bits, pick, emit, sort) on the first n windows of one record
+int emu_sketch_shard(const char* bases, i64 nbytes, i64 n, int k, int s, u64* out, int* out_len, int block) {
+    int ks[1] = {k}; int kcsel; KList kl = make_klist(ks, 1, &kcsel);
+    const i64 offs[2] = {0, nbytes};
+    HostBatch b; fill_batch(b, bases, offs, 1, kl, block);
+    std::vector<u32> hist(SHARD_BINS, 0);
+    u64 pick[2] = {0, 0};
+    const u32* pc = b.codes.data(); const u32* pm = b.nmask.data(); u32* ph = hist.data(); u64* pp = pick;
+    dispatch(kcsel, [&](auto tag) {
+        constexpr int KS = decltype(tag)::value;
+        emu::launch(dim3(2), dim3(block), 0, [=] { shard_hist_kernel<KS>(pc, pm, n, kl, ph); });
+    });
+    emu::launch(dim3(1), dim3(1024), 0, [=] { shard_pick_kernel(ph, (u64)s, pp); });
+    const u64 kept = pick[1];
+    *out_len = 0;
+    if (kept == 0) return 0;
+    const int P = next_pow2((i64)std::max<u64>(kept, 2));
+    std::vector<u64> cand(P, 0);
+    unsigned long long ncand = 0;
+    u64* pcand = cand.data(); unsigned long long* pn = &ncand;
+    dispatch(kcsel, [&](auto tag) {
+        constexpr int KS = decltype(tag)::value;
+        emu::launch(dim3(2), dim3(block), 0, [=] { shard_emit_kernel<KS>(pc, pm, n, kl, pp, pcand, pn, kept); });
+    });
+    if (ncand != kept) return -2;
+    emu::launch(dim3(1), dim3(block), 0, [=] { shard_sort_kernel(pcand, (int)kept, P); });
+    const int m = (int)std::min<u64>(kept, (u64)s);
+    std::copy(cand.begin(), cand.begin() + m, out);
+    *out_len = m;
+    return 0;
+}
+
 int emu_merge(const u64* parts, const int* part_lens, int nparts, int s, u64* out, int* out_len, int block, int in_smem) {
     const int P = next_pow2(std::max(s, 2));
     std::vector<u64> scr(P);

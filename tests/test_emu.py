@@ -159,3 +159,20 @@ def test_memo_count_and_min_occ(emu, oracle):
         for path in (0, 1):                       # with a -M mask baked the sieve / tile kernels are not eligible
             _memo_case(emu, oracle, refs[:4], reads, 8, 200, counts=c, min_occ=m, path=path)
     _memo_case(emu, oracle, refs[:4], reads, 8, 200, counts=c, min_occ=30, path=4)     # falls back to the warp kernel
+
+
+def test_sketch_shard_kernels(emu, oracle):
+    """rkg_sketch_shard's histogram / pick / emit / sort kernels == minhashes(calc_hashes()) of the oracle: more windows
+    than s, fewer than s, invalid bases, a period-4 repeat whose few hashes occur thousands of times, and a middle shard."""
+    rng = np.random.default_rng(3)
+    seq = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=30000, p=[.245, .245, .245, .245, .02]).tobytes()
+    for k, s in ((21, 500), (12, 64), (5, 3000)):
+        n = len(seq) - k
+        assert np.array_equal(emu.sketch_shard(seq, n, k, s), oracle.minhashes(oracle.calc_hashes(seq, [k]), s)), (k, s)
+    mid = seq[5000:9000 + 21]
+    assert np.array_equal(emu.sketch_shard(mid, 4000, 21, 300), oracle.minhashes(oracle.calc_hashes(mid, [21]), 300))
+    tiny = seq[:400]
+    assert np.array_equal(emu.sketch_shard(tiny, len(tiny) - 21, 21, 1000), oracle.minhashes(oracle.calc_hashes(tiny, [21]), 1000))
+    assert len(emu.sketch_shard(b"N" * 300, 279, 21, 50)) == 0
+    rep = b"ACGT" * 2000
+    assert np.array_equal(emu.sketch_shard(rep, len(rep) - 21, 21, 100), oracle.minhashes(oracle.calc_hashes(rep, [21]), 100))
