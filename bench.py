@@ -31,6 +31,10 @@ WORKLOAD = ("BASELINE config 2: rkmh stream -r all_pave_ref.fa -k 12 -s 1000, sy
             "(90% sampled from the 182 refs, 0.5% subs, 0.1% N; 10% random)")
 # DRAM bytes per read (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of a 2 M-read launch,
 # divided by the reads); `roofline.traffic` scales it to the reads of one launch.  Kernels without a capture report null.
+# Warp instructions per read of each kernel (smsp__inst_executed.sum of the same captures / reads): with the live launch time
+# and SM clock they give the fraction of the chip's issue slots (148 SMs x 4 schedulers x 1 instruction per clock) in use,
+# which is the resource these kernels are bound by (the HBM `roofline` above is reported because the contract asks for it).
+WARP_INSTR_PER_READ = {"classify_memo_sieve_kernel": 657.6, "classify_memo_warp_kernel": 803.6, "classify_group_kernel": 1805.8}
 TRAFFIC_PER_READ = {"classify_memo_sieve_kernel": 188.6,      # profiles/r01_sieve_final_ncu_raw.json (377.2 MB / 2 M reads)
                     "classify_memo_warp_kernel": 1831.4,      # profiles/r01_memo_warp_ncu_raw.json
                     "classify_group_kernel": 91.0}            # profiles/r01_group_kernel_ncu_raw.json
@@ -323,6 +327,10 @@ def main_ours(args, rank, world, local_rank):
             with open(pk) as fh:
                 peaks = json.load(fh)
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        try:
+            sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        except Exception:
+            sm_count = 148
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         # dominant kernel = the one with the largest share of the timed region
         dom = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else ("none", {"ms": 0.0, "launches": 1})
@@ -340,6 +348,16 @@ def main_ours(args, rank, world, local_rank):
         else:
             note = ("the kernel is INT-pipe bound (2 x MurmurHash3_x64_128 per k-mer), not HBM bound; see DESIGN.md "
                     "section 5")
+        issue_slots = None
+        try:
+            if dom[0] in WARP_INSTR_PER_READ and dom_ms > 0:
+                got = WARP_INSTR_PER_READ[dom[0]] * n / (dom_ms / 1e3)
+                peak = sm_count * 4 * float(clocks.get("sm_mhz") or 1965.0) * 1e6
+                issue_slots = {"kernel": dom[0], "warp_instructions_per_read": WARP_INSTR_PER_READ[dom[0]],
+                               "achieved": got / 1e12, "peak": peak / 1e12, "unit": "T warp-instructions/s", "frac": got / peak,
+                               "source": "instruction count from ncu (profiles/), launch time and SM clock live"}
+        except Exception:                                 # explanatory only: never in the way of the bench line
+            issue_slots = None
         line = {
             "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
@@ -359,6 +377,7 @@ def main_ours(args, rank, world, local_rank):
             "roofline": {"kernel": dom[0], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": (TRAFFIC_PER_READ[dom[0]] * n if dom[0] in TRAFFIC_PER_READ else None), "peak_source": peak_src,
                          "algorithmic_bytes_per_read": bytes_per_read, "note": note},
+            "issue_slots": issue_slots,
             "dominant_kernel": {"kernel": dom[0], "ms_per_launch": dom_ms,
                                 "kmers_per_s_per_gpu": (n * (READ_LEN - K)) / (dom_ms / 1e3) if dom_ms > 0 else 0.0},
         }
