@@ -128,7 +128,10 @@ int rkg_synchronize(rkg_ctx* ctx);
  * the read count table (rkg_count_table) keeps the reference's layout.  On by default (environment
  * RKMH_NO_MEMO=1 or rkg_set_memo(ctx, 0) force the Murmur path for every k); a change takes effect at
  * the next rkg_load_refs.  After all-reducing the table obtained from rkg_count_table, call
- * rkg_count_table again before any later all-reduce: the call marks the table as changed. */
+ * rkg_count_table again before any later all-reduce: the call marks the table as changed.
+ * Short reads (every k-mer is in the sketch), at most 256 references and no min_occ take the sieve kernel (sketch
+ * membership from a shared-memory Bloom filter, hits through an L2-resident code map; RKMH_NO_SIEVE=1 turns it off,
+ * RKMH_TILE=1 selects the thread-per-read variant instead); every variant returns the same records. */
 int rkg_set_memo(rkg_ctx* ctx, int enable);
 int rkg_memo_active(const rkg_ctx* ctx);
 
@@ -146,7 +149,9 @@ int rkg_hash_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t
  * context (sequence sharding for `hash` on a multi-GPU box; one k-mer size): `bases` holds record bytes
  * [kmer_begin, min(kmer_end, record_len - k) + k), record_len is the length of the WHOLE record (so
  * that the reference's len-k window count applies only at the true end).  Emits this shard's bottom-s
- * multiset; the caller all-gathers the shards and calls rkg_merge_sketches. */
+ * multiset; the caller all-gathers the shards and calls rkg_merge_sketches.  The shard is hashed on the device as
+ * one record (two passes: histogram of the top hash bits, then the hashes below the s-th smallest are kept and
+ * sorted); a pinned `bases` buffer (rkg_host_alloc) makes the upload run at link speed. */
 int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t kmer_begin, int64_t kmer_end,
                      int64_t record_len, uint64_t* sketch, int32_t* len);
 /* Multiset merge of `nparts` sorted sketches (parts is [nparts * s]) keeping the first s. */
