@@ -59,6 +59,9 @@ CLI_CASES = {
     "filter_zika_z1_N5": ("filter", ["filter", "-r", "zika.fa.gz", "-f", "z1.fq.gz", "-k", "20", "-s", "2000", "-N", "5"]),
     "filter_hpv16_minion_N50": ("filter", ["filter", "-r", "hpv_16.fa.gz", "-f", "minION25.fq.gz", "-k", "12", "-s", "1000", "-N", "50"]),
     "filter_dengue_z1": ("filter", ["filter", "-r", "dengue.fa.gz", "-f", "z1.fq.gz", "-k", "20", "-s", "2000"]),
+    "pave_two_read_files_k12": ("stream", ["stream", "-r", "all_pave_ref.fa.gz", "-f", "z1.fq.gz", "-f", "mix2k.fq.gz", "-k", "12", "-s", "1000"]),
+    "pave_fasta_reads_k12": ("stream", ["stream", "-r", "all_pave_ref.fa.gz", "-f", "hpv_16_allFasta.fa.gz", "-k", "12", "-s", "1000"]),
+    "two_ref_files_multik_M2": ("stream", ["classify", "-r", "hpv_16_allFasta.fa.gz", "-r", "new_refs.fa.gz", "-f", "minION25.fq.gz", "-k", "10", "-k", "14", "-s", "500", "-M", "2", "-N", "5", "-D", "2"]),
     "filter_viral4_z1_M2_D2": ("filter", ["filter", "-r", "zika.fa.gz", "-r", "dengue.fa.gz", "-r", "yellow_fever.fa.gz", "-r", "hpv_16.fa.gz", "-f", "z1.fq.gz", "-k", "20", "-s", "2000", "-M", "2", "-D", "2"]),
 }
 
