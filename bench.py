@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step (config 2: 10 M)")
-    ap.add_argument("--cpu-sample", type=int, default=300_000, help="reads in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="reads in the CPU baseline sample (about 10 s of the reference on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
