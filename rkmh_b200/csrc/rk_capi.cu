@@ -313,7 +313,8 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
         ctx->sieve_fill = (double)set_bits / (32.0 * nwords);
         mm.zero_codes = hstats[1];
         if (ctx->sieve_fill <= 0.5) {
-            const u32 cap = (u32)next_pow2(std::max<i64>(8 * (i64)hstats[0], 1024));   // load <= 1/8: one probe, nearly always
+            // load <= 1/16: one probe, nearly always (config 2, sieve kernel per 10 M reads: load 1/2 9.4 ms, 1/4 8.1, 1/8 7.8, 1/16 7.7, 1/32 7.8)
+            const u32 cap = (u32)next_pow2(std::max<i64>(16 * (i64)hstats[0], 1024));
             int log2cap = 0; while ((1u << log2cap) < cap) ++log2cap;
             CK(ctx->memo_cmap.ensure(sizeof(u64) * (size_t)cap));
             CK(cudaMemsetAsync(ctx->memo_cmap.p, 0xFF, sizeof(u64) * (size_t)cap, st));

@@ -572,7 +572,7 @@ classify_memo_warp_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
 //     touch global memory at all; the 64 MB rank table is not read (it only half fits a die's L2: ncu showed 37 % of
 //     its lookups going to HBM);
 //   * those windows are looked up AFTER the read has been streamed, all lanes at once, in a compact open-addressing
-//     map code -> table slot + 1 (8 B entries, ~4 MB at 182 references, L2 resident), which replaces the two dependent
+//     map code -> table slot + 1 (8 B entries, load 1/16: 32 MB at 182 references, L2 resident), which replaces the two dependent
 //     lookups tab[code] -> ref[rank]; the bitset rows follow as before.  A read costs two dependent L2 round trips
 //     instead of seven;
 //   * the number of counted windows (sketch_len) is the number of valid windows: no table value is needed for it
