@@ -199,6 +199,7 @@ static inline unsigned long long __umul64hi(unsigned long long a, unsigned long 
     return (unsigned long long)(((unsigned __int128)a * b) >> 64);
 }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline T __ldcs(const T* p) { return *p; }
 template <typename T> static inline T min(T a, T b) { return a < b ? a : b; }
 template <typename T> static inline T max(T a, T b) { return a > b ? a : b; }
 
