@@ -66,3 +66,15 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"oracle[/.]|rkmh_oracle|liboracle|rko_", txt):
                     bad.append(os.path.join(base, f))
     assert not bad, bad
+
+
+def test_numa_binding_helper_is_harmless_without_a_gpu():
+    """bind_host_thread_to_gpu never raises and never empties the affinity mask (None when NVML / the GPU is missing)."""
+    import os
+    import rkmh_b200
+    before = os.sched_getaffinity(0)
+    got = rkmh_b200.bind_host_thread_to_gpu(0)
+    after = os.sched_getaffinity(0)
+    assert after and after <= before
+    assert got is None or set(got) == after
+    os.sched_setaffinity(0, before)
