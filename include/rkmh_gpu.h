@@ -18,6 +18,11 @@
  *     host<->device copies asynchronous.
  *   - there is NO CPU fallback: every entry point fails with RKG_ERR_CUDA when no sm_100 device is usable.
  *   - k-mer sizes 1..32 are supported (the reference accepts any int; its data sets use 10..21).
+ *   - sketch sizes 1..2^26; nrefs x sketch_size <= 2^29.  The reference table is DENSE in the references (one bit per
+ *     reference per distinct sketch hash): its size is about 2 nrefs s x (1 + ceil(nrefs / 64)) x 8 bytes, i.e.
+ *     quadratic in nrefs -- 182 references at s = 1000 take 16 MB, 5,000 about 11 GB, 20,000 do not fit a B200.  The
+ *     reference's own cost is O(nrefs x s) memory and O(nrefs x s) time PER READ; nothing on this path needs more
+ *     than a few thousand references (rkg_load_refs fails with RKG_ERR_NOMEM when the table does not fit).
  */
 #ifndef RKMH_GPU_H
 #define RKMH_GPU_H
@@ -66,7 +71,9 @@ int rkg_set_params(rkg_ctx* ctx, const int* ks, int nk, int sketch_size,
                    uint64_t read_table_size, uint64_t ref_table_size);
 
 /* Pinned host memory for batch buffers (replaces the per-record `new char[]` of parse_fastas,
- * src/rkmh.cpp:238-263). */
+ * src/rkmh.cpp:238-263).  These two calls are THREAD-SAFE: they may run concurrently with any other call on the
+ * same context (a parser thread pins chunks while a worker thread classifies); on failure the text is in
+ * rkg_last_error(NULL) of the calling thread, the context's own error slot is not touched. */
 int rkg_host_alloc(rkg_ctx* ctx, size_t bytes, void** ptr);
 int rkg_host_free(rkg_ctx* ctx, void* ptr);
 
@@ -94,6 +101,14 @@ int rkg_count_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_
  * all-reduce it (ncclAllReduce / torch.distributed.all_reduce, sum, int32) between pass 1 and pass 2:
  * the `#pragma omp for` barrier at src/rkmh.cpp:910 is the only global point of the path. */
 int rkg_count_table(rkg_ctx* ctx, void** device_ptr, uint64_t* nslots);
+/* The same exchange with 12.5x fewer bytes when the memoised path is active (single k <= 12, see below): pass 1 then
+ * keeps its increments per k-mer CODE (4^k int32 slots, 64 MB at k = 12, + a few slots for the windows with an invalid
+ * base) and folds them into counts[hash % size] afterwards.  The fold is linear, so summing the per-code arrays of all
+ * ranks BEFORE the fold gives every rank the table the reference builds (src/rkmh.cpp:904-910).  Call after this
+ * rank's rkg_count_batch calls (count_zeros = the flag they used; a rank without reads calls it all the same),
+ * all-reduce (sum, int32) device_ptr[0 .. nslots) in place, then go on with rkg_classify_batch / rkg_count_table: the
+ * summed array is folded at its next use.  RKG_ERR_STATE when the memoised path is not active (use rkg_count_table). */
+int rkg_count_partial(rkg_ctx* ctx, int count_zeros, void** device_ptr, uint64_t* nslots);
 /* Parity/debug: counts[keys[i] % read_table_size] for n keys. */
 int rkg_count_lookup(rkg_ctx* ctx, const uint64_t* keys, int64_t n, int32_t* out);
 
@@ -103,6 +118,13 @@ int rkg_count_lookup(rkg_ctx* ctx, const uint64_t* keys, int64_t n, int32_t* out
  * src/rkmh.cpp:845-898, 911-948 and 1251-1298.  Host buffers in, host results out. */
 int rkg_classify_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads,
                        int min_occ, rkg_hit* out);
+
+/* The same for a batch of FIXED-LENGTH reads (Illumina: every record of a chunk has read_len bases, read i is
+ * bases[i * read_len .. (i + 1) * read_len)): no offsets array crosses the PCIe link -- the path is bound by the
+ * host-to-device copy, and 8 bytes of offset per 150-base read are 5 % of it.  Same results as rkg_classify_batch /
+ * rkg_count_batch on the equivalent offsets. */
+int rkg_classify_fixed(rkg_ctx* ctx, const char* bases, int64_t read_len, int64_t nreads, int min_occ, rkg_hit* out);
+int rkg_count_fixed(rkg_ctx* ctx, const char* bases, int64_t read_len, int64_t nreads, int count_zeros);
 
 /* The same in two steps for callers that keep batches resident in HBM (and for kernel-only timing):
  * upload once, classify any number of times, fetch results. */
@@ -130,8 +152,8 @@ int rkg_synchronize(rkg_ctx* ctx);
  * the next rkg_load_refs.  After all-reducing the table obtained from rkg_count_table, call
  * rkg_count_table again before any later all-reduce: the call marks the table as changed.
  * Short reads (every k-mer is in the sketch), at most 256 references and no min_occ take the sieve kernel (sketch
- * membership from a shared-memory Bloom filter, hits through an L2-resident code map; RKMH_NO_SIEVE=1 turns it off,
- * RKMH_TILE=1 selects the thread-per-read variant instead); every variant returns the same records. */
+ * membership from a shared-memory Bloom filter, hits through an L2-resident code map; RKMH_NO_SIEVE=1 turns it off);
+ * every variant returns the same records. */
 int rkg_set_memo(rkg_ctx* ctx, int enable);
 int rkg_memo_active(const rkg_ctx* ctx);
 
@@ -159,6 +181,10 @@ int rkg_merge_sketches(rkg_ctx* ctx, const uint64_t* parts, const int32_t* part_
                        uint64_t* sketch, int32_t* len);
 
 /* ---- measurement --------------------------------------------------------------------------------- */
+/* The host<->device copies of rkg_classify_batch (offs != NULL) or rkg_classify_fixed (offs == NULL, read_len) on the
+ * same chunking and streams, WITHOUT the kernels: the ceiling the end-to-end rate can reach on this host.  `out`
+ * receives whatever the device hit buffer holds. */
+int rkg_copy_probe(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t read_len, int64_t nreads, rkg_hit* out);
 /* Number of kernels this context has launched so far. */
 int64_t rkg_launch_count(const rkg_ctx* ctx);
 /* Per-kernel device time: when enabled every launch is bracketed by CUDA events on its stream. */

@@ -168,6 +168,19 @@ class RkmhGpu:
 
         return torch.as_tensor(_Mem(), device=f"cuda:{self.device}")
 
+    def count_partial_tensor(self, count_zeros=False):
+        """The per-code partial counts of pass 1 (memoised path, 4^k + 32 int32 slots) as a torch int32 CUDA tensor
+        sharing the library's memory: all-reduce THIS instead of the 200 M-slot table (include/rkmh_gpu.h)."""
+        import torch
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.rkg_count_partial(self.handle, int(count_zeros), C.byref(p), C.byref(n)))
+        ptr, n = p.value, n.value
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+
+        return torch.as_tensor(_Mem(), device=f"cuda:{self.device}")
+
     def count_lookup(self, keys):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         out = np.zeros(max(keys.size, 1), np.int32)
@@ -187,6 +200,25 @@ class RkmhGpu:
 
     def classify_raw(self, bases_ptr, offs_ptr, nreads, min_occ, out_ptr):
         self._check(self.lib.rkg_classify_batch(self.handle, bases_ptr, offs_ptr, nreads, int(min_occ), out_ptr))
+
+    def classify_fixed_raw(self, bases_ptr, read_len, nreads, min_occ, out_ptr):
+        self._check(self.lib.rkg_classify_fixed(self.handle, bases_ptr, int(read_len), int(nreads), int(min_occ), out_ptr))
+
+    def classify_fixed(self, bases, read_len, min_occ=-1):
+        """rkg_classify_fixed: every read has read_len bases (no offsets cross the link)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        n = bases.size // read_len if read_len else 0
+        out = np.zeros(max(n, 1), HIT_DTYPE)
+        self.classify_fixed_raw(bases.ctypes.data, read_len, n, min_occ, out.ctypes.data)
+        return out[:n]
+
+    def count_fixed(self, bases, read_len, count_zeros=False):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        n = bases.size // read_len if read_len else 0
+        self._check(self.lib.rkg_count_fixed(self.handle, bases.ctypes.data, int(read_len), n, int(count_zeros)))
+
+    def copy_probe_raw(self, bases_ptr, offs_ptr, read_len, nreads, out_ptr):
+        self._check(self.lib.rkg_copy_probe(self.handle, bases_ptr, offs_ptr, int(read_len), int(nreads), out_ptr))
 
     def upload(self, bases, offs):
         bases, offs = self._buffers(bases, offs)

@@ -26,14 +26,13 @@ thread_local std::string g_create_error;
 
 enum KernelId { K_INGEST, K_HASH, K_COUNT, K_COUNT_DISTINCT, K_SKETCH, K_MERGE, K_TABLE, K_CLASSIFY_GROUP,
                 K_CLASSIFY_BLOCK, K_MEMO_BUILD, K_MEMO_MAINT, K_COUNT_MEMO, K_CLASSIFY_MEMO_WARP, K_CLASSIFY_MEMO_BLOCK,
-                K_CLASSIFY_MEMO_TILE, K_CLASSIFY_MEMO_SIEVE,
+                K_CLASSIFY_MEMO_SIEVE,
                 K_NUM };
 const char* const kKernelNames[K_NUM] = {"ingest_kernel", "hash_kernel", "count_kernel", "count_distinct_kernel",
                                          "sketch_kernel", "merge_kernel", "table_build_kernels",
                                          "classify_group_kernel", "classify_block_kernel", "memo_build_kernels",
                                          "memo_fold_apply_kernels", "count_memo_kernel", "classify_memo_warp_kernel",
-                                         "classify_memo_block_kernel", "classify_memo_tile_kernel",
-                                         "classify_memo_sieve_kernel"};
+                                         "classify_memo_block_kernel", "classify_memo_sieve_kernel"};
 
 struct DevBuf {
     void* p = nullptr;
@@ -85,8 +84,8 @@ struct rkg_ctx {
     cudaStream_t stream = nullptr;
     rkg_batch* slots[2] = {nullptr, nullptr};   // internal double buffer of rkg_classify_batch / count
     // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
-    bool memo_enabled = true, memo_ready = false, tile_kernel = false, sieve_enabled = true;
-    DevBuf memo_tab, memo_sieve_t, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc, memo_sieve, memo_cmap;
+    bool memo_enabled = true, memo_ready = false, sieve_enabled = true;
+    DevBuf memo_tab, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc, memo_sieve, memo_cmap;
     double sieve_fill = 0.0;             // fraction of the sieve's bits that are set (false-positive rate = fill^2)
     Memo memo{};
     bool memo_pending = false;           // code_counts holds increments not yet folded into the read count table
@@ -114,7 +113,8 @@ int fail(rkg_ctx* c, int code, const char* fmt, ...) {
     do {                                                                                              \
         cudaError_t e__ = (call);                                                                     \
         if (e__ != cudaSuccess)                                                                       \
-            return fail(ctx, RKG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? RKG_ERR_NOMEM : RKG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                 \
     } while (0)
 
 struct Timed {   // brackets one launch with events when profiling is on
@@ -141,7 +141,11 @@ void profile_collect(rkg_ctx* c) {
     c->events.clear();
 }
 
-int next_pow2(i64 v) { int p = 1; while (p < v) p <<= 1; return p; }
+// smallest power of two >= v; 0 when it would not fit the 2^30 the callers can index with (they fail with RKG_ERR_ARG)
+int next_pow2(i64 v) {
+    if (v > (i64)1 << 30) return 0;
+    int p = 1; while (p < v) p <<= 1; return p;
+}
 
 // Launch helper over the key-length-variant template parameter (NUM_KV = mixed variants).
 #define DISPATCH_KCSEL(sel, ...)                  \
@@ -195,10 +199,18 @@ int launch_ingest(rkg_ctx* ctx, rkg_batch* b) {
 // The Murmur-path kernels read the packed codes; the memoised path reads the ASCII bases and never needs them.
 int ensure_packed(rkg_ctx* ctx, rkg_batch* b) { return b->packed ? RKG_OK : launch_ingest(ctx, b); }
 
+// offs[i] = base0 + i * len for i in [0, n]: the offsets of a batch of fixed-length reads, made on the device so that
+// they never cross the PCIe link (8 bytes per read: 5 % of the host-to-device bytes of 150-base reads)
+__global__ void __launch_bounds__(256)
+fixed_offs_kernel(i64* __restrict__ offs, i64 n, i64 base0, i64 len) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (i64)gridDim.x * blockDim.x) offs[i] = base0 + i * len;
+}
+
 // Copy reads [r0, r1) of the caller's buffers into the batch (asynchronous on b->stream); packing is done on demand.
-int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* offs, i64 r0, i64 r1) {
+// offs == nullptr: every read has `fixed_len` bases and read i starts at bases[i * fixed_len].
+int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* offs, i64 r0, i64 r1, i64 fixed_len = 0) {
     const i64 n = r1 - r0;
-    const i64 base0 = offs[r0], total = offs[r1] - base0;
+    const i64 base0 = offs ? offs[r0] : r0 * fixed_len, total = offs ? offs[r1] - base0 : n * fixed_len;
     b->nseq = n; b->total = total; b->base0 = base0;
     const i64 nwords32 = (total + 31) / 32;
     CK(b->bases.ensure((size_t)nwords32 * 32 + 64));
@@ -209,13 +221,18 @@ int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* off
     CK(b->redo.ensure(sizeof(int) * (size_t)std::max<i64>(n, 1)));
     CK(b->misc.ensure(256));
     if (total > 0) CK(cudaMemcpyAsync(b->bases.p, bases + base0, (size_t)total, cudaMemcpyHostToDevice, b->stream));
-    CK(cudaMemcpyAsync(b->offs.p, offs + r0, sizeof(i64) * (size_t)(n + 1), cudaMemcpyHostToDevice, b->stream));
+    if (offs) CK(cudaMemcpyAsync(b->offs.p, offs + r0, sizeof(i64) * (size_t)(n + 1), cudaMemcpyHostToDevice, b->stream));
+    else {
+        ++ctx->launches;
+        fixed_offs_kernel<<<(int)std::min<i64>((n + 256) / 256, (i64)ctx->sm_count * 8), 256, 0, b->stream>>>(b->offs.as<i64>(), n, base0, fixed_len);
+        CK(cudaGetLastError());
+    }
     // the reader may touch one word past the end: keep the padding defined
     CK(cudaMemsetAsync(b->codes.as<u32>() + 2 * nwords32, 0, sizeof(u32) * 8, b->stream));
     CK(cudaMemsetAsync(b->nmask.as<u32>() + nwords32, 0xFF, sizeof(u32) * 8, b->stream));
     // longest read of the batch (sizes the exact path's scratch); overlaps the copies above
-    i64 max_len = 0;
-    for (i64 r = r0; r < r1; ++r) max_len = std::max<i64>(max_len, offs[r + 1] - offs[r]);
+    i64 max_len = offs ? 0 : fixed_len;
+    if (offs) for (i64 r = r0; r < r1; ++r) max_len = std::max<i64>(max_len, offs[r + 1] - offs[r]);
     b->max_len = max_len;
     i64 mt = 0;
     for (int j = 0; j < ctx->kl.nk; ++j) mt += std::max<i64>(max_len - ctx->kl.k[j], 0);
@@ -257,14 +274,15 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     CK(cudaMemsetAsync(ctx->memo_misc.p, 0, 256, st));
     Memo mm{};
     mm.tab = ctx->memo_tab.as<u32>(); mm.ref = ctx->memo_ref.as<u32>(); mm.hash = ctx->memo_hash.as<u64>();
-    mm.inval = ctx->memo_misc.as<unsigned long long>();
+    mm.inval = nullptr;
     int* err = ctx->memo_misc.as<int>() + 8;
     mm.ncodes = ncodes; mm.kmask = (1u << k) - 1u; mm.k = k;
     mm.code_counts = nullptr;
     if (ctx->read_ct.counts) {
-        CK(ctx->memo_counts.ensure(sizeof(int) * (size_t)ncodes));
-        CK(cudaMemsetAsync(ctx->memo_counts.p, 0, sizeof(int) * (size_t)ncodes, st));
+        CK(ctx->memo_counts.ensure(sizeof(int) * ((size_t)ncodes + MEMO_PARTIAL_PAD)));
+        CK(cudaMemsetAsync(ctx->memo_counts.p, 0, sizeof(int) * ((size_t)ncodes + MEMO_PARTIAL_PAD), st));
         mm.code_counts = ctx->memo_counts.as<int>();
+        mm.inval = ctx->memo_counts.as<u32>() + ncodes;
     }
     {
         Timed t(ctx, st, K_MEMO_BUILD);
@@ -288,7 +306,7 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     if (herr) return RKG_OK;          // a hash bucket larger than the sort capacity: keep the Murmur path (still exact)
     // sieve + code map of classify_memo_sieve_kernel (rk_memo.cuh).  The sieve takes what a 1024-thread block can
     // have beside its candidate queues; it is dropped when it would let more than a quarter of all windows through.
-    mm.sieve = nullptr; mm.sieve_t = nullptr; mm.cmap = nullptr; mm.sieve_words = 0; mm.sieve_t_words = 0; mm.zero_codes = 0;
+    mm.sieve = nullptr; mm.cmap = nullptr; mm.sieve_words = 0; mm.zero_codes = 0;
     ctx->sieve_fill = 0.0;
     const size_t queues = (size_t)32 * SIEVE_QCAP * 4 + 1024;
     if (ctx->sieve_enabled && ctx->tb.entries != nullptr && ctx->smem_optin > queues + 8192) {
@@ -327,24 +345,6 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
             CK(cudaStreamSynchronize(st));
             mm.sieve = ctx->memo_sieve.as<u32>(); mm.sieve_words = nwords;
             mm.cmap = ctx->memo_cmap.as<unsigned long long>(); mm.cmap_mask = cap - 1; mm.cmap_shift = 32 - log2cap;
-            // the thread-per-read tile kernel shares its block's shared memory with the staged reads: a smaller sieve
-            if (ctx->tile_kernel && ctx->smem_optin > TILE_FIXED_SMEM + 1024 + 16384) {
-                const u32 nwt = (u32)((ctx->smem_optin - TILE_FIXED_SMEM - 1024) / 4);
-                CK(ctx->memo_sieve_t.ensure(sizeof(u32) * (size_t)nwt));
-                CK(cudaMemsetAsync(ctx->memo_sieve_t.p, 0, sizeof(u32) * (size_t)nwt, st));
-                {
-                    Timed t(ctx, st, K_MEMO_BUILD);
-                    memo_sieve_kernel<<<grid, 256, 0, st>>>(mm, ctx->memo_sieve_t.as<u32>(), nwt, stats + 2);
-                    ctx->launches += 1;
-                }
-                CK(cudaGetLastError());
-                std::vector<u32> image_t(nwt);
-                CK(cudaMemcpyAsync(image_t.data(), ctx->memo_sieve_t.p, sizeof(u32) * (size_t)nwt, cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                size_t bits_t = 0;
-                for (u32 w : image_t) bits_t += (size_t)__builtin_popcount(w);
-                if ((double)bits_t / (32.0 * nwt) <= 0.5) { mm.sieve_t = ctx->memo_sieve_t.as<u32>(); mm.sieve_t_words = nwt; }
-            }
         }
     }
     ctx->memo = mm;
@@ -434,7 +434,7 @@ GroupGeom group_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
 }
 
 // Geometry of the two memoised classification kernels for this batch, or ok = false (Murmur path instead).
-struct MemoGeom { bool ok, use_warp, use_tile; int warp_block, rwords; size_t warp_smem; int vcap, hs_cap, rpad; size_t block_smem; i64 scratch_stride; };
+struct MemoGeom { bool ok, use_warp; int warp_block, rwords; size_t warp_smem; int vcap, hs_cap, rpad; size_t block_smem; i64 scratch_stride; };
 
 MemoGeom memo_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
     MemoGeom g{};
@@ -457,10 +457,6 @@ MemoGeom memo_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
             const size_t smem = (size_t)(block / 32) * (sizeof(MemoWarpSmem) + (size_t)g.rwords * 4);
             if (smem <= ctx->smem_optin) { g.use_warp = true; g.warp_block = block; g.warp_smem = smem; break; }
         }
-        // thread per read (opt-in, RKMH_TILE=1: measured 2x slower than the sieve kernel on config 2 -- 12 warps per SM and
-        // divergent per-thread resolve loops): every read of the batch has at most TILE_MAXWIN windows
-        g.use_tile = g.use_warp && ctx->tb.nb <= 4 && ctx->memo.sieve_t != nullptr && ctx->memo.zero_codes == 0 &&
-                     b->max_ntotal <= TILE_MAXWIN;
     }
     return g;
 }
@@ -481,25 +477,7 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
         if (mg.ok) {
             int rc = memo_prepare(ctx, min_occ);
             if (rc) return rc;
-            if (mg.use_tile && ctx->memo_occ == INT_MIN) {   // short reads, <= 256 references, no -M mask: a thread per read
-                Timed t(ctx, b->stream, K_CLASSIFY_MEMO_TILE);
-                const int grid = ctx->sm_count;
-                const size_t TILE_SMEM = TILE_FIXED_SMEM + (size_t)ctx->memo.sieve_t_words * 4;
-#define RK_TILE_LAUNCH(NWV)                                                                                              \
-    do {                                                                                                                 \
-        CK(cudaFuncSetAttribute(classify_memo_tile_kernel<NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM)); \
-        classify_memo_tile_kernel<NWV><<<grid, TILE_THREADS, TILE_SMEM, b->stream>>>(sb, ctx->s, ctx->memo, ctx->tb, redo, \
-                                                                                      redo_count, hits);                \
-    } while (0)
-                switch (ctx->tb.nb) {
-                    case 1: RK_TILE_LAUNCH(2); break;
-                    case 2: RK_TILE_LAUNCH(4); break;
-                    case 3: RK_TILE_LAUNCH(6); break;
-                    default: RK_TILE_LAUNCH(8); break;
-                }
-#undef RK_TILE_LAUNCH
-                CK(cudaGetLastError());
-            } else if (mg.use_warp && ctx->tb.nb <= 4 && ctx->memo.sieve != nullptr && ctx->memo.zero_codes == 0 &&
+            if (mg.use_warp && ctx->tb.nb <= 4 && ctx->memo.sieve != nullptr && ctx->memo.zero_codes == 0 &&
                        ctx->memo_occ == INT_MIN) {
                 // <= 256 references, no FAILM flags baked, no zero hash: sketch membership from a shared-memory sieve
                 Timed t(ctx, b->stream, K_CLASSIFY_MEMO_SIEVE);
@@ -603,7 +581,10 @@ int launch_sketch(rkg_ctx* ctx, rkg_batch* b, CountTable ct, int filter_mode, in
     const int sort_in_smem = ((size_t)sort_cap * 8 <= ctx->smem_optin - 4096) ? 1 : 0;
     const size_t smem = sort_in_smem ? (size_t)sort_cap * 8 : 0;
     i64 stride = std::max<i64>(b->max_ntotal, 1);
-    if (d_sorted_all) stride = next_pow2(stride);
+    if (d_sorted_all) {
+        if (stride > ((i64)1 << 30)) return fail(ctx, RKG_ERR_ARG, "per-sample -I counting: a reference of more than 2^30 k-mers is not supported");
+        stride = next_pow2(stride);
+    }
     const int grid = (int)std::min<i64>(b->nseq, (i64)ctx->sm_count * 2);
     CK(b->scratch.ensure(sizeof(u64) * (size_t)grid * (size_t)(stride + sort_cap) + 64));
     Timed t(ctx, b->stream, K_SKETCH);
@@ -670,7 +651,6 @@ int rkg_create(int device, rkg_ctx** out) {
     ctx->device = device;
     { const char* nm = getenv("RKMH_NO_MEMO"); ctx->memo_enabled = !(nm && nm[0] && nm[0] != '0'); }
     { const char* nm = getenv("RKMH_NO_SIEVE"); ctx->sieve_enabled = !(nm && nm[0] && nm[0] != '0'); }
-    { const char* tk = getenv("RKMH_TILE"); ctx->tile_kernel = tk && tk[0] && tk[0] != '0'; }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -689,7 +669,7 @@ void rkg_destroy(rkg_ctx* ctx) {
     for (int i = 0; i < 2; ++i) batch_release(ctx->slots[i]);
     for (DevBuf* d : {&ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
                       &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
-                      &ctx->memo_tab, &ctx->memo_sieve_t, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
+                      &ctx->memo_tab, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
                       &ctx->memo_sieve, &ctx->memo_cmap})
         d->release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -702,7 +682,8 @@ int rkg_set_params(rkg_ctx* ctx, const int* ks, int nk, int sketch_size, uint64_
                    uint64_t ref_table_size) {
     if (!ctx) return RKG_ERR_ARG;
     if (!ks || nk < 1 || nk > MAX_NK) return fail(ctx, RKG_ERR_ARG, "rkg_set_params: 1..%d k-mer sizes, got %d", MAX_NK, nk);
-    if (sketch_size < 1) return fail(ctx, RKG_ERR_ARG, "rkg_set_params: sketch size %d", sketch_size);
+    if (sketch_size < 1 || sketch_size > (1 << 26))
+        return fail(ctx, RKG_ERR_ARG, "rkg_set_params: sketch size %d (supported: 1..2^26)", sketch_size);
     CK(cudaSetDevice(ctx->device));
     KList kl{};
     kl.nk = nk;
@@ -738,16 +719,21 @@ int rkg_set_params(rkg_ctx* ctx, const int* ks, int nk, int sketch_size, uint64_
     return RKG_OK;
 }
 
+// Thread-safe (see the header): they read ctx->device only and report errors through the thread-local slot of
+// rkg_last_error(NULL), so a parser thread may pin chunks while a worker thread is inside a batch call on the same context.
 int rkg_host_alloc(rkg_ctx* ctx, size_t bytes, void** ptr) {
     if (!ctx || !ptr) return RKG_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
-    CK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(nullptr, e == cudaErrorMemoryAllocation ? RKG_ERR_NOMEM : RKG_ERR_CUDA,
+                                      "rkg_host_alloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
     return RKG_OK;
 }
 
 int rkg_host_free(rkg_ctx* ctx, void* ptr) {
     if (!ctx) return RKG_ERR_ARG;
-    CK(cudaFreeHost(ptr));
+    const cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) return fail(nullptr, RKG_ERR_CUDA, "rkg_host_free: %s", cudaGetErrorString(e));
     return RKG_OK;
 }
 
@@ -765,6 +751,8 @@ int rkg_load_refs(rkg_ctx* ctx, const char* bases, const int64_t* offs, int nref
     if (!bases || !offs || nrefs < 1) return fail(ctx, RKG_ERR_ARG, "rkg_load_refs: need at least one reference");
     if (max_ref_occ >= 0 && ctx->ref_ct.counts == nullptr)
         return fail(ctx, RKG_ERR_STATE, "max_ref_occ >= 0 needs a reference count table (rkg_set_params ref_table_size)");
+    if (2 * (i64)nrefs * ctx->s > ((i64)1 << 30))
+        return fail(ctx, RKG_ERR_ARG, "rkg_load_refs: %d references x sketch size %d exceeds the 2^29 table entries supported", nrefs, ctx->s);
     CK(cudaSetDevice(ctx->device));
     int rc = ensure_slots(ctx);
     if (rc) return rc;
@@ -815,6 +803,8 @@ int rkg_load_refs(rkg_ctx* ctx, const char* bases, const int64_t* offs, int nref
         return rc;
 
     // table geometry
+    // The table is dense in the references: cap x (1 + ceil(nrefs / 64)) words with cap >= 2 nrefs s, i.e. quadratic in
+    // the number of references (5,000 references at s = 1000 take about 11 GB; include/rkmh_gpu.h states the limit).
     const i64 nent = (i64)nrefs * s;
     const u32 cap = (u32)next_pow2(std::max<i64>(2 * nent, 1024));
     const u32 nb = (u32)((nrefs + 63) / 64);
@@ -877,8 +867,7 @@ int rkg_count_reset(rkg_ctx* ctx) {
     // not be ordered before the count kernels that follow
     CK(cudaMemsetAsync(ctx->read_ct.counts, 0, sizeof(int) * ctx->read_tbl_size, ctx->stream));
     if (ctx->memo_ready && ctx->memo.code_counts) {
-        CK(cudaMemsetAsync(ctx->memo.code_counts, 0, sizeof(int) * (size_t)ctx->memo.ncodes, ctx->stream));
-        CK(cudaMemsetAsync(ctx->memo.inval, 0, sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->memo.code_counts, 0, sizeof(int) * ((size_t)ctx->memo.ncodes + MEMO_PARTIAL_PAD), ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->memo_pending = false;
@@ -897,6 +886,23 @@ int rkg_count_table(rkg_ctx* ctx, void** device_ptr, uint64_t* nslots) {
     return RKG_OK;
 }
 
+int rkg_count_partial(rkg_ctx* ctx, int count_zeros, void** device_ptr, uint64_t* nslots) {
+    if (!ctx || !device_ptr || !nslots) return RKG_ERR_ARG;
+    if (!ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "no read count table");
+    if (!ctx->memo_ready || !ctx->memo.code_counts)
+        return fail(ctx, RKG_ERR_STATE, "rkg_count_partial: the memoised path is not active (all-reduce rkg_count_table instead)");
+    if (ctx->memo_pending && ctx->memo_pending_zeros != (count_zeros != 0))
+        return fail(ctx, RKG_ERR_ARG, "rkg_count_partial: count_zeros differs from the pending rkg_count_batch calls");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());              // the count kernels of every batch stream have finished
+    // whatever the caller sums into the array is folded into the read count table at its next use, also on a rank
+    // that counted no read itself
+    ctx->memo_pending = true; ctx->memo_pending_zeros = count_zeros != 0;
+    *device_ptr = ctx->memo.code_counts;
+    *nslots = (uint64_t)ctx->memo.ncodes + MEMO_PARTIAL_PAD;
+    return RKG_OK;
+}
+
 int rkg_count_lookup(rkg_ctx* ctx, const uint64_t* keys, int64_t n, int32_t* out) {
     if (!ctx || !keys || !out) return RKG_ERR_ARG;
     if (!ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "no read count table");
@@ -911,19 +917,24 @@ int rkg_count_lookup(rkg_ctx* ctx, const uint64_t* keys, int64_t n, int32_t* out
 }
 
 static int host_pipeline(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, int mode, int arg,
-                         rkg_hit* out) {
-    // mode 0: count (arg = count_zeros); mode 1: classify (arg = min_occ)
+                         rkg_hit* out, int64_t fixed_len = 0) {
+    // mode 0: count (arg = count_zeros); mode 1: classify (arg = min_occ); mode 2: the copies of mode 1 without its kernels
     int rc = ensure_slots(ctx);
     if (rc) return rc;
-    auto chunks = make_chunks(offs, nreads, CHUNK_BYTES, CHUNK_READS);
+    std::vector<std::pair<i64, i64>> chunks;
+    if (offs) chunks = make_chunks(offs, nreads, CHUNK_BYTES, CHUNK_READS);
+    else {
+        const i64 per = std::max<i64>(1, std::min<i64>(CHUNK_READS, CHUNK_BYTES / std::max<i64>(fixed_len, 1)));
+        for (i64 r0 = 0; r0 < nreads; r0 += per) chunks.emplace_back(r0, std::min<i64>(nreads, r0 + per));
+    }
     for (size_t c = 0; c < chunks.size(); ++c) {
         rkg_batch* b = ctx->slots[c & 1];
         CK(cudaStreamSynchronize(b->stream));     // the slot's previous chunk (c - 2) is finished
-        if ((rc = batch_fill(ctx, b, bases, offs, chunks[c].first, chunks[c].second))) return rc;
+        if ((rc = batch_fill(ctx, b, bases, offs, chunks[c].first, chunks[c].second, fixed_len))) return rc;
         if (mode == 0) {
             if ((rc = launch_count(ctx, b, ctx->read_ct, arg))) return rc;
         } else {
-            if ((rc = launch_classify(ctx, b, arg))) return rc;
+            if (mode == 1 && (rc = launch_classify(ctx, b, arg))) return rc;
             CK(cudaMemcpyAsync(out + chunks[c].first, b->hits.p, sizeof(Hit) * (size_t)b->nseq, cudaMemcpyDeviceToHost,
                                b->stream));
         }
@@ -951,6 +962,35 @@ int rkg_classify_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int
     if (nreads == 0) return RKG_OK;
     CK(cudaSetDevice(ctx->device));
     return host_pipeline(ctx, bases, offs, nreads, 1, min_occ, out);
+}
+
+int rkg_classify_fixed(rkg_ctx* ctx, const char* bases, int64_t read_len, int64_t nreads, int min_occ, rkg_hit* out) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->refs_loaded) return fail(ctx, RKG_ERR_STATE, "rkg_classify_fixed before rkg_load_refs");
+    if (nreads < 0 || read_len < 0 || (!bases && nreads > 0) || (!out && nreads > 0))
+        return fail(ctx, RKG_ERR_ARG, "rkg_classify_fixed: bad buffers");
+    if (nreads == 0) return RKG_OK;
+    CK(cudaSetDevice(ctx->device));
+    return host_pipeline(ctx, bases, nullptr, nreads, 1, min_occ, out, read_len);
+}
+
+int rkg_count_fixed(rkg_ctx* ctx, const char* bases, int64_t read_len, int64_t nreads, int count_zeros) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_count_fixed before rkg_set_params");
+    if (!ctx->read_ct.counts) return fail(ctx, RKG_ERR_STATE, "no read count table (rkg_set_params read_table_size)");
+    if (nreads < 0 || read_len < 0 || (!bases && nreads > 0)) return fail(ctx, RKG_ERR_ARG, "rkg_count_fixed: bad buffers");
+    if (nreads == 0) return RKG_OK;
+    CK(cudaSetDevice(ctx->device));
+    return host_pipeline(ctx, bases, nullptr, nreads, 0, count_zeros, nullptr, read_len);
+}
+
+int rkg_copy_probe(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t read_len, int64_t nreads, rkg_hit* out) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_copy_probe before rkg_set_params");
+    if (nreads < 0 || (!bases && nreads > 0) || (!out && nreads > 0)) return fail(ctx, RKG_ERR_ARG, "rkg_copy_probe: bad buffers");
+    if (nreads == 0) return RKG_OK;
+    CK(cudaSetDevice(ctx->device));
+    return host_pipeline(ctx, bases, offs, nreads, 2, 0, out, read_len);
 }
 
 int rkg_batch_upload(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, rkg_batch** batch) {

@@ -28,6 +28,7 @@ constexpr u32 MEMO_REF = 1u, MEMO_ZERO = 2u, MEMO_FAILM = 4u;
 constexpr u32 MEMO_SKIP = 0xFFFFFFFFu;          // "window does not count": never a real entry (5 flag bits unused)
 constexpr int MEMO_BUCKET_CAP = 1024;           // rank build: largest hash bucket that is sorted in shared memory
 constexpr int MEMO_BINS = 4096;
+constexpr int MEMO_PARTIAL_PAD = 32;             // int32 slots after code_counts[ncodes): [0] = invalid windows, rest zero (keeps the array 128-byte sized)
 constexpr int MEMO_RING = 64;                   // block kernel: per-warp ring of sketch members waiting for their rows                 // radix-select histogram (12 bits of the 24-bit rank per level)
 
 struct Memo {
@@ -35,14 +36,13 @@ struct Memo {
     u32* ref;
     const u64* hash;
     int* code_counts;               // nullptr when the context has no read count table
-    unsigned long long* inval;      // windows with an invalid base seen by the count pass (count_zeros mode)
+    u32* inval;                     // = code_counts + ncodes: windows with an invalid base seen by the count pass (count_zeros mode;
+                                    //   modulo 2^32 like the int32 slot it is added to), so that ONE all-reduce covers both
     u32 ncodes;
     u32 kmask;                      // (1 << k) - 1
     int k;
     // sieve kernel (classify_memo_sieve_kernel): shared-memory Bloom filter image and the code -> slot + 1 map
     const u32* sieve;               // nullptr: not built / too full to be useful
-    const u32* sieve_t;             // the (smaller) sieve of the thread-per-read tile kernel
-    u32 sieve_t_words;
     const unsigned long long* cmap;
     u32 sieve_words, cmap_mask;
     int cmap_shift;
@@ -216,7 +216,7 @@ memo_fold_kernel(Memo mm, CountTable ct, int count_zeros) {
         if (h != 0 || count_zeros) atomicAdd(&ct.counts[fastmod(h, ct.mod)], n);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const unsigned long long inv = *mm.inval;
+        const u32 inv = *mm.inval;
         *mm.inval = 0;
         if (count_zeros && inv) atomicAdd(&ct.counts[0], (int)inv);     // an invalid window hashes to 0 (rkmh.cpp:331-336)
     }
@@ -258,7 +258,7 @@ count_memo_kernel(SeqBatch sb, Memo mm, int count_zeros, int wpr) {
     }
     if (count_zeros) {
         inv = warp_sum(inv);
-        if (lane == 0 && inv) atomicAdd(mm.inval, (unsigned long long)inv);
+        if (lane == 0 && inv) atomicAdd(mm.inval, inv);
     }
 }
 
@@ -850,318 +850,6 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
         }
         __syncwarp();
         rid = nrid; beg = nbeg; len64 = nlen; wa = nwa; wb = nwb2;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// classify_memo_tile_kernel: ONE THREAD PER READ for short reads (at most TILE_MAXWIN windows: the config-2 shape),
-// at most 256 references, same preconditions as the sieve kernel (no FAILM flag baked, no code that hashes to 0).
-//
-// A block stages a tile of consecutive reads (their ASCII bases as parsed, <= TILE_BYTES) in shared memory with one
-// TMA bulk copy (cp.async.bulk + mbarrier); every thread then walks its own read, so nothing in the per-window work
-// is a warp collective:
-//   1. sixteen bases at a time: four aligned shared-memory words are realigned (funnel shift), decoded (sv_decode)
-//      into one 32-bit word of 2-bit codes, and the codes of the 16 windows that start in it -- funnel shifts of two
-//      consecutive code words -- are tested against the shared-memory sieve.  The code words overwrite the read's own
-//      bytes in the tile (4x smaller, always behind the bytes still to be decoded); the 16-bit masks of the windows
-//      that pass go to a small per-thread area;
-//   2. the windows that passed are looked up in the L2-resident code map, four lookups in flight; the table slots of
-//      the true sketch members are kept (for the copy number of a hash that occurs more than once in the read --
-//      multiset semantics, SURVEY F10 -- a 64-bit Bloom word decides whether the earlier ones are compared at all);
-//   3. their reference bitset rows are added, two rows in flight, into BIT-SLICED per-reference counters held in
-//      registers (plane p of word w = bit p of the counts of references 32 w .. 32 w + 31);
-//   4. the scan of src/rkmh.cpp:874-883 on the bit-sliced counters: most significant plane first, the set of
-//      references that can still hold the maximum shrinks; its lowest index is the winner, and the same walk over the
-//      references in front of it gives the previous best.
-// ~20 thread-instructions per window instead of ~5 warp-instructions.  Reads that do not fit (more windows than s or
-// TILE_MAXWIN, more hits than the key area holds, a count above 31, too short to hold their own code words, longer
-// than a tile) are handed to the block kernel through `redo`.
-constexpr int TILE_THREADS = 384;
-constexpr int TILE_BYTES = 61440;
-constexpr int TILE_MAXWIN = 160;                // candidate masks: ten 16-bit groups
-constexpr int TILE_XWORDS = 16;                 // per-thread extra words: 5 of candidate masks + 11 hit slots
-constexpr int TILE_PLANES = 5;
-constexpr size_t TILE_FIXED_SMEM = (size_t)TILE_BYTES + (size_t)TILE_XWORDS * TILE_THREADS * 4;
-
-struct TileCtl { i64 b0; int m; int skip; };
-
-template <int NW>
-__global__ void __launch_bounds__(TILE_THREADS, 1)
-classify_memo_tile_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
-                          int* __restrict__ redo, int* __restrict__ redo_count, Hit* __restrict__ out) {
-#ifdef RK_EMU
-    unsigned char* dsm = reinterpret_cast<unsigned char*>(EMU_DYN_SMEM());
-#else
-    extern __shared__ __align__(128) unsigned char dsm[];
-#endif
-    __shared__ TileCtl ctl;
-    __shared__ __align__(8) unsigned long long bar;
-    // dynamic shared memory: [tile bytes][per-thread extra words][sieve]
-    unsigned char* rd = dsm;
-    u32* tw = reinterpret_cast<u32*>(dsm);
-    u32* xw = reinterpret_cast<u32*>(dsm + TILE_BYTES);
-    u32* sv = xw + TILE_XWORDS * TILE_THREADS;
-    const u32 nwords = mm.sieve_t_words;
-    const int t = threadIdx.x;
-    const int k = mm.k;
-    const u32 kmask = mm.kmask;
-    const u32 cmask2 = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
-    const unsigned long long* __restrict__ cmap = mm.cmap;
-    const u32 cmask = mm.cmap_mask;
-    const int cshift = mm.cmap_shift;
-
-    for (u32 i = (u32)t; i < nwords; i += TILE_THREADS) sv[i] = mm.sieve_t[i];
-#ifndef RK_EMU
-    const u32 bar_addr = (u32)__cvta_generic_to_shared(&bar);
-    if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_addr), "r"(1) : "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    u32 phase = 0;
-#endif
-    __syncthreads();
-
-    for (i64 t0 = (i64)blockIdx.x * TILE_THREADS; t0 < sb.nseq; t0 += (i64)gridDim.x * TILE_THREADS) {
-        const i64 rend = min(sb.nseq, t0 + (i64)TILE_THREADS);
-        i64 r = t0;
-        while (r < rend) {
-            // ---- the next run of reads that fits in the tile ----------------------------------------------------
-            if (t == 0) {
-                const i64 b0 = sb.offs[r];
-                const i64 lim = (i64)TILE_BYTES - 64;
-                int lo = 1, hi = (int)(rend - r), m = 0;
-                while (lo <= hi) {                           // largest m with offs[r + m] - b0 <= lim
-                    const int mid = (lo + hi) >> 1;
-                    if (sb.offs[r + mid] - b0 <= lim) { m = mid; lo = mid + 1; } else hi = mid - 1;
-                }
-                ctl.b0 = b0; ctl.m = m; ctl.skip = 0;
-                if (m == 0) { redo[atomicAdd(redo_count, 1)] = (int)r; ctl.skip = 1; }   // one read longer than a tile
-            }
-            __syncthreads();
-            const int m = ctl.m;
-            if (ctl.skip) { r += 1; __syncthreads(); continue; }
-            const i64 gb0 = ctl.b0 - sb.base0;               // first byte of the run in sb.bases
-            const i64 ga = gb0 & ~(i64)15;                   // 16-byte aligned start of the copy
-            const int shift = (int)(gb0 - ga);
-            const int nbytes = (int)(sb.offs[r + m] - ctl.b0);
-            const u32 copy_bytes = (u32)((shift + nbytes + 15) & ~15);
-#ifdef RK_EMU
-            for (u32 i = (u32)t; i < copy_bytes; i += TILE_THREADS) rd[i] = sb.bases[ga + i];
-            __syncthreads();
-#else
-            if (t == 0) {
-                const u32 dst = (u32)__cvta_generic_to_shared(rd);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the previous tile was accessed through the generic proxy
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_addr), "r"(copy_bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(dst), "l"(sb.bases + ga), "r"(copy_bytes), "r"(bar_addr) : "memory");
-            }
-            {
-                u32 done = 0;
-                while (!done) {
-                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                                 : "=r"(done) : "r"(bar_addr), "r"(phase) : "memory");
-                }
-                phase ^= 1u;
-            }
-#endif
-            if (t < m) {
-                const i64 rid = r + t;
-                const i64 o0 = sb.offs[rid], o1 = sb.offs[rid + 1];
-                const int len = (int)(o1 - o0);
-                const int n = len - k > 0 ? len - k : 0;
-                const u32 addr = (u32)(shift + (int)(o0 - ctl.b0));          // first byte of the read in the tile
-                const u32 aw = addr >> 2, sh8 = 8u * (addr & 3u);
-                const u32 last_w = (addr + (u32)(len > 0 ? len - 1 : 0)) >> 2;   // the word that holds the read's last base
-                const int ng = (n + 15) >> 4;                                // groups of 16 windows
-                const int nsw = ng + 1;                                      // code words kept for step 2
-                u32* privw = tw + ((addr + 3u) >> 2);                        // the words that lie wholly inside the read
-                const int privn = (int)((addr + (u32)len) >> 2) - (int)((addr + 3u) >> 2);
-                const int kcap0 = privn - nsw;                               // hit slots inside the read's own bytes
-                u32* myx = xw + t;                                           // extra words, strided by TILE_THREADS
-                bool give_up = n > s || n > TILE_MAXWIN || kcap0 < 0;
-                int best = 0, id = 0, prev = -1, ninv = 0;
-                if (!give_up && n > 0) {
-                    // ---- 1: decode, sieve ---------------------------------------------------------------------------
-                    auto decode = [&](int g, u32& cw, u32& bw) {
-                        // words past the read's last one belong to the next read's thread, which overwrites them: not read
-                        const u32* w = tw + aw + 4 * g;
-                        const int left = (int)last_w - (int)(aw + 4 * g);            // index of the last readable word of w[]
-                        const u32 w0 = left >= 0 ? w[0] : 0x41414141u, w1 = left >= 1 ? w[1] : 0x41414141u,
-                                  w2 = left >= 2 ? w[2] : 0x41414141u, w3 = left >= 3 ? w[3] : 0x41414141u,
-                                  w4 = left >= 4 ? w[4] : 0x41414141u;
-                        u32 p0, p1, p2, p3, b0, b1, b2, b3;
-                        sv_decode(__funnelshift_r(w0, w1, sh8), p0, b0);
-                        sv_decode(__funnelshift_r(w1, w2, sh8), p1, b1);
-                        sv_decode(__funnelshift_r(w2, w3, sh8), p2, b2);
-                        sv_decode(__funnelshift_r(w3, w4, sh8), p3, b3);
-                        cw = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
-                        bw = 0;
-                        if (b0 | b1 | b2 | b3) bw = sv_bad4(b0) | (sv_bad4(b1) << 4) | (sv_bad4(b2) << 8) | (sv_bad4(b3) << 12);
-                    };
-                    u32 cw_cur, bw_cur, gm_lo = 0;
-                    decode(0, cw_cur, bw_cur);
-                    for (int g = 0; g < ng; ++g) {
-                        u32 cw_next, bw_next;
-                        decode(g + 1, cw_next, bw_next);
-                        privw[g] = cw_cur;                   // bases 4 g .. 4 g + 6 of the read: decoded long ago
-                        u32 gm = 0;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const u32 code = (j ? __funnelshift_r(cw_cur, cw_next, 2 * j) : cw_cur) & cmask2;
-                            const u32 h = code * SIEVE_MUL;
-                            const u32 bits = sieve_bits(h);
-                            if ((sv[__umulhi(h, nwords)] & bits) == bits) gm |= 1u << j;
-                        }
-                        const int rem = n - 16 * g;
-                        const u32 inr = rem < 16 ? ((1u << rem) - 1u) : 0xFFFFu;
-                        gm &= inr;
-                        const u32 bb = bw_cur | (bw_next << 16);
-                        if (bb) {                            // some base near these windows is not ACGTacgt (rare)
-                            u32 invm = 0;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) if ((bb >> j) & kmask) invm |= 1u << j;
-                            invm &= inr;
-                            ninv += __popc(invm);
-                            gm &= ~invm;
-                        }
-                        if (g & 1) myx[(g >> 1) * TILE_THREADS] = gm_lo | (gm << 16); else gm_lo = gm;
-                        cw_cur = cw_next; bw_cur = bw_next;
-                    }
-                    privw[ng] = cw_cur;
-                    if (ng & 1) myx[(ng >> 1) * TILE_THREADS] = gm_lo;
-                    // ---- 2: windows that passed -> table slots of the true sketch members -----------------------------
-                    const int kcap = kcap0 + (TILE_XWORDS - 5);
-                    auto key_ref = [&](int i) -> u32& { return i < kcap0 ? privw[nsw + i] : myx[(5 + i - kcap0) * TILE_THREADS]; };
-                    int nk = 0;
-                    for (int gi = 0; gi < (ng + 1) / 2 && !give_up; ++gi) {
-                        u32 mbits = myx[gi * TILE_THREADS];
-                        while (mbits) {
-                            u32 code[4], idx[4];
-                            unsigned long long e[4];
-                            int cnt = 0;
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                code[u] = 0xFFFFFFFFu; idx[u] = 0; e[u] = ~0ULL;
-                                if (mbits) {
-                                    const int p = 32 * gi + __ffs((int)mbits) - 1;
-                                    mbits &= mbits - 1;
-                                    code[u] = __funnelshift_r(privw[p >> 4], privw[(p >> 4) + 1], 2 * (p & 15)) & cmask2;
-                                    idx[u] = (code[u] * SIEVE_MUL) >> cshift;
-                                    e[u] = __ldg(&cmap[idx[u]]);
-                                    cnt = u + 1;
-                                }
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                if (u >= cnt) break;
-                                while ((u32)e[u] != code[u] && (u32)e[u] != 0xFFFFFFFFu) { idx[u] = (idx[u] + 1) & cmask; e[u] = __ldg(&cmap[idx[u]]); }
-                                if ((u32)e[u] == code[u]) {
-                                    if (nk < kcap) key_ref(nk) = (u32)(e[u] >> 32);
-                                    ++nk;
-                                }
-                            }
-                        }
-                    }
-                    if (nk > kcap) give_up = true;
-                    // ---- 3: bitset rows -> bit-sliced counters ----------------------------------------------------------
-                    if (!give_up && nk > 0) {
-                        u32 P[TILE_PLANES][NW];
-#pragma unroll
-                        for (int pl = 0; pl < TILE_PLANES; ++pl)
-#pragma unroll
-                            for (int w = 0; w < NW; ++w) P[pl][w] = 0;
-                        unsigned long long bloom = 0;
-                        u32 carry_out = 0;
-                        for (int j0 = 0; j0 < nk; j0 += 2) {
-                            const u64* rowp[2];
-#pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                rowp[u] = nullptr;
-                                const int j = j0 + u;
-                                if (j < nk) {
-                                    const u32 key = key_ref(j);
-                                    const unsigned long long bit = 1ULL << ((key * 0x9E3779B1u) >> 26);
-                                    u32 copy = 0;
-                                    if (bloom & bit) for (int jj = 0; jj < j; ++jj) copy += key_ref(jj) == key;
-                                    bloom |= bit;
-                                    rowp[u] = table_row(tb, (int)key - 1, copy);
-                                }
-                            }
-                            u32 x[2][NW];
-#pragma unroll
-                            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                                for (int w = 0; w < NW / 2; ++w) {
-                                    const u64 v = rowp[u] ? __ldg(&rowp[u][w]) : 0ULL;
-                                    x[u][2 * w] = (u32)v; x[u][2 * w + 1] = (u32)(v >> 32);
-                                }
-#pragma unroll
-                            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                                for (int w = 0; w < NW; ++w) {
-                                    u32 cy = x[u][w];
-                                    if (cy) {
-#pragma unroll
-                                        for (int pl = 0; pl < TILE_PLANES; ++pl) { const u32 tt = P[pl][w] & cy; P[pl][w] ^= cy; cy = tt; }
-                                        carry_out |= cy;
-                                    }
-                                }
-                        }
-                        if (carry_out) give_up = true;           // some count reached 2^TILE_PLANES
-                        else {
-                            // ---- 4: first index of the maximum, and the maximum before it --------------------------------
-                            u32 cand[NW];
-#pragma unroll
-                            for (int w = 0; w < NW; ++w) cand[w] = 0xFFFFFFFFu;
-#pragma unroll
-                            for (int pl = TILE_PLANES - 1; pl >= 0; --pl) {
-                                u32 tsel[NW], any = 0;
-#pragma unroll
-                                for (int w = 0; w < NW; ++w) { tsel[w] = cand[w] & P[pl][w]; any |= tsel[w]; }
-                                if (any) {
-                                    best |= 1 << pl;
-#pragma unroll
-                                    for (int w = 0; w < NW; ++w) cand[w] = tsel[w];
-                                }
-                            }
-                            if (best > 0) {
-                                int idw = 0;
-#pragma unroll
-                                for (int w = NW - 1; w >= 0; --w) if (cand[w]) idw = w;
-                                u32 cw = 0;
-#pragma unroll
-                                for (int w = 0; w < NW; ++w) if (w == idw) cw = cand[w];
-                                const int idb = __ffs((int)cw) - 1;
-                                id = 32 * idw + idb;
-                                if (id > 0) {
-                                    u32 below[NW];
-#pragma unroll
-                                    for (int w = 0; w < NW; ++w) below[w] = w < idw ? 0xFFFFFFFFu : (w == idw ? ((1u << idb) - 1u) : 0u);
-                                    int pbest = 0;
-#pragma unroll
-                                    for (int pl = TILE_PLANES - 1; pl >= 0; --pl) {
-                                        u32 tsel[NW], any = 0;
-#pragma unroll
-                                        for (int w = 0; w < NW; ++w) { tsel[w] = below[w] & P[pl][w]; any |= tsel[w]; }
-                                        if (any) {
-                                            pbest |= 1 << pl;
-#pragma unroll
-                                            for (int w = 0; w < NW; ++w) below[w] = tsel[w];
-                                        }
-                                    }
-                                    prev = pbest;
-                                }
-                            }
-                        }
-                    }
-                }
-                if (give_up) redo[atomicAdd(redo_count, 1)] = (int)rid;
-                else { Hit hh; hh.ref_id = id; hh.best = best; hh.prev = prev; hh.sketch_len = n - ninv; out[rid] = hh; }
-            }
-            __syncthreads();                                 // the tile is reused by the next run
-            r += m;
-        }
     }
 }
 

@@ -29,6 +29,8 @@ def read_fastx(path) -> Iterator[Tuple[bytes, bytes, bytes]]:
         i += 1
     while i < n:
         i += 1  # past '>' / '@'
+        if i >= n:
+            return  # a header byte that is the last byte of the input starts no record (ks_getuntil returns -1, kseq.hpp:97)
         j = i
         while j < n and not chr(data[j]).isspace():
             j += 1

@@ -161,6 +161,9 @@ class FastxReader {
     bool slow() {
         name_.clear(); seq_.clear(); qual_.clear();
         int c = in_.get();
+        // a header byte that is the last byte of the input starts no record: ks_getuntil returns -1 before it reads a
+        // name when the stream is exhausted (kseq.hpp:97, `ks->begin >= ks->end && ks->is_eof`) and kseq_read ends the file
+        if (c == -1) { c_ = -1; return false; }
         while (c != -1 && !isspace(c)) { name_.push_back((char)c); c = in_.get(); }
         while (c != -1 && c != '\n') c = in_.get();      // comment
         c = in_.get();

@@ -8,7 +8,8 @@
 // one worker thread per GPU pushes chunks through rkg_count_batch / rkg_classify_batch, four threads format the result
 // lines, and the main thread writes them in input order, so host memory stays bounded whatever the input size (the reference loads every read
 // first, src/rkmh.cpp:238-292).  `-f -` reads standard input.  With -M the read files are streamed twice (pass 1
-// counts, pass 2 classifies); only when a read file is standard input are the reads buffered instead.
+// counts, pass 2 classifies); a read file that is not a regular file (standard input, a FIFO,
+// /dev/fd/N) cannot be read twice: the reads are buffered instead.
 //
 // Extra, non-reference option: -g/--gpus N (default: RKMH_GPUS or 1) shards reads over N GPUs.  -t is accepted
 // and ignored (the reference's OpenMP thread count).
@@ -517,9 +518,11 @@ uint64_t stream_reads(Fleet& fl, ChunkPool& pool, const std::vector<const char*>
     std::thread reader([&] {
         uint64_t seq = 0;
         nrecords = parse_files(files, pool, keep_qual, [&](Chunk* c) { c->seq = seq++; work_q.push(c); });
-        total_chunks = (int64_t)seq;
-        for (size_t d = 0; d < fl.ctx.size(); ++d) work_q.push(nullptr);
+        // stored under the writer's mutex: a notify between the writer's predicate check and its wait would otherwise
+        // be lost, and with every chunk already emitted (or none at all: an empty input) nothing would wake it again
+        { std::lock_guard<std::mutex> g(dm); total_chunks = (int64_t)seq; }
         dcv.notify_all();
+        for (size_t d = 0; d < fl.ctx.size(); ++d) work_q.push(nullptr);
     });
     std::vector<std::thread> workers;
     for (size_t d = 0; d < fl.ctx.size(); ++d)
@@ -563,8 +566,15 @@ uint64_t stream_reads(Fleet& fl, ChunkPool& pool, const std::vector<const char*>
     return nrecords;
 }
 
-bool any_stdin(const std::vector<const char*>& files) {
-    for (const char* f : files) if (f[0] == '-' && f[1] == 0) return true;
+// -M reads the input twice (pass 1 counts, pass 2 classifies): only regular files can be re-opened.  Standard input,
+// FIFOs, /dev/stdin, /dev/fd/N (`<(zcat ...)`) and anything else that is not a regular file is buffered instead, as the
+// reference does for every input (src/rkmh.cpp:786-788).
+bool any_unrewindable(const std::vector<const char*>& files) {
+    for (const char* f : files) {
+        if (f[0] == '-' && f[1] == 0) return true;
+        struct stat st;
+        if (stat(f, &st) != 0 || !S_ISREG(st.st_mode)) return true;
+    }
     return false;
 }
 
@@ -574,18 +584,25 @@ void run_streamed(Fleet& fl, const Options& o, bool keep_qual, bool count_zeros,
     ChunkPool pool;
     pool.open(fl.ctx[0], 2 * (int)fl.ctx.size() + 6 + 3 * parse_threads(), chunk_bytes());
     const auto write_out = [](Chunk& c) { fwrite(c.out.data(), 1, c.out.size(), stdout); };
+    uint64_t pass1 = 0;
     if (o.do_read_depth) {                              // pass 1: global k-mer count table (src/rkmh.cpp:904-910)
         fl.each([&](int, rkg_ctx* c) { RK(c, rkg_count_reset(c)); });
-        stream_reads(fl, pool, o.reads, false,
+        pass1 = stream_reads(fl, pool, o.reads, false,
                      [&](int, rkg_ctx* c, Chunk& ch) { RK(c, rkg_count_batch(c, ch.data(), ch.offs, (int64_t)ch.nreads, count_zeros)); },
                      nullptr, [](Chunk&) {});
         allreduce_counts(fl);
     }
-    stream_reads(fl, pool, o.reads, keep_qual,
+    const uint64_t pass2 = stream_reads(fl, pool, o.reads, keep_qual,
                  [&](int, rkg_ctx* c, Chunk& ch) {
                      RK(c, rkg_classify_batch(c, ch.data(), ch.offs, (int64_t)ch.nreads, o.do_read_depth ? o.min_occ : -1, ch.hits));
                  },
                  format, write_out);
+    if (o.do_read_depth && pass1 != pass2) {            // an input that changed (or drained) between the two passes
+        fflush(stdout);
+        fprintf(stderr, "rkmh: -M pass 1 saw %llu records, pass 2 %llu: the read files changed between the passes\n",
+                (unsigned long long)pass1, (unsigned long long)pass2);
+        exit(2);
+    }
 }
 
 // result line of stream / classify: src/rkmh.cpp:884-893
@@ -626,7 +643,7 @@ int main_stream(int argc, char** argv) {
     if (refs.size() == 0) { fprintf(stderr, "rkmh: no reference sequences (the reference binary is undefined here)\n"); return 2; }
     Fleet fl; fl.open(std::max(1, o.gpus));
     setup_refs(fl, o, refs, STREAM_TABLE, false);
-    if (!(o.do_read_depth && any_stdin(o.reads))) {
+    if (!(o.do_read_depth && any_unrewindable(o.reads))) {
         run_streamed(fl, o, false, false, [&](Chunk& c) {
             c.out.reserve(c.nreads * 64);
             for (size_t i = 0; i < c.nreads; ++i) { const auto nm = c.name(i); format_stream_line(c.out, o, refs, nm.first, nm.second, c.hits[i]); }
@@ -658,7 +675,7 @@ int main_filter(int argc, char** argv) {
     if (refs.size() == 0) { fprintf(stderr, "rkmh: no reference sequences\n"); return 2; }
     Fleet fl; fl.open(std::max(1, o.gpus));
     setup_refs(fl, o, refs, FILTER_TABLE, true);
-    if (!(o.do_read_depth && any_stdin(o.reads))) {
+    if (!(o.do_read_depth && any_unrewindable(o.reads))) {
         run_streamed(fl, o, true, true, [&](Chunk& c) {
             for (size_t i = 0; i < c.nreads; ++i) {
                 const auto nm = c.name(i), ql = c.qual(i);

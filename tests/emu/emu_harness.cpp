@@ -256,12 +256,12 @@ int emu_classify(const char* ref_bases, const i64* ref_offs, int nrefs, const ch
 
 // ---- memoised path (rk_memo.cuh) -------------------------------------------------------------------------
 struct HostMemo {
-    std::vector<u32> tab, ref, tmp, sieve, sieve_t;
+    std::vector<u32> tab, ref, tmp, sieve;
     std::vector<unsigned long long> cmap;
-    u32 stats[2] = {0, 0}, stats_t[2] = {0, 0};
+    u32 stats[2] = {0, 0};
     std::vector<u64> hash;
     std::vector<int> code_counts;
-    unsigned long long inval = 0;
+    u32 inval = 0;
     int err = 0;
     Memo mm{};
 };
@@ -297,11 +297,6 @@ static void build_memo(HostMemo& hm, int k, const RefTable& tb, int block) {
         emu::launch(dim3(2), dim3(block), 0, [=] { memo_cmap_kernel(mm, cmap, cap - 1, 32 - log2cap); });
         hm.mm.sieve = sieve; hm.mm.sieve_words = nwords; hm.mm.cmap = cmap; hm.mm.cmap_mask = cap - 1; hm.mm.cmap_shift = 32 - log2cap;
         hm.mm.zero_codes = hm.stats[1];
-        const u32 nwt = 193;
-        hm.sieve_t.assign(nwt, 0);
-        u32* sieve_t = hm.sieve_t.data(); u32* stats_t = hm.stats_t;
-        emu::launch(dim3(2), dim3(block), 0, [=] { memo_sieve_kernel(mm, sieve_t, nwt, stats_t); });
-        hm.mm.sieve_t = sieve_t; hm.mm.sieve_t_words = nwt;
     }
 }
 
@@ -343,15 +338,7 @@ int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, con
     std::vector<int> redo((size_t)std::max<i64>(nreads, 1)); int redo_count = 0;
     int* predo = redo.data(); int* pcount = &redo_count;
     const int grid = 2;
-    if (path == 3 && tb.nb <= 4 && mm.sieve_t != nullptr && mm.zero_codes == 0 && min_occ < 0) {       // thread per read (tile kernel)
-        const size_t TILE_SMEM = TILE_FIXED_SMEM + (size_t)mm.sieve_t_words * 4;
-        switch (tb.nb) {
-            case 1: emu::launch(dim3(grid), dim3(TILE_THREADS), TILE_SMEM, [=] { classify_memo_tile_kernel<2>(sb, s, mm, tb, predo, pcount, out); }); break;
-            case 2: emu::launch(dim3(grid), dim3(TILE_THREADS), TILE_SMEM, [=] { classify_memo_tile_kernel<4>(sb, s, mm, tb, predo, pcount, out); }); break;
-            case 3: emu::launch(dim3(grid), dim3(TILE_THREADS), TILE_SMEM, [=] { classify_memo_tile_kernel<6>(sb, s, mm, tb, predo, pcount, out); }); break;
-            default: emu::launch(dim3(grid), dim3(TILE_THREADS), TILE_SMEM, [=] { classify_memo_tile_kernel<8>(sb, s, mm, tb, predo, pcount, out); }); break;
-        }
-    } else if (path == 4 && tb.nb <= 4 && mm.sieve != nullptr && mm.zero_codes == 0 && min_occ < 0) {
+    if (path == 4 && tb.nb <= 4 && mm.sieve != nullptr && mm.zero_codes == 0 && min_occ < 0) {
         // (path 4: the sieve kernel; falls through to the warp kernel when its preconditions do not hold)
         const size_t smem = ((size_t)mm.sieve_words + (size_t)(block / 32) * SIEVE_QCAP) * 4;
         switch (tb.nb) {
@@ -360,7 +347,7 @@ int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, con
             case 3: emu::launch(dim3(grid), dim3(block), smem, [=] { classify_memo_sieve_kernel<6>(sb, s, mm, tb, predo, pcount, out); }); break;
             default: emu::launch(dim3(grid), dim3(block), smem, [=] { classify_memo_sieve_kernel<8>(sb, s, mm, tb, predo, pcount, out); }); break;
         }
-    } else if ((path == 1 || path == 4 || path == 3) && tb.nb <= 4) {
+    } else if ((path == 1 || path == 4) && tb.nb <= 4) {
         // (path 1: the register-row warp kernel for <= 256 references)
         switch (tb.nb) {
             case 1: emu::launch(dim3(grid), dim3(block), 0, [=] { classify_memo_warp_kernel<2>(sb, s, mm, tb, predo, pcount, out); }); break;

@@ -47,6 +47,14 @@ def main():
     torch.cuda.synchronize()
     global_sum = int(table.sum().item())
     hits = gpu.classify_batch(*rkmh_b200.pack_sequences(reads[lo:hi]), min_occ=m)
+    # the same exchange on the per-code partial counts (64 MB instead of 800 MB): identical table, identical records
+    gpu.count_reset()
+    gpu.count_batch(*rkmh_b200.pack_sequences(reads[lo:hi]))
+    allreduce_count_table(gpu.count_partial_tensor())
+    torch.cuda.synchronize()
+    compact_sum = int(gpu.count_table_tensor().sum().item())
+    hits_c = gpu.classify_batch(*rkmh_b200.pack_sequences(reads[lo:hi]), min_occ=m)
+    compact_ok = compact_sum == global_sum and bool(np.array_equal(hits_c.view(np.int32), hits.view(np.int32)))
     mine = torch.from_numpy(np.stack([hits[f] for f in ("ref_id", "best", "prev", "sketch_len")], 1).astype(np.int32)).cuda()
     sizes = [shard_range(len(reads), r, world) for r in range(world)]
     bufs = [torch.empty((b - a, 4), dtype=torch.int32, device="cuda") for a, b in sizes]
@@ -63,7 +71,7 @@ def main():
     parts, lens = allgather_sketches(part, s2, device="cuda")
     merged = gpu.merge_sketches(parts, lens)
 
-    ok = True
+    ok = compact_ok
     if rank == 0:
         from oracle.oracle import Oracle
         ora = Oracle()
@@ -79,7 +87,7 @@ def main():
         print(f"multi_gpu_check world={world}: count sum local {local_sum} global {global_sum} (oracle {int(counts.sum())}), "
               f"-M hits equal {np.array_equal(got, exp)}, sharded sketch equal {np.array_equal(merged, whole)}")
     flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.broadcast(flag, 0)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     gpu.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)

@@ -136,7 +136,6 @@ def test_memo_classify_fixtures(emu, oracle):
     assert _memo_case(emu, oracle, refs, short[:40], 8, 1000, path=1) == 0
     _memo_case(emu, oracle, refs, short[:300] + reads[:1], 8, 1000, path=4)     # sieve kernel (+ its redo list)
     _memo_case(emu, oracle, refs, short[:120], 6, 1000, path=4)                 # dense sieve: many false positives
-    assert _memo_case(emu, oracle, refs, short[:500] + reads[:1], 8, 1000, path=3) == 1   # tile kernel: two runs of reads + a long read
 
 
 def test_memo_count_and_min_occ(emu, oracle):
@@ -156,7 +155,7 @@ def test_memo_count_and_min_occ(emu, oracle):
     c = np.zeros(size, np.int32)
     oracle.count_batch(reads, [8], c)
     for m in (1, 30, 200):
-        for path in (0, 1):                       # with a -M mask baked the sieve / tile kernels are not eligible
+        for path in (0, 1):                       # with a -M mask baked the sieve kernel is not eligible
             _memo_case(emu, oracle, refs[:4], reads, 8, 200, counts=c, min_occ=m, path=path)
     _memo_case(emu, oracle, refs[:4], reads, 8, 200, counts=c, min_occ=30, path=4)     # falls back to the warp kernel
 

@@ -286,7 +286,7 @@ def test_full_size_properties(gpu, oracle):
     assert np.array_equal(_fields(hits[idx]), _fields(exp))
 
 
-@pytest.mark.parametrize("variant", ["sieve", "warp", "tile"])
+@pytest.mark.parametrize("variant", ["sieve", "warp"])
 def test_memo_path_is_taken_and_matches_murmur(oracle, variant, monkeypatch):
     """The memoised kernels run for a single k <= 12 and give the same records as the Murmur kernels: short reads
     (warp kernel), long reads (block kernel, bottom-s by rank), with and without -M."""
@@ -298,8 +298,7 @@ def test_memo_path_is_taken_and_matches_murmur(oracle, variant, monkeypatch):
     sb, so = _synthetic_reads(rng, rs, 20000, 150)
     lb, lo = ont_reads(rng, hpv, 300, 10000)
     res = {}
-    # the three short-read kernels: shared-memory sieve (default), rank-table warp kernel, thread-per-read tile kernel
-    monkeypatch.setenv("RKMH_TILE", "1" if variant == "tile" else "0")
+    # the two short-read kernels: shared-memory sieve (default), rank-table warp kernel
     monkeypatch.setenv("RKMH_NO_SIEVE", "1" if variant == "warp" else "0")
     short_kernel = f"classify_memo_{variant}_kernel"
     for memo in (True, False):
@@ -366,3 +365,101 @@ def test_reference_count_variants(oracle, nrefs):
     reads = [bases[offs[i]:offs[i + 1]].tobytes() for i in idx]
     exp = oracle.classify_batch(reads, [12], 1000, sk, ln)
     assert np.array_equal(res[True][idx], _fields(exp))
+
+
+# ---- round 2: fixed-length entry points, per-code partial counts, copy probe --------------------------------
+def test_fixed_length_entry_points_equal_offsets(oracle):
+    """rkg_classify_fixed / rkg_count_fixed (no offsets cross the link) == rkg_classify_batch / rkg_count_batch on
+    the equivalent offsets, with and without -M, on both hashing paths; spot-checked against the oracle."""
+    import rkmh_b200
+    _, rs, _ = load_sequences([data_path("all_pave_ref.fa.gz")])
+    rng = np.random.default_rng(11)
+    bases, offs = _synthetic_reads(rng, rs, 30000, 150)
+    for memo in (True, False):
+        with rkmh_b200.RkmhGpu(0) as g:
+            g.set_memo(memo)
+            g.set_params([12], 1000, read_table_size=rkmh_b200.STREAM_TABLE_SIZE)
+            g.load_refs(*_pack(rs))
+            a = _fields(g.classify_batch(bases, offs))
+            b = _fields(g.classify_fixed(bases, 150))
+            assert np.array_equal(a, b)
+            g.count_reset(); g.count_batch(bases, offs)
+            t1 = g.count_table_tensor().clone()
+            am = _fields(g.classify_batch(bases, offs, min_occ=3))
+            g.count_reset(); g.count_fixed(bases, 150)
+            t2 = g.count_table_tensor()
+            assert bool((t1 == t2).all().item())
+            bm = _fields(g.classify_fixed(bases, 150, min_occ=3))
+            assert np.array_equal(am, bm)
+            # the copies alone (rkg_copy_probe) run on the same buffers without touching the results of later calls
+            out = np.zeros(30000, rkmh_b200.HIT_DTYPE)
+            g.copy_probe_raw(bases.ctypes.data, None, 150, 30000, out.ctypes.data)
+            g.copy_probe_raw(bases.ctypes.data, offs.ctypes.data, 0, 30000, out.ctypes.data)
+            assert np.array_equal(_fields(g.classify_fixed(bases, 150)), a)
+    sk, ln = oracle.sketch_batch(rs, [12], 1000)
+    reads = [bases[offs[i]:offs[i + 1]].tobytes() for i in range(200)]
+    assert np.array_equal(a[:200], _fields(oracle.classify_batch(reads, [12], 1000, sk, ln)))
+
+
+@pytest.mark.parametrize("count_zeros", [False, True])
+def test_count_partial_exchange_equals_one_table(count_zeros):
+    """The -M exchange on the per-code partial counts (rkg_count_partial, 64 MB at k = 12): two contexts stand in for
+    two ranks, each counts half of the reads, the partial arrays are summed into both (what the all-reduce does), and
+    every context then holds the table -- and gives the records -- that one context counting all reads does.  One of
+    the two "ranks" counts NO read in a second round (a rank with an empty shard still folds the sum)."""
+    import rkmh_b200
+    import torch
+    from rkmh_b200.synth import ont_reads
+    _, hpv, _ = load_sequences([data_path("hpv_16_allFasta.fa.gz")])
+    rng = np.random.default_rng(5)
+    bases, offs = ont_reads(rng, hpv, 120, 6000)
+    bases = bases.copy()
+    bases[rng.integers(0, bases.size, 500)] = ord("N")       # invalid windows: the count_zeros mode counts them in slot 0
+    size = rkmh_b200.FILTER_TABLE_SIZE if count_zeros else rkmh_b200.STREAM_TABLE_SIZE
+    half = 60
+    lo = (bases[:offs[half]], offs[:half + 1])
+    hi = (bases[offs[half]:], offs[half:] - offs[half])
+    ctxs = []
+    for _ in range(3):
+        g = rkmh_b200.RkmhGpu(0)
+        g.set_params([12], 1000, read_table_size=size)
+        g.load_refs(*_pack(hpv))
+        g.count_reset()
+        ctxs.append(g)
+    one, ra, rb = ctxs
+    try:
+        one.count_batch(bases, offs, count_zeros=count_zeros)
+        ref_table = one.count_table_tensor().clone()
+        ref_hits = _fields(one.classify_batch(bases, offs, min_occ=4))
+        for shards in ((lo, hi), ((bases, offs), None)):
+            for g, sh in zip((ra, rb), shards):
+                g.count_reset()
+                if sh is not None:
+                    g.count_batch(*sh, count_zeros=count_zeros)
+            pa, pb = ra.count_partial_tensor(count_zeros), rb.count_partial_tensor(count_zeros)
+            assert pa.numel() == 4 ** 12 + 32
+            total = pa + pb
+            pa.copy_(total); pb.copy_(total)
+            torch.cuda.synchronize()
+            for g in (ra, rb):
+                assert bool((g.count_table_tensor() == ref_table).all().item())
+                assert np.array_equal(_fields(g.classify_batch(bases, offs, min_occ=4)), ref_hits)
+    finally:
+        for g in ctxs:
+            g.close()
+
+
+def test_limits_fail_loudly():
+    """Arguments past the documented limits are refused with an error, never looped on or silently truncated."""
+    import rkmh_b200
+    with rkmh_b200.RkmhGpu(0) as g:
+        with pytest.raises(rkmh_b200.RkmhError, match="sketch size"):
+            g.set_params([12], (1 << 26) + 1)
+        g.set_params([12], 1 << 26)
+        with pytest.raises(rkmh_b200.RkmhError, match="2\\^29"):
+            g.load_refs(*_pack([b"ACGTACGTACGTACGTACGT"] * 9))
+        g.set_memo(False)
+        g.set_params([20], 100, read_table_size=1000)
+        g.load_refs(*_pack([b"ACGTACGTACGTACGTACGTTTGACA" * 3]))
+        with pytest.raises(rkmh_b200.RkmhError, match="memoised path is not active"):
+            g.count_partial_tensor()
