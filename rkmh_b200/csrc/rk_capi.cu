@@ -14,6 +14,7 @@
 #include "../../include/rkmh_gpu.h"
 #include "rk_kernels.cuh"
 #include "rk_memo.cuh"
+#include "rk_warp.cuh"
 
 using namespace rk;
 
@@ -24,13 +25,13 @@ namespace {
 
 thread_local std::string g_create_error;
 
-enum KernelId { K_INGEST, K_HASH, K_COUNT, K_COUNT_DISTINCT, K_SKETCH, K_MERGE, K_TABLE, K_CLASSIFY_GROUP,
+enum KernelId { K_INGEST, K_HASH, K_COUNT, K_COUNT_DISTINCT, K_SKETCH, K_MERGE, K_TABLE, K_CLASSIFY_GROUP, K_CLASSIFY_WARP,
                 K_CLASSIFY_BLOCK, K_MEMO_BUILD, K_MEMO_MAINT, K_COUNT_MEMO, K_CLASSIFY_MEMO_WARP, K_CLASSIFY_MEMO_BLOCK,
                 K_CLASSIFY_MEMO_SIEVE,
                 K_NUM };
 const char* const kKernelNames[K_NUM] = {"ingest_kernel", "hash_kernel", "count_kernel", "count_distinct_kernel",
                                          "sketch_kernel", "merge_kernel", "table_build_kernels",
-                                         "classify_group_kernel", "classify_block_kernel", "memo_build_kernels",
+                                         "classify_group_kernel", "classify_warp_kernel", "classify_block_kernel", "memo_build_kernels",
                                          "memo_fold_apply_kernels", "count_memo_kernel", "classify_memo_warp_kernel",
                                          "classify_memo_block_kernel", "classify_memo_sieve_kernel"};
 
@@ -84,7 +85,7 @@ struct rkg_ctx {
     cudaStream_t stream = nullptr;
     rkg_batch* slots[2] = {nullptr, nullptr};   // internal double buffer of rkg_classify_batch / count
     // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
-    bool memo_enabled = true, memo_ready = false, sieve_enabled = true;
+    bool memo_enabled = true, memo_ready = false, sieve_enabled = true, group_kernel = false;
     DevBuf memo_tab, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc, memo_sieve, memo_cmap;
     double sieve_fill = 0.0;             // fraction of the sieve's bits that are set (false-positive rate = fill^2)
     Memo memo{};
@@ -531,7 +532,24 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
     { int rc = ensure_packed(ctx, b); if (rc) return rc; }
 
     GroupGeom gg = group_geometry(ctx, b);
-    if (gg.ok) {
+    // <= 256 references: the warp-cooperative kernel (rk_warp.cuh); more: the sub-warp group kernel with shared-memory counters
+    const size_t warp_smem = (size_t)gg.filter_words * 4 + (size_t)32 * WARP_QCAP * 8;
+    if (gg.ok && ctx->tb.nb <= 4 && !ctx->group_kernel && warp_smem <= ctx->smem_optin) {
+        Timed t(ctx, b->stream, K_CLASSIFY_WARP);
+        const int grid = ctx->sm_count;
+        DISPATCH_KCSEL(ctx->kcsel, {
+            if (ctx->tb.nb <= 1) {
+                CK(cudaFuncSetAttribute(classify_warp_kernel<KS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
+                classify_warp_kernel<KS, 2><<<grid, 1024, warp_smem, b->stream>>>(sb, ctx->kl, ctx->s, ct, min_occ, ctx->tb, gg.filter_words,
+                                                                                   redo, redo_count, hits);
+            } else {
+                CK(cudaFuncSetAttribute(classify_warp_kernel<KS, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
+                classify_warp_kernel<KS, 8><<<grid, 1024, warp_smem, b->stream>>>(sb, ctx->kl, ctx->s, ct, min_occ, ctx->tb, gg.filter_words,
+                                                                                   redo, redo_count, hits);
+            }
+        });
+        CK(cudaGetLastError());
+    } else if (gg.ok) {
         Timed t(ctx, b->stream, K_CLASSIFY_GROUP);
         int grid = ctx->sm_count;
         DISPATCH_KCSEL(ctx->kcsel, {
@@ -651,6 +669,7 @@ int rkg_create(int device, rkg_ctx** out) {
     ctx->device = device;
     { const char* nm = getenv("RKMH_NO_MEMO"); ctx->memo_enabled = !(nm && nm[0] && nm[0] != '0'); }
     { const char* nm = getenv("RKMH_NO_SIEVE"); ctx->sieve_enabled = !(nm && nm[0] && nm[0] != '0'); }
+    { const char* nm = getenv("RKMH_GROUP_KERNEL"); ctx->group_kernel = nm && nm[0] && nm[0] != '0'; }   // round-1 Murmur fast path (A/B timing)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -1190,10 +1209,11 @@ int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t km
         cudaMemsetAsync(d_hist.p, 0, sizeof(u32) * SHARD_BINS, b->stream);
         cudaMemsetAsync(d_pick.p, 0, 64, b->stream);
         const int grid = ctx->sm_count * 8;
+        const i64 lastw = 2 * ((b->total + 31) / 32) + 7, lastm = (b->total + 31) / 32 + 7;   // batch_fill pads 8 words
         u64 hpick[2] = {0, 0};
         {
             Timed t(ctx, b->stream, K_SKETCH);
-            DISPATCH_KCSEL(ctx->kcsel, (shard_hist_kernel<KS><<<grid, 256, 0, b->stream>>>(b->codes.as<u32>(), b->nmask.as<u32>(), n, ctx->kl,
+            DISPATCH_KCSEL(ctx->kcsel, (shard_hist_kernel<KS><<<grid, 256, 0, b->stream>>>(b->codes.as<u32>(), b->nmask.as<u32>(), lastw, lastm, n, ctx->kl,
                                                                                          d_hist.as<u32>())));
             shard_pick_kernel<<<1, 1024, 0, b->stream>>>(d_hist.as<u32>(), (u64)ctx->s, d_pick.as<u64>());
             ctx->launches += 2;
@@ -1208,7 +1228,7 @@ int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t km
         unsigned long long* ncand = d_pick.as<unsigned long long>() + 4;
         {
             Timed t(ctx, b->stream, K_SKETCH);
-            DISPATCH_KCSEL(ctx->kcsel, (shard_emit_kernel<KS><<<grid, 256, 0, b->stream>>>(b->codes.as<u32>(), b->nmask.as<u32>(), n, ctx->kl,
+            DISPATCH_KCSEL(ctx->kcsel, (shard_emit_kernel<KS><<<grid, 256, 0, b->stream>>>(b->codes.as<u32>(), b->nmask.as<u32>(), lastw, lastm, n, ctx->kl,
                                                                                          d_pick.as<u64>(), d_cand.as<u64>(), ncand, kept)));
             shard_sort_kernel<<<1, 1024, 0, b->stream>>>(d_cand.as<u64>(), (int)kept, P);
             ctx->launches += 2;

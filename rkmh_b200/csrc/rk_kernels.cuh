@@ -13,10 +13,9 @@
 // The file is also compiled by g++ against tests/emu/cuda_emu.h (RK_EMU) to debug the logic on CPU.
 #pragma once
 #include "rk_common.cuh"
+#include "rk_hash.cuh"
 
 namespace rk {
-
-typedef long long i64;
 
 struct Hit { int ref_id, best, prev, sketch_len; };   // == rkg_hit
 template <int V> struct KcTag { static constexpr int value = V; };
@@ -131,49 +130,9 @@ RK_D u64 apply_min_occ(u64 h, const CountTable& ct, int min_occ) {
     return (min_occ <= freq) ? h : 0;
 }
 
-// Hash k-mers [c0, c1) of the sequence starting at packed position seq_begin and hand each to emit(i, h).
-template <int KC, typename F>
-RK_D void hash_range(const u32* codes, const u32* nmask, i64 seq_begin, i64 c0, i64 c1, int k, F&& emit) {
-    BaseReader rd; rd.init(codes, nmask, seq_begin + c0);
-    KmerWindow<KC> win; win.reset();
-    const WinSel ws = make_winsel(k);
-    u32 code; bool inv;
-    for (int j = 0; j < k - 1; ++j) { rd.next(code, inv); win.push(code, inv, ws); }
-    for (i64 i = c0; i < c1; ++i) {
-        rd.next(code, inv); win.push(code, inv, ws);
-        emit(i, win.hash(k));
-    }
-}
-
-// A team of nthreads threads (thread tid) covers k-mers [0, n) of one sequence in chunks of `chunk`.
-template <int KC, typename F>
-RK_D void team_hash(const u32* codes, const u32* nmask, i64 seq_begin, i64 n, int k, int tid, int nthreads,
-                    int chunk, F&& emit) {
-    for (i64 c0 = (i64)tid * chunk; c0 < n; c0 += (i64)nthreads * chunk) {
-        i64 c1 = c0 + chunk < n ? c0 + chunk : n;
-        hash_range<KC>(codes, nmask, seq_begin, c0, c1, k, emit);
-    }
-}
-
-// Dispatch on the key-length variant.  KCSEL 0..9: every k of the list is of that variant (no switch in
-// the instantiation); KCSEL 10 (= NUM_KV): mixed variants, switch per k.
-template <int KCSEL, typename F>
-RK_D void team_hash_k(int kv, const u32* codes, const u32* nmask, i64 seq_begin, i64 n, int k, int tid, int nthreads,
-                      int chunk, F&& emit) {
-    if (KCSEL < NUM_KV) { team_hash<(KCSEL < NUM_KV ? KCSEL : 0)>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); return; }
-    switch (kv) {
-        case 0: team_hash<0>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
-        case 1: team_hash<1>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
-        case 2: team_hash<2>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
-        case 3: team_hash<3>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
-        case 4: team_hash<4>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
-        case 5: team_hash<5>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
-        case 6: team_hash<6>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
-        case 7: team_hash<7>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
-        case 8: team_hash<8>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
-        default: team_hash<9>(codes, nmask, seq_begin, n, k, tid, nthreads, chunk, emit); break;
-    }
-}
+// last loadable word of a batch's codes[] / nmask[] (batch_fill pads 8 words): the readers clamp their loads to it
+RK_D i64 codes_last_word(const SeqBatch& sb) { return 2 * ((sb.total + 31) / 32) + 7; }
+RK_D i64 nmask_last_word(const SeqBatch& sb) { return (sb.total + 31) / 32 + 7; }
 
 RK_D i64 nkmers(i64 len, int k) { return len - k > 0 ? len - k : 0; }   // len - k windows, SURVEY F7
 RK_D i64 nkmers_total(i64 len, const KList& kl) {
@@ -198,8 +157,8 @@ hash_kernel(SeqBatch sb, KList kl, int kidx, u64* __restrict__ out, const i64* _
         i64 koff = 0;
         for (int j = 0; j < kidx; ++j) koff += nkmers(len, kl.k[j]);
         u64* dst = out + out_offs[s] + koff;
-        team_hash<KC>(sb.codes, sb.nmask, beg, nkmers(len, k), k, lane, 32, 8,
-                      [&](i64 i, u64 h) { dst[i] = h; });
+        team_hash_k<KC>(kl.kv[kidx], sb.codes, sb.nmask, codes_last_word(sb), nmask_last_word(sb), beg, nkmers(len, k), k, lane, 32,
+                        [&](i64 i, u64 h) { dst[i] = h; });
     }
 }
 
@@ -217,7 +176,7 @@ count_kernel(SeqBatch sb, KList kl, CountTable ct, int count_zeros) {
         i64 beg = sb.offs[s] - sb.base0, len = sb.offs[s + 1] - sb.offs[s];
         for (int j = 0; j < kl.nk; ++j) {
             const int k = kl.k[j];
-            team_hash_k<KCSEL>(kl.kv[j], sb.codes, sb.nmask, beg, nkmers(len, k), k, lane, 32, 8,
+            team_hash_k<KCSEL>(kl.kv[j], sb.codes, sb.nmask, codes_last_word(sb), nmask_last_word(sb), beg, nkmers(len, k), k, lane, 32,
                                [&](i64, u64 h) {
                                    if (h != 0 || count_zeros) atomicAdd(&ct.counts[fastmod(h, ct.mod)], 1);
                                });
@@ -365,7 +324,7 @@ sketch_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int filter_mode, int 
         for (int j = 0; j < kl.nk; ++j) {
             const int k = kl.k[j];
             i64 nj = nkmers(len, k);
-            team_hash_k<KCSEL>(kl.kv[j], sb.codes, sb.nmask, beg, nj, k, threadIdx.x, blockDim.x, 9,
+            team_hash_k<KCSEL>(kl.kv[j], sb.codes, sb.nmask, codes_last_word(sb), nmask_last_word(sb), beg, nj, k, threadIdx.x, blockDim.x,
                                [&](i64 i, u64 h) {
                                    if (h != 0 && filter_mode != 0) {
                                        int freq = ct.counts[fastmod(h, ct.mod)];
@@ -422,12 +381,13 @@ constexpr i64 SHARD_SEG = 4096;                 // windows per warp task
 
 template <int KCSEL>
 __global__ void __launch_bounds__(256)
-shard_hist_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, i64 n, KList kl, u32* __restrict__ hist) {
+shard_hist_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, i64 last_word, i64 last_mword, i64 n, KList kl,
+                  u32* __restrict__ hist) {
     const int lane = threadIdx.x & 31, k = kl.k[0];
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
     for (i64 w0 = warp * SHARD_SEG; w0 < n; w0 += nwarps * SHARD_SEG) {
         const i64 cnt = min(SHARD_SEG, n - w0);
-        team_hash_k<KCSEL>(kl.kv[0], codes, nmask, w0, cnt, k, lane, 32, 8,
+        team_hash_k<KCSEL>(kl.kv[0], codes, nmask, last_word, last_mword, w0, cnt, k, lane, 32,
                            [&](i64, u64 h) { if (h) atomicAdd(&hist[(u32)(h >> 48)], 1u); });
     }
 }
@@ -460,14 +420,15 @@ shard_pick_kernel(const u32* __restrict__ hist, u64 s, u64* __restrict__ out) {
 
 template <int KCSEL>
 __global__ void __launch_bounds__(256)
-shard_emit_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, i64 n, KList kl, const u64* __restrict__ pick,
+shard_emit_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, i64 last_word, i64 last_mword, i64 n, KList kl,
+                  const u64* __restrict__ pick,
                   u64* __restrict__ cand, unsigned long long* __restrict__ ncand, u64 cap) {
     const int lane = threadIdx.x & 31, k = kl.k[0];
     const u32 bin = (u32)pick[0];
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
     for (i64 w0 = warp * SHARD_SEG; w0 < n; w0 += nwarps * SHARD_SEG) {
         const i64 cnt = min(SHARD_SEG, n - w0);
-        team_hash_k<KCSEL>(kl.kv[0], codes, nmask, w0, cnt, k, lane, 32, 8, [&](i64, u64 h) {
+        team_hash_k<KCSEL>(kl.kv[0], codes, nmask, last_word, last_mword, w0, cnt, k, lane, 32, [&](i64, u64 h) {
             if (h && (u32)(h >> 48) <= bin) {
                 const unsigned long long at = atomicAdd(ncand, 1ULL);
                 if (at < cap) cand[at] = h;
@@ -673,7 +634,7 @@ classify_block_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, 
         for (int j = 0; j < kl.nk; ++j) {
             const int k = kl.k[j];
             i64 nj = nkmers(len, k);
-            team_hash_k<KCSEL>(kl.kv[j], sb.codes, sb.nmask, beg, nj, k, threadIdx.x, blockDim.x, 9,
+            team_hash_k<KCSEL>(kl.kv[j], sb.codes, sb.nmask, codes_last_word(sb), nmask_last_word(sb), beg, nj, k, threadIdx.x, blockDim.x,
                                [&](i64 i, u64 h) {
                                    h = apply_min_occ(h, ct, min_occ);
                                    H[base + i] = h;

@@ -28,6 +28,8 @@ class Emu:
         lib.emu_fastmod.restype = C.c_uint64
         lib.emu_kmer_hash.argtypes = [C.c_char_p, C.c_int]
         lib.emu_kmer_hash.restype = C.c_uint64
+        lib.emu_window_hash.argtypes = [C.c_char_p, C.c_int]
+        lib.emu_window_hash.restype = C.c_uint64
         P, I, L, U = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
         lib.emu_hash.argtypes = [P, P, L, P, I, P, P, I]
         lib.emu_count.argtypes = [P, P, L, P, I, P, U, I, I]

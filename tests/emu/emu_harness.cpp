@@ -11,6 +11,7 @@ EMU_DEFINE_STATE
 
 #include "../../rkmh_b200/csrc/rk_kernels.cuh"
 #include "../../rkmh_b200/csrc/rk_memo.cuh"
+#include "../../rkmh_b200/csrc/rk_warp.cuh"
 
 using namespace rk;
 
@@ -167,9 +168,10 @@ int emu_sketch_shard(const char* bases, i64 nbytes, i64 n, int k, int s, u64* ou
     std::vector<u32> hist(SHARD_BINS, 0);
     u64 pick[2] = {0, 0};
     const u32* pc = b.codes.data(); const u32* pm = b.nmask.data(); u32* ph = hist.data(); u64* pp = pick;
+    const i64 lastw = (i64)b.codes.size() - 1, lastm = (i64)b.nmask.size() - 1;
     dispatch(kcsel, [&](auto tag) {
         constexpr int KS = decltype(tag)::value;
-        emu::launch(dim3(2), dim3(block), 0, [=] { shard_hist_kernel<KS>(pc, pm, n, kl, ph); });
+        emu::launch(dim3(2), dim3(block), 0, [=] { shard_hist_kernel<KS>(pc, pm, lastw, lastm, n, kl, ph); });
     });
     emu::launch(dim3(1), dim3(1024), 0, [=] { shard_pick_kernel(ph, (u64)s, pp); });
     const u64 kept = pick[1];
@@ -181,7 +183,7 @@ int emu_sketch_shard(const char* bases, i64 nbytes, i64 n, int k, int s, u64* ou
     u64* pcand = cand.data(); unsigned long long* pn = &ncand;
     dispatch(kcsel, [&](auto tag) {
         constexpr int KS = decltype(tag)::value;
-        emu::launch(dim3(2), dim3(block), 0, [=] { shard_emit_kernel<KS>(pc, pm, n, kl, pp, pcand, pn, kept); });
+        emu::launch(dim3(2), dim3(block), 0, [=] { shard_emit_kernel<KS>(pc, pm, lastw, lastm, n, kl, pp, pcand, pn, kept); });
     });
     if (ncand != kept) return -2;
     emu::launch(dim3(1), dim3(block), 0, [=] { shard_sort_kernel(pcand, (int)kept, P); });
@@ -232,6 +234,18 @@ int emu_classify(const char* ref_bases, const i64* ref_offs, int nrefs, const ch
             });
         });
     }
+    if (path == 2) {                                    // warp-cooperative Murmur kernel (<= 256 references)
+        const int nwb = block / 32;
+        const int filter_words = (int)((1u << tb.filter_log2) / 32u);
+        size_t smem = (size_t)filter_words * 4 + (size_t)nwb * WARP_QCAP * 8;
+        dispatch(kcsel, [&](auto tag) {
+            constexpr int KS = decltype(tag)::value;
+            emu::launch(dim3(grid), dim3(block), smem, [=] {
+                if (tb.nb <= 1) classify_warp_kernel<KS, 2>(sb, kl, s, ct, min_occ, tb, filter_words, predo, pcount, out);
+                else classify_warp_kernel<KS, 8>(sb, kl, s, ct, min_occ, tb, filter_words, predo, pcount, out);
+            });
+        });
+    }
     if (redo_count_out) *redo_count_out = redo_count;
     {
         const int hs_cap = next_pow2(2 * (i64)std::min<i64>(s, std::max<i64>(b.max_ntotal, 1)));
@@ -242,7 +256,7 @@ int emu_classify(const char* ref_bases, const i64* ref_offs, int nrefs, const ch
         size_t smem = (size_t)hbuf_cap * 8 + (hs_in_smem ? (size_t)hs_cap * 8 : 0) + (size_t)rpad * 4;
         std::vector<u64> scratch((size_t)grid * (size_t)(stride + hs_cap) + 8);
         u64* ps = scratch.data();
-        const int* list = (path == 1) ? predo : nullptr;
+        const int* list = (path == 1 || path == 2) ? predo : nullptr;
         dispatch(kcsel, [&](auto tag) {
             constexpr int KS = decltype(tag)::value;
             emu::launch(dim3(grid), dim3(block), smem, [=] {
@@ -382,6 +396,20 @@ int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, con
 
 // host-side arithmetic checks
 u64 emu_fastmod(u64 n, u64 d) { FastMod f = make_fastmod(d); return fastmod(n, f); }
+
+u64 emu_window_hash(const char* kmer, int k) {   // canonical hash of one window through window_hash (rk_hash.cuh)
+    u32 lo = 0, hi = 0;
+    for (int i = 0; i < 32; ++i) {                 // junk codes beyond k must not matter
+        const u32 c = i < k ? base_code((u32)(unsigned char)kmer[i]) : (u32)((i * 7 + 1) & 3);
+        if (i < 16) lo |= c << (2 * i); else hi |= c << (2 * (i - 16));
+    }
+    u64 result = 0;
+    dispatch(kvariant_of(k), [&](auto tag) {
+        constexpr int KC = decltype(tag)::value < NUM_KV ? decltype(tag)::value : 0;
+        result = window_hash<KC>(lo, hi, k);
+    });
+    return result;
+}
 
 u64 emu_kmer_hash(const char* kmer, int k) {   // canonical hash of one window through the rolling window code
     u64 result = 0;

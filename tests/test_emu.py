@@ -29,6 +29,7 @@ def test_rolling_murmur_all_k(emu, oracle):
         for _ in range(10):
             km = "".join(rnd.choice("ACGT") for _ in range(k)).encode()
             assert emu.lib.emu_kmer_hash(km, k) == oracle.calc_hash(km)
+            assert emu.lib.emu_window_hash(km, k) == oracle.calc_hash(km)       # lane-per-window path (rk_hash.cuh)
 
 
 @pytest.mark.parametrize("ks", [[8], [4], [9, 16], [17], [25], [32], [12, 20]])
@@ -53,7 +54,7 @@ def _classify_case(emu, oracle, ref_files, read_file, ks, s, nreads=None, nrefs=
     return redo
 
 
-@pytest.mark.parametrize("kw", [dict(path=0), dict(path=1, glog2=3), dict(path=1, glog2=5),
+@pytest.mark.parametrize("kw", [dict(path=0), dict(path=1, glog2=3), dict(path=1, glog2=5), dict(path=2),
                                 dict(path=0, hbuf_global=True, hs_global=True)])
 def test_classify_awkward(emu, oracle, kw):
     _classify_case(emu, oracle, ["awkward_refs.fa.gz"], "awkward_reads.fq.gz", [8], 50, **kw)
@@ -62,6 +63,16 @@ def test_classify_awkward(emu, oracle, kw):
 def test_classify_small_sketch_and_multik(emu, oracle):
     _classify_case(emu, oracle, ["awkward_refs.fa.gz"], "awkward_reads.fq.gz", [8], 10, path=1, glog2=4)
     _classify_case(emu, oracle, ["awkward_refs.fa.gz"], "awkward_reads.fq.gz", [6, 17], 20, path=1, glog2=4)
+    _classify_case(emu, oracle, ["awkward_refs.fa.gz"], "awkward_reads.fq.gz", [8], 10, path=2)
+    _classify_case(emu, oracle, ["awkward_refs.fa.gz"], "awkward_reads.fq.gz", [6, 17], 20, path=2)
+    _classify_case(emu, oracle, ["awkward_refs.fa.gz"], "awkward_reads.fq.gz", [3, 21, 13, 32], 3000, path=2)
+
+
+@pytest.mark.parametrize("k", [1, 4, 5, 12, 15, 16, 17, 20, 24, 25, 31, 32])
+def test_classify_warp_kernel_every_variant(emu, oracle, k):
+    """classify_warp_kernel (rk_warp.cuh) for every key-length variant: sketch = every hash, no read on the redo list"""
+    redo = _classify_case(emu, oracle, ["awkward_refs.fa.gz"], "awkward_reads.fq.gz", [k], 5000, path=2)
+    assert redo == 0 or k < 10          # tiny k: more than 32 hits per read is the rule, those reads take the exact path
 
 
 def test_classify_fixtures(emu, oracle):
@@ -70,6 +81,9 @@ def test_classify_fixtures(emu, oracle):
                           glog2=4) == 0
     _classify_case(emu, oracle, ["zika.fa.gz", "dengue.fa.gz", "yellow_fever.fa.gz", "hpv_16.fa.gz"], "z1.fq.gz", [20],
                    2000, nreads=64, path=1, glog2=4)
+    assert _classify_case(emu, oracle, ["all_pave_ref.fa.gz"], "z1.fq.gz", [12], 1000, nreads=48, nrefs=70, path=2) == 0
+    _classify_case(emu, oracle, ["zika.fa.gz", "dengue.fa.gz", "yellow_fever.fa.gz", "hpv_16.fa.gz"], "z1.fq.gz", [20],
+                   2000, nreads=64, path=2)
 
 
 def test_count_mask_and_filters(emu, oracle):
