@@ -35,7 +35,54 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__thread_inst_executed_per_inst_executed.ratio"]
 
 
+def current(argv):
+    """--current out.json rep:reads [rep:reads ...]: the per-launch counters bench.py turns into `roofline.traffic` and
+    `issue_slots`, keyed by kernel name, stamped with the hash of the kernel sources of the tree they were taken from."""
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import source_hash
+    out_path, specs = argv[0], argv[1:]
+    res = {"source_hash": source_hash(), "kernels": {}}
+    for spec in specs:
+        rep, reads = spec.rsplit(":", 1)
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+        rows = list(csv.reader(txt.splitlines()))
+        hdr = rows[0]
+        for vals in rows[2:]:
+            d = dict(zip(hdr, vals))
+            name = d.get("Kernel Name", "").split("<")[0].split("(")[0].replace("rk::", "").strip()
+
+            def num(key):
+                try:
+                    return float(d[key].replace(",", ""))
+                except (KeyError, ValueError):
+                    return None
+            if name in res["kernels"]:
+                continue
+            res["kernels"][name] = {
+                "reads": int(reads), "report": os.path.basename(rep), "full_name": d.get("Kernel Name", ""),
+                "dram_bytes": (num("dram__bytes_read.sum") or 0.0) + (num("dram__bytes_write.sum") or 0.0),
+                "warp_instructions": num("smsp__inst_executed.sum"),
+                "duration_ns_under_ncu": num("gpu__time_duration.sum"),
+                "issue_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "alu_pct": num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                "fma_pct": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                "lsu_pct": num("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+                "lts_pct": num("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+                "lts_hit_pct": num("lts__t_sector_hit_rate.pct"),
+                "dram_pct": num("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                "warps_active_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "smem_wavefronts": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+                "smem_bank_conflicts": num("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+                "registers": num("launch__registers_per_thread")}
+    with open(out_path, "w") as fh:
+        json.dump(res, fh, indent=1)
+        fh.write("\n")
+
+
 def main():
+    if sys.argv[1] == "--current":
+        return current(sys.argv[2:])
     rep = sys.argv[1]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))

@@ -68,6 +68,8 @@ struct rkg_ctx {
     int device = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
+    size_t l2_persist_max = 0, l2_window_max = 0;   // persisting-L2 carve-out and largest access-policy window of the device
+    bool l2_policy = true;                          // RKMH_NO_L2_POLICY=1 turns the access-policy windows off (A/B timing)
     std::string err;
     KList kl{};
     int kcsel = 0;
@@ -75,7 +77,7 @@ struct rkg_ctx {
     int s = 1000;
     bool params_set = false;
     u64 read_tbl_size = 0, ref_tbl_size = 0;
-    DevBuf read_counts, ref_counts;
+    DevBuf read_counts, ref_counts, hash_lut;   // hash_lut: the tables of rk_hash.cuh (16 KB, built in rkg_create)
     CountTable read_ct{nullptr, {}}, ref_ct{nullptr, {}};
     // references
     bool refs_loaded = false;
@@ -389,6 +391,29 @@ int memo_prepare(rkg_ctx* ctx, int min_occ) {
     return RKG_OK;
 }
 
+// Keep `bytes` at `ptr` resident in L2 for the kernels launched on `st` from now on: hits on the window persist, every
+// other access of those kernels (the read bases, streamed once) is marked streaming and is evicted first.  Without it
+// the 1 byte per base streaming through L2 evicts the randomly accessed table (ncu, round 1: the count kernel wrote
+// 319 MB back to DRAM per 200 MB of bases, L2 hit rate 65 %).  bytes = 0 clears the window.
+void l2_window(rkg_ctx* ctx, cudaStream_t st, const void* ptr, size_t bytes) {
+    if (!ctx->l2_policy || ctx->l2_persist_max == 0 || ctx->l2_window_max == 0) return;
+    cudaStreamAttrValue v{};
+    if (bytes > 0) {
+        const size_t win = std::min(bytes, ctx->l2_window_max);
+        v.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+        v.accessPolicyWindow.num_bytes = win;
+        // the fraction of the window that fits the carve-out persists, the rest is treated as normal
+        v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)ctx->l2_persist_max / (double)win);
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } else {
+        v.accessPolicyWindow.num_bytes = 0;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+}
+
 int launch_count(rkg_ctx* ctx, rkg_batch* b, CountTable ct, int count_zeros) {
     if (b->nseq == 0) return RKG_OK;
     if (ctx->memo_ready && ctx->memo.code_counts && ct.counts == ctx->read_ct.counts) {
@@ -397,8 +422,12 @@ int launch_count(rkg_ctx* ctx, rkg_batch* b, CountTable ct, int count_zeros) {
         const int wpr = (b->total / b->nseq > 2048) ? 8 : 1;            // a block per long read, a warp per short one
         const i64 teams = (b->nseq + 0) * 1;
         const int grid = (int)std::min<i64>((teams * wpr + 7) / 8, (i64)ctx->sm_count * 8);
-        Timed t(ctx, b->stream, K_COUNT_MEMO);
-        count_memo_kernel<<<grid, 256, 0, b->stream>>>(seq_view(b), ctx->memo, count_zeros, wpr);
+        l2_window(ctx, b->stream, ctx->memo.code_counts, sizeof(int) * (size_t)ctx->memo.ncodes);
+        {
+            Timed t(ctx, b->stream, K_COUNT_MEMO);
+            count_memo_kernel<<<grid, 256, 0, b->stream>>>(seq_view(b), ctx->memo, count_zeros, wpr);
+        }
+        l2_window(ctx, b->stream, nullptr, 0);
         CK(cudaGetLastError());
         return RKG_OK;
     }
@@ -520,10 +549,15 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, classify_memo_block_kernel, 256, mg.block_smem));
             const int grid = ctx->sm_count * std::max(1, std::min(per_sm, 8));
             CK(b->scratch.ensure(sizeof(u32) * (size_t)grid * (size_t)mg.scratch_stride + 64));
-            Timed t(ctx, b->stream, K_CLASSIFY_MEMO_BLOCK);
-            classify_memo_block_kernel<<<grid, 256, mg.block_smem, b->stream>>>(
-                sb, ctx->s, ctx->memo, ctx->tb, mg.use_warp ? redo : nullptr, mg.use_warp ? redo_count : nullptr, b->nseq,
-                mg.vcap, mg.hs_cap, mg.rpad, b->scratch.as<u32>(), mg.scratch_stride, hits);
+            // every window of every read looks its rank up in the 4^k-entry table: keep it in L2, stream the bases
+            if (!mg.use_warp) l2_window(ctx, b->stream, ctx->memo.tab, sizeof(u32) * (size_t)ctx->memo.ncodes);
+            {
+                Timed t(ctx, b->stream, K_CLASSIFY_MEMO_BLOCK);
+                classify_memo_block_kernel<<<grid, 256, mg.block_smem, b->stream>>>(
+                    sb, ctx->s, ctx->memo, ctx->tb, mg.use_warp ? redo : nullptr, mg.use_warp ? redo_count : nullptr, b->nseq,
+                    mg.vcap, mg.hs_cap, mg.rpad, b->scratch.as<u32>(), mg.scratch_stride, hits);
+            }
+            if (!mg.use_warp) l2_window(ctx, b->stream, nullptr, 0);
             CK(cudaGetLastError());
             return RKG_OK;
         }
@@ -534,7 +568,7 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
     GroupGeom gg = group_geometry(ctx, b);
     // <= 256 references: the warp-cooperative kernel (rk_warp.cuh); more: the sub-warp group kernel with shared-memory counters
     const size_t warp_smem = (size_t)gg.filter_words * 4 + (size_t)32 * WARP_QCAP * 8;
-    if (gg.ok && ctx->tb.nb <= 4 && !ctx->group_kernel && warp_smem <= ctx->smem_optin) {
+    if (gg.ok && ctx->tb.nb <= 4 && !ctx->group_kernel && warp_smem + sizeof(u64) * HASH_LUT_ENTRIES + 1024 <= ctx->smem_optin) {
         Timed t(ctx, b->stream, K_CLASSIFY_WARP);
         const int grid = ctx->sm_count;
         DISPATCH_KCSEL(ctx->kcsel, {
@@ -565,7 +599,7 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
         const int block = 512;
         const int hs_cap = next_pow2(2 * (i64)std::min<i64>(ctx->s, std::max<i64>(b->max_ntotal, 1)));
         const int rpad = (ctx->nrefs + 63) / 64 * 64;
-        const size_t budget = ctx->smem_optin / 2 - 1024;            // two blocks per SM
+        const size_t budget = ctx->smem_optin / 2 - 1024 - sizeof(u64) * HASH_LUT_ENTRIES;   // two blocks per SM, each with the hashing tables
         size_t fixed = (size_t)rpad * 4;
         int hs_in_smem = ((size_t)hs_cap * 8 + fixed <= budget / 2) ? 1 : 0;
         if (hs_in_smem) fixed += (size_t)hs_cap * 8;
@@ -596,7 +630,7 @@ int launch_sketch(rkg_ctx* ctx, rkg_batch* b, CountTable ct, int filter_mode, in
     { int rc = ensure_packed(ctx, b); if (rc) return rc; }
     const int block = 512;
     const int sort_cap = next_pow2(std::max<i64>(std::min<i64>(ctx->s, std::max<i64>(b->max_ntotal, 1)), 2));
-    const int sort_in_smem = ((size_t)sort_cap * 8 <= ctx->smem_optin - 4096) ? 1 : 0;
+    const int sort_in_smem = ((size_t)sort_cap * 8 + sizeof(u64) * HASH_LUT_ENTRIES <= ctx->smem_optin - 4096) ? 1 : 0;
     const size_t smem = sort_in_smem ? (size_t)sort_cap * 8 : 0;
     i64 stride = std::max<i64>(b->max_ntotal, 1);
     if (d_sorted_all) {
@@ -672,9 +706,24 @@ int rkg_create(int device, rkg_ctx** out) {
     { const char* nm = getenv("RKMH_GROUP_KERNEL"); ctx->group_kernel = nm && nm[0] && nm[0] != '0'; }   // round-1 Murmur fast path (A/B timing)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    { const char* nm = getenv("RKMH_NO_L2_POLICY"); ctx->l2_policy = !(nm && nm[0] && nm[0] != '0'); }
+    // a persisting-L2 carve-out for the tables the streaming kernels hit at random (access-policy windows below)
+    ctx->l2_persist_max = (size_t)std::max(prop.persistingL2CacheMaxSize, 0);
+    ctx->l2_window_max = (size_t)std::max(prop.accessPolicyMaxWindowSize, 0);
+    if (ctx->l2_policy && ctx->l2_persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, RKG_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    {   // key * constant tables of the Murmur path (rk_hash.cuh), copied into shared memory by every hashing kernel
+        std::vector<u64> lut(HASH_LUT_ENTRIES);
+        build_hash_lut(lut.data());
+        if (ctx->hash_lut.ensure(sizeof(u64) * HASH_LUT_ENTRIES) != cudaSuccess ||
+            cudaMemcpy(ctx->hash_lut.p, lut.data(), sizeof(u64) * HASH_LUT_ENTRIES, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaStreamDestroy(ctx->stream);
+            delete ctx;
+            return fail(nullptr, RKG_ERR_CUDA, "rkg_create: cannot allocate the hashing tables");
+        }
     }
     *out = ctx;
     return RKG_OK;
@@ -686,7 +735,7 @@ void rkg_destroy(rkg_ctx* ctx) {
     cudaDeviceSynchronize();
     profile_collect(ctx);
     for (int i = 0; i < 2; ++i) batch_release(ctx->slots[i]);
-    for (DevBuf* d : {&ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
+    for (DevBuf* d : {&ctx->hash_lut, &ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
                       &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
                       &ctx->memo_tab, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
                       &ctx->memo_sieve, &ctx->memo_cmap})
@@ -717,6 +766,7 @@ int rkg_set_params(rkg_ctx* ctx, const int* ks, int nk, int sketch_size, uint64_
         kmax = std::max(kmax, ks[j]); kmin = std::min(kmin, ks[j]);
     }
     kl.kmax = kmax;
+    kl.lut = ctx->hash_lut.as<u64>();
     ctx->kl = kl; ctx->kcsel = kcsel; ctx->kmax = kmax; ctx->kmin = kmin; ctx->s = sketch_size;
     ctx->refs_loaded = false;
     ctx->memo_ready = false;

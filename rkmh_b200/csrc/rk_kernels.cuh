@@ -31,7 +31,7 @@ struct SeqBatch {
     i64 base0;                    // offs[] are offsets into the caller's buffer; the batch starts at base0
 };
 
-struct KList { int nk; int k[MAX_NK]; int kv[MAX_NK]; int kmax; int ksum; };   // kv = kvariant_of(k)
+struct KList { int nk; int k[MAX_NK]; int kv[MAX_NK]; int kmax; int ksum; const u64* lut; };   // kv = kvariant_of(k); lut: rk_hash.cuh tables (global memory)
 
 struct CountTable {
     int* counts;      // nullptr = absent
@@ -147,7 +147,8 @@ RK_D i64 nkmers_total(i64 len, const KList& kl) {
 // (launched once per k); out_offs[seq] + koff(seq) is where this k's hashes of seq start.
 template <int KC>
 __global__ void __launch_bounds__(256)
-hash_kernel(SeqBatch sb, KList kl, int kidx, u64* __restrict__ out, const i64* __restrict__ out_offs) {
+hash_kernel(SeqBatch sb, const __grid_constant__ KList kl, int kidx, u64* __restrict__ out, const i64* __restrict__ out_offs) {
+    const u64* lut = hash_lut_load(kl.lut);
     int lane = threadIdx.x & 31;
     i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
@@ -157,7 +158,7 @@ hash_kernel(SeqBatch sb, KList kl, int kidx, u64* __restrict__ out, const i64* _
         i64 koff = 0;
         for (int j = 0; j < kidx; ++j) koff += nkmers(len, kl.k[j]);
         u64* dst = out + out_offs[s] + koff;
-        team_hash_k<KC>(kl.kv[kidx], sb.codes, sb.nmask, codes_last_word(sb), nmask_last_word(sb), beg, nkmers(len, k), k, lane, 32,
+        team_hash_k<KC>(kl.kv[kidx], lut, sb.codes, sb.nmask, codes_last_word(sb), nmask_last_word(sb), beg, nkmers(len, k), k, lane, 32,
                         [&](i64 i, u64 h) { dst[i] = h; });
     }
 }
@@ -168,7 +169,8 @@ hash_kernel(SeqBatch sb, KList kl, int kidx, u64* __restrict__ out, const i64* _
 //   count_zeros = 1: every window, an invalid one counts slot 0 % size (rkmh.cpp:331-336)
 template <int KCSEL>
 __global__ void __launch_bounds__(256)
-count_kernel(SeqBatch sb, KList kl, CountTable ct, int count_zeros) {
+count_kernel(SeqBatch sb, const __grid_constant__ KList kl, CountTable ct, int count_zeros) {
+    const u64* lut = hash_lut_load(kl.lut);
     int lane = threadIdx.x & 31;
     i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
@@ -176,7 +178,7 @@ count_kernel(SeqBatch sb, KList kl, CountTable ct, int count_zeros) {
         i64 beg = sb.offs[s] - sb.base0, len = sb.offs[s + 1] - sb.offs[s];
         for (int j = 0; j < kl.nk; ++j) {
             const int k = kl.k[j];
-            team_hash_k<KCSEL>(kl.kv[j], sb.codes, sb.nmask, codes_last_word(sb), nmask_last_word(sb), beg, nkmers(len, k), k, lane, 32,
+            team_hash_k<KCSEL>(kl.kv[j], lut, sb.codes, sb.nmask, codes_last_word(sb), nmask_last_word(sb), beg, nkmers(len, k), k, lane, 32,
                                [&](i64, u64 h) {
                                    if (h != 0 || count_zeros) atomicAdd(&ct.counts[fastmod(h, ct.mod)], 1);
                                });
@@ -300,9 +302,10 @@ RK_D bool select_member(u64 h, const Select& sel, int* take) {
 // not fit in shared memory.  Dynamic smem: sort_cap_smem u64 (0 = sort in global scratch).
 template <int KCSEL>
 __global__ void __launch_bounds__(512)
-sketch_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int filter_mode, int occ,
+sketch_kernel(SeqBatch sb, const __grid_constant__ KList kl, int s, CountTable ct, int filter_mode, int occ,
               u64* __restrict__ scratch, i64 scratch_stride, int sort_cap, int sort_in_smem,
               u64* __restrict__ sketches, int* __restrict__ lens, u64* __restrict__ sorted_all, const i64* __restrict__ all_offs) {
+    const u64* lut = hash_lut_load(kl.lut);
 #ifdef RK_EMU
     u64* dsm = reinterpret_cast<u64*>(EMU_DYN_SMEM());
 #else
@@ -324,7 +327,7 @@ sketch_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int filter_mode, int 
         for (int j = 0; j < kl.nk; ++j) {
             const int k = kl.k[j];
             i64 nj = nkmers(len, k);
-            team_hash_k<KCSEL>(kl.kv[j], sb.codes, sb.nmask, codes_last_word(sb), nmask_last_word(sb), beg, nj, k, threadIdx.x, blockDim.x,
+            team_hash_k<KCSEL>(kl.kv[j], lut, sb.codes, sb.nmask, codes_last_word(sb), nmask_last_word(sb), beg, nj, k, threadIdx.x, blockDim.x,
                                [&](i64 i, u64 h) {
                                    if (h != 0 && filter_mode != 0) {
                                        int freq = ct.counts[fastmod(h, ct.mod)];
@@ -381,13 +384,14 @@ constexpr i64 SHARD_SEG = 4096;                 // windows per warp task
 
 template <int KCSEL>
 __global__ void __launch_bounds__(256)
-shard_hist_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, i64 last_word, i64 last_mword, i64 n, KList kl,
+shard_hist_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, i64 last_word, i64 last_mword, i64 n, const __grid_constant__ KList kl,
                   u32* __restrict__ hist) {
+    const u64* lut = hash_lut_load(kl.lut);
     const int lane = threadIdx.x & 31, k = kl.k[0];
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
     for (i64 w0 = warp * SHARD_SEG; w0 < n; w0 += nwarps * SHARD_SEG) {
         const i64 cnt = min(SHARD_SEG, n - w0);
-        team_hash_k<KCSEL>(kl.kv[0], codes, nmask, last_word, last_mword, w0, cnt, k, lane, 32,
+        team_hash_k<KCSEL>(kl.kv[0], lut, codes, nmask, last_word, last_mword, w0, cnt, k, lane, 32,
                            [&](i64, u64 h) { if (h) atomicAdd(&hist[(u32)(h >> 48)], 1u); });
     }
 }
@@ -420,15 +424,16 @@ shard_pick_kernel(const u32* __restrict__ hist, u64 s, u64* __restrict__ out) {
 
 template <int KCSEL>
 __global__ void __launch_bounds__(256)
-shard_emit_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, i64 last_word, i64 last_mword, i64 n, KList kl,
+shard_emit_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, i64 last_word, i64 last_mword, i64 n, const __grid_constant__ KList kl,
                   const u64* __restrict__ pick,
                   u64* __restrict__ cand, unsigned long long* __restrict__ ncand, u64 cap) {
+    const u64* lut = hash_lut_load(kl.lut);
     const int lane = threadIdx.x & 31, k = kl.k[0];
     const u32 bin = (u32)pick[0];
     const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
     for (i64 w0 = warp * SHARD_SEG; w0 < n; w0 += nwarps * SHARD_SEG) {
         const i64 cnt = min(SHARD_SEG, n - w0);
-        team_hash_k<KCSEL>(kl.kv[0], codes, nmask, last_word, last_mword, w0, cnt, k, lane, 32, [&](i64, u64 h) {
+        team_hash_k<KCSEL>(kl.kv[0], lut, codes, nmask, last_word, last_mword, w0, cnt, k, lane, 32, [&](i64, u64 h) {
             if (h && (u32)(h >> 48) <= bin) {
                 const unsigned long long at = atomicAdd(ncand, 1ULL);
                 if (at < cap) cand[at] = h;
@@ -599,10 +604,11 @@ RK_D void block_argmax(const u32* counts, int R, ArgmaxScratch* as, Hit* out, in
 // go to `scratch` (scratch_stride u64 per block).  hs_in_smem == 0 puts the hit set in scratch as well.
 template <int KCSEL>
 __global__ void __launch_bounds__(512)
-classify_block_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, RefTable tb,
+classify_block_kernel(SeqBatch sb, const __grid_constant__ KList kl, int s, CountTable ct, int min_occ, RefTable tb,
                       const int* __restrict__ list, const int* __restrict__ nlist_ptr, i64 nseq,
                       int hbuf_cap, int hs_cap, int hs_in_smem, int rpad,
                       u64* __restrict__ scratch, i64 scratch_stride, Hit* __restrict__ out) {
+    const u64* lut = hash_lut_load(kl.lut);
 #ifdef RK_EMU
     unsigned char* dsm = reinterpret_cast<unsigned char*>(EMU_DYN_SMEM());
 #else
@@ -634,7 +640,7 @@ classify_block_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, 
         for (int j = 0; j < kl.nk; ++j) {
             const int k = kl.k[j];
             i64 nj = nkmers(len, k);
-            team_hash_k<KCSEL>(kl.kv[j], sb.codes, sb.nmask, codes_last_word(sb), nmask_last_word(sb), beg, nj, k, threadIdx.x, blockDim.x,
+            team_hash_k<KCSEL>(kl.kv[j], lut, sb.codes, sb.nmask, codes_last_word(sb), nmask_last_word(sb), beg, nj, k, threadIdx.x, blockDim.x,
                                [&](i64 i, u64 h) {
                                    h = apply_min_occ(h, ct, min_occ);
                                    H[base + i] = h;
@@ -711,7 +717,7 @@ struct GroupLane {
 
 template <int KCSEL>
 __global__ void __launch_bounds__(1024, 1)
-classify_group_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, RefTable tb,
+classify_group_kernel(SeqBatch sb, const __grid_constant__ KList kl, int s, CountTable ct, int min_occ, RefTable tb,
                       int glog2, int rwords, int filter_words,
                       int* __restrict__ redo, int* __restrict__ redo_count, Hit* __restrict__ out) {
 #ifdef RK_EMU

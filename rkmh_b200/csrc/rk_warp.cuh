@@ -25,13 +25,14 @@ constexpr int WARP_QCAP = 128;                // queued candidates per read
 
 template <int KCSEL, int NW>
 __global__ void __launch_bounds__(1024, 1)
-classify_warp_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, RefTable tb, int filter_words,
+classify_warp_kernel(SeqBatch sb, const __grid_constant__ KList kl, int s, CountTable ct, int min_occ, RefTable tb, int filter_words,
                      int* __restrict__ redo, int* __restrict__ redo_count, Hit* __restrict__ out) {
 #ifdef RK_EMU
     unsigned char* dsm = reinterpret_cast<unsigned char*>(EMU_DYN_SMEM());
 #else
     extern __shared__ __align__(16) unsigned char dsm[];
 #endif
+    const u64* lut = hash_lut_load(kl.lut);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     u32* filt = reinterpret_cast<u32*>(dsm);
     u64* q = reinterpret_cast<u64*>(filt + filter_words) + (size_t)wib * WARP_QCAP;
@@ -53,7 +54,7 @@ classify_warp_kernel(SeqBatch sb, KList kl, int s, CountTable ct, int min_occ, R
         if (!give_up) {
             for (int j = 0; j < kl.nk; ++j) {
                 const int k = kl.k[j];
-                warp_hash_sel<KCSEL>(kl.kv[j], sb.codes, sb.nmask, last_word, last_mword, beg, 0, nkmers(len, k), k, lane,
+                warp_hash_sel<KCSEL>(kl.kv[j], lut, sb.codes, sb.nmask, last_word, last_mword, beg, 0, nkmers(len, k), k, lane,
                                      [&](i64, u64 h, bool) {
                                          h = apply_min_occ(h, ct, min_occ);
                                          bool cand = false;

@@ -28,6 +28,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __grid_constant__
 #define __align__(n) __attribute__((aligned(n)))
 
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };

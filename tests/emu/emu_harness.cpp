@@ -30,8 +30,15 @@ struct HostBatch {
     }
 };
 
+const u64* host_hash_lut() {
+    static std::vector<u64> lut;
+    if (lut.empty()) { lut.resize(HASH_LUT_ENTRIES); build_hash_lut(lut.data()); }
+    return lut.data();
+}
+
 KList make_klist(const int* ks, int nk, int* kcsel) {
     KList kl{};
+    kl.lut = host_hash_lut();
     kl.nk = nk;
     int sel = -1;
     for (int j = 0; j < nk; ++j) {
@@ -406,7 +413,8 @@ u64 emu_window_hash(const char* kmer, int k) {   // canonical hash of one window
     u64 result = 0;
     dispatch(kvariant_of(k), [&](auto tag) {
         constexpr int KC = decltype(tag)::value < NUM_KV ? decltype(tag)::value : 0;
-        result = window_hash<KC>(lo, hi, k);
+        const HashCorr hc = make_hash_corr<KC>(k);
+        result = window_hash<KC>(lo, hi, k, host_hash_lut(), hc);
     });
     return result;
 }

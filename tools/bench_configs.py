@@ -38,11 +38,11 @@ def timed(fn, reps):
 def config3(args, gpu):
     import rkmh_b200
     from rkmh_b200.fastx import load_sequences
-    from rkmh_b200.synth import ont_reads
+    from rkmh_b200.synth import fast_ont_reads
     _, refs, _ = load_sequences([os.path.join(DATA, "hpv_16_allFasta.fa.gz")])
     n, L, k, s = args.reads or 50_000, 10_000, 12, 1000
     m = max(1, round(100 * n / 2_000_000))            # -M 100 at 2 M reads, scaled to the sample
-    bases, offs = ont_reads(np.random.default_rng(3), refs, n, L)
+    bases, offs = fast_ont_reads(3, refs, 0, n, L)
     gpu.set_params([k], s, read_table_size=rkmh_b200.STREAM_TABLE_SIZE)
     gpu.load_refs(*rkmh_b200.pack_sequences(refs))
     batch = gpu.upload(bases, offs)
