@@ -157,6 +157,21 @@ int rkg_synchronize(rkg_ctx* ctx);
 int rkg_set_memo(rkg_ctx* ctx, int enable);
 int rkg_memo_active(const rkg_ctx* ctx);
 
+/* ---- hpv16: full hash sets instead of sketches ------------------------------------------------------- */
+/* The tiered HPV16 classifier (src/rkmh.cpp:2366-2723) compares every hash of a read -- no bottom-s -- with FULL hash
+ * sets: the 182 type references (hash_set_intersection_size, mkmh/mkmh.hpp:842-863: distinct non-zero values in
+ * common) and the lineage / sublineage specific k-mer tables (sort_by_similarity -> hash_intersection_size against
+ * sets of distinct values: the same number).  rkg_load_ref_sets builds the HBM table hash -> set bitset from nsets
+ * hash sets given as one array plus nsets + 1 offsets (any order; zeros and duplicates are ignored); it replaces the
+ * table of rkg_load_refs, and rkg_classify_batch is refused until rkg_load_refs is called again. */
+int rkg_load_ref_sets(rkg_ctx* ctx, const uint64_t* hashes, const int64_t* set_offs, int nsets);
+/* Per read: calc_hashes over every k of the list, mask_by_frequency when min_occ >= 0, then count[j] = number of
+ * distinct non-zero hashes of the read that set j holds.  out[r] = {first index in [0, ntypes) of the largest count,
+ * that count, prev, number of distinct-or-not non-zero hashes}: src/rkmh.cpp:2655-2664; extra [nreads x (nsets -
+ * ntypes)] = the counts of the remaining sets, in set order (src/rkmh.cpp:2672-2683). */
+int rkg_classify_sets(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, int min_occ, int ntypes,
+                      rkg_hit* out, int32_t* extra);
+
 /* ---- hash command -------------------------------------------------------------------------------- */
 /* Bottom-s sketches of nseq records (sorted ascending, duplicates kept, zeros dropped): calc_hashes +
  * minhashes (mkmh/mkmh.hpp:689-711, 931-950), the intended behaviour of `rkmh hash` (src/rkmh.cpp:

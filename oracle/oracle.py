@@ -73,6 +73,10 @@ class Oracle:
                                         _i32p, C.c_uint64, C.c_int, C.c_int]
         lib.rko_classify_batch.argtypes = [C.c_void_p, _i64p, C.c_int64, _i32p, C.c_int, C.c_int,
                                            _u64p, _i32p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        lib.rko_set_intersection_size.argtypes = [_u64p, C.c_int64, _u64p, C.c_int64]
+        lib.rko_set_intersection_size.restype = C.c_int
+        lib.rko_classify_sets.argtypes = [C.c_void_p, _i64p, C.c_int64, _i32p, C.c_int, _u64p, _i64p, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
 
     # -- primitives -------------------------------------------------------------------------
     def murmur3_x64_128(self, key: bytes, seed: int) -> bytes:
@@ -165,6 +169,29 @@ class Oracle:
         self.lib.rko_classify_batch(bases.ctypes.data, offs, len(seqs), ks, len(ks), s, rs, rl, len(rl),
                                     cptr, csz, min_occ, out.ctypes.data)
         return out[:len(seqs)]
+
+    # -- hpv16 ---------------------------------------------------------------------
+    def set_intersection_size(self, a, b) -> int:
+        """mkmh/mkmh.hpp:842-863 on two ascending arrays"""
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        b = np.ascontiguousarray(b, dtype=np.uint64)
+        return int(self.lib.rko_set_intersection_size(a, len(a), b, len(b)))
+
+    def classify_sets(self, seqs, ks, sets, ntypes, counts=None, min_occ=0):
+        """src/rkmh.cpp:2643-2706: (hits over sets[:ntypes], extra counts [n, len(sets) - ntypes]).  `sets` is a list of
+        ASCENDING uint64 arrays (zeros and duplicates allowed, as the reference's type arrays have them)."""
+        bases, offs = _as_bases(seqs)
+        ks = np.atleast_1d(np.asarray(ks, dtype=np.int32))
+        so = np.zeros(len(sets) + 1, np.int64)
+        so[1:] = np.cumsum([len(x) for x in sets])
+        sh = np.ascontiguousarray(np.concatenate([np.asarray(x, np.uint64) for x in sets]) if sets else np.zeros(1, np.uint64))
+        out = np.zeros(max(len(seqs), 1), _HIT)
+        extra = np.zeros((max(len(seqs), 1), max(len(sets) - ntypes, 1)), np.int32)
+        cptr = counts.ctypes.data if counts is not None else None
+        csz = counts.size if counts is not None else 0
+        self.lib.rko_classify_sets(bases.ctypes.data, offs, len(seqs), ks, len(ks), sh, so, len(sets), ntypes,
+                                   cptr, csz, min_occ, out.ctypes.data, extra.ctypes.data)
+        return out[:len(seqs)], extra[:len(seqs), :len(sets) - ntypes]
 
 
 class RefMkmh:

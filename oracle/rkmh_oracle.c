@@ -270,3 +270,48 @@ void rko_classify_batch(const char* bases, const int64_t* offs, int64_t nreads, 
     }
     free(mins); free(shared);
 }
+
+/* ------------------------------------------------------------------ hpv16 ------- */
+/* mkmh/mkmh.hpp:842-863 : walk over two ascending arrays counting the DISTINCT non-zero values they share
+ * (`prev` keeps a value from being counted twice; an equal pair that does not count advances alpha only) */
+int rko_set_intersection_size(const uint64_t* a, int64_t na, const uint64_t* b, int64_t nb) {
+    int64_t i = 0, j = 0;
+    int shared = 0;
+    uint64_t prev = 0;
+    while (i < na && j < nb) {
+        if (a[i] == b[j] && a[i] != prev && a[i] != 0) { ++shared; prev = a[i]; ++i; ++j; }
+        else if (a[i] > b[j]) ++j;
+        else ++i;
+    }
+    return shared;
+}
+
+/* The per-read block of main_hpv16 (src/rkmh.cpp:2643-2706): every hash of the read over every k (zeros included),
+ * masked by frequency when counts != NULL, sorted ascending; sets [0, ntypes) are compared with
+ * hash_set_intersection_size and reduced to the first index of the strict maximum starting from -1
+ * (src/rkmh.cpp:2655-2664); sets [ntypes, nsets) -- the lineage / sublineage specific tables -- with
+ * hash_intersection_size as sort_by_similarity does (mkmh/mkmh.hpp:1304-1333), into extra [nreads x (nsets - ntypes)].
+ * Every set must be ascending (the reference's type arrays are: minhashes() sorts them in place, src/rkmh.cpp:2547). */
+void rko_classify_sets(const char* bases, const int64_t* offs, int64_t nreads, const int* ks, int nk,
+                       const uint64_t* set_hashes, const int64_t* set_offs, int nsets, int ntypes,
+                       const int32_t* counts, uint64_t counts_size, int min_occ, rko_hit* out, int32_t* extra) {
+    for (int64_t r = 0; r < nreads; ++r) {
+        int64_t len = offs[r + 1] - offs[r];
+        char* seq = upper_copy(bases, offs[r], offs[r + 1]);
+        int64_t cap = rko_num_hashes(len, ks, nk);
+        uint64_t* h = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(cap > 0 ? cap : 1));
+        int64_t n = rko_calc_hashes_multi(seq, len, ks, nk, h);
+        if (counts) rko_mask_by_frequency(h, n, counts, counts_size, min_occ);
+        qsort(h, (size_t)n, sizeof(uint64_t), cmp_u64);
+        int best = -1, id = 0;
+        for (int j = 0; j < ntypes; ++j) {
+            int shared = rko_set_intersection_size(h, n, set_hashes + set_offs[j], set_offs[j + 1] - set_offs[j]);
+            if (shared > best) { best = shared; id = j; }
+        }
+        out[r].ref_id = id; out[r].best = best; out[r].prev = -1; out[r].sketch_len = (int32_t)n;
+        for (int j = ntypes; j < nsets; ++j)
+            extra[(size_t)r * (size_t)(nsets - ntypes) + (size_t)(j - ntypes)] =
+                rko_intersection_size(h, (int)n, set_hashes + set_offs[j], (int)(set_offs[j + 1] - set_offs[j]));
+        free(h); free(seq);
+    }
+}

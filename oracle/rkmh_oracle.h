@@ -83,6 +83,15 @@ void rko_classify_batch(const char* bases, const int64_t* offs, int64_t nreads, 
                         const int32_t* counts, uint64_t counts_size, int min_occ,
                         rko_hit* out);
 
+/* ---- hpv16 -------------------------------------------------------------------- */
+/* mkmh/mkmh.hpp:842-863 */
+int rko_set_intersection_size(const uint64_t* a, int64_t na, const uint64_t* b, int64_t nb);
+/* src/rkmh.cpp:2643-2706: out[r] = {first type with the most shared distinct hashes, that count, -1, number of
+ * hashes of the read}; extra [nreads x (nsets - ntypes)] = hash_intersection_size with the remaining sets */
+void rko_classify_sets(const char* bases, const int64_t* offs, int64_t nreads, const int* ks, int nk,
+                       const uint64_t* set_hashes, const int64_t* set_offs, int nsets, int ntypes,
+                       const int32_t* counts, uint64_t counts_size, int min_occ, rko_hit* out, int32_t* extra);
+
 #ifdef __cplusplus
 }
 #endif

@@ -229,6 +229,26 @@ class RkmhGpu:
     def synchronize(self):
         self._check(self.lib.rkg_synchronize(self.handle))
 
+    # -- hpv16: full hash sets ---------------------------------------------------------------------
+    def load_ref_sets(self, sets):
+        """sets: list of uint64 arrays (any order; zeros / duplicates ignored) -> the hash -> set-bitset table."""
+        so = np.zeros(len(sets) + 1, np.int64)
+        so[1:] = np.cumsum([len(x) for x in sets])
+        sh = np.ascontiguousarray(np.concatenate([np.asarray(x, np.uint64) for x in sets])) if so[-1] else np.zeros(1, np.uint64)
+        self._check(self.lib.rkg_load_ref_sets(self.handle, sh.ctypes.data, so.ctypes.data, len(sets)))
+        self.nrefs = len(sets)
+
+    def classify_sets(self, bases, offs, ntypes, min_occ=-1):
+        """-> (hits over sets [0, ntypes), counts [n, nsets - ntypes] of the remaining sets)"""
+        bases, offs = self._buffers(bases, offs)
+        n = len(offs) - 1
+        nextra = self.nrefs - ntypes
+        out = np.zeros(max(n, 1), HIT_DTYPE)
+        extra = np.zeros((max(n, 1), max(nextra, 1)), np.int32)
+        self._check(self.lib.rkg_classify_sets(self.handle, bases.ctypes.data, offs.ctypes.data, n, int(min_occ), int(ntypes),
+                                               out.ctypes.data, extra.ctypes.data))
+        return out[:n], extra[:n, :nextra]
+
     # -- hash command -----------------------------------------------------------------------------
     def sketch_batch(self, bases, offs, min_occ=-1):
         """minhashes(calc_hashes(seq)) per record: ([n, s] uint64, [n] int32 lengths)."""

@@ -81,6 +81,7 @@ struct rkg_ctx {
     CountTable read_ct{nullptr, {}}, ref_ct{nullptr, {}};
     // references
     bool refs_loaded = false;
+    bool set_table = false;              // the table was built by rkg_load_ref_sets (set semantics, hpv16)
     int nrefs = 0;
     DevBuf ref_sketches, ref_lens, tb_entries, tb_maxmult, tb_dupbase, tb_dupbits, tb_filter, tb_cursor;
     RefTable tb{};
@@ -912,6 +913,7 @@ int rkg_load_refs(rkg_ctx* ctx, const char* bases, const int64_t* offs, int nref
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(b->stream));
     ctx->tb = tb;
+    ctx->set_table = false;
     if ((rc = memo_build(ctx, b->stream))) return rc;
     ctx->refs_loaded = true;
     return RKG_OK;
@@ -919,7 +921,7 @@ int rkg_load_refs(rkg_ctx* ctx, const char* bases, const int64_t* offs, int nref
 
 int rkg_get_ref_sketches(rkg_ctx* ctx, uint64_t* sketches, int32_t* lens) {
     if (!ctx) return RKG_ERR_ARG;
-    if (!ctx->refs_loaded) return fail(ctx, RKG_ERR_STATE, "no references loaded");
+    if (!ctx->refs_loaded || ctx->set_table) return fail(ctx, RKG_ERR_STATE, "no references loaded");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpy(sketches, ctx->ref_sketches.p, sizeof(u64) * (size_t)ctx->nrefs * ctx->s, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(lens, ctx->ref_lens.p, sizeof(int) * (size_t)ctx->nrefs, cudaMemcpyDeviceToHost));
@@ -1025,7 +1027,7 @@ int rkg_count_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_
 // ---- classification ---------------------------------------------------------------------------------
 int rkg_classify_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, int min_occ, rkg_hit* out) {
     if (!ctx) return RKG_ERR_ARG;
-    if (!ctx->refs_loaded) return fail(ctx, RKG_ERR_STATE, "rkg_classify_batch before rkg_load_refs");
+    if (!ctx->refs_loaded || ctx->set_table) return fail(ctx, RKG_ERR_STATE, "rkg_classify_batch before rkg_load_refs");
     if (nreads < 0 || !offs || (!bases && nreads > 0) || (!out && nreads > 0))
         return fail(ctx, RKG_ERR_ARG, "rkg_classify_batch: bad buffers");
     if (nreads == 0) return RKG_OK;
@@ -1035,7 +1037,7 @@ int rkg_classify_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int
 
 int rkg_classify_fixed(rkg_ctx* ctx, const char* bases, int64_t read_len, int64_t nreads, int min_occ, rkg_hit* out) {
     if (!ctx) return RKG_ERR_ARG;
-    if (!ctx->refs_loaded) return fail(ctx, RKG_ERR_STATE, "rkg_classify_fixed before rkg_load_refs");
+    if (!ctx->refs_loaded || ctx->set_table) return fail(ctx, RKG_ERR_STATE, "rkg_classify_fixed before rkg_load_refs");
     if (nreads < 0 || read_len < 0 || (!bases && nreads > 0) || (!out && nreads > 0))
         return fail(ctx, RKG_ERR_ARG, "rkg_classify_fixed: bad buffers");
     if (nreads == 0) return RKG_OK;
@@ -1078,7 +1080,7 @@ int rkg_batch_upload(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64
 
 int rkg_batch_classify(rkg_ctx* ctx, rkg_batch* batch, int min_occ) {
     if (!ctx || !batch) return RKG_ERR_ARG;
-    if (!ctx->refs_loaded) return fail(ctx, RKG_ERR_STATE, "rkg_batch_classify before rkg_load_refs");
+    if (!ctx->refs_loaded || ctx->set_table) return fail(ctx, RKG_ERR_STATE, "rkg_batch_classify before rkg_load_refs");
     CK(cudaSetDevice(ctx->device));
     return launch_classify(ctx, batch, min_occ);
 }
@@ -1118,6 +1120,127 @@ int rkg_batch_free(rkg_ctx* ctx, rkg_batch* batch) {
     cudaSetDevice(ctx->device);
     batch_release(batch);
     return RKG_OK;
+}
+
+// ---- hpv16: full hash sets instead of sketches ------------------------------------------------------------
+int rkg_load_ref_sets(rkg_ctx* ctx, const uint64_t* hashes, const int64_t* set_offs, int nsets) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_load_ref_sets before rkg_set_params");
+    if (!hashes || !set_offs || nsets < 1) return fail(ctx, RKG_ERR_ARG, "rkg_load_ref_sets: need at least one set");
+    const i64 nent = set_offs[nsets] - set_offs[0];
+    if (nent < 0 || 2 * nent > ((i64)1 << 30)) return fail(ctx, RKG_ERR_ARG, "rkg_load_ref_sets: %lld elements (supported: 2^29)", (long long)nent);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    ctx->refs_loaded = false; ctx->memo_ready = false;
+    const u32 cap = (u32)next_pow2(std::max<i64>(2 * nent, 1024));
+    const u32 nb = (u32)((nsets + 63) / 64);
+    RefTable tb{};
+    tb.cap_mask = cap - 1; tb.nb = nb; tb.stride = 1 + nb; tb.nrefs = (u32)nsets;
+    int flog2 = 10;
+    while (flog2 < 20 && (1LL << flog2) < 16 * nent) ++flog2;
+    tb.filter_log2 = (u32)flog2;
+    CK(ctx->tb_entries.ensure(sizeof(u64) * (size_t)cap * tb.stride));
+    CK(ctx->tb_maxmult.ensure(sizeof(u32) * (size_t)cap));
+    CK(ctx->tb_dupbase.ensure(sizeof(u32) * (size_t)cap));
+    CK(ctx->tb_dupbits.ensure(64));
+    CK(ctx->tb_filter.ensure(sizeof(u32) * ((size_t)1 << flog2) / 32));
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(ctx->tb_entries.p, 0, sizeof(u64) * (size_t)cap * tb.stride, st));
+    CK(cudaMemsetAsync(ctx->tb_maxmult.p, 0, sizeof(u32) * (size_t)cap, st));
+    CK(cudaMemsetAsync(ctx->tb_dupbase.p, 0, sizeof(u32) * (size_t)cap, st));
+    CK(cudaMemsetAsync(ctx->tb_filter.p, 0, sizeof(u32) * ((size_t)1 << flog2) / 32, st));
+    tb.entries = ctx->tb_entries.as<u64>();
+    tb.maxmult = ctx->tb_maxmult.as<u32>();
+    tb.dup_base = ctx->tb_dupbase.as<u32>();
+    tb.dup_bits = ctx->tb_dupbits.as<u64>();
+    tb.filter = ctx->tb_filter.as<u32>();
+    DevBuf d_h, d_o;
+    int rc = RKG_OK;
+    do {
+        if (d_h.ensure(sizeof(u64) * (size_t)std::max<i64>(nent, 1)) || d_o.ensure(sizeof(i64) * (size_t)(nsets + 1))) {
+            rc = fail(ctx, RKG_ERR_NOMEM, "rkg_load_ref_sets: device allocation failed");
+            break;
+        }
+        std::vector<i64> rel((size_t)nsets + 1);
+        for (int i = 0; i <= nsets; ++i) rel[i] = set_offs[i] - set_offs[0];
+        cudaMemcpyAsync(d_h.p, hashes + set_offs[0], sizeof(u64) * (size_t)nent, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_o.p, rel.data(), sizeof(i64) * (size_t)(nsets + 1), cudaMemcpyHostToDevice, st);
+        {
+            Timed t(ctx, st, K_TABLE);
+            const int grid = (int)std::min<i64>((nent + 255) / 256 + 1, (i64)ctx->sm_count * 8);
+            table_insert_set_kernel<<<grid, 256, 0, st>>>(d_h.as<u64>(), d_o.as<i64>(), nsets, tb, ctx->tb_filter.as<u32>());
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = fail(ctx, RKG_ERR_CUDA, "rkg_load_ref_sets: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    d_h.release(); d_o.release();
+    if (rc) return rc;
+    ctx->tb = tb;
+    ctx->nrefs = nsets;
+    ctx->set_table = true;
+    ctx->refs_loaded = true;
+    return RKG_OK;
+}
+
+int rkg_classify_sets(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, int min_occ, int ntypes,
+                      rkg_hit* out, int32_t* extra) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->refs_loaded || !ctx->set_table) return fail(ctx, RKG_ERR_STATE, "rkg_classify_sets before rkg_load_ref_sets");
+    if (ntypes < 1 || ntypes > ctx->nrefs) return fail(ctx, RKG_ERR_ARG, "rkg_classify_sets: ntypes %d of %d sets", ntypes, ctx->nrefs);
+    const int nextra = ctx->nrefs - ntypes;
+    if (nreads < 0 || !offs || (!bases && nreads > 0) || (!out && nreads > 0) || (nextra > 0 && !extra && nreads > 0))
+        return fail(ctx, RKG_ERR_ARG, "rkg_classify_sets: bad buffers");
+    if (min_occ >= 0 && ctx->read_ct.counts == nullptr)
+        return fail(ctx, RKG_ERR_STATE, "min_occ >= 0 needs a read count table (rkg_set_params read_table_size)");
+    if (nreads == 0) return RKG_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_slots(ctx);
+    if (rc) return rc;
+    { rc = memo_flush(ctx); if (rc) return rc; }
+    const CountTable ct = (min_occ >= 0) ? ctx->read_ct : CountTable{nullptr, {}};
+    DevBuf d_extra[2];
+    auto chunks = make_chunks(offs, nreads, CHUNK_BYTES, CHUNK_READS);
+    for (size_t c = 0; c < chunks.size() && rc == RKG_OK; ++c) {
+        rkg_batch* b = ctx->slots[c & 1];
+        DevBuf& dx = d_extra[c & 1];
+        if (cudaStreamSynchronize(b->stream) != cudaSuccess) { rc = fail(ctx, RKG_ERR_CUDA, "rkg_classify_sets: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        if ((rc = batch_fill(ctx, b, bases, offs, chunks[c].first, chunks[c].second))) break;
+        if ((rc = ensure_packed(ctx, b))) break;
+        if (dx.ensure(sizeof(int) * (size_t)std::max<i64>(b->nseq * std::max(nextra, 1), 1)) != cudaSuccess) { rc = fail(ctx, RKG_ERR_NOMEM, "rkg_classify_sets: device allocation failed"); break; }
+        // every hash of the read takes part (no bottom-s): the exact block kernel with an unbounded sketch size
+        const int s_all = 1 << 30;
+        const int block = 512;
+        const int hs_cap = next_pow2(2 * std::max<i64>(b->max_ntotal, 1));
+        if (hs_cap == 0) { rc = fail(ctx, RKG_ERR_ARG, "rkg_classify_sets: a read of more than 2^29 k-mers"); break; }
+        const int rpad = (ctx->nrefs + 63) / 64 * 64;
+        const size_t budget = ctx->smem_optin / 2 - 1024 - sizeof(u64) * HASH_LUT_ENTRIES;
+        size_t fixed = (size_t)rpad * 4;
+        const int hs_in_smem = ((size_t)hs_cap * 8 + fixed <= budget / 2) ? 1 : 0;
+        if (hs_in_smem) fixed += (size_t)hs_cap * 8;
+        i64 hbuf_cap = 0;
+        if (fixed + (size_t)b->max_ntotal * 8 <= budget) hbuf_cap = b->max_ntotal;
+        const size_t smem = fixed + (size_t)hbuf_cap * 8;
+        const i64 stride = (hbuf_cap >= b->max_ntotal) ? 0 : b->max_ntotal;
+        const int grid = ctx->sm_count * 2;
+        if (b->scratch.ensure(sizeof(u64) * (size_t)grid * (size_t)(stride + hs_cap) + 64) != cudaSuccess) { rc = fail(ctx, RKG_ERR_NOMEM, "rkg_classify_sets: device allocation failed"); break; }
+        {
+            Timed t(ctx, b->stream, K_CLASSIFY_BLOCK);
+            DISPATCH_KCSEL(ctx->kcsel, {
+                cudaFuncSetAttribute(classify_block_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                classify_block_kernel<KS><<<grid, block, smem, b->stream>>>(seq_view(b), ctx->kl, s_all, ct, min_occ, ctx->tb, nullptr, nullptr,
+                                                                             b->nseq, (int)hbuf_cap, hs_cap, hs_in_smem, rpad,
+                                                                             b->scratch.as<u64>(), stride, b->hits.as<Hit>(), 1, ntypes, dx.as<int>());
+            });
+        }
+        if (cudaGetLastError() != cudaSuccess) { rc = fail(ctx, RKG_ERR_CUDA, "rkg_classify_sets: launch failed"); break; }
+        cudaMemcpyAsync(out + chunks[c].first, b->hits.p, sizeof(Hit) * (size_t)b->nseq, cudaMemcpyDeviceToHost, b->stream);
+        if (nextra > 0)
+            cudaMemcpyAsync(extra + (size_t)chunks[c].first * nextra, dx.p, sizeof(int) * (size_t)b->nseq * nextra, cudaMemcpyDeviceToHost, b->stream);
+    }
+    for (int i = 0; i < 2; ++i)
+        if (cudaStreamSynchronize(ctx->slots[i]->stream) != cudaSuccess && rc == RKG_OK)
+            rc = fail(ctx, RKG_ERR_CUDA, "rkg_classify_sets: %s", cudaGetErrorString(cudaGetLastError()));
+    d_extra[0].release(); d_extra[1].release();
+    return rc;
 }
 
 // ---- hash command -----------------------------------------------------------------------------------

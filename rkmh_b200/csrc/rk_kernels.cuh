@@ -549,6 +549,32 @@ table_fill_dup_kernel(const u64* __restrict__ sketches, const int* __restrict__ 
     }
 }
 
+// Set semantics (hpv16: hash_set_intersection_size, mkmh/mkmh.hpp:842-863, against FULL hash sets): every non-zero
+// element of set j, in any order, duplicates allowed, gets bit j; no duplicate rows (a hash counts once per set).
+__global__ void __launch_bounds__(256)
+table_insert_set_kernel(const u64* __restrict__ hashes, const i64* __restrict__ set_offs, int nsets, RefTable tb,
+                        u32* __restrict__ filter_rw) {
+    const i64 total = set_offs[nsets];
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        const u64 v = hashes[t];
+        if (v == 0) continue;
+        int lo = 0, hi = nsets;                                  // the set this element belongs to
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (set_offs[mid] <= t) lo = mid; else hi = mid; }
+        const int j = lo;
+        u32 slot = table_slot(v, tb.cap_mask);
+        for (;;) {
+            u64* e = tb.entries + (i64)slot * tb.stride;
+            const u64 old = atomicCAS(e, 0ULL, v);
+            if (old == 0ULL || old == v) break;
+            slot = (slot + 1) & tb.cap_mask;
+        }
+        atomicOr(tb.entries + (i64)slot * tb.stride + 1 + (j >> 6), 1ULL << (j & 63));
+        const u32 fb = filter_bit(v, tb.filter_log2);
+        atomicOr(&filter_rw[fb >> 5], 1u << (fb & 31));
+        tb.maxmult[slot] = 1u;
+    }
+}
+
 // Probe: returns the slot of h or -1.
 RK_D int table_find(const RefTable& tb, u64 h) {
     u32 slot = table_slot(h, tb.cap_mask);
@@ -607,7 +633,8 @@ __global__ void __launch_bounds__(512)
 classify_block_kernel(SeqBatch sb, const __grid_constant__ KList kl, int s, CountTable ct, int min_occ, RefTable tb,
                       const int* __restrict__ list, const int* __restrict__ nlist_ptr, i64 nseq,
                       int hbuf_cap, int hs_cap, int hs_in_smem, int rpad,
-                      u64* __restrict__ scratch, i64 scratch_stride, Hit* __restrict__ out) {
+                      u64* __restrict__ scratch, i64 scratch_stride, Hit* __restrict__ out,
+                      int set_mode = 0, int nargmax = 0, int* __restrict__ extra = nullptr) {
     const u64* lut = hash_lut_load(kl.lut);
 #ifdef RK_EMU
     unsigned char* dsm = reinterpret_cast<unsigned char*>(EMU_DYN_SMEM());
@@ -671,6 +698,7 @@ classify_block_kernel(SeqBatch sb, const __grid_constant__ KList kl, int s, Coun
                 p = (p + 1) & hs_mask;
             }
             u32 rank = atomicAdd(&hs_cnt[p], 1u);
+            if (set_mode && rank > 0) continue;                   // set semantics: a hash of the read counts once
             const u64* row = table_row(tb, slot, rank);
             if (row == nullptr) continue;
             for (u32 w = 0; w < tb.nb; ++w) {
@@ -683,6 +711,13 @@ classify_block_kernel(SeqBatch sb, const __grid_constant__ KList kl, int s, Coun
             }
         }
         __syncthreads();
+        if (set_mode) {
+            // hpv16 (src/rkmh.cpp:2655-2664): the first type with the most shared hashes; the remaining sets' counts as they are
+            const int nextra = (int)tb.nrefs - nargmax;
+            for (int j = threadIdx.x; j < nextra; j += blockDim.x) extra[rid * (i64)nextra + j] = (int)counts[nargmax + j];
+            block_argmax(counts, nargmax, &as, &out[rid], L);
+            continue;
+        }
         block_argmax(counts, (int)tb.nrefs, &as, &out[rid], L);
     }
 }

@@ -26,6 +26,7 @@
 #include <deque>
 #include <functional>
 #include <map>
+#include <set>
 #include <mutex>
 #include <cstdlib>
 #include <cstring>
@@ -58,11 +59,12 @@ struct Options {
 
 void usage(const char* argv0) {
     fprintf(stderr,
-            "Usage: %s { classify | stream | filter | hash } [options]\n"
+            "Usage: %s { classify | stream | filter | hash | hpv16 } [options]\n"
             "    classify: match each read to the reference it most closely resembles using MinHash sketches.\n"
             "    stream:   the same (classify forwards to stream, as in the reference).\n"
             "    filter:   spit out reads that meet thresholds for match to ref, uniqueness, etc.\n"
             "    hash:     compute the MinHash sketches of a set of reads and/or references.\n"
+            "    hpv16:    HPV type, HPV16 lineage and sublineage of each read (-R <dir with all_pave_ref.fa and new_refs.fa>).\n"
             "Options:\n"
             "  --reference/-r <REF>      reference FASTA/FASTQ (repeatable)\n"
             "  --fasta/-f <FASTAFILE>    reads (repeatable)\n"
@@ -239,6 +241,7 @@ struct Chunk {
     std::vector<uint64_t> name_at, qual_at; // name i = text[name_at[i], name_at[i + 1]); qualities likewise when kept
     uint64_t seq = 0;                      // position of the chunk in the input order
     std::string out;                       // formatted result lines
+    std::vector<int32_t> extra;            // hpv16: per read, the counts of the lineage / sublineage tables
     const char* data() const { return big.empty() ? bases : big.data(); }
     void reset(uint64_t s) {
         nreads = 0; offs[0] = 0; big.clear(); big.shrink_to_fit(); text.clear(); name_at.clear(); qual_at.clear(); out.clear(); seq = s;
@@ -770,6 +773,206 @@ int main_hash(int argc, char** argv) {
     return 0;
 }
 
+// ---- hpv16: src/rkmh.cpp:2366-2723 ----------------------------------------------------------------------
+// The tiered HPV16 classifier: every hash of a read (no sketch) against the FULL hash sets of the 182 HPV type references
+// (hash_set_intersection_size, mkmh/mkmh.hpp:842-863) and against the lineage / sublineage specific k-mer tables built
+// from <refpath>/new_refs.fa (sort_by_similarity, mkmh/mkmh.hpp:1304-1333).  Hashing, the set table and the per-read
+// counts run on the GPU (rkg_hash_batch, rkg_load_ref_sets, rkg_classify_sets); the lineage tables are small host-side
+// set differences, done with the same containers as the reference so that their order (and the file the reference
+// writes next to its output, lineage_specific_hashes.<k>.tst) comes out the same.
+std::string find_ref_file(const std::string& dir, const char* name) {
+    const std::string plain = dir + "/" + name;
+    struct stat st;
+    if (stat(plain.c_str(), &st) == 0) return plain;
+    const std::string gz = plain + ".gz";                   // the fixtures of this repository are stored compressed
+    if (stat(gz.c_str(), &st) == 0) return gz;
+    return plain;
+}
+
+template <typename Key>
+void specific_tables(const std::map<Key, std::set<uint64_t>>& groups, std::vector<std::string>& names,
+                     std::vector<std::vector<uint64_t>>& tables, const std::function<std::string(const Key&)>& name_of) {
+    for (const auto& x : groups) {                          // src/rkmh.cpp:2568-2596 / 2620-2644
+        std::vector<uint64_t> diff(x.second.size() + 1000);
+        std::vector<uint64_t> xdiff(x.second.begin(), x.second.end());
+        for (const auto& y : groups) {
+            if (x.first == y.first) continue;
+            auto it = std::set_difference(xdiff.begin(), xdiff.end(), y.second.begin(), y.second.end(), diff.begin());
+            diff.resize((size_t)(it - diff.begin()));
+            xdiff = diff;
+        }
+        names.push_back(name_of(x.first));
+        std::sort(xdiff.begin(), xdiff.end());
+        tables.push_back(xdiff);
+    }
+}
+
+void append_double(std::string& s, double v) { char b[40]; int n = snprintf(b, sizeof b, "%g", v); s.append(b, n); }   // ostream << double
+
+int main_hpv16(int argc, char** argv) {
+    if (argc <= 2) { usage(argv[0]); exit(1); }
+    std::vector<const char*> read_files;
+    std::string refpath = "data";
+    std::vector<int> ks;
+    int min_kmer_occ = 0, gpus = 1;
+    bool do_read_depth = false;
+    if (const char* env = getenv("RKMH_GPUS")) gpus = atoi(env);
+    static struct option long_options[] = {
+        {"help", no_argument, 0, 'h'}, {"kmer", no_argument, 0, 'k'}, {"fasta", required_argument, 0, 'f'},
+        {"reference", required_argument, 0, 'r'}, {"sketch", required_argument, 0, 's'}, {"threads", required_argument, 0, 't'},
+        {"min-kmer-occurence", required_argument, 0, 'M'}, {"min-matches", required_argument, 0, 'N'},
+        {"min-diff", required_argument, 0, 'D'}, {"max-samples", required_argument, 0, 'I'}, {"gpus", required_argument, 0, 'g'},
+        {0, 0, 0, 0}};
+    optind = 2;
+    for (;;) {
+        int idx = 0;
+        const int c = getopt_long(argc, argv, "hk:f:R:s:t:M:N:D:g:", long_options, &idx);      // src/rkmh.cpp:2408
+        if (c == -1) break;
+        switch (c) {
+            case 't': case 's': case 'N': case 'D': break;          // parsed by the reference, without effect on the output
+            case 'f': read_files.push_back(optarg); break;
+            case 'R': refpath = optarg; break;
+            case 'k': if (optarg) ks.push_back(atoi(optarg)); break;
+            case 'M': min_kmer_occ = atoi(optarg); do_read_depth = true; break;
+            case 'g': gpus = atoi(optarg); break;
+            case '?': case 'h': usage(argv[0]); exit(1);
+            default: usage(argv[0]); abort();
+        }
+    }
+    if (ks.empty()) {
+        fprintf(stderr, "NO KMER SIZE PROVIDED. USING A DEFAULT KMER SIZE OF 16\n");
+        ks.push_back(16);
+    }
+    const std::string type_file = find_ref_file(refpath, "all_pave_ref.fa"), sub_file = find_ref_file(refpath, "new_refs.fa");
+    SeqSet types, subs;
+    load_all({type_file.c_str()}, types, false);
+    load_all({sub_file.c_str()}, subs, false);
+    if (types.size() == 0) { fprintf(stderr, "rkmh: no type references in %s\n", type_file.c_str()); return 2; }
+    Fleet fl; fl.open(std::max(1, gpus));
+    rkg_ctx* c0 = fl.ctx[0];
+
+    // every hash of every reference with the FIRST k-mer size (src/rkmh.cpp:2546-2552)
+    const int k0 = ks[0];
+    RK(c0, rkg_set_params(c0, &k0, 1, 1, 0, 0));
+    auto hash_all = [&](const SeqSet& set, std::vector<uint64_t>& h, std::vector<int64_t>& ho) {
+        size_t total = 0;
+        for (size_t i = 0; i < set.size(); ++i) total += (size_t)std::max<int64_t>(set.offs[i + 1] - set.offs[i] - k0, 0);
+        h.assign(std::max<size_t>(total, 1), 0); ho.assign(set.size() + 1, 0);
+        if (set.size()) RK(c0, rkg_hash_batch(c0, set.bases.data(), set.offs.data(), (int64_t)set.size(), h.data(), ho.data()));
+    };
+    std::vector<uint64_t> type_h, sub_h;
+    std::vector<int64_t> type_ho, sub_ho;
+    hash_all(types, type_h, type_ho);
+    hash_all(subs, sub_h, sub_ho);
+
+    // lineage = first letter of the name, sublineage = first two (src/rkmh.cpp:2560-2566, 2612-2618)
+    std::map<char, std::set<uint64_t>> lin_to_hashes;
+    std::map<std::string, std::set<uint64_t>> sublin_to_hashes;
+    for (size_t i = 0; i < subs.size(); ++i) {
+        const std::string& key = subs.names[i];
+        const char lin = key.empty() ? '\0' : key[0];
+        const std::string sublin = key.substr(0, 2);
+        for (int64_t j = sub_ho[i]; j < sub_ho[i + 1]; ++j) { lin_to_hashes[lin].insert(sub_h[j]); sublin_to_hashes[sublin].insert(sub_h[j]); }
+    }
+    std::vector<std::string> lin_names, sublin_names;
+    std::vector<std::vector<uint64_t>> lin_tables, sublin_tables;
+    specific_tables<char>(lin_to_hashes, lin_names, lin_tables, [](const char& ch) { return std::string(1, ch); });
+    specific_tables<std::string>(sublin_to_hashes, sublin_names, sublin_tables, [](const std::string& x) { return x; });
+    {   // the side file and the messages of the reference (src/rkmh.cpp:2598-2610, 2646-2649)
+        const std::string fn = "lineage_specific_hashes." + std::to_string(k0) + ".tst";
+        if (FILE* fo = fopen(fn.c_str(), "w")) {
+            for (size_t i = 0; i < lin_names.size(); ++i) {
+                fprintf(fo, "%s\t", lin_names[i].c_str());
+                for (uint64_t x : lin_tables[i]) fprintf(fo, "%llu\t", (unsigned long long)x);
+                fputc('\n', fo);
+            }
+            fclose(fo);
+        }
+        fprintf(stderr, "Lineage specific kmer table created:\n");
+        for (size_t i = 0; i < lin_names.size(); ++i) fprintf(stderr, "\t%s\t%zu\n", lin_names[i].c_str(), lin_tables[i].size());
+        fprintf(stderr, "Sublineage specific kmer table created:\n");
+        for (size_t i = 0; i < sublin_names.size(); ++i) fprintf(stderr, "\t%s\t%zu\n", sublin_names[i].c_str(), sublin_tables[i].size());
+    }
+
+    // one table: the type references' full hash arrays, then the lineage and the sublineage tables
+    const int ntypes = (int)types.size(), nlin = (int)lin_names.size(), nsub = (int)sublin_names.size();
+    const int nextra = nlin + nsub;
+    std::vector<uint64_t> set_h(type_h.begin(), type_h.begin() + type_ho[ntypes]);
+    std::vector<int64_t> set_o(type_ho.begin(), type_ho.end());
+    for (const auto* tabs : {&lin_tables, &sublin_tables})
+        for (const auto& t : *tabs) { set_h.insert(set_h.end(), t.begin(), t.end()); set_o.push_back((int64_t)set_h.size()); }
+    if (set_h.empty()) set_h.push_back(0);
+    fl.each([&](int, rkg_ctx* c) {
+        RK(c, rkg_set_params(c, ks.data(), (int)ks.size(), 1, do_read_depth ? 800000000ULL : 0, 0));       // src/rkmh.cpp:2516
+        RK(c, rkg_load_ref_sets(c, set_h.data(), set_o.data(), ntypes + nextra));
+    });
+
+    auto format = [&](Chunk& c) {                           // src/rkmh.cpp:2665-2704
+        std::vector<std::pair<int, int>> helper;
+        for (size_t i = 0; i < c.nreads; ++i) {
+            const auto nm = c.name(i);
+            const int64_t len = c.offs[i + 1] - c.offs[i];
+            int64_t hashnum = 0;
+            for (int k : ks) hashnum += std::max<int64_t>(len - k, 0);
+            const rkg_hit& h = c.hits[i];
+            const int32_t* ex = c.extra.data() + i * (size_t)nextra;
+            c.out.append(nm.first, nm.second); c.out += '\t';
+            c.out += types.names[h.ref_id]; c.out += '\t';
+            append_int(c.out, h.best); c.out += '/'; append_int(c.out, hashnum); c.out += '\t';
+            std::string sims[2], inters[2];
+            for (int tier = 0; tier < 2; ++tier) {          // sort_by_similarity, mkmh/mkmh.hpp:1304-1333
+                const int n = tier ? nsub : nlin;
+                const int32_t* cnt = ex + (tier ? nlin : 0);
+                const std::vector<std::string>& names = tier ? sublin_names : lin_names;
+                helper.resize((size_t)n);
+                for (int j = 0; j < n; ++j) helper[j] = std::make_pair(j, (int)cnt[j]);
+                std::sort(helper.begin(), helper.end(),
+                          [](const std::pair<int, int>& lhs, const std::pair<int, int>& rhs) { return lhs.second > rhs.second; });
+                for (int j = 0; j < n; ++j) {
+                    sims[tier] += names[helper[j].first]; sims[tier] += ':';
+                    append_double(sims[tier], (double)helper[j].second / (double)hashnum); sims[tier] += ';';
+                    append_int(inters[tier], helper[j].second); inters[tier] += ';';
+                }
+            }
+            c.out += sims[0]; c.out += '\t'; c.out += sims[1]; c.out += '\t'; c.out += inters[0]; c.out += '\t'; c.out += inters[1];
+            c.out += '\n';
+        }
+    };
+    auto classify = [&](rkg_ctx* c, Chunk& ch) {
+        ch.extra.resize(std::max<size_t>(ch.nreads * (size_t)std::max(nextra, 1), 1));
+        RK(c, rkg_classify_sets(c, ch.data(), ch.offs, (int64_t)ch.nreads, do_read_depth ? min_kmer_occ : -1, ntypes, ch.hits, ch.extra.data()));
+    };
+    const auto write_out = [](Chunk& c) { fwrite(c.out.data(), 1, c.out.size(), stdout); };
+    ChunkPool pool;
+    pool.open(fl.ctx[0], 2 * (int)fl.ctx.size() + 6 + 3 * parse_threads(), chunk_bytes());
+    if (!(do_read_depth && any_unrewindable(read_files))) {
+        if (do_read_depth) {                                // src/rkmh.cpp:2514-2530: valid windows only
+            fl.each([&](int, rkg_ctx* c) { RK(c, rkg_count_reset(c)); });
+            stream_reads(fl, pool, read_files, false,
+                         [&](int, rkg_ctx* c, Chunk& ch) { RK(c, rkg_count_batch(c, ch.data(), ch.offs, (int64_t)ch.nreads, 0)); },
+                         nullptr, [](Chunk&) {});
+            allreduce_counts(fl);
+        }
+        stream_reads(fl, pool, read_files, false, [&](int, rkg_ctx* c, Chunk& ch) { classify(c, ch); }, format, write_out);
+        return 0;
+    }
+    // -M on an input that cannot be read twice: buffer the reads, then the same two passes through one big chunk
+    SeqSet reads;
+    load_all(read_files, reads, false);
+    RK(c0, rkg_count_reset(c0));
+    if (reads.size()) RK(c0, rkg_count_batch(c0, reads.bases.data(), reads.offs.data(), (int64_t)reads.size(), 0));
+    Chunk all;
+    std::vector<int64_t> offs(reads.offs);
+    std::vector<rkg_hit> hits(std::max<size_t>(reads.size(), 1));
+    all.bases = reads.bases.data(); all.offs = offs.data(); all.hits = hits.data(); all.nreads = reads.size();
+    for (size_t i = 0; i < reads.size(); ++i) { all.name_at.push_back(all.text.size()); all.text.insert(all.text.end(), reads.names[i].begin(), reads.names[i].end()); }
+    if (reads.size()) classify(c0, all);
+    format(all);
+    write_out(all);
+    all.bases = nullptr; all.offs = nullptr; all.hits = nullptr;
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -782,6 +985,7 @@ int main(int argc, char** argv) {
     if (cmd == "stream") return main_stream(argc, argv);
     if (cmd == "filter") return main_filter(argc, argv);
     if (cmd == "hash") return main_hash(argc, argv);
+    if (cmd == "hpv16") return main_hpv16(argc, argv);
     if (cmd == "parse-stream") {     // host-only: the records as the streaming front-end chunks them (parallel parser included)
         std::vector<const char*> files(argv + 2, argv + argc);
         ChunkPool pool;

@@ -65,6 +65,17 @@ CLI_CASES = {
     "filter_viral4_z1_M2_D2": ("filter", ["filter", "-r", "zika.fa.gz", "-r", "dengue.fa.gz", "-r", "yellow_fever.fa.gz", "-r", "hpv_16.fa.gz", "-f", "z1.fq.gz", "-k", "20", "-s", "2000", "-M", "2", "-D", "2"]),
 }
 
+# `rkmh hpv16` (src/rkmh.cpp:2366-2723): name -> argv without -R (the generator and the tests add it; the command reads
+# <refpath>/all_pave_ref.fa and <refpath>/new_refs.fa and writes lineage_specific_hashes.<k>.tst into its working directory)
+HPV16_CASES = {
+    "hpv16cmd_minion_k16": ["hpv16", "-f", "minION25.fq.gz", "-k", "16"],
+    "hpv16cmd_mix2k_k12": ["hpv16", "-f", "mix2k.fq.gz", "-k", "12"],
+    "hpv16cmd_minion_k10_k14": ["hpv16", "-f", "minION25.fq.gz", "-k", "10", "-k", "14"],
+    "hpv16cmd_mix2k_k16_M2": ["hpv16", "-f", "mix2k.fq.gz", "-k", "16", "-M", "2"],
+    "hpv16cmd_z1_k20": ["hpv16", "-f", "z1.fq.gz", "-k", "20"],
+    "hpv16cmd_two_files_k14_M3": ["hpv16", "-f", "minION25.fq.gz", "-f", "mix2k.fq.gz", "-k", "14", "-M", "3"],
+}
+
 # library-level cases: name -> (ref fixtures, read fixture, k list, s)
 LIB_CASES = {
     "hpv16_minion_k10": (["hpv_16_allFasta.fa.gz"], "minION25.fq.gz", [10], 1000),
@@ -132,6 +143,33 @@ def make_cli():
                           "lines": out.count(b"\n"), "binary": "rkmh_ref_filter" if which == "filter" else "rkmh_ref"}
         print(f"cli  {name:28s} {manifest[name]['lines']:6d} lines  md5 {manifest[name]['md5']}")
     with open(os.path.join(CLI, "manifest.json"), "w") as fh:
+        json.dump(manifest, fh, indent=1, sort_keys=True)
+
+
+def make_hpv16(manifest_path=None):
+    """stdout (and the side file) of the real binary's `hpv16` command.  It wants plain file NAMES under -R; gzopen reads
+    gzip content whatever the name, so a scratch directory of symlinks onto the committed .gz fixtures serves."""
+    import tempfile
+    manifest_path = manifest_path or os.path.join(CLI, "manifest.json")
+    with open(manifest_path) as fh:
+        manifest = json.load(fh)
+    exe = ref_binary()
+    assert exe, "build oracle/_ref first (make -C oracle)"
+    with tempfile.TemporaryDirectory() as tmp:
+        for f in ("all_pave_ref.fa", "new_refs.fa"):
+            os.symlink(os.path.join(DATA, f + ".gz"), os.path.join(tmp, f))
+        for name, argv in HPV16_CASES.items():
+            full = [exe] + [os.path.join(DATA, a) if a.endswith(".gz") else a for a in argv] + ["-R", tmp, "-t", "1"]
+            res = subprocess.run(full, cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+            k0 = argv[argv.index("-k") + 1]
+            with open(os.path.join(tmp, f"lineage_specific_hashes.{k0}.tst"), "rb") as fh:
+                side = fh.read()
+            gz_write(os.path.join(CLI, name + ".out.gz"), res.stdout)
+            manifest[name] = {"argv": argv, "md5": hashlib.md5(res.stdout).hexdigest(), "lines": res.stdout.count(b"\n"),
+                              "binary": "rkmh_ref", "side_file_md5": hashlib.md5(side).hexdigest(),
+                              "stderr_md5": hashlib.md5(res.stderr).hexdigest()}
+            print(f"cli  {name:28s} {manifest[name]['lines']:6d} lines  md5 {manifest[name]['md5']}")
+    with open(manifest_path, "w") as fh:
         json.dump(manifest, fh, indent=1, sort_keys=True)
 
 
@@ -228,10 +266,14 @@ def make_lib_vectors(ref: RefMkmh):
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["hpv16"]:               # only (re)generate the hpv16 command's goldens
+        make_hpv16()
+        sys.exit(0)
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
     ref = RefMkmh()
     make_data()
     make_cli()
+    make_hpv16()
     make_kats(ref)
     make_lib_vectors(ref)
     print("golden vectors written under", HERE)

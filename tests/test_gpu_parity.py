@@ -319,7 +319,7 @@ def test_memo_path_is_taken_and_matches_murmur(oracle, variant, monkeypatch):
                 out.append(_fields(g.classify_batch(sb, so, min_occ=m)))
             out.append(_fields(g.classify_batch(sb, so)))          # -M off again: FAILM flags cleared
             names = set(g.profile_read())
-            assert (short_kernel in names) == memo and ("classify_group_kernel" in names) == (not memo)
+            assert (short_kernel in names) == memo and ("classify_warp_kernel" in names) == (not memo)
             if memo and variant != "warp":                     # -M bakes FAILM flags: those passes take the rank-table kernel
                 assert "classify_memo_warp_kernel" in names
             assert ("count_memo_kernel" in names) == memo
@@ -463,3 +463,54 @@ def test_limits_fail_loudly():
         g.load_refs(*_pack([b"ACGTACGTACGTACGTACGTTTGACA" * 3]))
         with pytest.raises(rkmh_b200.RkmhError, match="memoised path is not active"):
             g.count_partial_tensor()
+
+
+# ---- hpv16: full hash sets ----------------------------------------------------------------------
+@pytest.mark.parametrize("ks,min_occ", [([8], -1), ([6, 17], -1), ([12], 2), ([21], -1)])
+def test_classify_sets_vs_oracle(oracle, ks, min_occ):
+    """rkg_load_ref_sets + rkg_classify_sets == hash_set_intersection_size / hash_intersection_size of the oracle
+    (mkmh/mkmh.hpp:842-863, 822-840 as main_hpv16 uses them): sets with zeros and duplicates, reads with repeated
+    k-mers, invalid bases and reads shorter than k, several k-mer sizes, -M masking, both hashing paths."""
+    import rkmh_b200
+    _, refs, _ = load_sequences([data_path("awkward_refs.fa.gz"), data_path("new_refs.fa.gz")])
+    _, reads, _ = load_sequences([data_path("awkward_reads.fq.gz"), data_path("mix2k.fq.gz")])
+    reads = reads[:300] + [b"ACGT" * 30, b"A" * 80, b"N" * 30, b"ACGTAC"]
+    k0 = ks[0]
+    sets = [oracle.calc_hashes(oracle.to_upper(r), [k0]) for r in refs]          # unsorted, zeros and duplicates inside
+    uniq = [np.setdiff1d(np.unique(sets[i]), np.concatenate(sets[:i] + sets[i + 1:])) for i in range(4)]
+    all_sets = sets + uniq                                                       # types first, then "specific" tables
+    ntypes = len(sets)
+    size = 1_000_003
+    counts = None
+    if min_occ >= 0:
+        counts = np.zeros(size, np.int32)
+        oracle.count_batch(reads, ks, counts)
+    exp_hits, exp_extra = oracle.classify_sets(reads, ks, [np.sort(x) for x in all_sets], ntypes, counts=counts, min_occ=max(min_occ, 0))
+    for memo in (True, False):
+        with rkmh_b200.RkmhGpu(0) as g:
+            g.set_memo(memo)
+            g.set_params(ks, 1, read_table_size=size if min_occ >= 0 else 0)
+            g.load_ref_sets(all_sets)
+            if min_occ >= 0:
+                g.count_reset()
+                g.count_batch(*_pack(reads))
+            hits, extra = g.classify_sets(*_pack(reads), ntypes, min_occ=min_occ)
+            with pytest.raises(rkmh_b200.RkmhError):
+                g.classify_batch(*_pack(reads))          # a set table is not a sketch table
+        assert np.array_equal(hits["ref_id"], exp_hits["ref_id"]) and np.array_equal(hits["best"], exp_hits["best"])
+        assert np.array_equal(extra, exp_extra)
+
+
+@pytest.mark.parametrize("name", ["hpv16cmd_minion_k16", "hpv16cmd_mix2k_k12"])
+def test_hpv16_through_the_c_abi_equals_the_real_binary(cli_manifest, name):
+    """the Python mirror of main_hpv16 with the GPU as its engine reproduces the real binary's stdout"""
+    import rkmh_b200
+    from tests.golden.make_golden import HPV16_CASES
+    from tests.hpv16_mirror import GpuEngine, hpv16_stdout
+    argv = HPV16_CASES[name]
+    ks = [int(argv[i + 1]) for i, a in enumerate(argv) if a == "-k"]
+    reads = [data_path(argv[i + 1]) for i, a in enumerate(argv) if a == "-f"]
+    with rkmh_b200.RkmhGpu(0) as g:
+        out, side = hpv16_stdout(GpuEngine(g), data_path("all_pave_ref.fa.gz"), data_path("new_refs.fa.gz"), reads, ks)
+    assert out == golden_cli_output(name)
+    assert hashlib.md5(side).hexdigest() == cli_manifest[name]["side_file_md5"]

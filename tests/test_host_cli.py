@@ -256,3 +256,28 @@ def test_minus_M_on_a_fifo_and_an_empty_input(rkmh_bin, cli_manifest, tmp_path):
             res = subprocess.run([rkmh_bin, "stream", "-r", "hpv_16.fa.gz", "-f", str(empty), "-k", "12", "-s", "100"] + extra,
                                  cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
             assert res.returncode == 0 and res.stdout == b""
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("name", ["hpv16cmd_minion_k16", "hpv16cmd_mix2k_k12", "hpv16cmd_minion_k10_k14", "hpv16cmd_mix2k_k16_M2",
+                                  "hpv16cmd_z1_k20", "hpv16cmd_two_files_k14_M3"])
+def test_hpv16_command_equals_reference(rkmh_bin, cli_manifest, tmp_path, name):
+    """`rkmh hpv16`: stdout, the messages on stderr and the side file lineage_specific_hashes.<k>.tst are the
+    real binary's, byte for byte; small chunks (many batches, -M streamed twice) and a FIFO input do not change them."""
+    from tests.golden.make_golden import HPV16_CASES
+    argv = [os.path.join(DATA, a) if a.endswith(".gz") else a for a in HPV16_CASES[name]] + ["-R", DATA]
+    k0 = argv[argv.index("-k") + 1]
+    res = subprocess.run([rkmh_bin] + argv, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert res.returncode == 0, res.stderr.decode()[-400:]
+    gold = golden_cli_output(name)
+    if res.stdout != gold:
+        a, b = res.stdout.splitlines(), gold.splitlines()
+        diff = [(i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y][:2]
+        pytest.fail(f"{name}: {len(a)} vs {len(b)} lines; first diffs {diff}")
+    assert hashlib.md5(res.stderr).hexdigest() == cli_manifest[name]["stderr_md5"], res.stderr.decode()[-300:]
+    side = (tmp_path / f"lineage_specific_hashes.{k0}.tst").read_bytes()
+    assert hashlib.md5(side).hexdigest() == cli_manifest[name]["side_file_md5"]
+    env = dict(os.environ, RKMH_CHUNK_BYTES="30000")
+    res = subprocess.run([rkmh_bin] + argv, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    assert res.returncode == 0 and res.stdout == gold

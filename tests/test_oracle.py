@@ -136,3 +136,31 @@ def test_count_and_mask_against_real_counter(oracle):
     oracle.lib.rko_mask_by_frequency(masked, masked.size, counts, size, 2)
     assert np.array_equal(masked, masked_ref)
     ref.lib.ref_counter_free(ctr)
+
+
+# ---- hpv16: the oracle's restatement pinned to the real binary's stdout --------------------------
+def test_set_intersection_size_semantics(oracle):
+    """mkmh/mkmh.hpp:842-863: distinct non-zero common values of two ascending arrays"""
+    f = oracle.set_intersection_size
+    assert f([3, 3, 5, 7], [3, 5, 5, 7, 7]) == 3
+    assert f([0, 0, 3, 3, 3], [0, 3, 3]) == 1
+    assert f([1, 2, 3], [4, 5]) == 0
+    assert f([], [1]) == 0
+    assert f([5, 5, 7], [5, 7]) == 2
+    # the multiset variant (mkmh/mkmh.hpp:822-840) counts min(multiplicity) instead
+    assert oracle.intersection_size(np.array([3, 3, 5, 7], np.uint64), np.array([3, 3, 5, 5], np.uint64)) == 3
+
+
+@pytest.mark.parametrize("name", ["hpv16cmd_minion_k16", "hpv16cmd_minion_k10_k14", "hpv16cmd_z1_k20"])
+def test_hpv16_mirror_on_the_oracle_equals_the_real_binary(oracle, cli_manifest, name):
+    """`rkmh hpv16` restated on the oracle's functions gives the real binary's stdout and side file byte for byte."""
+    import hashlib
+    from tests.golden.make_golden import HPV16_CASES
+    from tests.hpv16_mirror import OracleEngine, hpv16_stdout
+    from tests.util import data_path, golden_cli_output
+    argv = HPV16_CASES[name]
+    ks = [int(argv[i + 1]) for i, a in enumerate(argv) if a == "-k"]
+    reads = [data_path(argv[i + 1]) for i, a in enumerate(argv) if a == "-f"]
+    out, side = hpv16_stdout(OracleEngine(oracle), data_path("all_pave_ref.fa.gz"), data_path("new_refs.fa.gz"), reads, ks)
+    assert out == golden_cli_output(name)
+    assert hashlib.md5(side).hexdigest() == cli_manifest[name]["side_file_md5"]
