@@ -53,7 +53,7 @@ struct Options {
     std::vector<const char*> refs, reads;
     std::vector<int> ks;
     int sketch = 1000, threads = 1, min_occ = -1, min_matches = -1, min_diff = 0, max_samples = 100000;
-    bool do_read_depth = false, do_ref_depth = false, hash_sketch_given = false;
+    bool do_read_depth = false, do_ref_depth = false, hash_sketch_given = false, in_stream = false;
     int gpus = 1;
 };
 
@@ -105,7 +105,8 @@ void parse_common(int argc, char** argv, Options& o, const char* optstring) {
         int c = getopt_long(argc, argv, optstring, long_options, &idx);
         if (c == -1) break;
         switch (c) {
-            case 'm': case 'i': case 'z': break;                       // parsed, no effect (reference: same)
+            case 'i': o.in_stream = true; break;                       // filter: classify the records of standard input (below)
+            case 'm': case 'z': break;                                 // parsed, no effect (reference: same)
             case 'F': case 'R': case 'p': case 'q': case 'S': break;   // parsed, no effect
             case 't': o.threads = atoi(optarg); break;
             case 'r': o.refs.push_back(optarg); break;
@@ -679,24 +680,61 @@ int main_filter(int argc, char** argv) {
     Fleet fl; fl.open(std::max(1, o.gpus));
     setup_refs(fl, o, refs, FILTER_TABLE, true);
     if (!(o.do_read_depth && any_unrewindable(o.reads))) {
-        run_streamed(fl, o, true, true, [&](Chunk& c) {
-            for (size_t i = 0; i < c.nreads; ++i) {
-                const auto nm = c.name(i), ql = c.qual(i);
-                format_filter_record(c.out, o, nm.first, nm.second, c.data() + c.offs[i], c.offs[i + 1] - c.offs[i], ql.first, ql.second, c.hits[i]);
-            }
-        });
-        return 0;
+        if (!o.reads.empty() || !o.in_stream)
+            run_streamed(fl, o, true, true, [&](Chunk& c) {
+                for (size_t i = 0; i < c.nreads; ++i) {
+                    const auto nm = c.name(i), ql = c.qual(i);
+                    format_filter_record(c.out, o, nm.first, nm.second, c.data() + c.offs[i], c.offs[i + 1] - c.offs[i], ql.first, ql.second, c.hits[i]);
+                }
+            });
+    } else {
+        SeqSet reads;
+        load_all(o.reads, reads, true);
+        std::vector<rkg_hit> hits = classify_all(fl, o, reads, true);
+        std::string out;
+        for (size_t i = 0; i < reads.size(); ++i) {
+            format_filter_record(out, o, reads.names[i].data(), reads.names[i].size(), reads.bases.data() + reads.offs[i],
+                                 reads.offs[i + 1] - reads.offs[i], reads.quals[i].data(), reads.quals[i].size(), hits[i]);
+            if (out.size() > (1 << 22)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+        }
+        fwrite(out.data(), 1, out.size(), stdout);
     }
-    SeqSet reads;
-    load_all(o.reads, reads, true);
-    std::vector<rkg_hit> hits = classify_all(fl, o, reads, true);
-    std::string out;
-    for (size_t i = 0; i < reads.size(); ++i) {
-        format_filter_record(out, o, reads.names[i].data(), reads.names[i].size(), reads.bases.data() + reads.offs[i],
-                             reads.offs[i + 1] - reads.offs[i], reads.quals[i].data(), reads.quals[i].size(), hits[i]);
-        if (out.size() > (1 << 22)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+    if (!o.in_stream) return 0;
+    // -i / --in-stream (src/rkmh.cpp:1329-1414): after the read files, every record of STANDARD INPUT is sketched and classified
+    // against the references and REPORTED (not filtered), one line each:
+    //   Sample: <name> TAB Result: <reference or empty> TAB <shared> TAB <min(sketch length, reference sketch length)> TAB
+    //   [FAIL:DEPTH] TAB [FAIL:MATCHES] TAB [FAIL:DIFF]
+    // The reference's own code path cannot run (its OpenMP tasks read the kseq buffers after kseq_destroy; ASan: heap
+    // use after free at src/rkmh.cpp:1353), so this follows its text: -M m > 0 keeps the hashes that occur at least m times
+    // in the table counted from the read FILES (:1366-1376), best / previous best start from 0 (src/equiv.hpp:328-345).
+    std::vector<int32_t> ref_lens(refs.size());
+    {
+        std::vector<uint64_t> sk((size_t)refs.size() * (size_t)o.sketch);
+        RK(fl.ctx[0], rkg_get_ref_sketches(fl.ctx[0], sk.data(), ref_lens.data()));
     }
-    fwrite(out.data(), 1, out.size(), stdout);
+    const int occ = (o.do_read_depth && o.min_occ > 0) ? o.min_occ : -1;
+    ChunkPool pool;
+    pool.open(fl.ctx[0], 2 * (int)fl.ctx.size() + 6, chunk_bytes());
+    const std::vector<const char*> stdin_only{"-"};
+    stream_reads(fl, pool, stdin_only, false,
+                 [&](int, rkg_ctx* c, Chunk& ch) { RK(c, rkg_classify_batch(c, ch.data(), ch.offs, (int64_t)ch.nreads, occ, ch.hits)); },
+                 [&](Chunk& c) {
+                     for (size_t i = 0; i < c.nreads; ++i) {
+                         const auto nm = c.name(i);
+                         const rkg_hit& h = c.hits[i];
+                         const int best = std::max(h.best, 0), prev = std::max(h.prev, 0);
+                         const bool found = best > 0;
+                         c.out += "Sample: "; c.out.append(nm.first, nm.second); c.out += "\tResult: ";
+                         if (found) c.out += refs.names[h.ref_id];
+                         c.out += '\t'; append_int(c.out, best);
+                         c.out += '\t'; append_int(c.out, found ? std::min<int>(h.sketch_len, ref_lens[h.ref_id]) : 0);
+                         c.out += '\t'; if (h.sketch_len <= 0) c.out += "FAIL:DEPTH";
+                         c.out += '\t'; if (best < o.min_matches) c.out += "FAIL:MATCHES";
+                         c.out += '\t'; if (!(best - prev > o.min_diff)) c.out += "FAIL:DIFF";
+                         c.out += '\n';
+                     }
+                 },
+                 [](Chunk& c) { fwrite(c.out.data(), 1, c.out.size(), stdout); });
     return 0;
 }
 

@@ -281,3 +281,48 @@ def test_hpv16_command_equals_reference(rkmh_bin, cli_manifest, tmp_path, name):
     env = dict(os.environ, RKMH_CHUNK_BYTES="30000")
     res = subprocess.run([rkmh_bin] + argv, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
     assert res.returncode == 0 and res.stdout == gold
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [[], ["-N", "5", "-D", "1"], ["-M", "2", "-N", "3"]])
+def test_filter_in_stream_mode(rkmh_bin, oracle, extra):
+    """`rkmh filter ... -i` (src/rkmh.cpp:1329-1414): after the read files, every record of standard input is classified
+    and REPORTED as `Sample: <name>\\tResult: <ref>\\t<shared>\\t<min sketch length>\\t[FAIL:DEPTH]\\t[FAIL:MATCHES]\\t[FAIL:DIFF]`.
+    The reference's own code path cannot run (use after free in its OpenMP tasks, see rkmh_main.cpp), so the expected lines
+    are restated on the pinned oracle: parity for this mode is pinned by the oracle, not by the real binary."""
+    import numpy as np
+    from rkmh_b200.fastx import load_sequences
+    refs_f = ["zika.fa.gz", "dengue.fa.gz", "hpv_16.fa.gz"]
+    rn, rs, _ = load_sequences([os.path.join(DATA, f) for f in refs_f])
+    fn, fs, _ = load_sequences([os.path.join(DATA, "z1.fq.gz")])
+    payload = gzip.open(os.path.join(DATA, "z1.fq.gz"), "rb").read() + gzip.open(os.path.join(DATA, "minION25.fq.gz"), "rb").read() + \
+        b"@short\nACGTACGTACGTACGTACGTACGTAC\n+\nIIIIIIIIIIIIIIIIIIIIIIIIII\n@allN\nNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n"
+    k, s = 20, 2000
+    opt = dict(zip(extra[::2], map(int, extra[1::2])))
+    n_min, d_min, m = opt.get("-N", -1), opt.get("-D", 0), opt.get("-M", -1)
+    argv = [rkmh_bin, "filter"] + sum((["-r", f] for f in refs_f), []) + ["-f", "z1.fq.gz", "-k", str(k), "-s", str(s), "-i"] + extra
+    res = subprocess.run(argv, cwd=DATA, input=payload, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert res.returncode == 0, res.stderr.decode()[-400:]
+    # expected: the filtered records of the read file first (the ordinary filter output), then one line per stdin record
+    base = subprocess.run([a for a in argv if a != "-i"], cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout
+    assert res.stdout.startswith(base)
+    tmp_names, tmp_seqs = [], []
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".fq") as fh:
+        fh.write(payload); fh.flush()
+        tmp_names, tmp_seqs, _ = load_sequences([fh.name])
+    sk, ln = oracle.sketch_batch(rs, [k], s)
+    counts = None
+    if m > 0:
+        counts = np.zeros(10_000_000, np.int32)
+        oracle.count_batch(fs, [k], counts, valid_only=False)           # filter counts every hash of the read FILES, zeros too
+    hits = oracle.classify_batch(tmp_seqs, [k], s, sk, ln, counts=counts, min_occ=m if m > 0 else 0)
+    lines = []
+    for nm, h in zip(tmp_names, hits):
+        best, prev = max(int(h["best"]), 0), max(int(h["prev"]), 0)
+        found = best > 0
+        lines.append(b"Sample: " + nm + b"\tResult: " + (rn[int(h["ref_id"])] if found else b"") + b"\t%d\t%d\t" % (
+            best, min(int(h["sketch_len"]), int(ln[int(h["ref_id"])])) if found else 0) +
+            (b"FAIL:DEPTH" if int(h["sketch_len"]) <= 0 else b"") + b"\t" + (b"FAIL:MATCHES" if best < n_min else b"") + b"\t" +
+            (b"" if best - prev > d_min else b"FAIL:DIFF") + b"\n")
+    assert res.stdout[len(base):] == b"".join(lines)
