@@ -29,6 +29,7 @@
 #include <set>
 #include <mutex>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -85,6 +86,13 @@ void usage(const char* argv0) {
 }
 #define RK(ctx, call) do { if ((call) != RKG_OK) die(ctx, #call); } while (0)
 
+// RKMH_TIMING=1: wall-clock marks of the start-up and streaming stages on stderr
+const std::chrono::steady_clock::time_point g_t0 = std::chrono::steady_clock::now();
+void tmark(const char* what) {
+    static const bool on = getenv("RKMH_TIMING") != nullptr;
+    if (on) fprintf(stderr, "rkmh: %8.3f s  %s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t0).count(), what);
+}
+
 // getopt loop shared by stream/classify and filter (same letters in the reference; `d` and unknown letters
 // print the usage and abort(), 'h' / '?' print it and exit(1)).
 void parse_common(int argc, char** argv, Options& o, const char* optstring) {
@@ -136,16 +144,33 @@ void load_all(const std::vector<const char*>& files, SeqSet& set, bool keep_qual
 // One context per GPU, parameters and references replicated on each.
 struct Fleet {
     std::vector<rkg_ctx*> ctx;
-    void open(int n) {                                   // contexts are created concurrently: ~1.3 s each on a B200 box
-        ctx.assign((size_t)n, nullptr);
+    std::thread bg; std::mutex m; std::condition_variable cv; bool ready = true;
+    void create_all() {                                  // contexts are created concurrently: ~1.3 s each on a B200 box
         std::vector<std::thread> th;
-        for (int d = 0; d < n; ++d)
+        for (size_t d = 0; d < ctx.size(); ++d)
             th.emplace_back([this, d] {
-                if (rkg_create(d, &ctx[d]) != RKG_OK) { fprintf(stderr, "rkmh: %s\n", rkg_last_error(nullptr)); exit(2); }
+                if (rkg_create((int)d, &ctx[d]) != RKG_OK) { fprintf(stderr, "rkmh: %s\n", rkg_last_error(nullptr)); exit(2); }
             });
         for (auto& t : th) t.join();
+        tmark("CUDA contexts created");
     }
-    ~Fleet() { for (auto c : ctx) rkg_destroy(c); }
+    void open(int n) { ctx.assign((size_t)n, nullptr); create_all(); }
+    // The same on a background thread, followed by `after` (parameters, references): CUDA start-up takes over a second,
+    // during which the read files are already being parsed into chunks.  Users call wait() before touching a context.
+    void open_async(int n, std::function<void()> after) {
+        ctx.assign((size_t)n, nullptr);
+        ready = false;
+        bg = std::thread([this, after] {
+            create_all();
+            after();
+            tmark("references loaded");
+            { std::lock_guard<std::mutex> g(m); ready = true; }
+            cv.notify_all();
+        });
+    }
+    void wait() { std::unique_lock<std::mutex> g(m); cv.wait(g, [&] { return ready; }); }
+    bool is_ready() { std::lock_guard<std::mutex> g(m); return ready; }
+    ~Fleet() { if (bg.joinable()) bg.join(); for (auto c : ctx) rkg_destroy(c); }
     template <typename F> void each(F&& f) {
         std::vector<std::thread> th;
         for (size_t d = 0; d < ctx.size(); ++d) th.emplace_back([&, d] { f((int)d, ctx[d]); });
@@ -212,6 +237,7 @@ void setup_refs(Fleet& fl, const Options& o, const SeqSet& refs, uint64_t table,
 }
 
 std::vector<rkg_hit> classify_all(Fleet& fl, const Options& o, const SeqSet& reads, bool count_zeros) {
+    fl.wait();
     const int G = (int)fl.ctx.size();
     const size_t n = reads.size();
     std::vector<rkg_hit> hits(n);
@@ -241,6 +267,7 @@ struct Chunk {
     std::vector<char> text;                // names (and quality strings) of the chunk's reads, back to back
     std::vector<uint64_t> name_at, qual_at; // name i = text[name_at[i], name_at[i + 1]); qualities likewise when kept
     uint64_t seq = 0;                      // position of the chunk in the input order
+    bool pinned = false;                   // bases / offs / hits are cudaHostAlloc'ed (else malloc'ed: host-only modes, or made before CUDA was up)
     std::string out;                       // formatted result lines
     std::vector<int32_t> extra;            // hpv16: per read, the counts of the lineage / sublineage tables
     const char* data() const { return big.empty() ? bases : big.data(); }
@@ -274,23 +301,28 @@ template <typename T> class Channel {      // unbounded MPMC queue; the chunk po
 // Chunks are pinned on demand (page-locking costs ~0.5 s per GB: a small input should not pay for the whole pool) up to
 // `max_chunks`; after that the parser waits for the writer to hand one back.
 struct ChunkPool {
-    rkg_ctx* owner = nullptr;
+    Fleet* fleet = nullptr;                              // null: host-only modes (ordinary memory)
     std::vector<Chunk*> all;
     std::deque<Chunk*> free_list;
     std::mutex m; std::condition_variable cv;
     int max_chunks = 0;
     size_t cap_bases = 0;
-    void open(rkg_ctx* ctx, int n, size_t cap) { owner = ctx; max_chunks = n; cap_bases = cap; }
+    void open(Fleet* fl, int n, size_t cap) { fleet = fl; max_chunks = n; cap_bases = cap; }
     Chunk* make() {
         const size_t cap_reads = std::max<size_t>(cap_bases / 32, 1024);
         Chunk* c = new Chunk();
         void *pb = nullptr, *po = nullptr, *ph = nullptr;
+        // pinned once CUDA is up; the chunks made while the contexts are still being created are pageable (their copies
+        // are staged by the driver: slower, but they exist a second earlier)
+        rkg_ctx* owner = (fleet && fleet->is_ready()) ? fleet->ctx[0] : nullptr;
         if (owner) {
             RK(owner, rkg_host_alloc(owner, cap_bases, &pb));
             RK(owner, rkg_host_alloc(owner, sizeof(int64_t) * (cap_reads + 1), &po));
             RK(owner, rkg_host_alloc(owner, sizeof(rkg_hit) * cap_reads, &ph));
-        } else {                                         // `rkmh parse` (no GPU): ordinary memory
+            c->pinned = true;
+        } else {
             pb = malloc(cap_bases); po = malloc(sizeof(int64_t) * (cap_reads + 1)); ph = malloc(sizeof(rkg_hit) * cap_reads);
+            if (!pb || !po || !ph) { fprintf(stderr, "rkmh: out of memory\n"); exit(2); }
         }
         c->bases = (char*)pb; c->offs = (int64_t*)po; c->hits = (rkg_hit*)ph;
         c->cap_bases = cap_bases; c->cap_reads = cap_reads;
@@ -315,7 +347,7 @@ struct ChunkPool {
     void release(Chunk* c) { { std::lock_guard<std::mutex> g(m); free_list.push_back(c); } cv.notify_one(); }
     ~ChunkPool() {
         for (Chunk* c : all) if (c) {
-            if (owner) { rkg_host_free(owner, c->bases); rkg_host_free(owner, c->offs); rkg_host_free(owner, c->hits); }
+            if (c->pinned) { rkg_ctx* o = fleet->ctx[0]; rkg_host_free(o, c->bases); rkg_host_free(o, c->offs); rkg_host_free(o, c->hits); }
             else { free(c->bases); free(c->offs); free(c->hits); }
             delete c;
         }
@@ -325,17 +357,21 @@ struct ChunkPool {
 size_t chunk_bytes() {
     if (const char* b = getenv("RKMH_CHUNK_BYTES")) return (size_t)std::max<long>(atol(b), 64);   // testing knob
     const char* e = getenv("RKMH_CHUNK_MB");
-    const long mb = e ? atol(e) : 32;
+    // 8 MB of bases per chunk (about 55 k short reads): small enough that the pool of pinned chunks (a few per parser
+    // thread) page-locks in tens of milliseconds, large enough that a chunk's kernel launches do not show
+    const long mb = e ? atol(e) : 8;
     return (size_t)std::max<long>(mb, 1) << 20;
 }
 
-// RKMH_PARSE_THREADS > 1 turns the parallel segment parser on.  Default 1: measured on the B200 box (8 M reads, 2.5 GB of
-// FASTQ, best of 3) the sequential reader finishes the whole run in 1.95 s (1.2 s of it start-up) and the parallel one
-// in 2.9 / 3.4 / 4.0 s with 2 / 4 / 8 threads -- the mmap page faults and the extra pinned chunks cost more than the
-// parsing they save at this size.
+// Threads of the parallel segment parser (plain four-line FASTQ files of at least two segments; everything else is read
+// by the sequential state machine).  RKMH_PARSE_THREADS overrides; 1 turns the parallel parser off.  Round 1 measured the
+// parallel parser SLOWER than the sequential one on the B200 box (2.9 s against 1.95 s for 8 M reads): its pool of 32 MB
+// chunks page-locked 1.4 GB before the first read was classified.  With 8 MB chunks and two chunks of text per segment
+// the pool is 4x smaller and the parser scales.
 int parse_threads() {
     if (const char* e = getenv("RKMH_PARSE_THREADS")) return std::min(std::max(atoi(e), 1), 16);
-    return 1;
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::min(8u, std::max(1u, hw / 2));      // half of the cores, at most 8: the rest format, write and feed the GPUs
 }
 
 size_t parse_segment_bytes(size_t cap_bases) {          // about one chunk of bases per segment of FASTQ text
@@ -522,6 +558,7 @@ uint64_t stream_reads(Fleet& fl, ChunkPool& pool, const std::vector<const char*>
     std::thread reader([&] {
         uint64_t seq = 0;
         nrecords = parse_files(files, pool, keep_qual, [&](Chunk* c) { c->seq = seq++; work_q.push(c); });
+        tmark("input parsed");
         // stored under the writer's mutex: a notify between the writer's predicate check and its wait would otherwise
         // be lost, and with every chunk already emitted (or none at all: an empty input) nothing would wake it again
         { std::lock_guard<std::mutex> g(dm); total_chunks = (int64_t)seq; }
@@ -531,6 +568,7 @@ uint64_t stream_reads(Fleet& fl, ChunkPool& pool, const std::vector<const char*>
     std::vector<std::thread> workers;
     for (size_t d = 0; d < fl.ctx.size(); ++d)
         workers.emplace_back([&, d] {
+            fl.wait();                                   // contexts created, parameters and references in place
             for (;;) {
                 Chunk* c = work_q.pop();
                 if (!c) break;
@@ -586,10 +624,11 @@ bool any_unrewindable(const std::vector<const char*>& files) {
 void run_streamed(Fleet& fl, const Options& o, bool keep_qual, bool count_zeros,
                   const std::function<void(Chunk&)>& format) {
     ChunkPool pool;
-    pool.open(fl.ctx[0], 2 * (int)fl.ctx.size() + 6 + 3 * parse_threads(), chunk_bytes());
+    pool.open(&fl, 2 * (int)fl.ctx.size() + 6 + 3 * parse_threads(), chunk_bytes());
     const auto write_out = [](Chunk& c) { fwrite(c.out.data(), 1, c.out.size(), stdout); };
     uint64_t pass1 = 0;
     if (o.do_read_depth) {                              // pass 1: global k-mer count table (src/rkmh.cpp:904-910)
+        fl.wait();
         fl.each([&](int, rkg_ctx* c) { RK(c, rkg_count_reset(c)); });
         pass1 = stream_reads(fl, pool, o.reads, false,
                      [&](int, rkg_ctx* c, Chunk& ch) { RK(c, rkg_count_batch(c, ch.data(), ch.offs, (int64_t)ch.nreads, count_zeros)); },
@@ -645,8 +684,8 @@ int main_stream(int argc, char** argv) {
     SeqSet refs;
     load_all(o.refs, refs, false);
     if (refs.size() == 0) { fprintf(stderr, "rkmh: no reference sequences (the reference binary is undefined here)\n"); return 2; }
-    Fleet fl; fl.open(std::max(1, o.gpus));
-    setup_refs(fl, o, refs, STREAM_TABLE, false);
+    Fleet fl;
+    fl.open_async(std::max(1, o.gpus), [&] { setup_refs(fl, o, refs, STREAM_TABLE, false); });
     if (!(o.do_read_depth && any_unrewindable(o.reads))) {
         run_streamed(fl, o, false, false, [&](Chunk& c) {
             c.out.reserve(c.nreads * 64);
@@ -677,8 +716,8 @@ int main_filter(int argc, char** argv) {
     SeqSet refs;
     load_all(o.refs, refs, false);
     if (refs.size() == 0) { fprintf(stderr, "rkmh: no reference sequences\n"); return 2; }
-    Fleet fl; fl.open(std::max(1, o.gpus));
-    setup_refs(fl, o, refs, FILTER_TABLE, true);
+    Fleet fl;
+    fl.open_async(std::max(1, o.gpus), [&] { setup_refs(fl, o, refs, FILTER_TABLE, true); });
     if (!(o.do_read_depth && any_unrewindable(o.reads))) {
         if (!o.reads.empty() || !o.in_stream)
             run_streamed(fl, o, true, true, [&](Chunk& c) {
@@ -708,13 +747,14 @@ int main_filter(int argc, char** argv) {
     // use after free at src/rkmh.cpp:1353), so this follows its text: -M m > 0 keeps the hashes that occur at least m times
     // in the table counted from the read FILES (:1366-1376), best / previous best start from 0 (src/equiv.hpp:328-345).
     std::vector<int32_t> ref_lens(refs.size());
+    fl.wait();
     {
         std::vector<uint64_t> sk((size_t)refs.size() * (size_t)o.sketch);
         RK(fl.ctx[0], rkg_get_ref_sketches(fl.ctx[0], sk.data(), ref_lens.data()));
     }
     const int occ = (o.do_read_depth && o.min_occ > 0) ? o.min_occ : -1;
     ChunkPool pool;
-    pool.open(fl.ctx[0], 2 * (int)fl.ctx.size() + 6, chunk_bytes());
+    pool.open(&fl, 2 * (int)fl.ctx.size() + 6, chunk_bytes());
     const std::vector<const char*> stdin_only{"-"};
     stream_reads(fl, pool, stdin_only, false,
                  [&](int, rkg_ctx* c, Chunk& ch) { RK(c, rkg_classify_batch(c, ch.data(), ch.offs, (int64_t)ch.nreads, occ, ch.hits)); },
@@ -982,7 +1022,7 @@ int main_hpv16(int argc, char** argv) {
     };
     const auto write_out = [](Chunk& c) { fwrite(c.out.data(), 1, c.out.size(), stdout); };
     ChunkPool pool;
-    pool.open(fl.ctx[0], 2 * (int)fl.ctx.size() + 6 + 3 * parse_threads(), chunk_bytes());
+    pool.open(&fl, 2 * (int)fl.ctx.size() + 6 + 3 * parse_threads(), chunk_bytes());
     if (!(do_read_depth && any_unrewindable(read_files))) {
         if (do_read_depth) {                                // src/rkmh.cpp:2514-2530: valid windows only
             fl.each([&](int, rkg_ctx* c) { RK(c, rkg_count_reset(c)); });
@@ -1037,6 +1077,15 @@ int main(int argc, char** argv) {
             }
             pool.release(c);
         });
+        return 0;
+    }
+    if (cmd == "parse-count") {      // host-only: time the streaming front-end's parser alone (records and bases seen)
+        std::vector<const char*> files(argv + 2, argv + argc);
+        ChunkPool pool;
+        pool.open(nullptr, 6 + 3 * parse_threads(), chunk_bytes());
+        uint64_t nb = 0, nchunks = 0;
+        const uint64_t nrec = parse_files(files, pool, true, [&](Chunk* c) { nb += (uint64_t)c->offs[c->nreads]; ++nchunks; pool.release(c); });
+        printf("records %llu bases %llu chunks %llu\n", (unsigned long long)nrec, (unsigned long long)nb, (unsigned long long)nchunks);
         return 0;
     }
     if (cmd == "parse") {            // host-only debugging aid: dump the records the parser sees (no GPU needed)

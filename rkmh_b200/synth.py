@@ -63,19 +63,26 @@ def write_fastq(path, bases, offs, prefix="r"):
     length = int(offs[1] - offs[0]) if n else 0
     assert n == 0 or (np.diff(offs) == length).all(), "fixed-length batches only"
     mat = bases[: n * length].reshape(n, length)
+    pre = prefix.encode()
+    rec = 1 + len(pre) + 9 + 1 + length + 3 + length + 1          # "@" prefix 9 digits "\n" bases "\n+\n" quality "\n"
     with open(path, "wb") as fh:
-        step = 100000
-        qual = b"I" * length
+        step = 200000
         for c0 in range(0, n, step):
             rows = mat[c0:c0 + step]
-            parts = []
-            for i in range(rows.shape[0]):
-                parts.append(b"@%s%09d\n" % (prefix.encode(), c0 + i))
-                parts.append(rows[i].tobytes())
-                parts.append(b"\n+\n")
-                parts.append(qual)
-                parts.append(b"\n")
-            fh.write(b"".join(parts))
+            m = rows.shape[0]
+            out = np.empty((m, rec), np.uint8)
+            out[:, 0] = ord("@")
+            out[:, 1:1 + len(pre)] = np.frombuffer(pre, np.uint8)
+            idx = np.arange(c0, c0 + m, dtype=np.int64)
+            for d in range(9):
+                out[:, 1 + len(pre) + 8 - d] = 48 + (idx // 10 ** d) % 10
+            p = 1 + len(pre) + 9
+            out[:, p] = 10
+            out[:, p + 1:p + 1 + length] = rows
+            out[:, p + 1 + length:p + 4 + length] = np.frombuffer(b"\n+\n", np.uint8)
+            out[:, p + 4 + length:p + 4 + 2 * length] = ord("I")
+            out[:, rec - 1] = 10
+            fh.write(out.tobytes())
 
 
 def ont_reads(rng, genomes, n, length, sub=0.04, ins=0.03, dele=0.03, chunk=2048):

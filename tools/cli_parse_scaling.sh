@@ -10,10 +10,10 @@ import sys, gzip, shutil, os
 import numpy as np
 sys.path.insert(0, os.getcwd())
 from rkmh_b200.fastx import load_sequences
-from rkmh_b200.synth import sample_reads, write_fastq
+from rkmh_b200.synth import fast_sample_reads, write_fastq
 n, w = int(sys.argv[1]), sys.argv[2]
 _, refs, _ = load_sequences(["tests/golden/data/all_pave_ref.fa.gz"])
-b, o = sample_reads(np.random.default_rng(2), refs, n, 150)
+b, o = fast_sample_reads(2, refs, 0, n, 150)
 write_fastq(os.path.join(w, "reads.fq"), b, o)
 with gzip.open("tests/golden/data/all_pave_ref.fa.gz", "rb") as fi, open(os.path.join(w, "refs.fa"), "wb") as fo:
     shutil.copyfileobj(fi, fo)
@@ -30,4 +30,8 @@ for t in 1 2 4 8; do
   done
   echo "parse_threads=$t best_of_3_seconds=$best reads=$N md5=$(md5sum < "$W/out.txt" | cut -c1-12)"
 done
+echo "--- stage marks (RKMH_TIMING=1), default parser threads"
+RKMH_TIMING=1 rkmh_b200/bin/rkmh stream -r "$W/refs.fa" -f "$W/reads.fq" -k 12 -s 1000 2>&1 > "$W/out.txt" | grep "rkmh:" || true
+echo "--- parser alone (parse-count)"
+for t in 1 4 8; do s=$(date +%s.%N); RKMH_PARSE_THREADS=$t rkmh_b200/bin/rkmh parse-count "$W/reads.fq" > /dev/null; e=$(date +%s.%N); echo "parse-count threads=$t seconds=$(python -c "print(round($e-$s,3))")"; done
 rm -rf "$W"
