@@ -379,23 +379,33 @@ size_t parse_segment_bytes(size_t cap_bases) {          // about one chunk of ba
     return 2 * cap_bases;
 }
 
-// A plain (uncompressed, regular) FASTQ file mapped into memory for the parallel parser.
-struct MappedFile {
-    const char* data = nullptr; size_t size = 0; int fd = -1;
+// A plain (uncompressed, regular) FASTQ file for the parallel parser.  Segments are read with pread() into per-thread
+// buffers, not mapped: eight threads page-faulting a mapping hold the process's mmap lock against the CUDA driver, whose
+// start-up (itself full of mmap calls) ran 2.3 s instead of 1.2 s beside them on the B200 box.
+struct PlainFile {
+    size_t size = 0; int fd = -1;
     bool open(const char* path) {
         if (path[0] == '-' && path[1] == 0) return false;
         fd = ::open(path, O_RDONLY);
         if (fd < 0) return false;
         struct stat st;
         if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 4) return false;
-        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-        if (m == MAP_FAILED) return false;
-        data = (const char*)m; size = (size_t)st.st_size;
-        if ((unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b) return false;    // gzip: sequential reader
-        madvise(m, size, MADV_SEQUENTIAL);
+        size = (size_t)st.st_size;
+        unsigned char magic[2] = {0, 0};
+        if (pread(fd, magic, 2, 0) != 2 || (magic[0] == 0x1f && magic[1] == 0x8b)) return false;   // gzip: sequential reader
+        posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
         return true;
     }
-    ~MappedFile() { if (data) munmap((void*)data, size); if (fd >= 0) ::close(fd); }
+    // bytes [lo, hi) into dst; false on a short read
+    bool read(size_t lo, size_t hi, char* dst) const {
+        while (lo < hi) {
+            const ssize_t got = pread(fd, dst, hi - lo, (off_t)lo);
+            if (got <= 0) return false;
+            lo += (size_t)got; dst += got;
+        }
+        return true;
+    }
+    ~PlainFile() { if (fd >= 0) ::close(fd); }
 };
 
 // Appends a record to the chunk being filled, closing it (-> `full`) and taking a new one from the pool when needed.
@@ -425,28 +435,50 @@ struct ChunkFiller {
 // everything was parsed here, 0 when nothing was).
 size_t parse_parallel_prefix(const char* path, ChunkPool& pool, bool keep_qual, int threads, size_t seg_bytes,
                              const std::function<void(Chunk*)>& emit_chunk, uint64_t& nrecords) {
-    MappedFile mf;
-    if (threads < 2 || !mf.open(path) || mf.size < 2 * seg_bytes) return 0;
-    const char* d = mf.data;
-    const size_t size = mf.size, npos = (size_t)-1;
+    PlainFile pf;
+    if (threads < 2 || !pf.open(path) || pf.size < 2 * seg_bytes) return 0;
+    const size_t size = pf.size, npos = (size_t)-1;
+    // what a thread reads beyond its segment: the record that straddles the end, and the next one (which the search for a
+    // segment's first record wants to see whole); a record that needs more ends the parallel prefix
+    const size_t slack = std::min<size_t>(std::max<size_t>(seg_bytes / 2, 1 << 16), 4 << 20);
+    // RKMH_PARSE_MMAP=1: map the file instead (A/B timing of the two ways to read it)
+    const char* mapped = nullptr;
+    if (getenv("RKMH_PARSE_MMAP")) {
+        void* mp = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, pf.fd, 0);
+        if (mp != MAP_FAILED) { mapped = (const char*)mp; madvise(mp, size, MADV_SEQUENTIAL); }
+    }
+    struct Unmap { const char* p; size_t n; ~Unmap() { if (p) munmap((void*)p, n); } } unmap{mapped, size};
     size_t start0 = 0;
-    while (start0 < size && d[start0] != '>' && d[start0] != '@') ++start0;
-    if (start0 >= size || d[start0] != '@') return 0;
+    {
+        std::vector<char> head(std::min<size_t>(size, 1 << 16));
+        if (!pf.read(0, head.size(), head.data())) return 0;
+        while (start0 < head.size() && head[start0] != '>' && head[start0] != '@') ++start0;
+        if (start0 >= head.size() || head[start0] != '@') return 0;
+    }
     struct Seg { size_t first = (size_t)-1, end = (size_t)-1; bool anomaly = false, done = false; std::vector<Chunk*> chunks; uint64_t nrec = 0; };
     const size_t nseg = (size + seg_bytes - 1) / seg_bytes;
     std::vector<Seg> segs(nseg);
     std::mutex m; std::condition_variable cv;
     size_t next_seg = 0, verified = 0;
     std::atomic<bool> abort_all{false};
-    auto well_formed_at = [&](size_t pos, rkhost::Record& r, size_t& next) -> bool {     // d[pos] == '@'
-        size_t consumed = 0; int nh = -1;
-        if (rkhost::fastx_fast_record(d + pos + 1, d + size, true, r, consumed, nh) != 1) return false;
-        next = nh == -1 ? size : pos + consumed;
-        return true;
-    };
-    auto parse_segment = [&](size_t i) {
+    auto parse_segment = [&](size_t i, std::vector<char>& buf) {
         Seg& sg = segs[i];
         const size_t lo = i * seg_bytes, hi = std::min(size, lo + seg_bytes);
+        // file bytes [rlo, rhi) are in buf; d[x] is file byte x for x in that range
+        const size_t rlo = lo > 0 ? lo - 1 : 0, rhi = std::min(size, hi + slack);
+        sg.first = npos;
+        const char* d = mapped;
+        if (!mapped) {
+            if (buf.size() < rhi - rlo) buf.resize(rhi - rlo);
+            if (!pf.read(rlo, rhi, buf.data())) { sg.anomaly = true; return; }
+            d = buf.data() - rlo;
+        }
+        auto well_formed_at = [&](size_t pos, rkhost::Record& r, size_t& next) -> bool {     // d[pos] == '@'
+            size_t consumed = 0; int nh = -1;
+            if (rkhost::fastx_fast_record(d + pos + 1, d + rhi, rhi == size, r, consumed, nh) != 1) return false;
+            next = nh == -1 ? size : pos + consumed;
+            return true;
+        };
         rkhost::Record r; size_t nx = 0, nx2 = 0;
         size_t pos = npos;
         if (i == 0) pos = start0;
@@ -456,7 +488,7 @@ size_t parse_parallel_prefix(const char* path, ChunkPool& pool, bool keep_qual, 
                 if (!hit) break;
                 p = (size_t)(hit - d);
                 if (d[p - 1] != '\n') continue;
-                if (well_formed_at(p, r, nx) && (nx >= size || (d[nx] == '@' && well_formed_at(nx, r, nx2)))) { pos = p; break; }
+                if (well_formed_at(p, r, nx) && (nx >= size || (nx < rhi && d[nx] == '@' && well_formed_at(nx, r, nx2)))) { pos = p; break; }
             }
         sg.first = pos;
         if (pos == npos) return;
@@ -478,6 +510,7 @@ size_t parse_parallel_prefix(const char* path, ChunkPool& pool, bool keep_qual, 
     std::vector<std::thread> team;
     for (int t = 0; t < threads; ++t)
         team.emplace_back([&] {
+            std::vector<char> buf;                       // this thread's segment buffer, reused (touched once)
             for (;;) {
                 size_t i;
                 {
@@ -486,7 +519,7 @@ size_t parse_parallel_prefix(const char* path, ChunkPool& pool, bool keep_qual, 
                     if (abort_all || next_seg >= nseg) return;
                     i = next_seg++;
                 }
-                parse_segment(i);
+                parse_segment(i, buf);
                 { std::lock_guard<std::mutex> g(m); segs[i].done = true; }
                 cv.notify_all();
             }
@@ -601,6 +634,7 @@ uint64_t stream_reads(Fleet& fl, ChunkPool& pool, const std::vector<const char*>
         emit(*c);
         pool.release(c);
     }
+    tmark("results written");
     reader.join();
     for (auto& w : workers) w.join();
     for (int i = 0; i < nformat; ++i) format_q.push(nullptr);

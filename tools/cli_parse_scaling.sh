@@ -19,19 +19,24 @@ with gzip.open("tests/golden/data/all_pave_ref.fa.gz", "rb") as fi, open(os.path
     shutil.copyfileobj(fi, fo)
 PY
 cat "$W/reads.fq" > /dev/null
-for t in 1 2 4 8; do
+for t in 1 4 8 "8 RKMH_PARSE_MMAP=1" "4 RKMH_PARSE_MMAP=1"; do
+  set -- $t; t=$1; extra=${2:-RKMH_NOP=1}
   best=999
   for rep in 1 2 3; do
     s=$(date +%s.%N)
-    RKMH_PARSE_THREADS=$t rkmh_b200/bin/rkmh stream -r "$W/refs.fa" -f "$W/reads.fq" -k 12 -s 1000 > "$W/out.txt" 2>/dev/null
+    env $extra RKMH_PARSE_THREADS=$t rkmh_b200/bin/rkmh stream -r "$W/refs.fa" -f "$W/reads.fq" -k 12 -s 1000 > "$W/out.txt" 2>/dev/null
     e=$(date +%s.%N)
     d=$(python -c "print(round($e-$s,3))")
     best=$(python -c "print(min($best,$d))")
   done
-  echo "parse_threads=$t best_of_3_seconds=$best reads=$N md5=$(md5sum < "$W/out.txt" | cut -c1-12)"
+  echo "parse_threads=$t $extra best_of_3_seconds=$best reads=$N md5=$(md5sum < "$W/out.txt" | cut -c1-12)"
 done
 echo "--- stage marks (RKMH_TIMING=1), default parser threads"
 RKMH_TIMING=1 rkmh_b200/bin/rkmh stream -r "$W/refs.fa" -f "$W/reads.fq" -k 12 -s 1000 2>&1 > "$W/out.txt" | grep "rkmh:" || true
+echo "--- stage marks, one parser thread"
+RKMH_PARSE_THREADS=1 RKMH_TIMING=1 rkmh_b200/bin/rkmh stream -r "$W/refs.fa" -f "$W/reads.fq" -k 12 -s 1000 2>&1 > "$W/out.txt" | grep "rkmh:" || true
+echo "--- empty read file (start-up only)"
+: > "$W/empty.fq"; s=$(date +%s.%N); rkmh_b200/bin/rkmh stream -r "$W/refs.fa" -f "$W/empty.fq" -k 12 -s 1000 > /dev/null 2>&1; e=$(date +%s.%N); echo "startup_seconds=$(python -c "print(round($e-$s,3))")"
 echo "--- parser alone (parse-count)"
 for t in 1 4 8; do s=$(date +%s.%N); RKMH_PARSE_THREADS=$t rkmh_b200/bin/rkmh parse-count "$W/reads.fq" > /dev/null; e=$(date +%s.%N); echo "parse-count threads=$t seconds=$(python -c "print(round($e-$s,3))")"; done
 rm -rf "$W"
