@@ -88,7 +88,13 @@ int rkg_host_free(rkg_ctx* ctx, void* ptr);
  *                      reference, zero included (filter, src/rkmh.cpp:347-355). */
 int rkg_load_refs(rkg_ctx* ctx, const char* bases, const int64_t* offs, int nrefs,
                   int max_ref_occ, int per_sample_set);
-/* Parity/debug: copy the reference sketches out (sketches is [nrefs * s], lens is [nrefs]). */
+/* Pre-hashed references (the reference's --pre-references / -R option, src/rkmh.cpp:640, 660-662, parsed and never
+ * acted on): build the table from sketches computed earlier -- by rkg_get_ref_sketches, `rkmh hash -o`, or
+ * any minhashes() -- instead of from sequences.  sketches is [nrefs * s] with each row ascending, non-zero, lens[r] <= s
+ * long (checked), for the k list and sketch size of rkg_set_params.  Classification results are those of rkg_load_refs
+ * on the sequences the sketches were made from. */
+int rkg_load_ref_sketches(rkg_ctx* ctx, const uint64_t* sketches, const int32_t* lens, int nrefs);
+/* Copy the reference sketches out (sketches is [nrefs * s], lens is [nrefs]). */
 int rkg_get_ref_sketches(rkg_ctx* ctx, uint64_t* sketches, int32_t* lens);
 
 /* ---- -M : read-set k-mer count table ------------------------------------------------------------- */
@@ -109,6 +115,12 @@ int rkg_count_table(rkg_ctx* ctx, void** device_ptr, uint64_t* nslots);
  * all-reduce (sum, int32) device_ptr[0 .. nslots) in place, then go on with rkg_classify_batch / rkg_count_table: the
  * summed array is folded at its next use.  RKG_ERR_STATE when the memoised path is not active (use rkg_count_table). */
 int rkg_count_partial(rkg_ctx* ctx, int count_zeros, void** device_ptr, uint64_t* nslots);
+/* Persistence of a count table (the reference's --read-kmer-map-file / -p and --ref-kmer-map-file / -q options,
+ * src/rkmh.cpp:641-642, 744-761: parsed, loader commented out; docs/todo.md:1 "hash-counter serialization"): the
+ * non-zero slots of table `which` (0 = read table, 1 = reference table) as (slot, count) pairs.  rkg_count_export with
+ * slots == NULL only returns their number in *n; rkg_count_import clears the table and sets the given slots. */
+int rkg_count_export(rkg_ctx* ctx, int which, uint32_t* slots, int32_t* counts, uint64_t cap, uint64_t* n);
+int rkg_count_import(rkg_ctx* ctx, int which, const uint32_t* slots, const int32_t* counts, uint64_t n);
 /* Parity/debug: counts[keys[i] % read_table_size] for n keys. */
 int rkg_count_lookup(rkg_ctx* ctx, const uint64_t* keys, int64_t n, int32_t* out);
 

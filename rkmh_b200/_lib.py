@@ -17,7 +17,7 @@ RKG_SYMBOLS = [
     "rkg_batch_results", "rkg_batch_ingest", "rkg_batch_set_stream", "rkg_batch_free", "rkg_synchronize", "rkg_sketch_batch", "rkg_hash_batch",
     "rkg_sketch_shard", "rkg_merge_sketches", "rkg_launch_count", "rkg_profile_enable", "rkg_profile_read",
     "rkg_set_memo", "rkg_memo_active", "rkg_count_partial", "rkg_classify_fixed", "rkg_count_fixed", "rkg_copy_probe",
-    "rkg_load_ref_sets", "rkg_classify_sets",
+    "rkg_load_ref_sets", "rkg_classify_sets", "rkg_load_ref_sketches", "rkg_count_export", "rkg_count_import",
 ]
 
 
@@ -58,6 +58,9 @@ def load():
     lib.rkg_count_fixed.argtypes = [P, P, L, L, I]
     lib.rkg_copy_probe.argtypes = [P, P, P, L, L, P]
     lib.rkg_load_ref_sets.argtypes = [P, P, P, I]
+    lib.rkg_load_ref_sketches.argtypes = [P, P, P, I]
+    lib.rkg_count_export.argtypes = [P, I, P, P, U, C.POINTER(U)]
+    lib.rkg_count_import.argtypes = [P, I, P, P, U]
     lib.rkg_classify_sets.argtypes = [P, P, P, L, I, I, P, P]
     lib.rkg_classify_batch.argtypes = [P, P, P, L, I, P]
     lib.rkg_batch_upload.argtypes = [P, P, P, L, PP]

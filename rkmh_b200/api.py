@@ -130,6 +130,27 @@ class RkmhGpu:
                                            int(max_ref_occ), int(per_sample_set)))
         self.nrefs = len(offs) - 1
 
+    def load_ref_sketches(self, sketches, lens):
+        """Pre-hashed references: [nrefs, s] ascending non-zero rows + lengths (rkg_load_ref_sketches)."""
+        sk = np.ascontiguousarray(sketches, dtype=np.uint64)
+        ln = np.ascontiguousarray(lens, dtype=np.int32)
+        assert sk.ndim == 2 and sk.shape == (len(ln), self.s)
+        self._check(self.lib.rkg_load_ref_sketches(self.handle, sk.ctypes.data, ln.ctypes.data, len(ln)))
+        self.nrefs = len(ln)
+
+    def count_export(self, which=0):
+        """Non-zero slots of a count table: (uint32 slots, int32 counts), unordered."""
+        n = C.c_uint64()
+        self._check(self.lib.rkg_count_export(self.handle, int(which), None, None, 0, C.byref(n)))
+        slots, vals = np.zeros(max(n.value, 1), np.uint32), np.zeros(max(n.value, 1), np.int32)
+        self._check(self.lib.rkg_count_export(self.handle, int(which), slots.ctypes.data, vals.ctypes.data, n.value, C.byref(n)))
+        return slots[:n.value], vals[:n.value]
+
+    def count_import(self, slots, vals, which=0):
+        slots = np.ascontiguousarray(slots, dtype=np.uint32)
+        vals = np.ascontiguousarray(vals, dtype=np.int32)
+        self._check(self.lib.rkg_count_import(self.handle, int(which), slots.ctypes.data, vals.ctypes.data, len(slots)))
+
     def ref_sketches(self):
         sk = np.zeros((self.nrefs, self.s), np.uint64)
         lens = np.zeros(self.nrefs, np.int32)

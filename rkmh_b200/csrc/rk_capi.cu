@@ -651,6 +651,57 @@ int launch_sketch(rkg_ctx* ctx, rkg_batch* b, CountTable ct, int filter_mode, in
     return RKG_OK;
 }
 
+// The (hash, rank) -> reference-bitset table (+ the memoised tables) from the sorted sketches in ctx->ref_sketches / ref_lens.
+int build_ref_table(rkg_ctx* ctx, int nrefs, cudaStream_t st) {
+    const int s = ctx->s;
+    int rc = RKG_OK;
+    // table geometry
+    // The table is dense in the references: cap x (1 + ceil(nrefs / 64)) words with cap >= 2 nrefs s, i.e. quadratic in
+    // the number of references (5,000 references at s = 1000 take about 11 GB; include/rkmh_gpu.h states the limit).
+    const i64 nent = (i64)nrefs * s;
+    const u32 cap = (u32)next_pow2(std::max<i64>(2 * nent, 1024));
+    const u32 nb = (u32)((nrefs + 63) / 64);
+    RefTable tb{};
+    tb.cap_mask = cap - 1; tb.nb = nb; tb.stride = 1 + nb; tb.nrefs = (u32)nrefs;
+    int flog2 = 10;
+    while (flog2 < 20 && (1LL << flog2) < 16 * nent) ++flog2;
+    tb.filter_log2 = (u32)flog2;
+    CK(ctx->tb_entries.ensure(sizeof(u64) * (size_t)cap * tb.stride));
+    CK(ctx->tb_maxmult.ensure(sizeof(u32) * (size_t)cap));
+    CK(ctx->tb_dupbase.ensure(sizeof(u32) * (size_t)cap));
+    CK(ctx->tb_dupbits.ensure(sizeof(u64) * (size_t)std::max<i64>(nent, 1) * nb));
+    CK(ctx->tb_filter.ensure(sizeof(u32) * ((size_t)1 << flog2) / 32));
+    CK(ctx->tb_cursor.ensure(256));
+    CK(cudaMemsetAsync(ctx->tb_entries.p, 0, sizeof(u64) * (size_t)cap * tb.stride, st));
+    CK(cudaMemsetAsync(ctx->tb_maxmult.p, 0, sizeof(u32) * (size_t)cap, st));
+    CK(cudaMemsetAsync(ctx->tb_dupbase.p, 0, sizeof(u32) * (size_t)cap, st));
+    CK(cudaMemsetAsync(ctx->tb_dupbits.p, 0, sizeof(u64) * (size_t)std::max<i64>(nent, 1) * nb, st));
+    CK(cudaMemsetAsync(ctx->tb_filter.p, 0, sizeof(u32) * ((size_t)1 << flog2) / 32, st));
+    CK(cudaMemsetAsync(ctx->tb_cursor.p, 0, 256, st));
+    tb.entries = ctx->tb_entries.as<u64>();
+    tb.maxmult = ctx->tb_maxmult.as<u32>();
+    tb.dup_base = ctx->tb_dupbase.as<u32>();
+    tb.dup_bits = ctx->tb_dupbits.as<u64>();
+    tb.filter = ctx->tb_filter.as<u32>();
+    {
+        Timed t(ctx, st, K_TABLE);
+        int grid = (int)std::min<i64>((nent + 255) / 256, (i64)ctx->sm_count * 8);
+        table_insert_kernel<<<grid, 256, 0, st>>>(ctx->ref_sketches.as<u64>(), ctx->ref_lens.as<int>(), nrefs, s, tb,
+                                                         ctx->tb_filter.as<u32>());
+        table_alloc_dup_kernel<<<(int)std::min<i64>((cap + 255) / 256, (i64)ctx->sm_count * 8), 256, 0, st>>>(
+            tb, ctx->tb_cursor.as<u32>());
+        table_fill_dup_kernel<<<grid, 256, 0, st>>>(ctx->ref_sketches.as<u64>(), ctx->ref_lens.as<int>(), nrefs, s, tb);
+        ctx->launches += 2;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    ctx->tb = tb;
+    ctx->set_table = false;
+    if ((rc = memo_build(ctx, st))) return rc;
+    ctx->refs_loaded = true;
+    return RKG_OK;
+}
+
 int ensure_slots(rkg_ctx* ctx) {
     for (int i = 0; i < 2; ++i)
         if (!ctx->slots[i]) { int rc = batch_alloc(ctx, &ctx->slots[i]); if (rc) return rc; }
@@ -872,51 +923,31 @@ int rkg_load_refs(rkg_ctx* ctx, const char* bases, const int64_t* offs, int nref
                             ctx->ref_lens.as<int>(), nullptr, nullptr)))
         return rc;
 
-    // table geometry
-    // The table is dense in the references: cap x (1 + ceil(nrefs / 64)) words with cap >= 2 nrefs s, i.e. quadratic in
-    // the number of references (5,000 references at s = 1000 take about 11 GB; include/rkmh_gpu.h states the limit).
-    const i64 nent = (i64)nrefs * s;
-    const u32 cap = (u32)next_pow2(std::max<i64>(2 * nent, 1024));
-    const u32 nb = (u32)((nrefs + 63) / 64);
-    RefTable tb{};
-    tb.cap_mask = cap - 1; tb.nb = nb; tb.stride = 1 + nb; tb.nrefs = (u32)nrefs;
-    int flog2 = 10;
-    while (flog2 < 20 && (1LL << flog2) < 16 * nent) ++flog2;
-    tb.filter_log2 = (u32)flog2;
-    CK(ctx->tb_entries.ensure(sizeof(u64) * (size_t)cap * tb.stride));
-    CK(ctx->tb_maxmult.ensure(sizeof(u32) * (size_t)cap));
-    CK(ctx->tb_dupbase.ensure(sizeof(u32) * (size_t)cap));
-    CK(ctx->tb_dupbits.ensure(sizeof(u64) * (size_t)std::max<i64>(nent, 1) * nb));
-    CK(ctx->tb_filter.ensure(sizeof(u32) * ((size_t)1 << flog2) / 32));
-    CK(ctx->tb_cursor.ensure(256));
-    CK(cudaMemsetAsync(ctx->tb_entries.p, 0, sizeof(u64) * (size_t)cap * tb.stride, b->stream));
-    CK(cudaMemsetAsync(ctx->tb_maxmult.p, 0, sizeof(u32) * (size_t)cap, b->stream));
-    CK(cudaMemsetAsync(ctx->tb_dupbase.p, 0, sizeof(u32) * (size_t)cap, b->stream));
-    CK(cudaMemsetAsync(ctx->tb_dupbits.p, 0, sizeof(u64) * (size_t)std::max<i64>(nent, 1) * nb, b->stream));
-    CK(cudaMemsetAsync(ctx->tb_filter.p, 0, sizeof(u32) * ((size_t)1 << flog2) / 32, b->stream));
-    CK(cudaMemsetAsync(ctx->tb_cursor.p, 0, 256, b->stream));
-    tb.entries = ctx->tb_entries.as<u64>();
-    tb.maxmult = ctx->tb_maxmult.as<u32>();
-    tb.dup_base = ctx->tb_dupbase.as<u32>();
-    tb.dup_bits = ctx->tb_dupbits.as<u64>();
-    tb.filter = ctx->tb_filter.as<u32>();
-    {
-        Timed t(ctx, b->stream, K_TABLE);
-        int grid = (int)std::min<i64>((nent + 255) / 256, (i64)ctx->sm_count * 8);
-        table_insert_kernel<<<grid, 256, 0, b->stream>>>(ctx->ref_sketches.as<u64>(), ctx->ref_lens.as<int>(), nrefs, s, tb,
-                                                         ctx->tb_filter.as<u32>());
-        table_alloc_dup_kernel<<<(int)std::min<i64>((cap + 255) / 256, (i64)ctx->sm_count * 8), 256, 0, b->stream>>>(
-            tb, ctx->tb_cursor.as<u32>());
-        table_fill_dup_kernel<<<grid, 256, 0, b->stream>>>(ctx->ref_sketches.as<u64>(), ctx->ref_lens.as<int>(), nrefs, s, tb);
-        ctx->launches += 2;
+    return build_ref_table(ctx, nrefs, b->stream);
+}
+
+int rkg_load_ref_sketches(rkg_ctx* ctx, const uint64_t* sketches, const int32_t* lens, int nrefs) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_load_ref_sketches before rkg_set_params");
+    if (!sketches || !lens || nrefs < 1) return fail(ctx, RKG_ERR_ARG, "rkg_load_ref_sketches: need at least one reference");
+    const int s = ctx->s;
+    if (2 * (i64)nrefs * s > ((i64)1 << 30))
+        return fail(ctx, RKG_ERR_ARG, "rkg_load_ref_sketches: %d references x sketch size %d exceeds the 2^29 table entries supported", nrefs, s);
+    for (int r = 0; r < nrefs; ++r) {                       // what minhashes() guarantees: ascending, non-zero, at most s
+        if (lens[r] < 0 || lens[r] > s) return fail(ctx, RKG_ERR_ARG, "rkg_load_ref_sketches: sketch %d has length %d (sketch size %d)", r, lens[r], s);
+        const uint64_t* sk = sketches + (size_t)r * s;
+        for (int i = 0; i < lens[r]; ++i)
+            if (sk[i] == 0 || (i > 0 && sk[i] < sk[i - 1])) return fail(ctx, RKG_ERR_ARG, "rkg_load_ref_sketches: sketch %d is not an ascending list of non-zero hashes", r);
     }
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(b->stream));
-    ctx->tb = tb;
-    ctx->set_table = false;
-    if ((rc = memo_build(ctx, b->stream))) return rc;
-    ctx->refs_loaded = true;
-    return RKG_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    ctx->memo_ready = false; ctx->refs_loaded = false;
+    ctx->nrefs = nrefs;
+    CK(ctx->ref_sketches.ensure(sizeof(u64) * (size_t)nrefs * s));
+    CK(ctx->ref_lens.ensure(sizeof(int) * (size_t)nrefs));
+    CK(cudaMemcpyAsync(ctx->ref_sketches.p, sketches, sizeof(u64) * (size_t)nrefs * s, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ref_lens.p, lens, sizeof(int) * (size_t)nrefs, cudaMemcpyHostToDevice, ctx->stream));
+    return build_ref_table(ctx, nrefs, ctx->stream);
 }
 
 int rkg_get_ref_sketches(rkg_ctx* ctx, uint64_t* sketches, int32_t* lens) {
@@ -972,6 +1003,78 @@ int rkg_count_partial(rkg_ctx* ctx, int count_zeros, void** device_ptr, uint64_t
     *device_ptr = ctx->memo.code_counts;
     *nslots = (uint64_t)ctx->memo.ncodes + MEMO_PARTIAL_PAD;
     return RKG_OK;
+}
+
+// which: 0 = read count table, 1 = reference count table
+static CountTable* pick_table(rkg_ctx* ctx, int which, u64* nslots) {
+    if (which == 0 && ctx->read_ct.counts) { *nslots = ctx->read_tbl_size; return &ctx->read_ct; }
+    if (which == 1 && ctx->ref_ct.counts) { *nslots = ctx->ref_tbl_size; return &ctx->ref_ct; }
+    return nullptr;
+}
+
+int rkg_count_export(rkg_ctx* ctx, int which, uint32_t* slots, int32_t* counts, uint64_t cap, uint64_t* n) {
+    if (!ctx || !n) return RKG_ERR_ARG;
+    u64 nslots = 0;
+    CountTable* ct = pick_table(ctx, which, &nslots);
+    if (!ct) return fail(ctx, RKG_ERR_STATE, "rkg_count_export: table %d does not exist (rkg_set_params)", which);
+    if (nslots > 0xFFFFFFFFULL) return fail(ctx, RKG_ERR_ARG, "rkg_count_export: tables of more than 2^32 slots are not supported");
+    CK(cudaSetDevice(ctx->device));
+    if (which == 0) { int rc = memo_flush(ctx); if (rc) return rc; }
+    CK(cudaDeviceSynchronize());
+    DevBuf d_s, d_v, d_n;
+    int rc = RKG_OK;
+    do {
+        const u64 dcap = (slots && counts) ? cap : 0;
+        if (d_s.ensure(sizeof(u32) * (size_t)std::max<u64>(dcap, 1)) || d_v.ensure(sizeof(int) * (size_t)std::max<u64>(dcap, 1)) || d_n.ensure(64)) {
+            rc = fail(ctx, RKG_ERR_NOMEM, "rkg_count_export: device allocation failed"); break;
+        }
+        cudaMemsetAsync(d_n.p, 0, 64, ctx->stream);
+        {
+            Timed t(ctx, ctx->stream, K_MEMO_MAINT);
+            count_export_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ct->counts, nslots, d_s.as<u32>(), d_v.as<int>(), dcap,
+                                                                           d_n.as<unsigned long long>());
+        }
+        unsigned long long found = 0;
+        cudaMemcpyAsync(&found, d_n.p, sizeof(found), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = fail(ctx, RKG_ERR_CUDA, "rkg_count_export: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        *n = found;
+        if (dcap > 0) {
+            if (found > dcap) { rc = fail(ctx, RKG_ERR_ARG, "rkg_count_export: %llu non-zero slots, room for %llu", found, (unsigned long long)dcap); break; }
+            cudaMemcpy(slots, d_s.p, sizeof(u32) * (size_t)found, cudaMemcpyDeviceToHost);
+            cudaMemcpy(counts, d_v.p, sizeof(int) * (size_t)found, cudaMemcpyDeviceToHost);
+        }
+    } while (0);
+    d_s.release(); d_v.release(); d_n.release();
+    return rc;
+}
+
+int rkg_count_import(rkg_ctx* ctx, int which, const uint32_t* slots, const int32_t* counts, uint64_t n) {
+    if (!ctx || (n > 0 && (!slots || !counts))) return RKG_ERR_ARG;
+    u64 nslots = 0;
+    CountTable* ct = pick_table(ctx, which, &nslots);
+    if (!ct) return fail(ctx, RKG_ERR_STATE, "rkg_count_import: table %d does not exist (rkg_set_params)", which);
+    for (u64 i = 0; i < n; ++i)
+        if ((u64)slots[i] >= nslots) return fail(ctx, RKG_ERR_ARG, "rkg_count_import: slot %u of a %llu-slot table", slots[i], (unsigned long long)nslots);
+    CK(cudaSetDevice(ctx->device));
+    if (which == 0) { int rc = rkg_count_reset(ctx); if (rc) return rc; }
+    else { CK(cudaDeviceSynchronize()); CK(cudaMemsetAsync(ct->counts, 0, sizeof(int) * nslots, ctx->stream)); }
+    if (n == 0) { CK(cudaStreamSynchronize(ctx->stream)); return RKG_OK; }
+    DevBuf d_s, d_v;
+    int rc = RKG_OK;
+    do {
+        if (d_s.ensure(sizeof(u32) * (size_t)n) || d_v.ensure(sizeof(int) * (size_t)n)) { rc = fail(ctx, RKG_ERR_NOMEM, "rkg_count_import: device allocation failed"); break; }
+        cudaMemcpyAsync(d_s.p, slots, sizeof(u32) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_v.p, counts, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+        {
+            Timed t(ctx, ctx->stream, K_MEMO_MAINT);
+            count_import_kernel<<<(int)std::min<u64>((n + 255) / 256, (u64)ctx->sm_count * 8), 256, 0, ctx->stream>>>(ct->counts, nslots, d_s.as<u32>(),
+                                                                                                                    d_v.as<int>(), n);
+        }
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = fail(ctx, RKG_ERR_CUDA, "rkg_count_import: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    d_s.release(); d_v.release();
+    if (which == 0) ctx->memo_occ_stale = true;
+    return rc;
 }
 
 int rkg_count_lookup(rkg_ctx* ctx, const uint64_t* keys, int64_t n, int32_t* out) {

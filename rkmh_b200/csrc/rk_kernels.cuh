@@ -199,6 +199,23 @@ count_distinct_kernel(const u64* __restrict__ sorted, const i64* __restrict__ of
     }
 }
 
+// Persistence of a lossy count table: its non-zero slots as (slot, count) pairs, and back.
+__global__ void __launch_bounds__(256)
+count_export_kernel(const int* __restrict__ counts, u64 nslots, u32* __restrict__ slots, int* __restrict__ vals, u64 cap,
+                    unsigned long long* __restrict__ n) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += (u64)gridDim.x * blockDim.x) {
+        const int c = counts[i];
+        if (c == 0) continue;
+        const unsigned long long at = atomicAdd(n, 1ULL);
+        if (at < cap) { slots[at] = (u32)i; vals[at] = c; }
+    }
+}
+__global__ void __launch_bounds__(256)
+count_import_kernel(int* __restrict__ counts, u64 nslots, const u32* __restrict__ slots, const int* __restrict__ vals, u64 n) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        if ((u64)slots[i] < nslots) counts[slots[i]] = vals[i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // Block-wide helpers.
 

@@ -37,6 +37,7 @@
 
 #include "../../include/rkmh_gpu.h"
 #include "fastx.hpp"
+#include "sketch_io.hpp"
 
 #ifdef RKMH_WITH_NCCL
 #include <cuda_runtime.h>
@@ -56,6 +57,10 @@ struct Options {
     int sketch = 1000, threads = 1, min_occ = -1, min_matches = -1, min_diff = 0, max_samples = 100000;
     bool do_read_depth = false, do_ref_depth = false, hash_sketch_given = false, in_stream = false;
     int gpus = 1;
+    std::vector<const char*> pre_refs;       // -R: pre-hashed references (JSON written by `rkmh hash -o`)
+    const char* read_map_file = nullptr;      // -p: the read k-mer count table, loaded when the file exists, written otherwise
+    const char* outname = nullptr;            // hash -o: JSON sketches
+    bool wabbit = false;                      // hash -w: Vowpal Wabbit lines
 };
 
 void usage(const char* argv0) {
@@ -76,6 +81,10 @@ void usage(const char* argv0) {
             "  --min-matches/-N <N>      flag/filter reads with fewer than N matches\n"
             "  --min-diff/-D <N>         flag/filter reads whose best match is not N better than the runner-up\n"
             "  --max-samples/-I <N>      drop reference k-mers seen more than N times in the reference set\n"
+            "  --pre-references/-R <F>   stream / filter: reference sketches from a JSON file written by `hash -s N -o F`\n"
+            "  --read-kmer-map-file/-p <F>  with -M: load the read k-mer count table from F if it exists, else write it there\n"
+            "  -o <F> / -w               hash -s N: sketches as JSON into F / as Vowpal Wabbit lines\n"
+            "  --in-stream/-i            filter: then classify and report every record of standard input\n"
             "  --gpus/-g <N>             shard reads over N B200s (default $RKMH_GPUS or 1)\n",
             argv0);
 }
@@ -115,7 +124,12 @@ void parse_common(int argc, char** argv, Options& o, const char* optstring) {
         switch (c) {
             case 'i': o.in_stream = true; break;                       // filter: classify the records of standard input (below)
             case 'm': case 'z': break;                                 // parsed, no effect (reference: same)
-            case 'F': case 'R': case 'p': case 'q': case 'S': break;   // parsed, no effect
+            case 'R': o.pre_refs.push_back(optarg); break;            // the reference parses these and stops there (src/rkmh.cpp:659-670)
+            case 'p': o.read_map_file = optarg; break;
+            case 'F': case 'q': case 'S': break;                       // parsed, no effect
+            case 'o': o.outname = optarg; break;
+            case 'w': o.wabbit = true; break;
+            case 'c': case 'K': case 'T': break;                       // hash: parsed, no effect
             case 't': o.threads = atoi(optarg); break;
             case 'r': o.refs.push_back(optarg); break;
             case 'f': o.reads.push_back(optarg); break;
@@ -227,7 +241,50 @@ void shard(size_t n, int parts, int d, size_t& lo, size_t& hi) { lo = n * d / pa
 
 void append_int(std::string& s, long long v) { char b[24]; int n = snprintf(b, sizeof b, "%lld", v); s.append(b, n); }
 
-void setup_refs(Fleet& fl, const Options& o, const SeqSet& refs, uint64_t table, bool filter_mode) {
+// Pre-hashed references (-R file.json, written by `rkmh hash -o`): names into refs.names (zero-length sequences), sketches
+// kept for setup_refs.  The file's k list and sketch size must be the command line's.
+struct PreRefs { std::vector<uint64_t> sketches; std::vector<int32_t> lens; };
+void load_pre_refs(const Options& o, SeqSet& refs, PreRefs& pre) {
+    for (const char* path : o.pre_refs) {
+        rkhost::SketchFile f; std::string err;
+        if (!rkhost::read_sketch_json(path, f, err)) { fprintf(stderr, "rkmh: %s\n", err.c_str()); exit(2); }
+        if (f.recs.empty()) continue;
+        if (f.ks != o.ks || f.sketch_size != o.sketch) {
+            fprintf(stderr, "rkmh: %s holds sketches for -k %s -s %d, the command line asks for -k %s -s %d\n", path,
+                    rkhost::kmer_string(f.ks).c_str(), f.sketch_size, rkhost::kmer_string(o.ks).c_str(), o.sketch);
+            exit(2);
+        }
+        for (auto& r : f.recs) {
+            if ((int)r.hashes.size() > o.sketch) { fprintf(stderr, "rkmh: %s: a sketch longer than its sketch size\n", path); exit(2); }
+            refs.names.push_back(r.name);
+            refs.offs.push_back(refs.offs.back());
+            pre.lens.push_back((int32_t)r.hashes.size());
+            r.hashes.resize((size_t)o.sketch, 0);
+            pre.sketches.insert(pre.sketches.end(), r.hashes.begin(), r.hashes.end());
+        }
+    }
+}
+
+void setup_refs(Fleet& fl, const Options& o, const SeqSet& refs, uint64_t table, bool filter_mode, const PreRefs* pre = nullptr) {
+    if (pre && !pre->lens.empty()) {
+        // references that come as sequences are sketched on the GPU first, then all sketches make one table
+        const bool use_i_pre = filter_mode ? (o.max_samples < 100000) : o.do_ref_depth;
+        if (use_i_pre) { fprintf(stderr, "rkmh: -I needs the reference sequences (it filters by k-mer counts over them); not with -R\n"); exit(2); }
+        const size_t nseq = refs.size() - pre->lens.size();
+        fl.each([&](int, rkg_ctx* c) {
+            RK(c, rkg_set_params(c, o.ks.data(), (int)o.ks.size(), o.sketch, o.do_read_depth ? table : 0, 0));
+            std::vector<uint64_t> sk((size_t)refs.size() * (size_t)o.sketch, 0);
+            std::vector<int32_t> ln(refs.size(), 0);
+            if (nseq) {
+                RK(c, rkg_load_refs(c, refs.bases.data(), refs.offs.data(), (int)nseq, -1, filter_mode ? 1 : 0));
+                RK(c, rkg_get_ref_sketches(c, sk.data(), ln.data()));
+            }
+            std::copy(pre->sketches.begin(), pre->sketches.end(), sk.begin() + nseq * (size_t)o.sketch);
+            std::copy(pre->lens.begin(), pre->lens.end(), ln.begin() + nseq);
+            RK(c, rkg_load_ref_sketches(c, sk.data(), ln.data(), (int)refs.size()));
+        });
+        return;
+    }
     const bool use_i = filter_mode ? (o.max_samples < 100000) : o.do_ref_depth;
     fl.each([&](int, rkg_ctx* c) {
         RK(c, rkg_set_params(c, o.ks.data(), (int)o.ks.size(), o.sketch, o.do_read_depth ? table : 0, use_i ? table : 0));
@@ -236,18 +293,51 @@ void setup_refs(Fleet& fl, const Options& o, const SeqSet& refs, uint64_t table,
     });
 }
 
+// -p FILE (the reference's --read-kmer-map-file, parsed and ignored there): the read k-mer count table of pass 1 is loaded
+// from FILE when it exists -- pass 1 is then skipped --, and written to FILE after pass 1 otherwise.
+bool load_count_table(Fleet& fl, const Options& o, bool count_zeros) {
+    if (!o.read_map_file) return false;
+    struct stat st;
+    if (stat(o.read_map_file, &st) != 0) return false;
+    rkhost::CountFile cf; std::string err;
+    if (!rkhost::read_count_file(o.read_map_file, cf, err)) { fprintf(stderr, "rkmh: %s\n", err.c_str()); exit(2); }
+    void* p = nullptr; uint64_t nslots = 0;
+    RK(fl.ctx[0], rkg_count_table(fl.ctx[0], &p, &nslots));
+    if (cf.ks != o.ks || cf.nslots != nslots || cf.count_zeros != (count_zeros ? 1 : 0)) {
+        fprintf(stderr, "rkmh: %s was counted with other parameters (k list, table size or command)\n", o.read_map_file);
+        exit(2);
+    }
+    fl.each([&](int, rkg_ctx* c) { RK(c, rkg_count_import(c, 0, cf.slots.data(), cf.counts.data(), cf.slots.size())); });
+    return true;
+}
+
+void save_count_table(Fleet& fl, const Options& o, bool count_zeros) {
+    if (!o.read_map_file) return;
+    rkg_ctx* c = fl.ctx[0];
+    rkhost::CountFile cf;
+    cf.ks = o.ks; cf.count_zeros = count_zeros ? 1 : 0;
+    void* p = nullptr;
+    RK(c, rkg_count_table(c, &p, &cf.nslots));
+    uint64_t n = 0;
+    RK(c, rkg_count_export(c, 0, nullptr, nullptr, 0, &n));
+    cf.slots.resize((size_t)n); cf.counts.resize((size_t)n);
+    if (n) RK(c, rkg_count_export(c, 0, cf.slots.data(), cf.counts.data(), n, &n));
+    if (!rkhost::write_count_file(o.read_map_file, cf)) { fprintf(stderr, "rkmh: cannot write %s\n", o.read_map_file); exit(2); }
+}
+
 std::vector<rkg_hit> classify_all(Fleet& fl, const Options& o, const SeqSet& reads, bool count_zeros) {
     fl.wait();
     const int G = (int)fl.ctx.size();
     const size_t n = reads.size();
     std::vector<rkg_hit> hits(n);
-    if (o.do_read_depth) {                              // pass 1: global k-mer count table
+    if (o.do_read_depth && !load_count_table(fl, o, count_zeros)) {   // pass 1: global k-mer count table
         fl.each([&](int d, rkg_ctx* c) {
             size_t lo, hi; shard(n, G, d, lo, hi);
             RK(c, rkg_count_reset(c));
             if (hi > lo) RK(c, rkg_count_batch(c, reads.bases.data(), reads.offs.data() + lo, (int64_t)(hi - lo), count_zeros));
         });
         allreduce_counts(fl);
+        save_count_table(fl, o, count_zeros);
     }
     fl.each([&](int d, rkg_ctx* c) {
         size_t lo, hi; shard(n, G, d, lo, hi);
@@ -661,20 +751,25 @@ void run_streamed(Fleet& fl, const Options& o, bool keep_qual, bool count_zeros,
     pool.open(&fl, 2 * (int)fl.ctx.size() + 6 + 3 * parse_threads(), chunk_bytes());
     const auto write_out = [](Chunk& c) { fwrite(c.out.data(), 1, c.out.size(), stdout); };
     uint64_t pass1 = 0;
+    bool counted = false;
     if (o.do_read_depth) {                              // pass 1: global k-mer count table (src/rkmh.cpp:904-910)
         fl.wait();
-        fl.each([&](int, rkg_ctx* c) { RK(c, rkg_count_reset(c)); });
-        pass1 = stream_reads(fl, pool, o.reads, false,
-                     [&](int, rkg_ctx* c, Chunk& ch) { RK(c, rkg_count_batch(c, ch.data(), ch.offs, (int64_t)ch.nreads, count_zeros)); },
-                     nullptr, [](Chunk&) {});
-        allreduce_counts(fl);
+        if (!load_count_table(fl, o, count_zeros)) {
+            fl.each([&](int, rkg_ctx* c) { RK(c, rkg_count_reset(c)); });
+            pass1 = stream_reads(fl, pool, o.reads, false,
+                         [&](int, rkg_ctx* c, Chunk& ch) { RK(c, rkg_count_batch(c, ch.data(), ch.offs, (int64_t)ch.nreads, count_zeros)); },
+                         nullptr, [](Chunk&) {});
+            allreduce_counts(fl);
+            save_count_table(fl, o, count_zeros);
+            counted = true;
+        }
     }
     const uint64_t pass2 = stream_reads(fl, pool, o.reads, keep_qual,
                  [&](int, rkg_ctx* c, Chunk& ch) {
                      RK(c, rkg_classify_batch(c, ch.data(), ch.offs, (int64_t)ch.nreads, o.do_read_depth ? o.min_occ : -1, ch.hits));
                  },
                  format, write_out);
-    if (o.do_read_depth && pass1 != pass2) {            // an input that changed (or drained) between the two passes
+    if (counted && pass1 != pass2) {                    // an input that changed (or drained) between the two passes
         fflush(stdout);
         fprintf(stderr, "rkmh: -M pass 1 saw %llu records, pass 2 %llu: the read files changed between the passes\n",
                 (unsigned long long)pass1, (unsigned long long)pass2);
@@ -708,6 +803,16 @@ void format_filter_record(std::string& out, const Options& o, const char* name, 
     out += "\n+\n"; out.append(qual, qual_len); out += '\n';
 }
 
+// The end of a command: everything is written, so the process leaves without tearing down the CUDA contexts, the pinned
+// chunk pool and the device tables one by one (measured on the B200 box: more than a second for an 8 M-read run -- the
+// operating system reclaims all of it at once).  RKMH_CLEAN_EXIT=1 returns through the destructors instead (sanitizers).
+int leave(int rc) {
+    tmark("done");
+    if (getenv("RKMH_CLEAN_EXIT")) return rc;
+    fflush(stdout); fflush(stderr);
+    _exit(rc);
+}
+
 // ---- stream / classify: src/rkmh.cpp:584-989 ------------------------------------------------------------
 int main_stream(int argc, char** argv) {
     if (argc <= 2) { usage(argv[0]); exit(1); }
@@ -716,16 +821,18 @@ int main_stream(int argc, char** argv) {
     if (env) o.gpus = atoi(env);
     parse_common(argc, argv, o, "zmhdk:f:r:s:S:t:M:N:I:R:F:p:q:iD:g:");
     SeqSet refs;
+    PreRefs pre;
     load_all(o.refs, refs, false);
+    load_pre_refs(o, refs, pre);                         // after the sequences: reference indices follow this order
     if (refs.size() == 0) { fprintf(stderr, "rkmh: no reference sequences (the reference binary is undefined here)\n"); return 2; }
     Fleet fl;
-    fl.open_async(std::max(1, o.gpus), [&] { setup_refs(fl, o, refs, STREAM_TABLE, false); });
+    fl.open_async(std::max(1, o.gpus), [&] { setup_refs(fl, o, refs, STREAM_TABLE, false, &pre); });
     if (!(o.do_read_depth && any_unrewindable(o.reads))) {
         run_streamed(fl, o, false, false, [&](Chunk& c) {
             c.out.reserve(c.nreads * 64);
             for (size_t i = 0; i < c.nreads; ++i) { const auto nm = c.name(i); format_stream_line(c.out, o, refs, nm.first, nm.second, c.hits[i]); }
         });
-        return 0;
+        return leave(0);
     }
     SeqSet reads;                                        // -M on standard input: two passes need the reads twice
     load_all(o.reads, reads, false);
@@ -737,7 +844,7 @@ int main_stream(int argc, char** argv) {
         if (out.size() > (1 << 22) - 4096) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
     }
     fwrite(out.data(), 1, out.size(), stdout);
-    return 0;
+    return leave(0);
 }
 
 // ---- filter: src/rkmh.cpp:996-1424 (intended flow) ----------------------------------------------
@@ -748,10 +855,12 @@ int main_filter(int argc, char** argv) {
     if (env) o.gpus = atoi(env);
     parse_common(argc, argv, o, "hdk:f:r:s:S:t:M:N:I:R:F:p:q:iD:g:");
     SeqSet refs;
+    PreRefs pre;
     load_all(o.refs, refs, false);
+    load_pre_refs(o, refs, pre);
     if (refs.size() == 0) { fprintf(stderr, "rkmh: no reference sequences\n"); return 2; }
     Fleet fl;
-    fl.open_async(std::max(1, o.gpus), [&] { setup_refs(fl, o, refs, FILTER_TABLE, true); });
+    fl.open_async(std::max(1, o.gpus), [&] { setup_refs(fl, o, refs, FILTER_TABLE, true, &pre); });
     if (!(o.do_read_depth && any_unrewindable(o.reads))) {
         if (!o.reads.empty() || !o.in_stream)
             run_streamed(fl, o, true, true, [&](Chunk& c) {
@@ -772,7 +881,7 @@ int main_filter(int argc, char** argv) {
         }
         fwrite(out.data(), 1, out.size(), stdout);
     }
-    if (!o.in_stream) return 0;
+    if (!o.in_stream) return leave(0);
     // -i / --in-stream (src/rkmh.cpp:1329-1414): after the read files, every record of STANDARD INPUT is sketched and classified
     // against the references and REPORTED (not filtered), one line each:
     //   Sample: <name> TAB Result: <reference or empty> TAB <shared> TAB <min(sketch length, reference sketch length)> TAB
@@ -809,7 +918,7 @@ int main_filter(int argc, char** argv) {
                      }
                  },
                  [](Chunk& c) { fwrite(c.out.data(), 1, c.out.size(), stdout); });
-    return 0;
+    return leave(0);
 }
 
 // ---- hash: src/rkmh.cpp:1931-2116; with -s the intended behaviour (README.md:114-117), without it HEAD's ---------
@@ -861,7 +970,24 @@ int main_hash(int argc, char** argv) {
             else RK(c, rkg_merge_sketches(c, parts.data(), plens.data(), G, sk.data() + i * o.sketch, &lens[i]));
             ++i;
         }
+        if (o.outname) {                                  // -o FILE: the sketches as JSON (dump_hash_json's schema, sketch_io.hpp)
+            rkhost::SketchFile jf;
+            jf.ks = o.ks; jf.sketch_size = o.sketch;
+            for (size_t i2 = 0; i2 < n; ++i2) {
+                rkhost::SketchRecord r;
+                r.name = seqs.names[i2]; r.seq_len = seqs.offs[i2 + 1] - seqs.offs[i2];
+                r.hashes.assign(sk.begin() + i2 * (size_t)o.sketch, sk.begin() + i2 * (size_t)o.sketch + lens[i2]);
+                jf.recs.push_back(std::move(r));
+            }
+            if (!rkhost::write_sketch_json(o.outname, jf)) { fprintf(stderr, "rkmh: cannot write %s\n", o.outname); return 2; }
+            return leave(0);
+        }
         for (size_t i2 = 0; i2 < n; ++i2) {               // print_hashes format, mkmh.hpp:1438-1449
+            if (o.wabbit) {                               // -w: print_wabbit, src/rkmh.cpp:463-487
+                rkhost::wabbit_line(out, seqs.names[i2], sk.data() + i2 * (size_t)o.sketch, lens[i2], o.ks[0], o.sketch);
+                if (out.size() > (1 << 22)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+                continue;
+            }
             out += seqs.names[i2]; out += '\t';
             for (int j = 0; j < lens[i2]; ++j) { if (j) out += '\t'; char b[24]; out.append(b, snprintf(b, sizeof b, "%llu", (unsigned long long)sk[i2 * o.sketch + j])); }
             out += '\n';
@@ -882,7 +1008,7 @@ int main_hash(int argc, char** argv) {
         }
     }
     fwrite(out.data(), 1, out.size(), stdout);
-    return 0;
+    return leave(0);
 }
 
 // ---- hpv16: src/rkmh.cpp:2366-2723 ----------------------------------------------------------------------
@@ -1066,7 +1192,7 @@ int main_hpv16(int argc, char** argv) {
             allreduce_counts(fl);
         }
         stream_reads(fl, pool, read_files, false, [&](int, rkg_ctx* c, Chunk& ch) { classify(c, ch); }, format, write_out);
-        return 0;
+        return leave(0);
     }
     // -M on an input that cannot be read twice: buffer the reads, then the same two passes through one big chunk
     SeqSet reads;
@@ -1082,7 +1208,7 @@ int main_hpv16(int argc, char** argv) {
     format(all);
     write_out(all);
     all.bases = nullptr; all.offs = nullptr; all.hits = nullptr;
-    return 0;
+    return leave(0);
 }
 
 }  // namespace

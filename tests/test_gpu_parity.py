@@ -514,3 +514,35 @@ def test_hpv16_through_the_c_abi_equals_the_real_binary(cli_manifest, name):
         out, side = hpv16_stdout(GpuEngine(g), data_path("all_pave_ref.fa.gz"), data_path("new_refs.fa.gz"), reads, ks)
     assert out == golden_cli_output(name)
     assert hashlib.md5(side).hexdigest() == cli_manifest[name]["side_file_md5"]
+
+
+def test_pre_hashed_references_and_count_table_round_trip(oracle):
+    """rkg_load_ref_sketches on the sketches rkg_get_ref_sketches returns == rkg_load_refs on the sequences (records of a
+    read batch identical, memoised and Murmur path); rkg_count_export -> rkg_count_import restores the read count table
+    in a fresh context, whose -M classification then equals the original's.  Malformed sketches are refused."""
+    import rkmh_b200
+    _, rs, _ = load_sequences([data_path("all_pave_ref.fa.gz")])
+    rng = np.random.default_rng(23)
+    bases, offs = _synthetic_reads(rng, rs, 8000, 150)
+    for memo in (True, False):
+        with rkmh_b200.RkmhGpu(0) as a, rkmh_b200.RkmhGpu(0) as b:
+            for g in (a, b):
+                g.set_memo(memo)
+                g.set_params([12], 1000, read_table_size=rkmh_b200.STREAM_TABLE_SIZE)
+            a.load_refs(*_pack(rs))
+            sk, ln = a.ref_sketches()
+            b.load_ref_sketches(sk, ln)
+            assert b.memo_active() == memo
+            ha = _fields(a.classify_batch(bases, offs))
+            assert np.array_equal(ha, _fields(b.classify_batch(bases, offs)))
+            a.count_reset(); a.count_batch(bases, offs)
+            slots, vals = a.count_export()
+            assert len(slots) > 1000 and int(vals.sum()) == int(a.count_table_tensor().sum().item())
+            b.count_import(slots, vals)
+            assert bool((a.count_table_tensor() == b.count_table_tensor()).all().item())
+            assert np.array_equal(_fields(a.classify_batch(bases, offs, min_occ=3)), _fields(b.classify_batch(bases, offs, min_occ=3)))
+            bad = sk.copy(); bad[3, 5] = bad[3, 4] - np.uint64(1)
+            with pytest.raises(rkmh_b200.RkmhError, match="ascending"):
+                b.load_ref_sketches(bad, ln)
+    exp = oracle.classify_batch([bases[offs[i]:offs[i + 1]].tobytes() for i in range(100)], [12], 1000, *oracle.sketch_batch(rs, [12], 1000))
+    assert np.array_equal(ha[:100], _fields(exp))

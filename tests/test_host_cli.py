@@ -326,3 +326,56 @@ def test_filter_in_stream_mode(rkmh_bin, oracle, extra):
             (b"FAIL:DEPTH" if int(h["sketch_len"]) <= 0 else b"") + b"\t" + (b"FAIL:MATCHES" if best < n_min else b"") + b"\t" +
             (b"" if best - prev > d_min else b"FAIL:DIFF") + b"\n")
     assert res.stdout[len(base):] == b"".join(lines)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_persistence_pre_references_and_count_table(rkmh_bin, cli_manifest, tmp_path):
+    """SURVEY 8f N3.  `hash -s N -o refs.json` writes the reference sketches in the reference's JSON schema; `stream -R
+    refs.json` (no -r) then prints exactly what `stream -r refs.fa` prints (the real binary's golden).  With -M, `-p FILE`
+    writes the read k-mer count table after pass 1 and a second run loads it instead of counting: same stdout."""
+    import json
+    name = "pave_mix2k_k12_s100"
+    _, argv = CLI_CASES[name]
+    js = tmp_path / "refs.json"
+    res = subprocess.run([rkmh_bin, "hash", "-r", "all_pave_ref.fa.gz", "-k", "12", "-s", "100", "-o", str(js)], cwd=DATA,
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert res.returncode == 0 and res.stdout == b"", res.stderr.decode()[-300:]
+    doc = json.loads(js.read_text())
+    assert len(doc) == 182 and doc[0]["kmer"] == "12" and doc[0]["hashType"] == "MurmurHash3_x64_128" and doc[0]["hashSeed"] == 42
+    assert doc[0]["sketches"]["length"] == 100 and len(doc[0]["sketches"]["hashes"]) == 100
+    assert doc[0]["sketches"]["hashes"] == sorted(doc[0]["sketches"]["hashes"]) and doc[0]["seqLen"] > 7000
+    i = argv.index("-r")
+    pre = argv[:i] + ["-R", str(js)] + argv[i + 2:]
+    res = subprocess.run([rkmh_bin] + pre, cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert res.returncode == 0, res.stderr.decode()[-300:]
+    assert hashlib.md5(res.stdout).hexdigest() == cli_manifest[name]["md5"]
+    # sequences and pre-hashed references mixed: the two HPV16 reference files of this golden, the second one pre-hashed
+    name2 = "two_ref_files_multik_M2"
+    _, argv2 = CLI_CASES[name2]
+    js2 = tmp_path / "new_refs.json"
+    subprocess.run([rkmh_bin, "hash", "-r", "new_refs.fa.gz", "-k", "10", "-k", "14", "-s", "500", "-o", str(js2)], cwd=DATA, check=True,
+                   stderr=subprocess.PIPE)
+    j = [k for k, a in enumerate(argv2) if a == "-r"][1]
+    mixed = argv2[:j] + ["-R", str(js2)] + argv2[j + 2:]
+    res = subprocess.run([rkmh_bin] + mixed, cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert res.returncode == 0, res.stderr.decode()[-300:]
+    assert hashlib.md5(res.stdout).hexdigest() == cli_manifest[name2]["md5"]
+    # a file for other parameters is refused
+    bad = subprocess.run([rkmh_bin, "stream", "-R", str(js), "-f", "z1.fq.gz", "-k", "12", "-s", "1000"], cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert bad.returncode == 2 and b"-s 100" in bad.stderr
+    # the read k-mer count table
+    for name3 in ("newrefs_mix2k_M20_N10", "filter_viral4_z1_M2_D2"):
+        _, argv3 = CLI_CASES[name3]
+        tab = tmp_path / (name3 + ".cnt")
+        first = subprocess.run([rkmh_bin] + argv3 + ["-p", str(tab)], cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert first.returncode == 0 and tab.stat().st_size > 64
+        again = subprocess.run([rkmh_bin] + argv3 + ["-p", str(tab)], cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                               env=dict(os.environ, RKMH_TIMING="1"))
+        assert again.returncode == 0
+        assert hashlib.md5(first.stdout).hexdigest() == cli_manifest[name3]["md5"] == hashlib.md5(again.stdout).hexdigest()
+    # Vowpal Wabbit lines (print_wabbit): label, key with '|' -> '_', hash:1 pairs, the sketch namespace
+    res = subprocess.run([rkmh_bin, "hash", "-f", "hpv_16_allFasta.fa.gz", "-k", "12", "-s", "5", "-w"], cwd=DATA, stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, check=True)
+    line = res.stdout.splitlines()[0].decode()
+    assert line.startswith("XYX 1.0 `gi_") and "|vir " in line and line.endswith(" |sketch k:12 s:5") and line.count(":1") == 5
