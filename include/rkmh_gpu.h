@@ -184,6 +184,23 @@ int rkg_load_ref_sets(rkg_ctx* ctx, const uint64_t* hashes, const int64_t* set_o
 int rkg_classify_sets(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, int min_occ, int ntypes,
                       rkg_hit* out, int32_t* extra);
 
+/* ---- call: alignment-free variant calling from k-mer depth (src/rkmh.cpp:1455-1904) ------------------------ */
+/* The reference keeps the exact multiplicity of every hash of every read in an unordered_map (read_hash_to_depth,
+ * src/rkmh.cpp:1570, 1617-1622; the hash 0 of invalid windows included) and then walks the reference sequence.  Here:
+ *   rkg_depth_begin        an empty exact hash -> depth table in HBM with room for expected_windows windows (one k only)
+ *   rkg_depth_add          calc_hashes of every read, ++depth[hash]
+ *   rkg_depth_of_sequence  depth[hash] of each of the len - k windows of a reference sequence (src/rkmh.cpp:1777)
+ *   rkg_depth_rescue       for each listed window start: the depths of its 3k single-base substitutions (position p, the
+ *                          three other bases in rotate_snps order, src/rkmh.cpp:1646-1667: out[w][3p + i]) and of the k
+ *                          one-base deletions of the (k + 1)-mer that starts one base before it (base d = 1..k removed:
+ *                          out[w][3k + d - 1], src/rkmh.cpp:1840-1848); -1 where the reference tries nothing (window 0 has
+ *                          no deletions; a base outside ACGT has no substitutions).  out is [nwin x 4k].
+ * The sliding-window average, the thresholds and the VCF lines are the caller's (sequential and tiny). */
+int rkg_depth_begin(rkg_ctx* ctx, uint64_t expected_windows);
+int rkg_depth_add(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads);
+int rkg_depth_of_sequence(rkg_ctx* ctx, const char* seq, int64_t len, int32_t* depth);
+int rkg_depth_rescue(rkg_ctx* ctx, const char* seq, int64_t len, const int64_t* windows, int64_t nwin, int32_t* out);
+
 /* ---- hash command -------------------------------------------------------------------------------- */
 /* Bottom-s sketches of nseq records (sorted ascending, duplicates kept, zeros dropped): calc_hashes +
  * minhashes (mkmh/mkmh.hpp:689-711, 931-950), the intended behaviour of `rkmh hash` (src/rkmh.cpp:

@@ -270,6 +270,27 @@ class RkmhGpu:
                                                out.ctypes.data, extra.ctypes.data))
         return out[:n], extra[:n, :nextra]
 
+    # -- call: exact k-mer depth -------------------------------------------------------------------
+    def depth_begin(self, expected_windows):
+        self._check(self.lib.rkg_depth_begin(self.handle, int(expected_windows)))
+
+    def depth_add(self, bases, offs):
+        bases, offs = self._buffers(bases, offs)
+        self._check(self.lib.rkg_depth_add(self.handle, bases.ctypes.data, offs.ctypes.data, len(offs) - 1))
+
+    def depth_of_sequence(self, seq):
+        seq = np.ascontiguousarray(np.frombuffer(seq, np.uint8) if isinstance(seq, (bytes, bytearray)) else seq, dtype=np.uint8)
+        out = np.zeros(max(seq.size - self.ks[0], 1), np.int32)
+        self._check(self.lib.rkg_depth_of_sequence(self.handle, seq.ctypes.data, seq.size, out.ctypes.data))
+        return out[:max(seq.size - self.ks[0], 0)]
+
+    def depth_rescue(self, seq, windows):
+        seq = np.ascontiguousarray(np.frombuffer(seq, np.uint8) if isinstance(seq, (bytes, bytearray)) else seq, dtype=np.uint8)
+        windows = np.ascontiguousarray(windows, dtype=np.int64)
+        out = np.zeros((max(len(windows), 1), 4 * self.ks[0]), np.int32)
+        self._check(self.lib.rkg_depth_rescue(self.handle, seq.ctypes.data, seq.size, windows.ctypes.data, len(windows), out.ctypes.data))
+        return out[:len(windows)]
+
     # -- hash command -----------------------------------------------------------------------------
     def sketch_batch(self, bases, offs, min_occ=-1):
         """minhashes(calc_hashes(seq)) per record: ([n, s] uint64, [n] int32 lengths)."""

@@ -15,6 +15,7 @@
 #include "rk_kernels.cuh"
 #include "rk_memo.cuh"
 #include "rk_warp.cuh"
+#include "rk_call.cuh"
 
 using namespace rk;
 
@@ -77,6 +78,9 @@ struct rkg_ctx {
     int s = 1000;
     bool params_set = false;
     u64 read_tbl_size = 0, ref_tbl_size = 0;
+    DevBuf depth_keys, depth_counts, depth_zero;   // `call`: exact hash -> depth table (rk_call.cuh)
+    DepthTable depth{};
+    i64 depth_room = 0;                            // windows that may still be added before the table could fill
     DevBuf read_counts, ref_counts, hash_lut;   // hash_lut: the tables of rk_hash.cuh (16 KB, built in rkg_create)
     CountTable read_ct{nullptr, {}}, ref_ct{nullptr, {}};
     // references
@@ -787,7 +791,7 @@ void rkg_destroy(rkg_ctx* ctx) {
     cudaDeviceSynchronize();
     profile_collect(ctx);
     for (int i = 0; i < 2; ++i) batch_release(ctx->slots[i]);
-    for (DevBuf* d : {&ctx->hash_lut, &ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
+    for (DevBuf* d : {&ctx->depth_keys, &ctx->depth_counts, &ctx->depth_zero, &ctx->hash_lut, &ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
                       &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
                       &ctx->memo_tab, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
                       &ctx->memo_sieve, &ctx->memo_cmap})
@@ -1343,6 +1347,114 @@ int rkg_classify_sets(rkg_ctx* ctx, const char* bases, const int64_t* offs, int6
         if (cudaStreamSynchronize(ctx->slots[i]->stream) != cudaSuccess && rc == RKG_OK)
             rc = fail(ctx, RKG_ERR_CUDA, "rkg_classify_sets: %s", cudaGetErrorString(cudaGetLastError()));
     d_extra[0].release(); d_extra[1].release();
+    return rc;
+}
+
+// ---- call: exact k-mer depth ------------------------------------------------------------------------------
+int rkg_depth_begin(rkg_ctx* ctx, uint64_t expected_windows) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->params_set) return fail(ctx, RKG_ERR_STATE, "rkg_depth_begin before rkg_set_params");
+    if (ctx->kl.nk != 1) return fail(ctx, RKG_ERR_ARG, "rkg_depth_begin: exactly one k-mer size (src/rkmh.cpp:1545-1554)");
+    if (expected_windows > ((uint64_t)1 << 29)) return fail(ctx, RKG_ERR_ARG, "rkg_depth_begin: more than 2^29 windows");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    const u32 cap = (u32)next_pow2(std::max<i64>(2 * (i64)expected_windows, 1024));
+    CK(ctx->depth_keys.ensure(sizeof(u64) * (size_t)cap));
+    CK(ctx->depth_counts.ensure(sizeof(u32) * (size_t)cap));
+    CK(ctx->depth_zero.ensure(64));
+    CK(cudaMemsetAsync(ctx->depth_keys.p, 0, sizeof(u64) * (size_t)cap, ctx->stream));
+    CK(cudaMemsetAsync(ctx->depth_counts.p, 0, sizeof(u32) * (size_t)cap, ctx->stream));
+    CK(cudaMemsetAsync(ctx->depth_zero.p, 0, 64, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->depth.keys = ctx->depth_keys.as<u64>(); ctx->depth.counts = ctx->depth_counts.as<u32>();
+    ctx->depth.zero = ctx->depth_zero.as<unsigned long long>(); ctx->depth.cap_mask = cap - 1;
+    ctx->depth_room = (i64)expected_windows;
+    return RKG_OK;
+}
+
+int rkg_depth_add(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads) {
+    if (!ctx) return RKG_ERR_ARG;
+    if (!ctx->depth.keys) return fail(ctx, RKG_ERR_STATE, "rkg_depth_add before rkg_depth_begin");
+    if (nreads < 0 || !offs || (!bases && nreads > 0)) return fail(ctx, RKG_ERR_ARG, "rkg_depth_add: bad buffers");
+    if (nreads == 0) return RKG_OK;
+    const int k = ctx->kl.k[0];
+    i64 windows = 0;
+    for (int64_t r = 0; r < nreads; ++r) windows += std::max<i64>(offs[r + 1] - offs[r] - k, 0);
+    if (windows > ctx->depth_room) return fail(ctx, RKG_ERR_ARG, "rkg_depth_add: more windows than rkg_depth_begin was told to expect");
+    ctx->depth_room -= windows;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_slots(ctx);
+    if (rc) return rc;
+    auto chunks = make_chunks(offs, nreads, CHUNK_BYTES, CHUNK_READS);
+    for (size_t c = 0; c < chunks.size(); ++c) {
+        rkg_batch* b = ctx->slots[c & 1];
+        CK(cudaStreamSynchronize(b->stream));
+        if ((rc = batch_fill(ctx, b, bases, offs, chunks[c].first, chunks[c].second))) return rc;
+        if ((rc = ensure_packed(ctx, b))) return rc;
+        Timed t(ctx, b->stream, K_COUNT);
+        const int grid = (int)std::min<i64>((b->nseq + 7) / 8, (i64)ctx->sm_count * 8);
+        DISPATCH_KCSEL(ctx->kcsel, (depth_add_kernel<KS><<<grid, 256, 0, b->stream>>>(seq_view(b), ctx->kl, ctx->depth)));
+        CK(cudaGetLastError());
+    }
+    for (int i = 0; i < 2; ++i) CK(cudaStreamSynchronize(ctx->slots[i]->stream));
+    return RKG_OK;
+}
+
+int rkg_depth_of_sequence(rkg_ctx* ctx, const char* seq, int64_t len, int32_t* depth) {
+    if (!ctx || !seq || !depth) return RKG_ERR_ARG;
+    if (!ctx->depth.keys) return fail(ctx, RKG_ERR_STATE, "rkg_depth_of_sequence before rkg_depth_begin");
+    const int k = ctx->kl.k[0];
+    const i64 n = std::max<i64>(len - k, 0);
+    if (n == 0) return RKG_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_slots(ctx);
+    if (rc) return rc;
+    rkg_batch* b = ctx->slots[0];
+    CK(cudaStreamSynchronize(b->stream));
+    const int64_t one[2] = {0, len};
+    if ((rc = batch_fill(ctx, b, seq, one, 0, 1))) return rc;
+    if ((rc = ensure_packed(ctx, b))) return rc;
+    DevBuf d;
+    if (d.ensure(sizeof(int) * (size_t)n) != cudaSuccess) return fail(ctx, RKG_ERR_NOMEM, "rkg_depth_of_sequence: device allocation failed");
+    {
+        Timed t(ctx, b->stream, K_HASH);
+        const int grid = (int)std::min<i64>((n + WARP_CHUNK * 8 - 1) / (WARP_CHUNK * 8), (i64)ctx->sm_count * 8);
+        DISPATCH_KCSEL(ctx->kcsel, (depth_lookup_kernel<KS><<<grid, 256, 0, b->stream>>>(seq_view(b), ctx->kl, ctx->depth, n, d.as<int>())));
+    }
+    cudaMemcpyAsync(depth, d.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, b->stream);
+    const cudaError_t e = cudaStreamSynchronize(b->stream);
+    d.release();
+    CK(e);
+    return RKG_OK;
+}
+
+int rkg_depth_rescue(rkg_ctx* ctx, const char* seq, int64_t len, const int64_t* windows, int64_t nwin, int32_t* out) {
+    if (!ctx || !seq || (nwin > 0 && (!windows || !out))) return RKG_ERR_ARG;
+    if (!ctx->depth.keys) return fail(ctx, RKG_ERR_STATE, "rkg_depth_rescue before rkg_depth_begin");
+    if (nwin <= 0) return RKG_OK;
+    const int k = ctx->kl.k[0];
+    for (int64_t i = 0; i < nwin; ++i)
+        if (windows[i] < 0 || windows[i] + k > len) return fail(ctx, RKG_ERR_ARG, "rkg_depth_rescue: window %lld outside the sequence", (long long)windows[i]);
+    CK(cudaSetDevice(ctx->device));
+    DevBuf d_seq, d_win, d_out;
+    int rc = RKG_OK;
+    do {
+        const size_t nout = (size_t)nwin * 4 * (size_t)k;
+        if (d_seq.ensure((size_t)len + 64) || d_win.ensure(sizeof(i64) * (size_t)nwin) || d_out.ensure(sizeof(int) * nout)) {
+            rc = fail(ctx, RKG_ERR_NOMEM, "rkg_depth_rescue: device allocation failed"); break;
+        }
+        cudaMemcpyAsync(d_seq.p, seq, (size_t)len, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_win.p, windows, sizeof(i64) * (size_t)nwin, cudaMemcpyHostToDevice, ctx->stream);
+        {
+            Timed t(ctx, ctx->stream, K_HASH);
+            const int grid = (int)std::min<i64>(((i64)nout + 255) / 256, (i64)ctx->sm_count * 8);
+            DISPATCH_KCSEL(ctx->kl.kv[0], (depth_rescue_kernel<(KS < NUM_KV ? KS : 0)><<<grid, 256, 0, ctx->stream>>>(
+                                               d_seq.as<unsigned char>(), len, ctx->kl, ctx->depth, d_win.as<i64>(), nwin, d_out.as<int>())));
+        }
+        cudaMemcpyAsync(out, d_out.p, sizeof(int) * nout, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = fail(ctx, RKG_ERR_CUDA, "rkg_depth_rescue: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    } while (0);
+    d_seq.release(); d_win.release(); d_out.release();
     return rc;
 }
 

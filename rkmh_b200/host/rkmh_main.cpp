@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <deque>
 #include <functional>
+#include <list>
 #include <map>
 #include <set>
 #include <mutex>
@@ -65,11 +66,12 @@ struct Options {
 
 void usage(const char* argv0) {
     fprintf(stderr,
-            "Usage: %s { classify | stream | filter | hash | hpv16 } [options]\n"
+            "Usage: %s { classify | stream | filter | hash | hpv16 | call } [options]\n"
             "    classify: match each read to the reference it most closely resembles using MinHash sketches.\n"
             "    stream:   the same (classify forwards to stream, as in the reference).\n"
             "    filter:   spit out reads that meet thresholds for match to ref, uniqueness, etc.\n"
             "    hash:     compute the MinHash sketches of a set of reads and/or references.\n"
+            "    call:     alignment-free variant calls (VCF) of a read set against a reference, from k-mer depth (-w window).\n"
             "    hpv16:    HPV type, HPV16 lineage and sublineage of each read (-R <dir with all_pave_ref.fa and new_refs.fa>).\n"
             "Options:\n"
             "  --reference/-r <REF>      reference FASTA/FASTQ (repeatable)\n"
@@ -1211,6 +1213,143 @@ int main_hpv16(int argc, char** argv) {
     return leave(0);
 }
 
+// ---- call: src/rkmh.cpp:1455-1904 -----------------------------------------------------------------------
+// Alignment-free variant calling: the exact k-mer depth of the read set is kept on the GPU (rkg_depth_*); for every window
+// of the reference whose depth is under half of the running average over the last `window_len` windows, every single-base
+// substitution and every one-base deletion is looked up, and the ones that "rescue" the depth become VCF lines.  The walk
+// along the reference, the thresholds and the bookkeeping of the calls are the reference's, statement for statement.
+int main_call(int argc, char** argv) {
+    if (argc <= 2) { usage(argv[0]); exit(1); }
+    std::vector<const char*> ref_files, read_files;
+    std::vector<int> ks;
+    int window_len = 100, gpus = 1;
+    bool show_depth = false, output_vcf = true;
+    static struct option long_options[] = {
+        {"help", no_argument, 0, 'h'}, {"kmer", no_argument, 0, 'k'}, {"fasta", required_argument, 0, 'f'},
+        {"reference", required_argument, 0, 'r'}, {"sketch", required_argument, 0, 's'}, {"threads", required_argument, 0, 't'},
+        {"show-depth", required_argument, 0, 'd'}, {"window-len", required_argument, 0, 'w'}, {"gpus", required_argument, 0, 'g'},
+        {0, 0, 0, 0}};
+    optind = 2;
+    for (;;) {
+        int idx = 0;
+        const int c = getopt_long(argc, argv, "hdk:f:r:s:t:w:g:", long_options, &idx);     // src/rkmh.cpp:1494
+        if (c == -1) break;
+        switch (c) {
+            case 't': case 's': break;                        // parsed, without effect on the output
+            case 'r': ref_files.push_back(optarg); break;
+            case 'f': read_files.push_back(optarg); break;
+            case 'k': if (optarg) ks.push_back(atoi(optarg)); break;
+            case 'w': window_len = atoi(optarg); break;
+            case 'd': show_depth = true; output_vcf = false; break;
+            case 'g': gpus = atoi(optarg); break;
+            case '?': case 'h': usage(argv[0]); exit(1);
+            default: usage(argv[0]); abort();
+        }
+    }
+    (void)gpus;
+    if (ks.empty()) {
+        fprintf(stderr, "No kmer size(s) provided. Will use a default kmer size of 16.\n");
+        ks.push_back(16);
+    } else if (ks.size() > 1) {
+        fprintf(stderr, "Only a single kmer size may be used for calling.\nSizes provided: ");
+        for (int k : ks) fprintf(stderr, "%d ", k);
+        fprintf(stderr, "\nPlease choose a single kmer size.\n");
+        exit(1);
+    }
+    fprintf(stderr, "Parsing sequences...\n");
+    if (ref_files.empty()) {
+        fprintf(stderr, "No references were provided. Please provide at least one reference file in fasta/fastq format.\n");
+        usage(argv[0]); exit(1);
+    }
+    if (read_files.empty()) {
+        fprintf(stderr, "No reads were provided. Please provide at least one read file in fasta/fastq format.\n");
+        usage(argv[0]); exit(1);
+    }
+    SeqSet refs, reads;
+    load_all(ref_files, refs, false);
+    load_all(read_files, reads, false);
+    const int k = ks[0];
+    Fleet fl; fl.open(1);
+    rkg_ctx* c = fl.ctx[0];
+    RK(c, rkg_set_params(c, &k, 1, 1, 0, 0));
+    uint64_t windows = 0;
+    for (size_t i = 0; i < reads.size(); ++i) windows += (uint64_t)std::max<int64_t>(reads.offs[i + 1] - reads.offs[i] - k, 0);
+    RK(c, rkg_depth_begin(c, windows));
+    if (reads.size()) RK(c, rkg_depth_add(c, reads.bases.data(), reads.offs.data(), (int64_t)reads.size()));
+
+    if (refs.size() > 1) fprintf(stderr, "WARNING: more than one ref provided. VCF will not be correct\n");
+    std::string out;
+    if (output_vcf) {                                     // src/rkmh.cpp:1727-1733 (the RD and OD lines share one line there)
+        out += "##fileformat=VCF4.2\n##source=rkmh\n##reference="; out += ref_files[0]; out += '\n';
+        out += "##INFO=<ID=KD,Number=1,Type=Integer,Description=\"Number of times call for specific kmer appears\">\n";
+        out += "##INFO=<ID=MD,Number=1,Type=Integer,Description=\"Maximum depth found for the rescue kmer.\">\n";
+        out += "##INFO=<ID=RD,Number=1,Type=Integer,Description=\"Average depth in region\">";
+        out += "##INFO=<ID=OD,Number=1,Type=Integer,Description=\"Depth of original kmer at site before modification.\">\n";
+    }
+    std::map<std::string, int> call_count, call_max_depth, call_avg_depth, call_orig_depth;
+    std::list<int> d_window;                              // not reset between references (the reference's is per thread)
+    long long d_sum = 0;
+    struct Low { int64_t j; int depth, avg_d; };
+    for (size_t i = 0; i < refs.size(); ++i) {
+        const char* seq = refs.bases.data() + refs.offs[i];
+        const int64_t len = refs.offs[i + 1] - refs.offs[i], nh = std::max<int64_t>(len - k, 0);
+        std::vector<int32_t> depth((size_t)std::max<int64_t>(nh, 1));
+        if (nh) RK(c, rkg_depth_of_sequence(c, seq, len, depth.data()));
+        std::vector<Low> low;
+        std::vector<int64_t> low_pos;
+        for (int64_t j = 0; j < nh; ++j) {                // src/rkmh.cpp:1772-1792
+            d_window.push_back(depth[j]); d_sum += depth[j];
+            if ((int)d_window.size() > window_len) { d_sum -= d_window.front(); d_window.pop_front(); }
+            const int avg_d = (int)((double)(int)d_sum / (double)d_window.size());
+            if (depth[j] < .5 * avg_d) { low.push_back({j, depth[j], avg_d}); low_pos.push_back(j); }
+        }
+        if (low.empty() || show_depth) continue;          // -d: the reference builds depth lines and never prints them
+        std::vector<int32_t> alt((size_t)low.size() * 4 * (size_t)k);
+        RK(c, rkg_depth_rescue(c, seq, len, low_pos.data(), (int64_t)low_pos.size(), alt.data()));
+        auto upper = [](char ch) { return (char)(((int)(signed char)ch - 91 > 0) ? ch - 32 : ch); };
+        static const char rot[4][3] = {{'C', 'T', 'G'}, {'T', 'G', 'A'}, {'C', 'G', 'A'}, {'A', 'C', 'T'}};   // A C T G
+        auto record = [&](const std::string& key, int avg_d, int dep, int alt_depth) {
+            call_count[key] += 1;
+            call_avg_depth[key] = std::max(avg_d, call_avg_depth[key]);
+            call_orig_depth[key] = std::max(call_orig_depth[key], dep);
+            if (alt_depth > call_max_depth[key]) call_max_depth[key] = alt_depth;
+        };
+        for (size_t w = 0; w < low.size(); ++w) {
+            const Low& lw = low[w];
+            const int32_t* a = alt.data() + w * 4 * (size_t)k;
+            for (int p = 0; p < k; ++p) {                 // substitutions, src/rkmh.cpp:1796-1831
+                const char orig = upper(seq[lw.j + p]);
+                const int row = orig == 'A' ? 0 : orig == 'C' ? 1 : orig == 'T' ? 2 : orig == 'G' ? 3 : -1;
+                if (row < 0) continue;
+                for (int x = 0; x < 3; ++x) {
+                    const int alt_depth = a[3 * p + x];
+                    if (alt_depth < 0) continue;
+                    if ((alt_depth >= .1 * lw.avg_d) & (alt_depth > lw.depth)) {
+                        std::string key = refs.names[i]; key += '\t'; append_int(key, lw.j + p + 1); key += "\t.\t"; key += orig; key += '\t'; key += rot[row][x];
+                        record(key, lw.avg_d, lw.depth, alt_depth);
+                    }
+                }
+            }
+            if (lw.j > 0)                                 // deletions, src/rkmh.cpp:1840-1858
+                for (int d = 1; d <= k; ++d) {
+                    const int alt_depth = a[3 * k + d - 1];
+                    if (alt_depth < 0) continue;
+                    if (output_vcf && alt_depth > 0.9 * lw.avg_d) {
+                        std::string key = refs.names[i]; key += '\t'; append_int(key, lw.j + d + 1); key += "\t.\t"; key += upper(seq[lw.j - 1 + d]); key += "\t-";
+                        record(key, lw.avg_d, lw.depth, alt_depth);
+                    }
+                }
+        }
+    }
+    if (output_vcf)
+        for (const auto& x : call_count) {                // src/rkmh.cpp:1876-1879
+            out += x.first; out += "\t99\tPASS\tKC="; append_int(out, x.second); out += ";MD="; append_int(out, call_max_depth[x.first]);
+            out += ";RD="; append_int(out, call_avg_depth[x.first]); out += ";OD="; append_int(out, call_orig_depth[x.first]); out += '\n';
+        }
+    fwrite(out.data(), 1, out.size(), stdout);
+    return leave(0);
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -1224,6 +1363,7 @@ int main(int argc, char** argv) {
     if (cmd == "filter") return main_filter(argc, argv);
     if (cmd == "hash") return main_hash(argc, argv);
     if (cmd == "hpv16") return main_hpv16(argc, argv);
+    if (cmd == "call") return main_call(argc, argv);
     if (cmd == "parse-stream") {     // host-only: the records as the streaming front-end chunks them (parallel parser included)
         std::vector<const char*> files(argv + 2, argv + argc);
         ChunkPool pool;

@@ -76,6 +76,16 @@ HPV16_CASES = {
     "hpv16cmd_two_files_k14_M3": ["hpv16", "-f", "minION25.fq.gz", "-f", "mix2k.fq.gz", "-k", "14", "-M", "3"],
 }
 
+# `rkmh call` (src/rkmh.cpp:1455-1904): VCF of k-mer-depth calls; argv relative to tests/golden/data like CLI_CASES
+CALL_CASES = {
+    "call_hpv16_minion_k12": ["call", "-r", "hpv_16.fa.gz", "-f", "minION25.fq.gz", "-k", "12"],
+    "call_hpv16_mix2k_k16": ["call", "-r", "hpv_16.fa.gz", "-f", "mix2k.fq.gz", "-k", "16"],
+    "call_zika_z1_k20_w50": ["call", "-r", "zika.fa.gz", "-f", "z1.fq.gz", "-k", "20", "-w", "50"],
+    "call_newrefs_mix2k_k14": ["call", "-r", "new_refs.fa.gz", "-f", "mix2k.fq.gz", "-f", "minION25.fq.gz", "-k", "14"],
+    "call_hpv16_mix2k_k24_w10": ["call", "-r", "hpv_16.fa.gz", "-f", "mix2k.fq.gz", "-k", "24", "-w", "10"],
+    "call_show_depth": ["call", "-r", "hpv_16.fa.gz", "-f", "minION25.fq.gz", "-k", "12", "-d"],
+}
+
 # library-level cases: name -> (ref fixtures, read fixture, k list, s)
 LIB_CASES = {
     "hpv16_minion_k10": (["hpv_16_allFasta.fa.gz"], "minION25.fq.gz", [10], 1000),
@@ -143,6 +153,21 @@ def make_cli():
                           "lines": out.count(b"\n"), "binary": "rkmh_ref_filter" if which == "filter" else "rkmh_ref"}
         print(f"cli  {name:28s} {manifest[name]['lines']:6d} lines  md5 {manifest[name]['md5']}")
     with open(os.path.join(CLI, "manifest.json"), "w") as fh:
+        json.dump(manifest, fh, indent=1, sort_keys=True)
+
+
+def make_call(manifest_path=None):
+    manifest_path = manifest_path or os.path.join(CLI, "manifest.json")
+    with open(manifest_path) as fh:
+        manifest = json.load(fh)
+    exe = ref_binary()
+    assert exe, "build oracle/_ref first (make -C oracle)"
+    for name, argv in CALL_CASES.items():
+        out = subprocess.run([exe] + argv + ["-t", "1"], cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+        gz_write(os.path.join(CLI, name + ".out.gz"), out)
+        manifest[name] = {"argv": argv, "md5": hashlib.md5(out).hexdigest(), "lines": out.count(b"\n"), "binary": "rkmh_ref"}
+        print(f"cli  {name:28s} {manifest[name]['lines']:6d} lines  md5 {manifest[name]['md5']}")
+    with open(manifest_path, "w") as fh:
         json.dump(manifest, fh, indent=1, sort_keys=True)
 
 
@@ -269,11 +294,15 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["hpv16"]:               # only (re)generate the hpv16 command's goldens
         make_hpv16()
         sys.exit(0)
+    if sys.argv[1:] == ["call"]:
+        make_call()
+        sys.exit(0)
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
     ref = RefMkmh()
     make_data()
     make_cli()
     make_hpv16()
+    make_call()
     make_kats(ref)
     make_lib_vectors(ref)
     print("golden vectors written under", HERE)

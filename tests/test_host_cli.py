@@ -378,4 +378,21 @@ def test_persistence_pre_references_and_count_table(rkmh_bin, cli_manifest, tmp_
     res = subprocess.run([rkmh_bin, "hash", "-f", "hpv_16_allFasta.fa.gz", "-k", "12", "-s", "5", "-w"], cwd=DATA, stdout=subprocess.PIPE,
                          stderr=subprocess.PIPE, check=True)
     line = res.stdout.splitlines()[0].decode()
-    assert line.startswith("XYX 1.0 `gi_") and "|vir " in line and line.endswith(" |sketch k:12 s:5") and line.count(":1") == 5
+    assert line.startswith("XYX 1.0 `gi_") and "|vir " in line and line.endswith(" |sketch k:12 s:5") and line.count(":1 ") == 5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["call_hpv16_minion_k12", "call_hpv16_mix2k_k16", "call_zika_z1_k20_w50", "call_newrefs_mix2k_k14",
+                                  "call_hpv16_mix2k_k24_w10", "call_show_depth"])
+def test_call_command_equals_reference(rkmh_bin, cli_manifest, name):
+    """`rkmh call`: the VCF the real binary prints, byte for byte -- exact k-mer depths, sliding-window
+    average carried across references, substitution and deletion rescues, calls in std::map order."""
+    from tests.golden.make_golden import CALL_CASES
+    res = subprocess.run([rkmh_bin] + CALL_CASES[name], cwd=DATA, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert res.returncode == 0, res.stderr.decode()[-400:]
+    gold = golden_cli_output(name)
+    if res.stdout != gold:
+        a, b = res.stdout.splitlines(), gold.splitlines()
+        diff = [(i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y][:3]
+        pytest.fail(f"{name}: {len(a)} vs {len(b)} lines; first diffs {diff}")
+    assert hashlib.md5(res.stdout).hexdigest() == cli_manifest[name]["md5"]
