@@ -82,7 +82,7 @@ CALL_CASES = {
     "call_hpv16_mix2k_k16": ["call", "-r", "hpv_16.fa.gz", "-f", "mix2k.fq.gz", "-k", "16"],
     "call_zika_z1_k20_w50": ["call", "-r", "zika.fa.gz", "-f", "z1.fq.gz", "-k", "20", "-w", "50"],
     "call_newrefs_mix2k_k14": ["call", "-r", "new_refs.fa.gz", "-f", "mix2k.fq.gz", "-f", "minION25.fq.gz", "-k", "14"],
-    "call_hpv16_mix2k_k24_w10": ["call", "-r", "hpv_16.fa.gz", "-f", "mix2k.fq.gz", "-k", "24", "-w", "10"],
+    "call_zika_z1_k9_w10": ["call", "-r", "zika.fa.gz", "-f", "z1.fq.gz", "-k", "9", "-w", "10"],
     "call_show_depth": ["call", "-r", "hpv_16.fa.gz", "-f", "minION25.fq.gz", "-k", "12", "-d"],
 }
 

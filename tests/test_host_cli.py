@@ -383,7 +383,7 @@ def test_persistence_pre_references_and_count_table(rkmh_bin, cli_manifest, tmp_
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["call_hpv16_minion_k12", "call_hpv16_mix2k_k16", "call_zika_z1_k20_w50", "call_newrefs_mix2k_k14",
-                                  "call_hpv16_mix2k_k24_w10", "call_show_depth"])
+                                  "call_zika_z1_k9_w10", "call_show_depth"])
 def test_call_command_equals_reference(rkmh_bin, cli_manifest, name):
     """`rkmh call`: the VCF the real binary prints, byte for byte -- exact k-mer depths, sliding-window
     average carried across references, substitution and deletion rescues, calls in std::map order."""
