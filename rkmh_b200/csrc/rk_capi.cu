@@ -92,7 +92,7 @@ struct rkg_ctx {
     cudaStream_t stream = nullptr;
     rkg_batch* slots[2] = {nullptr, nullptr};   // internal double buffer of rkg_classify_batch / count
     // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
-    bool memo_enabled = true, memo_ready = false, sieve_enabled = true, group_kernel = false;
+    bool memo_enabled = true, memo_ready = false, sieve_enabled = true, group_kernel = false, coarse_table = true;
     DevBuf memo_coarse, memo_tab, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc, memo_sieve, memo_cmap;
     double sieve_fill = 0.0;             // fraction of the sieve's bits that are set (false-positive rate = fill^2)
     Memo memo{};
@@ -485,7 +485,7 @@ MemoGeom memo_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
     g.hs_cap = next_pow2(2 * (i64)std::min<i64>(ctx->s, std::max<i64>(b->max_ntotal, 1)));
     g.rpad = (ctx->nrefs + 63) / 64 * 64;
     const size_t budget = ctx->smem_optin / 2 - 4608;      // two blocks per SM: static scratch + hit rings + the 1 KB reserve
-    const size_t fixed = 4 * ((size_t)MEMO_BINS + 2 * (size_t)g.hs_cap + (size_t)g.rpad);
+    const size_t fixed = 4 * ((size_t)MEMO_HIST_WORDS + 2 * (size_t)g.hs_cap + (size_t)g.rpad);
     if (fixed + 4096 > budget) return g;
     const i64 room = (i64)((budget - fixed) / 4);
     g.vcap = (int)std::min<i64>(std::max<i64>(b->max_ntotal, 1), room);
@@ -563,12 +563,15 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
             const int grid = ctx->sm_count * std::max(1, std::min(per_sm, 8));
             CK(b->scratch.ensure(sizeof(u32) * (size_t)grid * (size_t)mg.scratch_stride + 64));
             // every window of every read looks its rank up in the 4^k-entry table: keep it in L2, stream the bases
-            if (!mg.use_warp) l2_window(ctx, b->stream, ctx->memo.tab, sizeof(u32) * (size_t)ctx->memo.ncodes);   // (the 16 MB byte table stays resident by itself)
+            if (!mg.use_warp) {
+                if (ctx->coarse_table) l2_window(ctx, b->stream, ctx->memo.coarse, (size_t)ctx->memo.ncodes);
+                else l2_window(ctx, b->stream, ctx->memo.tab, sizeof(u32) * (size_t)ctx->memo.ncodes);
+            }
             {
                 Timed t(ctx, b->stream, K_CLASSIFY_MEMO_BLOCK);
                 classify_memo_block_kernel<<<grid, 256, mg.block_smem, b->stream>>>(
                     sb, ctx->s, ctx->memo, ctx->tb, mg.use_warp ? redo : nullptr, mg.use_warp ? redo_count : nullptr, b->nseq,
-                    mg.vcap, mg.hs_cap, mg.rpad, b->scratch.as<u32>(), mg.scratch_stride, hits);
+                    mg.vcap, mg.hs_cap, mg.rpad, b->scratch.as<u32>(), mg.scratch_stride, hits, ctx->coarse_table ? 1 : 0);
             }
             if (!mg.use_warp) l2_window(ctx, b->stream, nullptr, 0);
             CK(cudaGetLastError());
@@ -767,6 +770,7 @@ int rkg_create(int device, rkg_ctx** out) {
     ctx->device = device;
     { const char* nm = getenv("RKMH_NO_MEMO"); ctx->memo_enabled = !(nm && nm[0] && nm[0] != '0'); }
     { const char* nm = getenv("RKMH_NO_SIEVE"); ctx->sieve_enabled = !(nm && nm[0] && nm[0] != '0'); }
+    { const char* nm = getenv("RKMH_NO_COARSE"); ctx->coarse_table = !(nm && nm[0] && nm[0] != '0'); }       // A/B timing of the byte table
     { const char* nm = getenv("RKMH_GROUP_KERNEL"); ctx->group_kernel = nm && nm[0] && nm[0] != '0'; }   // round-1 Murmur fast path (A/B timing)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;

@@ -29,6 +29,11 @@ constexpr u32 MEMO_COARSE_SKIP = 255u;         // coarse[] value of a code whose
 constexpr u32 MEMO_SKIP = 0xFFFFFFFFu;          // "window does not count": never a real entry (5 flag bits unused)
 constexpr int MEMO_BUCKET_CAP = 1024;           // rank build: largest hash bucket that is sorted in shared memory
 constexpr int MEMO_BINS = 4096;
+// The histogram is stored with one word of padding per 16 bins: memo_find_bin gives each thread 16 CONSECUTIVE bins, and
+// without the padding the 32 lanes of a warp read addresses 16 words apart -- two banks, a 16-way conflict on every load
+// (ncu, round 2: 64 % of this kernel's shared-memory wavefronts were such replays).
+constexpr int MEMO_HIST_WORDS = MEMO_BINS + MEMO_BINS / 16;
+RK_HD u32 memo_hidx(u32 bin) { return bin + (bin >> 4); }
 constexpr int MEMO_PARTIAL_PAD = 32;             // int32 slots after code_counts[ncodes): [0] = invalid windows, rest zero (keeps the array 128-byte sized)
 constexpr int MEMO_RING = 64;                   // block kernel: per-warp ring of sketch members waiting for their rows                 // radix-select histogram (12 bits of the 24-bit rank per level)
 
@@ -863,7 +868,7 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
 // shared memory (or L2 scratch for very long reads); the bottom-s multiset is a two-level radix select on the 24-bit
 // rank; its REF members are resolved against the reference table exactly like the Murmur path does.
 //
-// Dynamic shared memory (u32 units): [vcap values][MEMO_BINS histogram][hs_cap keys][hs_cap counts][rpad counters]
+// Dynamic shared memory (u32 units): [vcap values][MEMO_HIST_WORDS histogram][hs_cap keys][hs_cap counts][rpad counters]
 struct MemoBlockScratch { u32 part[32]; u32 bin, before; int nz, take, ncand; u32 cut; ArgmaxScratch as; };
 
 // the bin in which the running count of hist[0, MEMO_BINS) reaches `target` (1-based), and the count before it
@@ -871,7 +876,7 @@ RK_D void memo_find_bin(const u32* hist, u32 target, MemoBlockScratch* bs) {
     const int per = MEMO_BINS / (int)blockDim.x, b0 = (int)threadIdx.x * per;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     u32 sum = 0;
-    for (int i = 0; i < per; ++i) sum += hist[b0 + i];
+    for (int i = 0; i < per; ++i) sum += hist[memo_hidx((u32)(b0 + i))];
     u32 incl = sum;
     for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
     if (lane == 31) bs->part[wib] = incl;
@@ -882,7 +887,7 @@ RK_D void memo_find_bin(const u32* hist, u32 target, MemoBlockScratch* bs) {
     if (excl < target && target <= excl + sum) {
         u32 run = excl;
         for (int i = 0; i < per; ++i) {
-            const u32 c = hist[b0 + i];
+            const u32 c = hist[memo_hidx((u32)(b0 + i))];
             if (run + c >= target) { bs->bin = (u32)(b0 + i); bs->before = run; break; }
             run += c;
         }
@@ -893,17 +898,18 @@ RK_D void memo_find_bin(const u32* hist, u32 target, MemoBlockScratch* bs) {
 __global__ void __launch_bounds__(256, 2)
 classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* __restrict__ list,
                            const int* __restrict__ nlist_ptr, i64 nseq, int vcap, int hs_cap, int rpad,
-                           u32* __restrict__ scratch, i64 scratch_stride, Hit* __restrict__ out) {
+                           u32* __restrict__ scratch, i64 scratch_stride, Hit* __restrict__ out, int use_coarse_flag = 1) {
 #ifdef RK_EMU
     unsigned char* dsm = reinterpret_cast<unsigned char*>(EMU_DYN_SMEM());
 #else
     extern __shared__ __align__(16) unsigned char dsm[];
 #endif
+    const bool use_coarse = use_coarse_flag != 0 && mm.coarse != nullptr;
     __shared__ MemoBlockScratch bs;
     __shared__ u32 wq[8][MEMO_RING];                         // per-warp ring of hit ranks (blocks of 256 threads)
     u32* vals_smem = reinterpret_cast<u32*>(dsm);
     u32* hist = vals_smem + vcap;
-    u32* hs_keys = hist + MEMO_BINS;
+    u32* hs_keys = hist + MEMO_HIST_WORDS;
     u32* hs_cnt = hs_keys + hs_cap;
     u32* counts = hs_cnt + hs_cap;
     const u32 hs_mask = (u32)hs_cap - 1;
@@ -919,7 +925,7 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
         const i64 n = nkmers(len, k);
         u32* V = (n <= vcap) ? vals_smem : scratch + (i64)blockIdx.x * scratch_stride;
         if (threadIdx.x == 0) { bs.nz = 0; bs.take = 0; bs.ncand = 0; }
-        for (int i = threadIdx.x; i < MEMO_BINS; i += blockDim.x) hist[i] = 0;
+        for (int i = threadIdx.x; i < MEMO_HIST_WORDS; i += blockDim.x) hist[i] = 0;
         for (int i = threadIdx.x; i < 2 * hs_cap; i += blockDim.x) hs_keys[i] = 0;
         for (int i = threadIdx.x; i < rpad; i += blockDim.x) counts[i] = 0;
         __syncthreads();
@@ -930,30 +936,34 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
         // stays in L2, the 64 MB rank table does not (12 % of its lookups went to HBM); a read whose threshold turns out
         // to lie above `cut` (or that keeps all its k-mers) is simply streamed again with cut = 254, i.e. everything.
         for (int attempt = 0; attempt < 2; ++attempt) {
-            const u32 cut = (attempt == 0 && n > s) ? bs.cut : 254u;
+            const u32 cut = (use_coarse && attempt == 0 && n > s) ? bs.cut : 254u;
             const i64 per = ((((n + 31) >> 5) + nwb - 1) / nwb) << 5;
             const i64 s0 = (i64)wib * per, s1 = min(n, s0 + per);
             u32 local_nz = 0, local_cand = 0;
             // two pipeline stages of two rounds each: the byte of a window is examined two rounds after it was requested,
             // the rank it then asks for two rounds after that
-            u32 cA1 = MEMO_COARSE_SKIP, cA2 = MEMO_COARSE_SKIP, kA1 = 0, kA2 = 0;
+            u32 cA1 = use_coarse ? MEMO_COARSE_SKIP : MEMO_SKIP, cA2 = cA1, kA1 = 0, kA2 = 0;
             u32 mB1 = MEMO_SKIP, mB2 = MEMO_SKIP;
             i64 pA1 = 0, pA2 = 0, pB1 = 0, pB2 = 0;
             bool iA1 = false, iA2 = false, iB1 = false, iB2 = false;
             auto stageB = [&](i64 pos, bool in, u32 m) {    // a rank (or MEMO_SKIP) arrives
                 if (in) V[pos] = m;
-                if (m != MEMO_SKIP) { ++local_cand; atomicAdd(&hist[m >> 20], 1u); }
+                if (m != MEMO_SKIP) { ++local_cand; atomicAdd(&hist[memo_hidx(m >> 20)], 1u); }
             };
             auto stageA = [&](i64 pos, bool in, u32 cb, u32 code) {   // a coarse byte arrives
                 u32 m = MEMO_SKIP;
-                if (cb != MEMO_COARSE_SKIP) { ++local_nz; if (cb <= cut) m = __ldg(&mm.tab[code]); }
+                if (!use_coarse) {                           // (A/B switch: cb is the rank table's value itself)
+                    m = cb;
+                    if (m != MEMO_SKIP && (m & (MEMO_ZERO | MEMO_FAILM))) m = MEMO_SKIP;
+                    local_nz += m != MEMO_SKIP;
+                } else if (cb != MEMO_COARSE_SKIP) { ++local_nz; if (cb <= cut) m = __ldg(&mm.tab[code]); }
                 stageB(pB2, iB2, mB2);
                 mB2 = mB1; pB2 = pB1; iB2 = iB1;
                 mB1 = m; pB1 = pos; iB1 = in;
             };
             memo_stream(sb.bases + beg, len, k, mm.kmask, s0, s1, lane, [&](i64 pos, u32 code, bool in, bool valid) {
-                u32 cb = MEMO_COARSE_SKIP;
-                if (valid) cb = (u32)__ldg(&mm.coarse[code]);
+                u32 cb = use_coarse ? MEMO_COARSE_SKIP : MEMO_SKIP;
+                if (valid) cb = use_coarse ? (u32)__ldg(&mm.coarse[code]) : __ldg(&mm.tab[code]);
                 stageA(pA2, iA2, cA2, kA2);
                 cA2 = cA1; pA2 = pA1; iA2 = iA1; kA2 = kA1;
                 cA1 = cb; pA1 = pos; iA1 = in; kA1 = code;
@@ -971,7 +981,7 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
             __syncthreads();
             if (ok) break;
             if (threadIdx.x == 0) { bs.nz = 0; bs.ncand = 0; }
-            for (int i = threadIdx.x; i < MEMO_BINS; i += blockDim.x) hist[i] = 0;
+            for (int i = threadIdx.x; i < MEMO_HIST_WORDS; i += blockDim.x) hist[i] = 0;
             __syncthreads();
         }
         const int nz = bs.nz;
@@ -982,11 +992,11 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
             memo_find_bin(hist, (u32)s, &bs);
             const u32 b1 = bs.bin, before1 = bs.before;
             __syncthreads();
-            for (int i = threadIdx.x; i < MEMO_BINS; i += blockDim.x) hist[i] = 0;
+            for (int i = threadIdx.x; i < MEMO_HIST_WORDS; i += blockDim.x) hist[i] = 0;
             __syncthreads();
             for (i64 i = threadIdx.x; i < n; i += blockDim.x) {
                 const u32 m = V[i];
-                if (m != MEMO_SKIP && (m >> 20) == b1) atomicAdd(&hist[(m >> 8) & 0xFFFu], 1u);
+                if (m != MEMO_SKIP && (m >> 20) == b1) atomicAdd(&hist[memo_hidx((m >> 8) & 0xFFFu)], 1u);
             }
             __syncthreads();
             memo_find_bin(hist, (u32)s - before1, &bs);

@@ -390,7 +390,7 @@ int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, con
         int vcap = (int)std::max<i64>(b.max_ntotal, 1);
         if (vcap_limit > 0) vcap = std::min(vcap, vcap_limit);
         const i64 stride = (b.max_ntotal > vcap) ? b.max_ntotal : 0;
-        size_t smem = 4 * ((size_t)vcap + MEMO_BINS + 2 * (size_t)hs_cap + rpad);
+        size_t smem = 4 * ((size_t)vcap + MEMO_HIST_WORDS + 2 * (size_t)hs_cap + rpad);
         std::vector<u32> scratch((size_t)grid * (size_t)stride + 8);
         u32* ps = scratch.data();
         const int* list = (path >= 1) ? predo : nullptr;
