@@ -92,8 +92,8 @@ struct rkg_ctx {
     cudaStream_t stream = nullptr;
     rkg_batch* slots[2] = {nullptr, nullptr};   // internal double buffer of rkg_classify_batch / count
     // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
-    bool memo_enabled = true, memo_ready = false, sieve_enabled = true, group_kernel = false, coarse_table = true;
-    DevBuf memo_coarse, memo_tab, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc, memo_sieve, memo_cmap;
+    bool memo_enabled = true, memo_ready = false, sieve_enabled = true, group_kernel = false;
+    DevBuf memo_tab, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc, memo_sieve, memo_cmap;
     double sieve_fill = 0.0;             // fraction of the sieve's bits that are set (false-positive rate = fill^2)
     Memo memo{};
     bool memo_pending = false;           // code_counts holds increments not yet folded into the read count table
@@ -271,7 +271,6 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     const int bucket_bits = std::max(2 * k - 8, 0);
     const u32 nb = 1u << bucket_bits;
     CK(ctx->memo_tab.ensure(sizeof(u32) * (size_t)ncodes));
-    CK(ctx->memo_coarse.ensure((size_t)ncodes + 64));
     CK(ctx->memo_ref.ensure(sizeof(u32) * (size_t)ncodes));
     CK(ctx->memo_hash.ensure(sizeof(u64) * (size_t)ncodes));
     CK(ctx->memo_tmp.ensure(sizeof(u32) * ((size_t)3 * nb + ncodes)));
@@ -283,7 +282,6 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     CK(cudaMemsetAsync(ctx->memo_misc.p, 0, 256, st));
     Memo mm{};
     mm.tab = ctx->memo_tab.as<u32>(); mm.ref = ctx->memo_ref.as<u32>(); mm.hash = ctx->memo_hash.as<u64>();
-    mm.coarse = ctx->memo_coarse.as<unsigned char>();
     mm.inval = nullptr;
     int* err = ctx->memo_misc.as<int>() + 8;
     mm.ncodes = ncodes; mm.kmask = (1u << k) - 1u; mm.k = k;
@@ -314,12 +312,6 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     CK(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (herr) return RKG_OK;          // a hash bucket larger than the sort capacity: keep the Murmur path (still exact)
-    {   // the one-byte rank table of the long-read kernel (no -M mask baked yet: min_occ = -1)
-        Timed t(ctx, st, K_MEMO_BUILD);
-        const int grid = (int)std::min<i64>(((i64)ncodes + 255) / 256, (i64)ctx->sm_count * 16);
-        memo_apply_occ_kernel<<<grid, 256, 0, st>>>(mm, CountTable{nullptr, {}}, -1);
-    }
-    CK(cudaGetLastError());
     // sieve + code map of classify_memo_sieve_kernel (rk_memo.cuh).  The sieve takes what a 1024-thread block can
     // have beside its candidate queues; it is dropped when it would let more than a quarter of all windows through.
     mm.sieve = nullptr; mm.cmap = nullptr; mm.sieve_words = 0; mm.zero_codes = 0;
@@ -563,15 +555,12 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
             const int grid = ctx->sm_count * std::max(1, std::min(per_sm, 8));
             CK(b->scratch.ensure(sizeof(u32) * (size_t)grid * (size_t)mg.scratch_stride + 64));
             // every window of every read looks its rank up in the 4^k-entry table: keep it in L2, stream the bases
-            if (!mg.use_warp) {
-                if (ctx->coarse_table) l2_window(ctx, b->stream, ctx->memo.coarse, (size_t)ctx->memo.ncodes);
-                else l2_window(ctx, b->stream, ctx->memo.tab, sizeof(u32) * (size_t)ctx->memo.ncodes);
-            }
+            if (!mg.use_warp) l2_window(ctx, b->stream, ctx->memo.tab, sizeof(u32) * (size_t)ctx->memo.ncodes);
             {
                 Timed t(ctx, b->stream, K_CLASSIFY_MEMO_BLOCK);
                 classify_memo_block_kernel<<<grid, 256, mg.block_smem, b->stream>>>(
                     sb, ctx->s, ctx->memo, ctx->tb, mg.use_warp ? redo : nullptr, mg.use_warp ? redo_count : nullptr, b->nseq,
-                    mg.vcap, mg.hs_cap, mg.rpad, b->scratch.as<u32>(), mg.scratch_stride, hits, ctx->coarse_table ? 1 : 0);
+                    mg.vcap, mg.hs_cap, mg.rpad, b->scratch.as<u32>(), mg.scratch_stride, hits);
             }
             if (!mg.use_warp) l2_window(ctx, b->stream, nullptr, 0);
             CK(cudaGetLastError());
@@ -770,7 +759,6 @@ int rkg_create(int device, rkg_ctx** out) {
     ctx->device = device;
     { const char* nm = getenv("RKMH_NO_MEMO"); ctx->memo_enabled = !(nm && nm[0] && nm[0] != '0'); }
     { const char* nm = getenv("RKMH_NO_SIEVE"); ctx->sieve_enabled = !(nm && nm[0] && nm[0] != '0'); }
-    { const char* nm = getenv("RKMH_NO_COARSE"); ctx->coarse_table = !(nm && nm[0] && nm[0] != '0'); }       // A/B timing of the byte table
     { const char* nm = getenv("RKMH_GROUP_KERNEL"); ctx->group_kernel = nm && nm[0] && nm[0] != '0'; }   // round-1 Murmur fast path (A/B timing)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
@@ -805,7 +793,7 @@ void rkg_destroy(rkg_ctx* ctx) {
     for (int i = 0; i < 2; ++i) batch_release(ctx->slots[i]);
     for (DevBuf* d : {&ctx->depth_keys, &ctx->depth_counts, &ctx->depth_zero, &ctx->hash_lut, &ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
                       &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
-                      &ctx->memo_coarse, &ctx->memo_tab, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
+                      &ctx->memo_tab, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
                       &ctx->memo_sieve, &ctx->memo_cmap})
         d->release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

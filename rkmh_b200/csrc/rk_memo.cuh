@@ -25,13 +25,12 @@ namespace rk {
 
 constexpr int MEMO_MAX_K = 12;
 constexpr u32 MEMO_REF = 1u, MEMO_ZERO = 2u, MEMO_FAILM = 4u;
-constexpr u32 MEMO_COARSE_SKIP = 255u;         // coarse[] value of a code whose windows do not count; ranks >= 254 << 16 share 254
 constexpr u32 MEMO_SKIP = 0xFFFFFFFFu;          // "window does not count": never a real entry (5 flag bits unused)
 constexpr int MEMO_BUCKET_CAP = 1024;           // rank build: largest hash bucket that is sorted in shared memory
 constexpr int MEMO_BINS = 4096;
 // The histogram is stored with one word of padding per 16 bins: memo_find_bin gives each thread 16 CONSECUTIVE bins, and
 // without the padding the 32 lanes of a warp read addresses 16 words apart -- two banks, a 16-way conflict on every load
-// (ncu, round 2: 64 % of this kernel's shared-memory wavefronts were such replays).
+// (ncu, round 2: 64 % of this kernel's shared-memory wavefronts were such replays; 6.6 % with the padding).
 constexpr int MEMO_HIST_WORDS = MEMO_BINS + MEMO_BINS / 16;
 RK_HD u32 memo_hidx(u32 bin) { return bin + (bin >> 4); }
 constexpr int MEMO_PARTIAL_PAD = 32;             // int32 slots after code_counts[ncodes): [0] = invalid windows, rest zero (keeps the array 128-byte sized)
@@ -39,8 +38,6 @@ constexpr int MEMO_RING = 64;                   // block kernel: per-warp ring o
 
 struct Memo {
     u32* tab;                       // indexed by the plane code (warp-streaming kernels)
-    unsigned char* coarse;          // top 8 bits of the 24-bit rank, MEMO_COARSE_SKIP for codes that do not count (ZERO / FAILM):
-                                    //   16 MB at k = 12, what the long-read kernel consults first (see classify_memo_block_kernel)
     u32* ref;
     const u64* hash;
     int* code_counts;               // nullptr when the context has no read count table
@@ -242,7 +239,6 @@ memo_apply_occ_kernel(Memo mm, CountTable ct, int min_occ) {
         }
         const u32 nt = (t & ~MEMO_FAILM) | fail;
         if (nt != t) mm.tab[c] = nt;
-        if (mm.coarse) mm.coarse[c] = (unsigned char)((nt & (MEMO_ZERO | MEMO_FAILM)) ? MEMO_COARSE_SKIP : min(nt >> 24, 254u));
     }
 }
 
@@ -869,7 +865,7 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
 // rank; its REF members are resolved against the reference table exactly like the Murmur path does.
 //
 // Dynamic shared memory (u32 units): [vcap values][MEMO_HIST_WORDS histogram][hs_cap keys][hs_cap counts][rpad counters]
-struct MemoBlockScratch { u32 part[32]; u32 bin, before; int nz, take, ncand; u32 cut; ArgmaxScratch as; };
+struct MemoBlockScratch { u32 part[32]; u32 bin, before; int nz, take; ArgmaxScratch as; };
 
 // the bin in which the running count of hist[0, MEMO_BINS) reaches `target` (1-based), and the count before it
 RK_D void memo_find_bin(const u32* hist, u32 target, MemoBlockScratch* bs) {
@@ -898,13 +894,12 @@ RK_D void memo_find_bin(const u32* hist, u32 target, MemoBlockScratch* bs) {
 __global__ void __launch_bounds__(256, 2)
 classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* __restrict__ list,
                            const int* __restrict__ nlist_ptr, i64 nseq, int vcap, int hs_cap, int rpad,
-                           u32* __restrict__ scratch, i64 scratch_stride, Hit* __restrict__ out, int use_coarse_flag = 1) {
+                           u32* __restrict__ scratch, i64 scratch_stride, Hit* __restrict__ out) {
 #ifdef RK_EMU
     unsigned char* dsm = reinterpret_cast<unsigned char*>(EMU_DYN_SMEM());
 #else
     extern __shared__ __align__(16) unsigned char dsm[];
 #endif
-    const bool use_coarse = use_coarse_flag != 0 && mm.coarse != nullptr;
     __shared__ MemoBlockScratch bs;
     __shared__ u32 wq[8][MEMO_RING];                         // per-warp ring of hit ranks (blocks of 256 threads)
     u32* vals_smem = reinterpret_cast<u32*>(dsm);
@@ -916,74 +911,51 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     const int k = mm.k;
 
-    if (threadIdx.x == 0) bs.cut = 254u;                     // the first read of the block looks everything up
-    __syncthreads();
     const i64 nlist = list ? (i64)*nlist_ptr : nseq;
     for (i64 q = blockIdx.x; q < nlist; q += gridDim.x) {
         const i64 rid = list ? (i64)list[q] : q;
         const i64 beg = sb.offs[rid] - sb.base0, len = sb.offs[rid + 1] - sb.offs[rid];
         const i64 n = nkmers(len, k);
         u32* V = (n <= vcap) ? vals_smem : scratch + (i64)blockIdx.x * scratch_stride;
-        if (threadIdx.x == 0) { bs.nz = 0; bs.take = 0; bs.ncand = 0; }
+        if (threadIdx.x == 0) { bs.nz = 0; bs.take = 0; }
         for (int i = threadIdx.x; i < MEMO_HIST_WORDS; i += blockDim.x) hist[i] = 0;
         for (int i = threadIdx.x; i < 2 * hs_cap; i += blockDim.x) hs_keys[i] = 0;
         for (int i = threadIdx.x; i < rpad; i += blockDim.x) counts[i] = 0;
         __syncthreads();
-        // ---- pass 1: table values of the windows that can be sketch members, histogram of their top 12 rank bits ---
-        // Every window first reads ONE BYTE: the top 8 bits of its rank (or "does not count").  Only the windows at or
-        // below `cut` -- a little above where the previous read of this block had its bottom-s threshold -- go on to the
-        // 4-byte rank table, the histogram and V[]; the others are counted and forgotten.  The byte table is 16 MB and
-        // stays in L2, the 64 MB rank table does not (12 % of its lookups went to HBM); a read whose threshold turns out
-        // to lie above `cut` (or that keeps all its k-mers) is simply streamed again with cut = 254, i.e. everything.
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            const u32 cut = (use_coarse && attempt == 0 && n > s) ? bs.cut : 254u;
+        // ---- pass 1: table values of every window, histogram of the top 12 rank bits ----------------------
+        {
             const i64 per = ((((n + 31) >> 5) + nwb - 1) / nwb) << 5;
             const i64 s0 = (i64)wib * per, s1 = min(n, s0 + per);
-            u32 local_nz = 0, local_cand = 0;
-            // two pipeline stages of two rounds each: the byte of a window is examined two rounds after it was requested,
-            // the rank it then asks for two rounds after that
-            u32 cA1 = use_coarse ? MEMO_COARSE_SKIP : MEMO_SKIP, cA2 = cA1, kA1 = 0, kA2 = 0;
-            u32 mB1 = MEMO_SKIP, mB2 = MEMO_SKIP;
-            i64 pA1 = 0, pA2 = 0, pB1 = 0, pB2 = 0;
-            bool iA1 = false, iA2 = false, iB1 = false, iB2 = false;
-            auto stageB = [&](i64 pos, bool in, u32 m) {    // a rank (or MEMO_SKIP) arrives
-                if (in) V[pos] = m;
-                if (m != MEMO_SKIP) { ++local_cand; atomicAdd(&hist[memo_hidx(m >> 20)], 1u); }
+            u32 local_nz = 0;
+            // the table value of a window is consumed FOUR rounds after its lookup was issued: five lookups of a warp are
+            // in flight (the 64 MB table does not fit one die's L2: a tenth of them go to HBM; with two rounds of delay ncu
+            // showed 2.3 long-scoreboard stalls per issued instruction).  The window of a delayed value is where the
+            // stream was four rounds ago, so no positions travel with the values.
+            constexpr int DELAY = 4;
+            u32 ring[DELAY];
+#pragma unroll
+            for (int d = 0; d < DELAY; ++d) ring[d] = MEMO_SKIP;
+            auto consume = [&](i64 pos, u32 m) {
+                if (m != MEMO_SKIP && (m & (MEMO_ZERO | MEMO_FAILM))) m = MEMO_SKIP;
+                if (pos >= s0 && pos < s1) V[pos] = m;
+                if (m != MEMO_SKIP) { ++local_nz; atomicAdd(&hist[memo_hidx(m >> 20)], 1u); }
             };
-            auto stageA = [&](i64 pos, bool in, u32 cb, u32 code) {   // a coarse byte arrives
+            i64 last = s0 + lane - 32;
+            memo_stream(sb.bases + beg, len, k, mm.kmask, s0, s1, lane, [&](i64 pos, u32 code, bool, bool valid) {
                 u32 m = MEMO_SKIP;
-                if (!use_coarse) {                           // (A/B switch: cb is the rank table's value itself)
-                    m = cb;
-                    if (m != MEMO_SKIP && (m & (MEMO_ZERO | MEMO_FAILM))) m = MEMO_SKIP;
-                    local_nz += m != MEMO_SKIP;
-                } else if (cb != MEMO_COARSE_SKIP) { ++local_nz; if (cb <= cut) m = __ldg(&mm.tab[code]); }
-                stageB(pB2, iB2, mB2);
-                mB2 = mB1; pB2 = pB1; iB2 = iB1;
-                mB1 = m; pB1 = pos; iB1 = in;
-            };
-            memo_stream(sb.bases + beg, len, k, mm.kmask, s0, s1, lane, [&](i64 pos, u32 code, bool in, bool valid) {
-                u32 cb = use_coarse ? MEMO_COARSE_SKIP : MEMO_SKIP;
-                if (valid) cb = use_coarse ? (u32)__ldg(&mm.coarse[code]) : __ldg(&mm.tab[code]);
-                stageA(pA2, iA2, cA2, kA2);
-                cA2 = cA1; pA2 = pA1; iA2 = iA1; kA2 = kA1;
-                cA1 = cb; pA1 = pos; iA1 = in; kA1 = code;
+                if (valid) m = __ldg(&mm.tab[code]);
+                consume(pos - 32 * DELAY, ring[DELAY - 1]);
+#pragma unroll
+                for (int d = DELAY - 1; d > 0; --d) ring[d] = ring[d - 1];
+                ring[0] = m;
+                last = pos;
             });
-            stageA(pA2, iA2, cA2, kA2);
-            stageA(pA1, iA1, cA1, kA1);
-            stageB(pB2, iB2, mB2);
-            stageB(pB1, iB1, mB1);
-            local_nz = warp_sum(local_nz); local_cand = warp_sum(local_cand);
+#pragma unroll
+            for (int d = DELAY - 1; d >= 0; --d) consume(last - 32 * d, ring[d]);
+            local_nz = warp_sum(local_nz);
             if (lane == 0 && local_nz) atomicAdd(&bs.nz, (int)local_nz);
-            if (lane == 0 && local_cand) atomicAdd(&bs.ncand, (int)local_cand);
-            __syncthreads();
-            // enough candidates for the bottom s?  (all of them when the read keeps everything: cut = 254 then)
-            const bool ok = cut == 254u || bs.ncand >= s;
-            __syncthreads();
-            if (ok) break;
-            if (threadIdx.x == 0) { bs.nz = 0; bs.ncand = 0; }
-            for (int i = threadIdx.x; i < MEMO_HIST_WORDS; i += blockDim.x) hist[i] = 0;
-            __syncthreads();
         }
+        __syncthreads();
         const int nz = bs.nz;
         const int L = nz < s ? nz : s;
         // ---- bottom-s threshold: rank T, of which `need` copies belong to the sketch -----------------------
@@ -1003,9 +975,7 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
             T = (b1 << 12) | bs.bin;
             need = s - (int)before1 - (int)bs.before;
             __syncthreads();
-            // next read: a quarter above this read's threshold (its top 8 bits), everything when that reaches the top
-            if (threadIdx.x == 0) { const u32 c8 = T >> 16; bs.cut = min(254u, c8 + (c8 >> 2) + 2u); }
-        } else if (threadIdx.x == 0) bs.cut = 254u;
+        }
         // ---- resolve the REF members of the sketch: 32 windows per warp step ---------------------------------
         const bool small = tb.nb == 1;
         u32 vp[5][2];

@@ -278,7 +278,6 @@ int emu_classify(const char* ref_bases, const i64* ref_offs, int nrefs, const ch
 // ---- memoised path (rk_memo.cuh) -------------------------------------------------------------------------
 struct HostMemo {
     std::vector<u32> tab, ref, tmp, sieve;
-    std::vector<unsigned char> coarse;
     std::vector<unsigned long long> cmap;
     u32 stats[2] = {0, 0};
     std::vector<u64> hash;
@@ -304,7 +303,6 @@ static void build_memo(HostMemo& hm, int k, const RefTable& tb, int block) {
     emu::launch(dim3(2), dim3(block), 0, [=] { memo_scatter_kernel(ncodes, hash, bstart, bfill, bcodes, bucket_bits); });
     emu::launch(dim3(2), dim3(block), 0, [=] { memo_rank_kernel(hash, bcount, bstart, bcodes, nb, tb, tab, ref); });
     hm.mm.tab = tab; hm.mm.ref = ref; hm.mm.hash = hash; hm.mm.code_counts = hm.code_counts.data();
-    hm.coarse.assign(ncodes, 255); hm.mm.coarse = hm.coarse.data();
     hm.mm.inval = &hm.inval; hm.mm.ncodes = ncodes; hm.mm.kmask = (1u << k) - 1u; hm.mm.k = k;
     Memo mm = hm.mm;
     // sieve + code map (classify_memo_sieve_kernel); a small sieve so that false positives do occur in the tests
