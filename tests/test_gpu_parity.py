@@ -546,3 +546,48 @@ def test_pre_hashed_references_and_count_table_round_trip(oracle):
                 b.load_ref_sketches(bad, ln)
     exp = oracle.classify_batch([bases[offs[i]:offs[i + 1]].tobytes() for i in range(100)], [12], 1000, *oracle.sketch_batch(rs, [12], 1000))
     assert np.array_equal(ha[:100], _fields(exp))
+
+
+def test_call_depth_entry_points_vs_oracle(oracle):
+    """rkg_depth_*: the exact multiplicity of every read hash (zeros = invalid windows included, as the reference's
+    unordered_map counts them, src/rkmh.cpp:1617-1622), the depth of every reference window, and the depths of the
+    substitution / deletion alternatives of listed windows, against counts made with the oracle's calc_hash."""
+    import collections
+    import rkmh_b200
+    _, refs, _ = load_sequences([data_path("hpv_16.fa.gz")])
+    _, reads, _ = load_sequences([data_path("mix2k.fq.gz")])
+    reads = reads[:400] + [b"ACGTNNNNACGTACGTAGGATCCANNNN", b"ACGTACG"]
+    ref = oracle.to_upper(refs[0])[:1500] + b"NNACGTRYACGT" + oracle.to_upper(refs[0])[1500:1700]
+    for k in (11, 16, 23):
+        depth = collections.Counter()
+        for r in reads:
+            depth.update(int(h) for h in oracle.calc_hashes(oracle.to_upper(r), [k]))
+        with rkmh_b200.RkmhGpu(0) as g:
+            g.set_params([k], 1)
+            g.depth_begin(sum(max(len(r) - k, 0) for r in reads))
+            g.depth_add(*_pack(reads))
+            with pytest.raises(rkmh_b200.RkmhError, match="expect"):
+                g.depth_add(*_pack(reads[:1]))
+            got = g.depth_of_sequence(ref)
+            exp = np.array([depth.get(int(h), 0) for h in oracle.calc_hashes(ref, [k])], np.int32)
+            assert np.array_equal(got, exp)
+            wins = np.array([0, 1, 7, 1490, 1495, 1502, len(ref) - k - 1], np.int64)
+            alt = g.depth_rescue(ref, wins)
+        rot = {ord("A"): b"CTG", ord("C"): b"TGA", ord("T"): b"CGA", ord("G"): b"ACT"}
+        for w, j in enumerate(wins):
+            j = int(j)
+            for p in range(k):
+                for x in range(3):
+                    orig = ref[j + p]
+                    if orig not in rot:
+                        assert alt[w, 3 * p + x] == -1
+                        continue
+                    km = ref[j:j + p] + bytes([rot[orig][x]]) + ref[j + p + 1:j + k]
+                    assert alt[w, 3 * p + x] == depth.get(oracle.calc_hash(km), 0), (k, j, p, x)
+            for d in range(1, k + 1):
+                if j == 0:
+                    assert alt[w, 3 * k + d - 1] == -1
+                    continue
+                big = ref[j - 1:j + k]
+                km = big[:d] + big[d + 1:]
+                assert alt[w, 3 * k + d - 1] == depth.get(oracle.calc_hash(km), 0), (k, j, d)
