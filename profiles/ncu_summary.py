@@ -35,32 +35,35 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__thread_inst_executed_per_inst_executed.ratio"]
 
 
+UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}
+
+
 def current(argv):
-    """--current out.json rep:reads [rep:reads ...]: the per-launch counters bench.py turns into `roofline.traffic` and
-    `issue_slots`, keyed by kernel name, stamped with the hash of the kernel sources of the tree they were taken from."""
+    """--current out.json raw.json:reads [raw.json:reads ...]: the per-launch counters bench.py turns into `roofline.traffic`
+    and `issue_slots`, keyed by kernel name, from *_ncu_raw.json summaries (made by this script from captures of
+    `tools/run_kernel.py`, which prints the reads per launch), stamped with the hash of the kernel sources of the tree
+    they are written in.  Bytes are bytes, durations nanoseconds."""
     import os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from bench import source_hash
     out_path, specs = argv[0], argv[1:]
     res = {"source_hash": source_hash(), "kernels": {}}
     for spec in specs:
-        rep, reads = spec.rsplit(":", 1)
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
-        rows = list(csv.reader(txt.splitlines()))
-        hdr = rows[0]
-        for vals in rows[2:]:
-            d = dict(zip(hdr, vals))
-            name = d.get("Kernel Name", "").split("<")[0].split("(")[0].replace("rk::", "").strip()
-
-            def num(key):
-                try:
-                    return float(d[key].replace(",", ""))
-                except (KeyError, ValueError):
-                    return None
+        raw, reads = spec.rsplit(":", 1)
+        with open(raw) as fh:
+            doc = json.load(fh)
+        for k in doc["kernels"]:
+            name = k["name"].replace("void ", "").split("<")[0].split("(")[0].replace("rk::", "").strip()
             if name in res["kernels"]:
                 continue
+
+            def num(key):
+                v = k.get(key)
+                if not v or not isinstance(v["value"], (int, float)):
+                    return None
+                return float(v["value"]) * UNIT_SCALE.get(v["unit"], 1.0)
             res["kernels"][name] = {
-                "reads": int(reads), "report": os.path.basename(rep), "full_name": d.get("Kernel Name", ""),
+                "reads": int(reads), "capture": os.path.basename(raw), "command": doc.get("_command", ""), "full_name": k["name"],
                 "dram_bytes": (num("dram__bytes_read.sum") or 0.0) + (num("dram__bytes_write.sum") or 0.0),
                 "warp_instructions": num("smsp__inst_executed.sum"),
                 "duration_ns_under_ncu": num("gpu__time_duration.sum"),

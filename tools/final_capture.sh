@@ -19,6 +19,6 @@ tools/ncu_capture.sh ${TAG}_warp_k20 classify_warp_kernel cfg4
 tools/ncu_capture.sh ${TAG}_count count_memo_kernel cfg3
 tools/ncu_capture.sh ${TAG}_block classify_memo_block_kernel cfg3
 SPECS=""
-for t in sieve warp_k12 count block; do SPECS="$SPECS /tmp/${TAG}_$t.ncu-rep:$(cat $OUT/${TAG}_$t.reads)"; done
+for t in sieve warp_k12 count block; do SPECS="$SPECS $OUT/${TAG}_${t}_ncu_raw.json:$(cat $OUT/${TAG}_$t.reads)"; done
 python profiles/ncu_summary.py --current $OUT/ncu_current.json $SPECS
 tail -2 $OUT/${TAG}_gputest.log; cat $OUT/${TAG}_smoke.log | tail -1; ls -la $OUT | head -50; du -sh $OUT
