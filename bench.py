@@ -440,8 +440,17 @@ def section_config2(args, R, gpu, refs, pins):
     e2e_ms = R.timed(e2e_fixed, args.steps, w)
     same = bool(np.array_equal(hits_host.view(np.int32), dev_hits.view(np.int32)))
     ceiling_ms = R.timed(copies_only, args.steps, 1)
+    # the same call with the packed transfer: the library packs every chunk to 2-bit codes + mask on this rank's host
+    # cores (inside the timed call) and ships 0.375 B/base; the records must be the same
+    threads = max(1, host_cores() // max(R.world, 1))
+    gpu.set_host_pack(True, threads)
+    hits_host[:] = 0
+    packed_ms = R.timed(e2e_fixed, args.steps, w)
+    same_packed = bool(np.array_equal(hits_host.view(np.int32), dev_hits.view(np.int32)))
+    gpu.set_host_pack(False)
     return {"n": n, "hb": hb, "ho": ho, "kernel_ms": kernel_ms, "launches": launches, "prof": prof, "dev_hits": dev_hits,
-            "e2e_ms": e2e_ms, "e2e_offs_ms": e2e_offs_ms, "same": same and same_offs, "ceiling_ms": ceiling_ms}
+            "e2e_ms": e2e_ms, "e2e_offs_ms": e2e_offs_ms, "same": same and same_offs, "ceiling_ms": ceiling_ms,
+            "packed_ms": packed_ms, "same_packed": same_packed, "pack_threads": threads}
 
 
 def section_strong(args, R, gpu, c2, pin_hits):
@@ -754,7 +763,12 @@ def main_ours(args, rank, world, local_rank):
 
     if rank == 0:
         total_reads = n * world
-        kernel_ms, e2e_ms = c2["kernel_ms"], c2["e2e_ms"]
+        kernel_ms = c2["kernel_ms"]
+        # the end-to-end figure is the faster of the two transfers the public call offers (plain bytes, or packed on the
+        # host inside the call); both are reported below
+        plain_ms = c2["e2e_ms"]
+        use_packed = c2["same_packed"] and c2["packed_ms"] < plain_ms
+        e2e_ms = c2["packed_ms"] if use_packed else plain_ms
         value = total_reads / (kernel_ms / 1e3)
         e2e_value = total_reads / (e2e_ms / 1e3)
         peaks = {}
@@ -802,15 +816,22 @@ def main_ours(args, rank, world, local_rank):
             "kmers_per_s": value * (READ_LEN - K),
             "kmers_note": "windows classified per second; on the memoised path they are looked up, murmur_path hashes them",
             "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(16 * n),
-                    "api": "rkg_classify_fixed (pinned host buffers, fixed-length reads: no offsets cross the link)",
-                    "matches_device_run": c2["same"],
+                    "h2d_bytes_per_step": (int(12 * ((n * READ_LEN + 31) // 32)) if use_packed else h2d), "d2h_bytes_per_step": int(16 * n),
+                    "api": ("rkg_classify_fixed after rkg_set_host_pack: pinned host buffers of ASCII bases in, packed to 2-bit codes + "
+                            "mask by the library on the host cores INSIDE the timed call, 0.375 B/base over the link"
+                            if use_packed else
+                            "rkg_classify_fixed (pinned host buffers, fixed-length reads: no offsets cross the link)"),
+                    "matches_device_run": c2["same"] and (c2["same_packed"] or not use_packed),
+                    "plain_transfer": {"ms_per_step": plain_ms, "value": total_reads / (plain_ms / 1e3), "h2d_bytes_per_step": h2d},
+                    "packed_transfer": {"ms_per_step": c2["packed_ms"], "value": total_reads / (c2["packed_ms"] / 1e3),
+                                        "h2d_bytes_per_step": int(12 * ((n * READ_LEN + 31) // 32)), "host_threads_per_rank": c2["pack_threads"],
+                                        "matches_device_run": c2["same_packed"]},
                     "with_offsets": {"api": "rkg_classify_batch", "ms_per_step": c2["e2e_offs_ms"],
                                      "value": total_reads / (c2["e2e_offs_ms"] / 1e3), "h2d_bytes_per_step": h2d + 8 * (n + 1)},
-                    "copy_ceiling_ms": c2["ceiling_ms"], "frac_of_copy_ceiling": c2["ceiling_ms"] / e2e_ms,
+                    "copy_ceiling_ms": c2["ceiling_ms"], "frac_of_copy_ceiling": c2["ceiling_ms"] / plain_ms,
                     "copy_ceiling_gbs_per_gpu": (h2d + 16 * n) / (c2["ceiling_ms"] / 1e3) / 1e9,
-                    "copy_ceiling_note": "rkg_copy_probe: the same chunked H2D + D2H copies on the same streams without the "
-                                         "kernels, all ranks at once, max over ranks"},
+                    "copy_ceiling_note": "rkg_copy_probe: the chunked H2D + D2H copies of the PLAIN transfer on the same streams "
+                                         "without the kernels, all ranks at once, max over ranks; frac = ceiling / plain e2e"},
             "gpu_launches": int(c2["launches"]),
             "clocks": clocks,
             "kernels": kernel_table(prof),

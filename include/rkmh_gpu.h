@@ -138,6 +138,14 @@ int rkg_classify_batch(rkg_ctx* ctx, const char* bases, const int64_t* offs, int
 int rkg_classify_fixed(rkg_ctx* ctx, const char* bases, int64_t read_len, int64_t nreads, int min_occ, rkg_hit* out);
 int rkg_count_fixed(rkg_ctx* ctx, const char* bases, int64_t read_len, int64_t nreads, int count_zeros);
 
+/* Packed transfer.  The path is bound by the host-to-device copy, so the library can make the
+ * 2-bit codes and the invalid-base mask -- what its ingest kernel makes on the device -- on the HOST, with `threads` host
+ * threads (0 = as many as the machine has, at most 16), chunk by chunk inside rkg_classify_batch / rkg_classify_fixed /
+ * rkg_count_batch / rkg_count_fixed and the other host-buffer calls, and ship 0.375 bytes per base instead of 1.  Same
+ * buffers in, same results out (upper-casing and the validity of a base are all the kernels take from a byte).  Off by
+ * default: it pays when the caller's cores are otherwise idle. */
+int rkg_set_host_pack(rkg_ctx* ctx, int enable, int threads);
+
 /* The same in two steps for callers that keep batches resident in HBM (and for kernel-only timing):
  * upload once, classify any number of times, fetch results. */
 int rkg_batch_upload(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, rkg_batch** batch);

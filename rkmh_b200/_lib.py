@@ -18,7 +18,7 @@ RKG_SYMBOLS = [
     "rkg_sketch_shard", "rkg_merge_sketches", "rkg_launch_count", "rkg_profile_enable", "rkg_profile_read",
     "rkg_set_memo", "rkg_memo_active", "rkg_count_partial", "rkg_classify_fixed", "rkg_count_fixed", "rkg_copy_probe",
     "rkg_load_ref_sets", "rkg_classify_sets", "rkg_load_ref_sketches", "rkg_count_export", "rkg_count_import",
-    "rkg_depth_begin", "rkg_depth_add", "rkg_depth_of_sequence", "rkg_depth_rescue",
+    "rkg_depth_begin", "rkg_depth_add", "rkg_depth_of_sequence", "rkg_depth_rescue", "rkg_set_host_pack",
 ]
 
 
@@ -62,6 +62,7 @@ def load():
     lib.rkg_load_ref_sketches.argtypes = [P, P, P, I]
     lib.rkg_count_export.argtypes = [P, I, P, P, U, C.POINTER(U)]
     lib.rkg_count_import.argtypes = [P, I, P, P, U]
+    lib.rkg_set_host_pack.argtypes = [P, I, I]
     lib.rkg_depth_begin.argtypes = [P, U]
     lib.rkg_depth_add.argtypes = [P, P, P, L]
     lib.rkg_depth_of_sequence.argtypes = [P, P, L, P]

@@ -157,6 +157,10 @@ class RkmhGpu:
         self._check(self.lib.rkg_get_ref_sketches(self.handle, sk.ctypes.data, lens.ctypes.data))
         return sk, lens
 
+    def set_host_pack(self, enable=True, threads=0):
+        """Pack bases to 2 bits + mask on the host before every host-to-device copy (rkg_set_host_pack)."""
+        self._check(self.lib.rkg_set_host_pack(self.handle, int(enable), int(threads)))
+
     def set_memo(self, enable=True):
         """Memoised hashing for a single k <= 12 (include/rkmh_gpu.h); takes effect at the next load_refs."""
         self._check(self.lib.rkg_set_memo(self.handle, int(enable)))

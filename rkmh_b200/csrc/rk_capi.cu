@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rkmh_gpu.h"
@@ -18,6 +19,8 @@
 #include "rk_call.cuh"
 
 using namespace rk;
+
+extern "C" void rk_pack_bases(const char* bases, int64_t n, uint32_t* codes, uint32_t* nmask, int threads);   // rk_pack.cpp
 
 static_assert(sizeof(rkg_hit) == sizeof(Hit), "rkg_hit layout");
 static_assert(RKG_MAX_K == MAX_K && RKG_MAX_NK == MAX_NK, "limits");
@@ -59,7 +62,8 @@ struct EventPair { cudaEvent_t a, b; int id; };
 struct rkg_batch {
     DevBuf bases, offs, codes, nmask, hits, redo, scratch, misc;   // misc: [0] redo_count
     i64 nseq = 0, total = 0, base0 = 0, max_ntotal = 0, max_len = 0;
-    bool packed = false;                 // codes / nmask hold this batch (ingest_kernel has run)
+    bool packed = false;                 // codes / nmask hold this batch (ingest_kernel has run, or the batch arrived packed)
+    bool ascii = true;                   // bases holds this batch's letters (false: it arrived packed and was not unpacked yet)
     cudaStream_t stream = nullptr;       // the stream every operation of this batch is issued on
     cudaStream_t own_stream = nullptr;   // created with the batch; `stream` may be redirected to a caller's stream
     cudaEvent_t done = nullptr;
@@ -91,6 +95,11 @@ struct rkg_ctx {
     RefTable tb{};
     cudaStream_t stream = nullptr;
     rkg_batch* slots[2] = {nullptr, nullptr};   // internal double buffer of rkg_classify_batch / count
+    // packed transfer (rkg_set_host_pack): per slot, pinned staging for the codes and the mask packed on the host
+    bool host_pack = false;
+    int pack_threads = 1;
+    void* stage[2] = {nullptr, nullptr};
+    size_t stage_cap[2] = {0, 0};
     // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
     bool memo_enabled = true, memo_ready = false, sieve_enabled = true, group_kernel = false;
     DevBuf memo_tab, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc, memo_sieve, memo_cmap;
@@ -207,6 +216,20 @@ int launch_ingest(rkg_ctx* ctx, rkg_batch* b) {
 // The Murmur-path kernels read the packed codes; the memoised path reads the ASCII bases and never needs them.
 int ensure_packed(rkg_ctx* ctx, rkg_batch* b) { return b->packed ? RKG_OK : launch_ingest(ctx, b); }
 
+// The memoised kernels read letters: a batch that arrived packed is unpacked on the device first (0.3 ms per 10 M reads).
+int ensure_ascii(rkg_ctx* ctx, rkg_batch* b) {
+    if (b->ascii) return RKG_OK;
+    const i64 nwords32 = (b->total + 31) / 32;
+    if (nwords32 > 0) {
+        Timed t(ctx, b->stream, K_INGEST);
+        const int grid = (int)std::min<i64>((nwords32 + 255) / 256, (i64)ctx->sm_count * 16);
+        unpack_kernel<<<grid, 256, 0, b->stream>>>(b->codes.as<u32>(), b->nmask.as<u32>(), b->bases.as<unsigned char>(), nwords32);
+    }
+    CK(cudaGetLastError());
+    b->ascii = true;
+    return RKG_OK;
+}
+
 // offs[i] = base0 + i * len for i in [0, n]: the offsets of a batch of fixed-length reads, made on the device so that
 // they never cross the PCIe link (8 bytes per read: 5 % of the host-to-device bytes of 150-base reads)
 __global__ void __launch_bounds__(256)
@@ -228,7 +251,25 @@ int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* off
     CK(b->hits.ensure(sizeof(Hit) * (size_t)std::max<i64>(n, 1)));
     CK(b->redo.ensure(sizeof(int) * (size_t)std::max<i64>(n, 1)));
     CK(b->misc.ensure(256));
-    if (total > 0) CK(cudaMemcpyAsync(b->bases.p, bases + base0, (size_t)total, cudaMemcpyHostToDevice, b->stream));
+    const int slot = (b == ctx->slots[0]) ? 0 : (b == ctx->slots[1]) ? 1 : -1;
+    const bool pack_here = ctx->host_pack && slot >= 0 && total > 0;
+    if (pack_here) {
+        // 0.375 bytes per base cross the link: codes (2 words per 32 bases) then the mask (1 word per 32 bases), packed by
+        // the host's threads into this slot's pinned staging buffer (free again: the caller waited for the slot's stream)
+        const size_t words = (size_t)nwords32 * 3;
+        if (ctx->stage_cap[slot] < words * 4) {
+            if (ctx->stage[slot]) cudaFreeHost(ctx->stage[slot]);
+            ctx->stage[slot] = nullptr; ctx->stage_cap[slot] = 0;
+            const size_t want = words * 4 + words / 2 + 4096;
+            CK(cudaHostAlloc(&ctx->stage[slot], want, cudaHostAllocPortable));
+            ctx->stage_cap[slot] = want;
+        }
+        u32* hc = static_cast<u32*>(ctx->stage[slot]);
+        u32* hm = hc + 2 * (size_t)nwords32;
+        rk_pack_bases(bases + base0, total, hc, hm, ctx->pack_threads);
+        CK(cudaMemcpyAsync(b->codes.p, hc, sizeof(u32) * 2 * (size_t)nwords32, cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemcpyAsync(b->nmask.p, hm, sizeof(u32) * (size_t)nwords32, cudaMemcpyHostToDevice, b->stream));
+    } else if (total > 0) CK(cudaMemcpyAsync(b->bases.p, bases + base0, (size_t)total, cudaMemcpyHostToDevice, b->stream));
     if (offs) CK(cudaMemcpyAsync(b->offs.p, offs + r0, sizeof(i64) * (size_t)(n + 1), cudaMemcpyHostToDevice, b->stream));
     else {
         ++ctx->launches;
@@ -245,7 +286,8 @@ int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* off
     i64 mt = 0;
     for (int j = 0; j < ctx->kl.nk; ++j) mt += std::max<i64>(max_len - ctx->kl.k[j], 0);
     b->max_ntotal = mt;
-    b->packed = false;
+    b->packed = pack_here;
+    b->ascii = !pack_here;
     return RKG_OK;
 }
 
@@ -424,6 +466,7 @@ int launch_count(rkg_ctx* ctx, rkg_batch* b, CountTable ct, int count_zeros) {
     if (ctx->memo_ready && ctx->memo.code_counts && ct.counts == ctx->read_ct.counts) {
         if (ctx->memo_pending && ctx->memo_pending_zeros != count_zeros) { int rc = memo_flush(ctx); if (rc) return rc; }
         ctx->memo_pending = true; ctx->memo_pending_zeros = count_zeros;
+        { int rc = ensure_ascii(ctx, b); if (rc) return rc; }
         const int wpr = (b->total / b->nseq > 2048) ? 8 : 1;            // a block per long read, a warp per short one
         const i64 teams = (b->nseq + 0) * 1;
         const int grid = (int)std::min<i64>((teams * wpr + 7) / 8, (i64)ctx->sm_count * 8);
@@ -512,6 +555,7 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
         if (mg.ok) {
             int rc = memo_prepare(ctx, min_occ);
             if (rc) return rc;
+            if ((rc = ensure_ascii(ctx, b))) return rc;
             if (mg.use_warp && ctx->tb.nb <= 4 && ctx->memo.sieve != nullptr && ctx->memo.zero_codes == 0 &&
                        ctx->memo_occ == INT_MIN) {
                 // <= 256 references, no FAILM flags baked, no zero hash: sketch membership from a shared-memory sieve
@@ -791,6 +835,7 @@ void rkg_destroy(rkg_ctx* ctx) {
     cudaDeviceSynchronize();
     profile_collect(ctx);
     for (int i = 0; i < 2; ++i) batch_release(ctx->slots[i]);
+    for (int i = 0; i < 2; ++i) if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
     for (DevBuf* d : {&ctx->depth_keys, &ctx->depth_counts, &ctx->depth_zero, &ctx->hash_lut, &ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
                       &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
                       &ctx->memo_tab, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
@@ -1169,6 +1214,13 @@ int rkg_copy_probe(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t
     if (nreads == 0) return RKG_OK;
     CK(cudaSetDevice(ctx->device));
     return host_pipeline(ctx, bases, offs, nreads, 2, 0, out, read_len);
+}
+
+int rkg_set_host_pack(rkg_ctx* ctx, int enable, int threads) {
+    if (!ctx) return RKG_ERR_ARG;
+    ctx->host_pack = enable != 0;
+    ctx->pack_threads = threads > 0 ? std::min(threads, 64) : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    return RKG_OK;
 }
 
 int rkg_batch_upload(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, rkg_batch** batch) {

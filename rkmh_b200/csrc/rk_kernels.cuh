@@ -95,6 +95,32 @@ ingest_kernel(const unsigned char* __restrict__ bases, i64 total, u32* __restric
     }
 }
 
+// unpack: the inverse of ingest for batches that crossed the link packed (rkg_set_host_pack): 32 bases per thread, the
+// letter of each code (A C T G), 'N' for every base the mask flags.  What the memoised kernels read is then the
+// upper-cased sequence with every invalid byte as N: same codes, same validity, hence the same hashes.
+__global__ void __launch_bounds__(256)
+unpack_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, unsigned char* __restrict__ bases, i64 nwords32) {
+    for (i64 w = (i64)blockIdx.x * blockDim.x + threadIdx.x; w < nwords32; w += (i64)gridDim.x * blockDim.x) {
+        const u64 c = ((u64)codes[2 * w + 1] << 32) | codes[2 * w];
+        const u32 m = nmask[w];
+        u32 out[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            u32 word = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = 4 * q + j;
+                const u32 letter = ((m >> i) & 1u) ? (u32)'N' : ((CODE_TO_ASCII >> (8 * (u32)((c >> (2 * i)) & 3ULL))) & 0xFFu);
+                word |= letter << (8 * j);
+            }
+            out[q] = word;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(bases + w * 32);
+        dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Sequential reader of packed bases for one thread: a 64-bit shift register of 2-bit codes and a 32-bit
 // one of invalid-base flags, refilled every 32 bases.  Threads that walk their chunks in lock step refill

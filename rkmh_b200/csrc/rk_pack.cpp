@@ -1,0 +1,90 @@
+// rk_pack.cpp -- host side of the packed transfer (include/rkmh_gpu.h: rkg_set_host_pack): the 2-bit codes and the
+// invalid-base mask that ingest_kernel would make on the device (rk_kernels.cuh: code = (ascii >> 1) & 3, 16 bases per code
+// word; one mask bit per base, set when the base is not one of ACGTacgt = valid_dna[], mkmh/mkmh.hpp:137-152) are made on
+// the HOST, so that 0.375 bytes per base cross the PCIe link instead of 1.  The link, not the GPU, bounds the end-to-end
+// rate of the path; the packing runs on the caller's cores inside the timed call.
+//
+// AVX2 + BMI2 when the CPU has them (32 bases per step: two movemasks give the two code bit planes, PDEP interleaves
+// them), a scalar loop otherwise.  Compiled by g++ (-mavx2 -mbmi2 for this file only, run-time dispatch).
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace {
+
+inline void pack_scalar(const unsigned char* b, int64_t n32, int64_t tail, uint32_t* codes, uint32_t* nmask) {
+    // n32 full groups of 32 bases, then `tail` (< 32) bases padded as invalid 'A' codes
+    for (int64_t w = 0; w <= n32; ++w) {
+        const int cnt = w < n32 ? 32 : (int)tail;
+        if (w == n32 && tail == 0) break;
+        uint64_t c = 0; uint32_t m = 0;
+        for (int i = 0; i < 32; ++i) {
+            const unsigned ch = i < cnt ? b[w * 32 + i] : 0u;
+            c |= (uint64_t)((ch >> 1) & 3u) << (2 * i);
+            const unsigned u = ch & 0xDFu;
+            m |= (uint32_t)!(u == 'A' || u == 'C' || u == 'G' || u == 'T') << i;
+        }
+        codes[2 * w] = (uint32_t)c; codes[2 * w + 1] = (uint32_t)(c >> 32);
+        nmask[w] = m;
+    }
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2,bmi2")))
+void pack_avx2(const unsigned char* b, int64_t n32, uint32_t* codes, uint32_t* nmask) {
+    const __m256i fold = _mm256_set1_epi8((char)0xDF);
+    const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'), cT = _mm256_set1_epi8('T');
+    for (int64_t w = 0; w < n32; ++w) {
+        const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(b + w * 32));
+        const uint32_t p0 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 6));     // bit 1 of every byte
+        const uint32_t p1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 5));     // bit 2 of every byte
+        const uint64_t c = _pdep_u64(p0, 0x5555555555555555ULL) | _pdep_u64(p1, 0xAAAAAAAAAAAAAAAAULL);
+        const __m256i u = _mm256_and_si256(x, fold);
+        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, cA), _mm256_cmpeq_epi8(u, cC)),
+                                           _mm256_or_si256(_mm256_cmpeq_epi8(u, cG), _mm256_cmpeq_epi8(u, cT)));
+        codes[2 * w] = (uint32_t)c; codes[2 * w + 1] = (uint32_t)(c >> 32);
+        nmask[w] = ~(uint32_t)_mm256_movemask_epi8(ok);
+    }
+}
+#endif
+
+bool have_avx2() {
+#if defined(__x86_64__)
+    static const bool ok = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+    return ok;
+#else
+    return false;
+#endif
+}
+
+void pack_range(const unsigned char* b, int64_t n32, int64_t tail, uint32_t* codes, uint32_t* nmask) {
+#if defined(__x86_64__)
+    if (have_avx2()) {
+        pack_avx2(b, n32, codes, nmask);
+        if (tail) pack_scalar(b + n32 * 32, 0, tail, codes + 2 * n32, nmask + n32);
+        return;
+    }
+#endif
+    pack_scalar(b, n32, tail, codes, nmask);
+}
+
+}  // namespace
+
+// codes: 2 * ceil(n / 32) words, nmask: ceil(n / 32) words (bases beyond n read as invalid).  `threads` host threads.
+extern "C" void rk_pack_bases(const char* bases, int64_t n, uint32_t* codes, uint32_t* nmask, int threads) {
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(bases);
+    const int64_t n32 = n / 32, tail = n - n32 * 32;
+    threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n32 / 4096 + 1));
+    if (threads == 1) { pack_range(b, n32, tail, codes, nmask); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) {
+        const int64_t lo = n32 * t / threads, hi = n32 * (t + 1) / threads;
+        th.emplace_back([=] { pack_range(b + lo * 32, hi - lo, t == threads - 1 ? tail : 0, codes + 2 * lo, nmask + lo); });
+    }
+    for (auto& x : th) x.join();
+}

@@ -591,3 +591,38 @@ def test_call_depth_entry_points_vs_oracle(oracle):
                 big = ref[j - 1:j + k]
                 km = big[:d] + big[d + 1:]
                 assert alt[w, 3 * k + d - 1] == depth.get(oracle.calc_hash(km), 0), (k, j, d)
+
+
+def test_packed_transfer_gives_the_same_records(oracle):
+    """rkg_set_host_pack: the bases are packed to 2-bit codes + an invalid-base mask on the HOST and cross the link at
+    0.375 B/base; the memoised kernels get them unpacked on the device (every invalid byte as N, every letter upper-cased).
+    Records, count tables and sketches are those of the plain transfer: ragged reads with lower case, N, IUPAC and
+    punctuation bytes, reads shorter than k, fixed-length batches, both hashing paths, with and without -M."""
+    import rkmh_b200
+    _, rs, _ = load_sequences([data_path("all_pave_ref.fa.gz")])
+    _, aw, _ = load_sequences([data_path("awkward_reads.fq.gz"), data_path("minION25.fq.gz")])
+    rng = np.random.default_rng(31)
+    sb, so = _synthetic_reads(rng, rs, 20000, 150)
+    weird = aw + [b"acgtnnacgtRYKMacgtacgt{}|~ACGTACGTACGTAC", b"ACGTACG", b"", b"N" * 70, rs[3][:3001].lower(), rs[5][100:9000]]
+    wb, wo = _pack(weird)
+    for memo in (True, False):
+        res = {}
+        for pack in (False, True):
+            with rkmh_b200.RkmhGpu(0) as g:
+                g.set_memo(memo)
+                g.set_host_pack(pack, 3)
+                g.set_params([12], 1000, read_table_size=rkmh_b200.STREAM_TABLE_SIZE)
+                g.load_refs(*_pack(rs))
+                out = [_fields(g.classify_batch(sb, so)), _fields(g.classify_fixed(sb, 150)), _fields(g.classify_batch(wb, wo))]
+                g.count_reset(); g.count_batch(wb, wo); g.count_fixed(sb, 150)
+                out.append(g.count_table_tensor().cpu().numpy().copy())
+                out.append(_fields(g.classify_batch(wb, wo, min_occ=2)))
+                out.append(_fields(g.classify_batch(sb, so, min_occ=3)))
+                sk, ln = g.sketch_batch(wb, wo)
+                out += [sk, ln]
+                res[pack] = out
+        for a, b in zip(res[False], res[True]):
+            assert np.array_equal(a, b)
+    sk, ln = oracle.sketch_batch(rs, [12], 1000)
+    exp = oracle.classify_batch(weird, [12], 1000, sk, ln)
+    assert np.array_equal(res[True][2], _fields(exp))
