@@ -256,7 +256,8 @@ int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* off
     if (pack_here) {
         // 0.375 bytes per base cross the link: codes (2 words per 32 bases) then the mask (1 word per 32 bases), packed by
         // the host's threads into this slot's pinned staging buffer (free again: the caller waited for the slot's stream)
-        const size_t words = (size_t)nwords32 * 3;
+        const size_t mask_at = ((size_t)2 * nwords32 + 7) & ~(size_t)7;      // the mask starts 32-byte aligned (streaming stores)
+        const size_t words = mask_at + (size_t)nwords32;
         if (ctx->stage_cap[slot] < words * 4) {
             if (ctx->stage[slot]) cudaFreeHost(ctx->stage[slot]);
             ctx->stage[slot] = nullptr; ctx->stage_cap[slot] = 0;
@@ -265,7 +266,7 @@ int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* off
             ctx->stage_cap[slot] = want;
         }
         u32* hc = static_cast<u32*>(ctx->stage[slot]);
-        u32* hm = hc + 2 * (size_t)nwords32;
+        u32* hm = hc + mask_at;
         rk_pack_bases(bases + base0, total, hc, hm, ctx->pack_threads);
         CK(cudaMemcpyAsync(b->codes.p, hc, sizeof(u32) * 2 * (size_t)nwords32, cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->nmask.p, hm, sizeof(u32) * (size_t)nwords32, cudaMemcpyHostToDevice, b->stream));

@@ -35,20 +35,39 @@ inline void pack_scalar(const unsigned char* b, int64_t n32, int64_t tail, uint3
 }
 
 #if defined(__x86_64__)
-__attribute__((target("avx2,bmi2")))
-void pack_avx2(const unsigned char* b, int64_t n32, uint32_t* codes, uint32_t* nmask) {
+__attribute__((target("avx2,bmi2"))) inline void pack_group_avx2(const unsigned char* p, uint64_t& c, uint32_t& m) {
     const __m256i fold = _mm256_set1_epi8((char)0xDF);
     const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'), cT = _mm256_set1_epi8('T');
-    for (int64_t w = 0; w < n32; ++w) {
-        const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(b + w * 32));
-        const uint32_t p0 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 6));     // bit 1 of every byte
-        const uint32_t p1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 5));     // bit 2 of every byte
-        const uint64_t c = _pdep_u64(p0, 0x5555555555555555ULL) | _pdep_u64(p1, 0xAAAAAAAAAAAAAAAAULL);
-        const __m256i u = _mm256_and_si256(x, fold);
-        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, cA), _mm256_cmpeq_epi8(u, cC)),
-                                           _mm256_or_si256(_mm256_cmpeq_epi8(u, cG), _mm256_cmpeq_epi8(u, cT)));
+    const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p));
+    const uint32_t p0 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 6));     // bit 1 of every byte
+    const uint32_t p1 = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 5));     // bit 2 of every byte
+    c = _pdep_u64(p0, 0x5555555555555555ULL) | _pdep_u64(p1, 0xAAAAAAAAAAAAAAAAULL);
+    const __m256i u = _mm256_and_si256(x, fold);
+    const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, cA), _mm256_cmpeq_epi8(u, cC)),
+                                       _mm256_or_si256(_mm256_cmpeq_epi8(u, cG), _mm256_cmpeq_epi8(u, cT)));
+    m = ~(uint32_t)_mm256_movemask_epi8(ok);
+}
+
+__attribute__((target("avx2,bmi2")))
+void pack_avx2(const unsigned char* b, int64_t n32, uint32_t* codes, uint32_t* nmask) {
+    int64_t w = 0;
+    // the staging buffer is written once and read by the DMA engine only: non-temporal stores (no read-for-ownership of
+    // the destination lines), eight groups = 64 B of codes + 32 B of mask at a time when the destination is aligned
+    if ((reinterpret_cast<uintptr_t>(codes) & 31) == 0 && (reinterpret_cast<uintptr_t>(nmask) & 31) == 0) {
+        for (; w + 8 <= n32; w += 8) {
+            uint64_t c[8]; uint32_t m[8];
+            for (int i = 0; i < 8; ++i) pack_group_avx2(b + (w + i) * 32, c[i], m[i]);
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(codes + 2 * w), _mm256_set_epi64x((long long)c[3], (long long)c[2], (long long)c[1], (long long)c[0]));
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(codes + 2 * w + 8), _mm256_set_epi64x((long long)c[7], (long long)c[6], (long long)c[5], (long long)c[4]));
+            _mm256_stream_si256(reinterpret_cast<__m256i*>(nmask + w), _mm256_set_epi32((int)m[7], (int)m[6], (int)m[5], (int)m[4], (int)m[3], (int)m[2], (int)m[1], (int)m[0]));
+        }
+        _mm_sfence();
+    }
+    for (; w < n32; ++w) {
+        uint64_t c; uint32_t m;
+        pack_group_avx2(b + w * 32, c, m);
         codes[2 * w] = (uint32_t)c; codes[2 * w + 1] = (uint32_t)(c >> 32);
-        nmask[w] = ~(uint32_t)_mm256_movemask_epi8(ok);
+        nmask[w] = m;
     }
 }
 #endif
@@ -83,7 +102,8 @@ extern "C" void rk_pack_bases(const char* bases, int64_t n, uint32_t* codes, uin
     if (threads == 1) { pack_range(b, n32, tail, codes, nmask); return; }
     std::vector<std::thread> th;
     for (int t = 0; t < threads; ++t) {
-        const int64_t lo = n32 * t / threads, hi = n32 * (t + 1) / threads;
+        // ranges start at multiples of 8 groups: the streaming stores want 32-byte aligned destinations
+        const int64_t lo = (n32 * t / threads) & ~(int64_t)7, hi = t == threads - 1 ? n32 : ((n32 * (t + 1) / threads) & ~(int64_t)7);
         th.emplace_back([=] { pack_range(b + lo * 32, hi - lo, t == threads - 1 ? tail : 0, codes + 2 * lo, nmask + lo); });
     }
     for (auto& x : th) x.join();
