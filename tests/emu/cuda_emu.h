@@ -16,6 +16,10 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <chrono>
+#include <sched.h>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -42,14 +46,20 @@ static inline int4 make_int4(int a, int b, int c, int d) { return int4{a, b, c, 
 
 namespace emu {
 
-struct Barrier {  // reusable counting barrier
-    std::mutex m; std::condition_variable cv; unsigned need, count = 0, gen = 0;
+struct Barrier {  // reusable counting barrier: futex waits (C++20 atomic wait), no mutex for the woken threads to fight over
+    std::atomic<unsigned> count{0}, gen{0};
+    unsigned need;
     explicit Barrier(unsigned n) : need(n) {}
     void wait() {
-        std::unique_lock<std::mutex> lk(m);
-        unsigned g = gen;
-        if (++count == need) { count = 0; ++gen; cv.notify_all(); }
-        else cv.wait(lk, [&] { return gen != g; });
+        const unsigned g = gen.load(std::memory_order_acquire);
+        if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == need) {
+            count.store(0, std::memory_order_relaxed);
+            gen.store(g + 1, std::memory_order_release);
+            gen.notify_all();
+        } else {
+            for (int spin = 0; spin < 64 && gen.load(std::memory_order_acquire) == g; ++spin) sched_yield();
+            while (gen.load(std::memory_order_acquire) == g) gen.wait(g, std::memory_order_acquire);
+        }
     }
 };
 
@@ -207,6 +217,16 @@ template <typename T> static inline T max(T a, T b) { return a > b ? a : b; }
 // ---- launch ----------------------------------------------------------------------------------------
 namespace emu {
 template <typename F> void launch(dim3 grid, dim3 block, size_t dyn_smem, F&& body) {
+    struct Trace {                                    // EMU_TRACE=1: wall time of every launch
+        std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        dim3 g, b;
+        ~Trace() {
+            if (getenv("EMU_TRACE"))
+                fprintf(stderr, "emu launch grid %u block %u: %.3f s\n", g.x, b.x,
+                        std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        }
+    } trace;
+    trace.g = grid; trace.b = block;
     std::vector<char> smem(dyn_smem + 256);
     g_dyn_smem = (char*)(((uintptr_t)smem.data() + 127) & ~(uintptr_t)127);
     for (unsigned b = 0; b < grid.x; ++b) {
