@@ -513,21 +513,30 @@ GroupGeom group_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
 }
 
 // Geometry of the two memoised classification kernels for this batch, or ok = false (Murmur path instead).
-struct MemoGeom { bool ok, use_warp; int warp_block, rwords; size_t warp_smem; int vcap, hs_cap, rpad; size_t block_smem; i64 scratch_stride; };
+struct MemoGeom { bool ok, use_warp; int warp_block, rwords; size_t warp_smem; int lcap, hs_cap, rpad, block_per_sm; size_t block_smem; i64 scratch_stride; };
 
 MemoGeom memo_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
     MemoGeom g{};
-    // block kernel: [vcap values][MEMO_BINS histogram][2 hs_cap hit set][rpad counters] in u32, two blocks per SM
+    // block kernel: [8 x lcap kept values][MEMO_HIST_WORDS histogram][2 hs_cap hit set][rpad counters] in u32.  A warp keeps
+    // about 2 s / 8 values of a long read (classify_memo_block_kernel); 1.6 x that leaves room for uneven shares.  As many
+    // blocks per SM as that allows, at most four (registers).
     g.hs_cap = next_pow2(2 * (i64)std::min<i64>(ctx->s, std::max<i64>(b->max_ntotal, 1)));
     g.rpad = (ctx->nrefs + 63) / 64 * 64;
-    const size_t budget = ctx->smem_optin / 2 - 4608;      // two blocks per SM: static scratch + hit rings + the 1 KB reserve
     const size_t fixed = 4 * ((size_t)MEMO_HIST_WORDS + 2 * (size_t)g.hs_cap + (size_t)g.rpad);
-    if (fixed + 4096 > budget) return g;
-    const i64 room = (i64)((budget - fixed) / 4);
-    g.vcap = (int)std::min<i64>(std::max<i64>(b->max_ntotal, 1), room);
-    g.scratch_stride = (b->max_ntotal > g.vcap) ? b->max_ntotal : 0;
-    g.block_smem = fixed + 4 * (size_t)g.vcap;
-    g.ok = true;
+    const i64 most = ((std::max<i64>(b->max_ntotal, 1) + 31) / 32 + 7) / 8 * 32;      // a warp's share of the longest read
+    const i64 want = std::min<i64>(most, std::max<i64>(128, ((i64)(0.4 * (double)ctx->s) + 31) / 32 * 32));
+    for (int per_sm = 4; per_sm >= 1 && !g.ok; --per_sm) {
+        const size_t budget = ctx->smem_optin / per_sm - 4608;     // static scratch + hit rings + the 1 KB reserve per block
+        if (fixed + 4 * 8 * (size_t)32 > budget) continue;
+        const i64 room = (i64)((budget - fixed) / (4 * 8)) / 32 * 32;
+        if (room < want && per_sm > 1) continue;
+        g.lcap = (int)std::min<i64>(want, room);
+        g.block_per_sm = per_sm;
+        g.ok = true;
+    }
+    if (!g.ok) return g;
+    g.scratch_stride = (std::max<i64>(b->max_ntotal, 1) + 32 * 8 + 31) / 32 * 32;      // the lists of the second attempt: every window
+    g.block_smem = fixed + 4 * 8 * (size_t)g.lcap;
     // warp kernel: the typical read keeps all its k-mers (n <= s)
     const i64 mean_n = std::max<i64>(b->total / b->nseq - ctx->kl.k[0], 0);
     g.rwords = (ctx->nrefs + 1) / 2;
@@ -597,7 +606,11 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
             CK(cudaFuncSetAttribute(classify_memo_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mg.block_smem));
             int per_sm = 2;                                  // as many resident blocks as registers and shared memory allow
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, classify_memo_block_kernel, 256, mg.block_smem));
-            const int grid = ctx->sm_count * std::max(1, std::min(per_sm, 8));
+            int grid = ctx->sm_count * std::max(1, std::min(per_sm, 8));
+            // the global lists (a read whose bound was too tight) are sized for the longest read of the batch: fewer blocks
+            // when that read is enormous
+            const i64 most_blocks = std::max<i64>(1, ((i64)4 << 30) / (4 * mg.scratch_stride));
+            grid = (int)std::min<i64>(grid, most_blocks);
             CK(b->scratch.ensure(sizeof(u32) * (size_t)grid * (size_t)mg.scratch_stride + 64));
             // every window of every read looks its rank up in the 4^k-entry table: keep it in L2, stream the bases
             if (!mg.use_warp) l2_window(ctx, b->stream, ctx->memo.tab, sizeof(u32) * (size_t)ctx->memo.ncodes);
@@ -605,7 +618,7 @@ int launch_classify(rkg_ctx* ctx, rkg_batch* b, int min_occ) {
                 Timed t(ctx, b->stream, K_CLASSIFY_MEMO_BLOCK);
                 classify_memo_block_kernel<<<grid, 256, mg.block_smem, b->stream>>>(
                     sb, ctx->s, ctx->memo, ctx->tb, mg.use_warp ? redo : nullptr, mg.use_warp ? redo_count : nullptr, b->nseq,
-                    mg.vcap, mg.hs_cap, mg.rpad, b->scratch.as<u32>(), mg.scratch_stride, hits);
+                    mg.lcap, mg.hs_cap, mg.rpad, b->scratch.as<u32>(), mg.scratch_stride, hits);
             }
             if (!mg.use_warp) l2_window(ctx, b->stream, nullptr, 0);
             CK(cudaGetLastError());

@@ -14,10 +14,10 @@
 //   ref[rank] u32  slot + 1 of the hash in the (hash, rank) -> bitset table     (equal hash <=> equal rank)
 //   code_counts[c] int32  -M pass 1 counters per code; folded into counts[hash % size] (HASHTCounter.cpp:46)
 //
-// A k-mer code is the pair of bit planes of its 2-bit base codes: bit j = low code bit of base j, bit k + j =
-// high code bit of base j.  The per-read kernels read the ASCII bases as parsed (no ingest pass): a warp turns 32
-// bases into three 32-bit planes with three ballots, and the code of the window that starts at lane l is two
-// funnel shifts.  Results are bit-identical to the Murmur path for every input (tests: memo on/off).
+// A k-mer code is its 2-bit base codes, base j at bits 2 j (first base lowest).  The per-read kernels read the ASCII
+// bases as parsed (no ingest pass): aligned 32-bit loads, four bases decoded per word (sv_decode), the 16 bases that
+// follow a lane's word assembled with three shuffles; the code of a window is one more shuffle, a shift and a mask.
+// Results are bit-identical to the Murmur path for every input (tests: memo on/off).
 #pragma once
 #include "rk_kernels.cuh"
 
@@ -37,7 +37,7 @@ constexpr int MEMO_PARTIAL_PAD = 32;             // int32 slots after code_count
 constexpr int MEMO_RING = 64;                   // block kernel: per-warp ring of sketch members waiting for their rows                 // radix-select histogram (12 bits of the 24-bit rank per level)
 
 struct Memo {
-    u32* tab;                       // indexed by the plane code (warp-streaming kernels)
+    u32* tab;                       // indexed by the k-mer code
     u32* ref;
     const u64* hash;
     int* code_counts;               // nullptr when the context has no read count table
@@ -70,36 +70,79 @@ RK_D bool memo_base_invalid(u32 ch) {
     return u > 19u || !((0x00080045u >> u) & 1u);           // bits 0 (A), 2 (C), 6 (G), 19 (T)
 }
 
+// Four bases of the read as one aligned 32-bit load: `piece` = their four 2-bit codes (first base in the low bits),
+// `bad` has a non-zero byte for every base that is not one of ACGTacgt (canonical(), mkmh.hpp:137-152): the letter is
+// rebuilt from its code (A 0x41, C 0x43, T 0x54, G 0x47 for codes 0, 1, 2, 3) and compared with the upper-cased byte.
+RK_D void sv_decode(u32 w, u32& piece, u32& bad) {
+    const u32 x = (w >> 1) & 0x03030303u;
+    piece = (x * 0x01041040u) >> 24;                         // byte i -> bits 2 i (the partial products do not overlap)
+    const u32 lo = x & 0x01010101u, hi = (x >> 1) & 0x01010101u;
+    const u32 e = 0x41414141u + 2u * lo + 0x13u * hi - 0xFu * (lo & hi);
+    bad = (w & 0xDFDFDFDFu) ^ e;
+}
+RK_D u32 sv_bad4(u32 bad) {
+    return ((bad & 0xFFu) ? 1u : 0u) | ((bad & 0xFF00u) ? 2u : 0u) | ((bad & 0xFF0000u) ? 4u : 0u) | ((bad & 0xFF000000u) ? 8u : 0u);
+}
+
 // ------------------------------------------------------------------------------------------------
 // One warp walks the k-mer starts [s0, s1) of the sequence p[0, len), 32 starts per round, and calls
-// f(pos, code, in_range, valid) on every lane (warp-convergent).  Bases beyond len read as invalid.
+// f(pos, code, in_range, valid) on every lane (warp-convergent; in_range = s0 <= pos < s1, valid = in_range and no
+// invalid base in the window).  k <= 12.
+//
+// The bytes are read as aligned 32-bit words, 128 bases of the stream per lane-wide load, three loads in flight (a warp
+// streams a long read straight from HBM).  Stream position 0 is the word-aligned byte at or before p + s0, so the
+// window that lane l handles in round r of a chunk starts at stream base 32 r + l = read position s0 - sh + ...:
+// the first sh positions of the stream lie before s0 and are reported out of range.
 template <typename F>
-RK_D void memo_stream(const unsigned char* __restrict__ p, i64 len, int k, u32 kmask, i64 s0, i64 s1, int lane, F&& f) {
+RK_D void memo_stream(const unsigned char* __restrict__ p, i64 len, int k, i64 s0, i64 s1, int lane, F&& f) {
     if (s0 >= s1) return;
-    auto load = [&](i64 base) -> u32 { const i64 i = base + lane; return i < len ? (u32)p[i] : 0u; };
-    u32 c0, c1, cv;
-    {
-        const u32 ch = load(s0), c2 = base_code(ch);
-        c0 = __ballot_sync(0xffffffffu, c2 & 1u); c1 = __ballot_sync(0xffffffffu, c2 & 2u);
-        cv = __ballot_sync(0xffffffffu, memo_base_invalid(ch));
-    }
-    // the bases are requested four rounds ahead: a warp streams a long read straight from HBM, and one 32-byte request
-    // in flight per warp (the first version) left it waiting ~500 cycles per round
-    u32 q0 = load(s0 + 32), q1 = load(s0 + 64), q2 = load(s0 + 96), q3 = load(s0 + 128);
-#pragma unroll 4
-    for (i64 base = s0; base < s1; base += 32) {
-        const u32 chn = q0;
-        q0 = q1; q1 = q2; q2 = q3; q3 = load(base + 160);
-        const u32 c2 = base_code(chn);
-        const u32 n0 = __ballot_sync(0xffffffffu, c2 & 1u), n1 = __ballot_sync(0xffffffffu, c2 & 2u);
-        const u32 nv = __ballot_sync(0xffffffffu, memo_base_invalid(chn));
-        const u32 f0 = __funnelshift_r(c0, n0, (u32)lane) & kmask;
-        const u32 f1 = __funnelshift_r(c1, n1, (u32)lane) & kmask;
-        const u32 fv = __funnelshift_r(cv, nv, (u32)lane) & kmask;
-        const i64 pos = base + lane;
-        const bool in = pos < s1;
-        f(pos, f0 | (f1 << k), in, in && fv == 0u);
-        c0 = n0; c1 = n1; cv = nv;
+    const unsigned char* q = p + s0;
+    const int sh = (int)(reinterpret_cast<size_t>(q) & 3u);
+    const u32* __restrict__ wp = reinterpret_cast<const u32*>(q - sh);
+    const i64 nbytes = sh + (len - s0);                     // bytes from wp to the end of the sequence
+    const i64 pend = sh + (s1 - s0);                        // stream positions [sh, pend) start a window of the range
+    // words that hold no base of the sequence are not loaded and decode as valid 'AAAA' (no window in range reaches them)
+    auto load_word = [&](i64 widx) -> u32 { return 4 * widx < nbytes ? __ldg(wp + widx) : 0x41414141u; };
+    const u32 cmask2 = (1u << (2 * k)) - 1u, kmask = (1u << k) - 1u;
+    // window at stream position 32 r + lane of a chunk: pieces 8 r + (lane >> 2) .. + 3, from base (lane & 3) on
+    const int src0 = lane >> 2;
+    const u32 osh = 2u * (u32)(lane & 3), ish = (u32)(lane & 3);
+    // piece j + i of lane j comes from the next chunk when j + i >= 32 (byte 1 of the shuffled pair instead of byte 0)
+    const u32 sel1 = lane >= 31 ? 0x3250u : 0x3240u, sel2 = lane >= 30 ? 0x3510u : 0x3410u, sel3 = lane >= 29 ? 0x5210u : 0x4210u;
+    u32 wb = load_word(32 + lane), wc = load_word(64 + lane);
+    u32 pc, bc;
+    sv_decode(load_word(lane), pc, bc);
+    for (i64 c0 = 0; c0 < pend; c0 += 128) {
+        u32 pn, bn;
+        sv_decode(wb, pn, bn);
+        wb = wc; wc = load_word((c0 >> 2) + 96 + lane);
+        const bool slow = __any_sync(0xffffffffu, (bc | bn) != 0u);
+        const u32 xq = pc | (pn << 8);
+        u32 Q = xq;                                          // the 16 bases from piece `lane` on
+        Q = __byte_perm(Q, __shfl_sync(0xffffffffu, xq, (lane + 1) & 31), sel1);
+        Q = __byte_perm(Q, __shfl_sync(0xffffffffu, xq, (lane + 2) & 31), sel2);
+        Q = __byte_perm(Q, __shfl_sync(0xffffffffu, xq, (lane + 3) & 31), sel3);
+        u32 IQ = 0;                                          // the same for the invalid flags (one bit per base)
+        if (slow) {
+            const u32 xi = sv_bad4(bc) | (sv_bad4(bn) << 4);
+            IQ = xi & 15u;
+#pragma unroll
+            for (int i = 1; i < 4; ++i) {
+                const u32 t = __shfl_sync(0xffffffffu, xi, (lane + i) & 31);
+                IQ |= ((lane + i < 32) ? (t & 15u) : (t >> 4)) << (4 * i);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (c0 + 32 * r >= pend) break;
+            const u32 code = (__shfl_sync(0xffffffffu, Q, src0 + 8 * r) >> osh) & cmask2;
+            bool inv = false;
+            if (slow) inv = ((__shfl_sync(0xffffffffu, IQ, src0 + 8 * r) >> ish) & kmask) != 0u;
+            const i64 pos = s0 + c0 + 32 * r + lane - sh;
+            const bool in = pos >= s0 && pos < s1;
+            f(pos, code, in, in && !inv);
+        }
+        pc = pn; bc = bn;
     }
 }
 
@@ -116,10 +159,10 @@ RK_D u64 memo_code_hash(u32 c, int k) {
 #pragma unroll
     for (int j = 0; j < 4 * NW; ++j) {
         if (j < k) {
-            const u32 cf = ((c >> j) & 1u) | (((c >> (k + j)) & 1u) << 1);
+            const u32 cf = (c >> (2 * j)) & 3u;
             f[j >> 2] |= (code_letters(cf) & 0xFFu) << (8 * (j & 3));
             const int src = k - 1 - j;                          // reverse complement: byte j = complement of base k-1-j
-            const u32 cr = ((c >> src) & 1u) | (((c >> (k + src)) & 1u) << 1);
+            const u32 cr = (c >> (2 * src)) & 3u;
             r[j >> 2] |= ((code_letters(cr) >> 8) & 0xFFu) << (8 * (j & 3));
         }
     }
@@ -256,7 +299,7 @@ count_memo_kernel(SeqBatch sb, Memo mm, int count_zeros, int wpr) {
         const i64 n = nkmers(len, mm.k);
         const i64 per = ((((n + 31) >> 5) + wpr - 1) / wpr) << 5;          // k-mer starts per warp, whole rounds
         const i64 s0 = (i64)wt * per, s1 = min(n, s0 + per);
-        memo_stream(sb.bases + beg, len, mm.k, mm.kmask, s0, s1, lane, [&](i64, u32 code, bool in, bool valid) {
+        memo_stream(sb.bases + beg, len, mm.k, s0, s1, lane, [&](i64, u32 code, bool in, bool valid) {
             if (valid) atomicAdd(&mm.code_counts[code], 1);
             else if (in) ++inv;
         });
@@ -357,7 +400,7 @@ classify_memo_wide_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, int rwords,
             __syncwarp();
         };
 
-        memo_stream(sb.bases + beg, len, k, mm.kmask, 0, n, lane, [&](i64, u32 code, bool, bool valid) {
+        memo_stream(sb.bases + beg, len, k, 0, n, lane, [&](i64, u32 code, bool, bool valid) {
             u32 m = MEMO_ZERO;
             if (valid) m = __ldg(&mm.tab[code]);
             const bool counted = !(m & (MEMO_ZERO | MEMO_FAILM));
@@ -464,8 +507,7 @@ RK_D void memo_scan_rows(const u32 (&x)[NW], int lane, int& best, int& id, int& 
 // classify_memo_warp_kernel: one warp per read whose sketch is "every counted k-mer" (number of k-mers <= s), for
 // at most 256 references (NW = number of 32-bit words of a reference bitset row, 2..8).
 //
-//   1. the warp streams the read 32 windows at a time (three ballots turn 32 ASCII bases into bit planes, two funnel
-//      shifts give a lane its window's code) and looks the code up in the L2-resident table;
+//   1. the warp streams the read 32 windows at a time (memo_stream) and looks every code up in the L2-resident table;
 //   2. the ranks of the REF windows are compacted into one lane each (reads with more than 32 of them take the block
 //      kernel: 0.1 % of the config-2 reads);
 //   3. each lane fetches its hit's reference bitset row (table slot from ref[rank]; the copy number of a hash that
@@ -484,7 +526,6 @@ classify_memo_warp_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     u32* q = qs[wib];
     const int k = mm.k;
-    const u32 kmask = mm.kmask;
     const u32 lt = (1u << lane) - 1u;
     const u32* __restrict__ tab = mm.tab;
 
@@ -497,32 +538,14 @@ classify_memo_warp_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
             continue;
         }
         const unsigned char* __restrict__ p = sb.bases + beg;
-        const int len = (int)len64, n = (int)n64;
+        const int n = (int)n64;
         // ---- 1 + 2: stream the windows, compact the REF ranks -------------------------------------------------
         int nc = 0;
         u32 nz = 0;
         if (n > 0) {
-            u32 c0, c1, cv;
-            {
-                const u32 ch = lane < len ? (u32)p[lane] : 0u, c2 = base_code(ch);
-                c0 = __ballot_sync(0xffffffffu, c2 & 1u); c1 = __ballot_sync(0xffffffffu, c2 & 2u);
-                cv = __ballot_sync(0xffffffffu, memo_base_invalid(ch));
-            }
-            // four rounds of bases in flight (a 150-base read is requested whole before its first window is looked up)
-            auto loadb = [&](int at) -> u32 { return at + lane < len ? (u32)p[at + lane] : 0u; };
-            u32 q0 = loadb(32), q1 = loadb(64), q2 = loadb(96), q3 = loadb(128);
-#pragma unroll 4
-            for (int base = 0; base < n; base += 32) {
-                const u32 chn = q0;
-                q0 = q1; q1 = q2; q2 = q3; q3 = loadb(base + 160);
-                const u32 c2 = base_code(chn);
-                const u32 n0 = __ballot_sync(0xffffffffu, c2 & 1u), n1 = __ballot_sync(0xffffffffu, c2 & 2u);
-                const u32 nv = __ballot_sync(0xffffffffu, memo_base_invalid(chn));
-                const u32 f0 = __funnelshift_r(c0, n0, (u32)lane) & kmask;
-                const u32 f1 = __funnelshift_r(c1, n1, (u32)lane) & kmask;
-                const u32 fv = __funnelshift_r(cv, nv, (u32)lane) & kmask;
+            memo_stream(p, len64, k, 0, n, lane, [&](i64, u32 code, bool, bool valid) {
                 u32 m = MEMO_ZERO;
-                if (base + lane < n && fv == 0u) m = __ldg(&tab[f0 | (f1 << k)]);
+                if (valid) m = __ldg(&tab[code]);
                 nz += !(m & (MEMO_ZERO | MEMO_FAILM));
                 const bool cand = (m & (MEMO_REF | MEMO_ZERO | MEMO_FAILM)) == MEMO_REF;
                 const u32 bal = __ballot_sync(0xffffffffu, cand);
@@ -531,8 +554,7 @@ classify_memo_warp_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
                     if (cand && at < 32) q[at] = m >> 8;
                     nc += __popc(bal);
                 }
-                c0 = n0; c1 = n1; cv = nv;
-            }
+            });
         }
         if (nc > 32) {
             if (lane == 0) redo[atomicAdd(redo_count, 1)] = (int)rid;
@@ -592,13 +614,6 @@ constexpr u32 SIEVE_MUL = 0x9E3779B1u;
 constexpr int SIEVE_QCAP = 64;                  // sieve-positive windows per read the kernel resolves itself
 constexpr u32 SIEVE_MAX_WORDS = 55040;          // 215 KB of the 227 KB a block may use
 
-// the sieve / code-map key of the k-mer with plane code c: base j at bits 2 j (what the kernel assembles from pieces)
-RK_HD u32 memo_il_code(u32 c, int k) {
-    u32 r = 0;
-    for (int j = 0; j < k; ++j) r |= (((c >> j) & 1u) | (((c >> (k + j)) & 1u) << 1)) << (2 * j);
-    return r;
-}
-
 RK_D u32 sieve_bits(u32 h) { return (1u << ((h >> 3) & 31u)) | (1u << ((h >> 11) & 31u)); }
 
 // stats[0] = codes that are members of a reference sketch, stats[1] = codes whose hash is 0
@@ -608,7 +623,7 @@ memo_sieve_kernel(Memo mm, u32* __restrict__ sieve, u32 nwords, u32* __restrict_
         const u32 t = mm.tab[c];
         if (t & MEMO_ZERO) atomicAdd(&stats[1], 1u);
         else if (t & MEMO_REF) {
-            const u32 h = memo_il_code(c, mm.k) * SIEVE_MUL;
+            const u32 h = c * SIEVE_MUL;
             atomicOr(&sieve[__umulhi(h, nwords)], sieve_bits(h));
             atomicAdd(&stats[0], 1u);
         }
@@ -621,7 +636,7 @@ memo_cmap_kernel(Memo mm, unsigned long long* __restrict__ cmap, u32 mask, int s
     for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < mm.ncodes; c += gridDim.x * blockDim.x) {
         const u32 t = mm.tab[c];
         if ((t & (MEMO_REF | MEMO_ZERO)) != MEMO_REF) continue;
-        const u32 il = memo_il_code(c, mm.k);
+        const u32 il = c;
         const unsigned long long e = ((unsigned long long)mm.ref[t >> 8] << 32) | il;
         u32 i = (il * SIEVE_MUL) >> shift;
         for (;;) {
@@ -652,20 +667,6 @@ RK_D u32 tr32(u32 x, const TrLane& t) {
     y = __shfl_xor_sync(0xffffffffu, x, 2); y = __funnelshift_l(y, y, t.rot2); x = (x & t.keep2) | (y & ~t.keep2);
     y = __shfl_xor_sync(0xffffffffu, x, 1); y = __funnelshift_l(y, y, t.rot1); x = (x & t.keep1) | (y & ~t.keep1);
     return x;
-}
-
-// Four bases of the read as one aligned 32-bit load: `piece` = their four 2-bit codes (first base in the low bits),
-// `bad` has a non-zero byte for every base that is not one of ACGTacgt (canonical(), mkmh.hpp:137-152): the letter is
-// rebuilt from its code (A 0x41, C 0x43, T 0x54, G 0x47 for codes 0, 1, 2, 3) and compared with the upper-cased byte.
-RK_D void sv_decode(u32 w, u32& piece, u32& bad) {
-    const u32 x = (w >> 1) & 0x03030303u;
-    piece = (x * 0x01041040u) >> 24;                         // byte i -> bits 2 i (the partial products do not overlap)
-    const u32 lo = x & 0x01010101u, hi = (x >> 1) & 0x01010101u;
-    const u32 e = 0x41414141u + 2u * lo + 0x13u * hi - 0xFu * (lo & hi);
-    bad = (w & 0xDFDFDFDFu) ^ e;
-}
-RK_D u32 sv_bad4(u32 bad) {
-    return ((bad & 0xFFu) ? 1u : 0u) | ((bad & 0xFF00u) ? 2u : 0u) | ((bad & 0xFF0000u) ? 4u : 0u) | ((bad & 0xFF000000u) ? 8u : 0u);
 }
 
 template <int NW>
@@ -860,12 +861,26 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
 
 // ------------------------------------------------------------------------------------------------
 // classify_memo_block_kernel: one block per read (grid-stride over `list`, or over every read when list is null).
-// Exact for every input.  The read's table values (rank | flags, MEMO_SKIP for windows that do not count) are kept in
-// shared memory (or L2 scratch for very long reads); the bottom-s multiset is a two-level radix select on the 24-bit
-// rank; its REF members are resolved against the reference table exactly like the Murmur path does.
+// Exact for every input.
 //
-// Dynamic shared memory (u32 units): [vcap values][MEMO_HIST_WORDS histogram][hs_cap keys][hs_cap counts][rpad counters]
-struct MemoBlockScratch { u32 part[32]; u32 bin, before; int nz, take; ArgmaxScratch as; };
+//   pass 1   every warp streams its share of the read and looks the table value (rank | flags) of every window up, the
+//            lookups MEMO_DELAY rounds ahead of their use.  The bottom-s multiset only needs the windows at or under its
+//            s-th smallest rank T, so a warp KEEPS (appends to its own list: no atomics, the order is irrelevant) only the
+//            counted windows whose rank is under a bound B, a guess of 2 T made from the read's length and the share of
+//            counted windows in the block's previous read; the kept values also enter the histogram of the top 12 rank
+//            bits.  A 10 kb read at s = 1000 keeps a fifth of its windows: the lists are `lcap` words per warp of shared
+//            memory, and everything after pass 1 touches the lists only.
+//   check    the guess holds when no list overflowed and the lists hold every counted window, or at least s of them
+//            (then the s smallest are among them, with all their copies).  Otherwise pass 1 runs again with B = infinity
+//            into lists in global memory that are sized for every window (also the first choice of a read of at most s
+//            windows whose share per warp exceeds lcap).
+//   select   two-level radix select of T on the 24-bit rank over the lists; `need` copies of rank T belong to the sketch.
+//   resolve  the REF members are compacted into a per-warp ring and resolved against the reference table 32 at a time,
+//            exactly like the Murmur path does (copy number of a repeated hash from a per-block set of table slots).
+//
+// Dynamic shared memory (u32 units): [nwarps x lcap lists][MEMO_HIST_WORDS histogram][hs_cap keys][hs_cap counts][rpad counters]
+struct MemoBlockScratch { u32 part[32]; u32 bin, before; int nz, take, kept, over; ArgmaxScratch as; };
+constexpr int MEMO_DELAY = 4;
 
 // the bin in which the running count of hist[0, MEMO_BINS) reaches `target` (1-based), and the count before it
 RK_D void memo_find_bin(const u32* hist, u32 target, MemoBlockScratch* bs) {
@@ -891,9 +906,9 @@ RK_D void memo_find_bin(const u32* hist, u32 target, MemoBlockScratch* bs) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* __restrict__ list,
-                           const int* __restrict__ nlist_ptr, i64 nseq, int vcap, int hs_cap, int rpad,
+                           const int* __restrict__ nlist_ptr, i64 nseq, int lcap, int hs_cap, int rpad,
                            u32* __restrict__ scratch, i64 scratch_stride, Hit* __restrict__ out) {
 #ifdef RK_EMU
     unsigned char* dsm = reinterpret_cast<unsigned char*>(EMU_DYN_SMEM());
@@ -901,63 +916,91 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
     extern __shared__ __align__(16) unsigned char dsm[];
 #endif
     __shared__ MemoBlockScratch bs;
-    __shared__ u32 wq[8][MEMO_RING];                         // per-warp ring of hit ranks (blocks of 256 threads)
-    u32* vals_smem = reinterpret_cast<u32*>(dsm);
-    u32* hist = vals_smem + vcap;
+    __shared__ u32 wq[8][MEMO_RING];                         // per-warp ring of hit ranks (blocks of at most 256 threads)
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    u32* lists = reinterpret_cast<u32*>(dsm);
+    u32* hist = lists + (size_t)nwb * lcap;
     u32* hs_keys = hist + MEMO_HIST_WORDS;
     u32* hs_cnt = hs_keys + hs_cap;
     u32* counts = hs_cnt + hs_cap;
     const u32 hs_mask = (u32)hs_cap - 1;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    const u32 ltm = (1u << lane) - 1u;
     const int k = mm.k;
+    float frac = 1.0f;                                       // counted windows / windows of this block's previous read
 
     const i64 nlist = list ? (i64)*nlist_ptr : nseq;
     for (i64 q = blockIdx.x; q < nlist; q += gridDim.x) {
         const i64 rid = list ? (i64)list[q] : q;
         const i64 beg = sb.offs[rid] - sb.base0, len = sb.offs[rid + 1] - sb.offs[rid];
         const i64 n = nkmers(len, k);
-        u32* V = (n <= vcap) ? vals_smem : scratch + (i64)blockIdx.x * scratch_stride;
-        if (threadIdx.x == 0) { bs.nz = 0; bs.take = 0; }
-        for (int i = threadIdx.x; i < MEMO_HIST_WORDS; i += blockDim.x) hist[i] = 0;
-        for (int i = threadIdx.x; i < 2 * hs_cap; i += blockDim.x) hs_keys[i] = 0;
-        for (int i = threadIdx.x; i < rpad; i += blockDim.x) counts[i] = 0;
-        __syncthreads();
-        // ---- pass 1: table values of every window, histogram of the top 12 rank bits ----------------------
-        {
-            const i64 per = ((((n + 31) >> 5) + nwb - 1) / nwb) << 5;
-            const i64 s0 = (i64)wib * per, s1 = min(n, s0 + per);
-            u32 local_nz = 0;
-            // the table value of a window is consumed FOUR rounds after its lookup was issued: five lookups of a warp are
-            // in flight (the 64 MB table does not fit one die's L2: a tenth of them go to HBM; with two rounds of delay ncu
-            // showed 2.3 long-scoreboard stalls per issued instruction).  The window of a delayed value is where the
-            // stream was four rounds ago, so no positions travel with the values.
-            constexpr int DELAY = 4;
-            u32 ring[DELAY];
+        const i64 per = ((((n + 31) >> 5) + nwb - 1) / nwb) << 5;          // k-mer starts per warp, whole rounds
+        const i64 s0 = (i64)wib * per, s1 = min(n, s0 + per);
+        // the bound on (rank << 8 | flags): twice the expected s-th smallest rank of the read's counted windows
+        u32 bound = 0xFFFFFFFFu;
+        if (n > s) {
+            const float est = frac * (float)n;                   // counted windows expected
+            const float cut = 2.0f * (float)s / (est > 1.0f ? est : 1.0f) * (float)mm.ncodes;
+            if (cut < (float)mm.ncodes) bound = (u32)cut << 8;
+        }
+        bool wide = bound == 0xFFFFFFFFu && per > (i64)lcap;
+        u32* L;
+        int cnt, nz;
+        for (;;) {
+            L = wide ? scratch + (i64)blockIdx.x * scratch_stride + (i64)wib * per : lists + (size_t)wib * lcap;
+            const int cap = wide ? (int)per : lcap;
+            if (threadIdx.x == 0) { bs.nz = 0; bs.take = 0; bs.kept = 0; bs.over = 0; }
+            for (int i = threadIdx.x; i < MEMO_HIST_WORDS; i += blockDim.x) hist[i] = 0;
+            for (int i = threadIdx.x; i < 2 * hs_cap; i += blockDim.x) hs_keys[i] = 0;
+            for (int i = threadIdx.x; i < rpad; i += blockDim.x) counts[i] = 0;
+            __syncthreads();
+            // ---- pass 1 ---------------------------------------------------------------------------------------------
+            // The table value of a window is consumed MEMO_DELAY rounds after its lookup was issued (the 64 MB table does
+            // not fit one die's L2: a tenth of the lookups go to HBM; with two rounds ncu showed 2.3 long-scoreboard
+            // stalls per issued instruction).
+            u32 ring[MEMO_DELAY];
 #pragma unroll
-            for (int d = 0; d < DELAY; ++d) ring[d] = MEMO_SKIP;
-            auto consume = [&](i64 pos, u32 m) {
-                if (m != MEMO_SKIP && (m & (MEMO_ZERO | MEMO_FAILM))) m = MEMO_SKIP;
-                if (pos >= s0 && pos < s1) V[pos] = m;
-                if (m != MEMO_SKIP) { ++local_nz; atomicAdd(&hist[memo_hidx(m >> 20)], 1u); }
+            for (int d = 0; d < MEMO_DELAY; ++d) ring[d] = MEMO_SKIP;
+            u32 local_nz = 0;
+            cnt = 0;
+            auto consume = [&](u32 m) {
+                const bool ok = !(m & (MEMO_ZERO | MEMO_FAILM));            // MEMO_SKIP has every flag set
+                local_nz += ok;
+                const bool keep = ok && m < bound;
+                const u32 bal = __ballot_sync(0xffffffffu, keep);
+                if (bal) {
+                    const int at = cnt + __popc(bal & ltm);
+                    if (keep) {
+                        if (at < cap) L[at] = m;
+                        atomicAdd(&hist[memo_hidx(m >> 20)], 1u);
+                    }
+                    cnt += __popc(bal);
+                }
             };
-            i64 last = s0 + lane - 32;
-            memo_stream(sb.bases + beg, len, k, mm.kmask, s0, s1, lane, [&](i64 pos, u32 code, bool, bool valid) {
+            memo_stream(sb.bases + beg, len, k, s0, s1, lane, [&](i64, u32 code, bool, bool valid) {
                 u32 m = MEMO_SKIP;
                 if (valid) m = __ldg(&mm.tab[code]);
-                consume(pos - 32 * DELAY, ring[DELAY - 1]);
+                consume(ring[MEMO_DELAY - 1]);
 #pragma unroll
-                for (int d = DELAY - 1; d > 0; --d) ring[d] = ring[d - 1];
+                for (int d = MEMO_DELAY - 1; d > 0; --d) ring[d] = ring[d - 1];
                 ring[0] = m;
-                last = pos;
             });
 #pragma unroll
-            for (int d = DELAY - 1; d >= 0; --d) consume(last - 32 * d, ring[d]);
+            for (int d = MEMO_DELAY - 1; d >= 0; --d) consume(ring[d]);
             local_nz = warp_sum(local_nz);
-            if (lane == 0 && local_nz) atomicAdd(&bs.nz, (int)local_nz);
+            if (lane == 0) {
+                if (local_nz) atomicAdd(&bs.nz, (int)local_nz);
+                if (cnt > cap) bs.over = 1; else if (cnt) atomicAdd(&bs.kept, cnt);
+            }
+            __syncthreads();
+            nz = bs.nz;
+            const bool good = wide || (!bs.over && (bs.kept == nz || bs.kept >= s));
+            if (good) break;
+            __syncthreads();                                 // every thread has read the verdict before it is cleared
+            wide = true;
+            bound = 0xFFFFFFFFu;
         }
-        __syncthreads();
-        const int nz = bs.nz;
-        const int L = nz < s ? nz : s;
+        frac = (float)nz / (float)(n > 0 ? n : 1);
+        const int Lr = nz < s ? nz : s;
         // ---- bottom-s threshold: rank T, of which `need` copies belong to the sketch -----------------------
         u32 T = 0xFFFFFFFFu; int need = 0;
         if (nz > s) {
@@ -966,9 +1009,9 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
             __syncthreads();
             for (int i = threadIdx.x; i < MEMO_HIST_WORDS; i += blockDim.x) hist[i] = 0;
             __syncthreads();
-            for (i64 i = threadIdx.x; i < n; i += blockDim.x) {
-                const u32 m = V[i];
-                if (m != MEMO_SKIP && (m >> 20) == b1) atomicAdd(&hist[memo_hidx((m >> 8) & 0xFFFu)], 1u);
+            for (int i = lane; i < cnt; i += 32) {
+                const u32 m = L[i];
+                if ((m >> 20) == b1) atomicAdd(&hist[memo_hidx((m >> 8) & 0xFFFu)], 1u);
             }
             __syncthreads();
             memo_find_bin(hist, (u32)s - before1, &bs);
@@ -997,7 +1040,6 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
         // long read) and compacts their ranks into a per-warp ring; rows are resolved 32 hits at a time, all lanes busy.
         u32* ring = wq[wib];
         int qhead = 0, qn = 0;
-        const u32 ltm = (1u << lane) - 1u;
         auto drain = [&](int cnt) {                          // resolve the first cnt (<= 32) queued ranks
             const u64* row = nullptr;
             if (lane < cnt) {
@@ -1042,11 +1084,12 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
                 }
             }
         };
-        for (i64 i0 = (i64)wib * 32; i0 < n; i0 += (i64)nwb * 32) {
-            const i64 i = i0 + lane;
-            const u32 m = i < n ? V[i] : MEMO_SKIP;
+        for (int i0 = 0; i0 < cnt; i0 += 32) {               // the warp's own list
+            const int i = i0 + lane;
             bool hit = false;
-            if (m != MEMO_SKIP) {
+            u32 m = 0;
+            if (i < cnt) {
+                m = L[i];
                 const u32 rank = m >> 8;
                 const bool member = rank < T || (rank == T && atomicAdd(&bs.take, 1) < need);
                 hit = member && (m & MEMO_REF);
@@ -1062,7 +1105,7 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
         if (qn > 0) { __syncwarp(); drain(qn); }
         if (small && vsteps) flush_planes();
         __syncthreads();
-        block_argmax(counts, (int)tb.nrefs, &bs.as, &out[rid], L);
+        block_argmax(counts, (int)tb.nrefs, &bs.as, &out[rid], Lr);
     }
 }
 

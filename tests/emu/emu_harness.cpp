@@ -338,7 +338,7 @@ int emu_count_memo(const char* bases, const i64* offs, i64 nseq, int k, int* cou
 }
 
 // path: 0 = block kernel for every read, 1 = warp kernel + block kernel on its redo list.  vcap_limit > 0 caps the
-// shared-memory value buffer (forces the global scratch for longer reads).
+// per-warp shared-memory lists of the block kernel (forces its second attempt with global lists).
 int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, const char* bases, const i64* offs, i64 nreads,
                       int k, int s, const int* counts, u64 size, int min_occ, int path, int block, int vcap_limit,
                       Hit* out, int* redo_count_out) {
@@ -385,15 +385,17 @@ int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, con
     {
         const int hs_cap = next_pow2(2 * (i64)std::min<i64>(s, std::max<i64>(b.max_ntotal, 1)));
         const int rpad = (nrefs + 63) / 64 * 64;
-        int vcap = (int)std::max<i64>(b.max_ntotal, 1);
-        if (vcap_limit > 0) vcap = std::min(vcap, vcap_limit);
-        const i64 stride = (b.max_ntotal > vcap) ? b.max_ntotal : 0;
-        size_t smem = 4 * ((size_t)vcap + MEMO_HIST_WORDS + 2 * (size_t)hs_cap + rpad);
+        const int nwb = block / 32;
+        const i64 most = ((std::max<i64>(b.max_ntotal, 1) + 31) / 32 + nwb - 1) / nwb * 32;
+        int lcap = (int)std::min<i64>(most, std::max<i64>(128, ((i64)(0.4 * s) + 31) / 32 * 32));
+        if (vcap_limit > 0) lcap = std::min(lcap, vcap_limit);
+        const i64 stride = (std::max<i64>(b.max_ntotal, 1) + 32 * nwb + 31) / 32 * 32;
+        size_t smem = 4 * ((size_t)nwb * lcap + MEMO_HIST_WORDS + 2 * (size_t)hs_cap + rpad);
         std::vector<u32> scratch((size_t)grid * (size_t)stride + 8);
         u32* ps = scratch.data();
         const int* list = (path >= 1) ? predo : nullptr;
         emu::launch(dim3(grid), dim3(block), smem, [=] {
-            classify_memo_block_kernel(sb, s, mm, tb, list, pcount, nreads, vcap, hs_cap, rpad, ps, stride, out);
+            classify_memo_block_kernel(sb, s, mm, tb, list, pcount, nreads, lcap, hs_cap, rpad, ps, stride, out);
         });
     }
     return 0;

@@ -142,6 +142,26 @@ def test_memo_classify_awkward(emu, oracle, kw):
         _memo_case(emu, oracle, refs, reads, k, s, **kw)
 
 
+@pytest.mark.parametrize("block", [64, 256])
+def test_memo_block_kernel_bound_cases(emu, oracle, block):
+    """classify_memo_block_kernel keeps only the windows under a GUESSED rank bound (from the previous read of the block)
+    and falls back to keeping everything when the guess fails: reads that make consecutive guesses wrong in both
+    directions (mostly-N after random, one repeated k-mer, tandem repeats, s close to the number of windows), with and
+    without a -M mask, must still give the oracle's records."""
+    rng = np.random.default_rng(11)
+    _, refs, _ = load_sequences([data_path("awkward_refs.fa.gz")])
+    def rnd(n, pn=0.0):
+        return rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=n, p=[(1 - pn) / 4] * 4 + [pn]).tobytes()
+    reads = [rnd(3000), rnd(3000, 0.15), b"A" * 2500, rnd(2600), (b"ACGGTCA" * 400), rnd(900) + b"N" * 1500 + rnd(700),
+             refs[0] * 3, rnd(1100), b"N" * 700, rnd(40), rnd(5000), refs[1] + rnd(2000) + refs[2]]
+    for s in (60, 1000):
+        _memo_case(emu, oracle, refs, reads, 8, s, path=0, block=block)
+    c = np.zeros(10_007, np.int32)
+    oracle.count_batch(reads, [8], c)
+    _memo_case(emu, oracle, refs, reads, 8, 300, counts=c, min_occ=40, path=0, block=block)
+    _memo_case(emu, oracle, refs, reads, 6, 500, path=0, block=block, vcap_limit=32)
+
+
 def test_memo_classify_fixtures(emu, oracle):
     _, refs, _ = load_sequences([data_path("hpv_16_allFasta.fa.gz")])
     _, reads, _ = load_sequences([data_path("minION25.fq.gz")])
