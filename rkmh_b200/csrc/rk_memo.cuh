@@ -99,8 +99,8 @@ RK_D void memo_stream(const unsigned char* __restrict__ p, i64 len, int k, i64 s
     const unsigned char* q = p + s0;
     const int sh = (int)(reinterpret_cast<size_t>(q) & 3u);
     const u32* __restrict__ wp = reinterpret_cast<const u32*>(q - sh);
-    const i64 nbytes = sh + (len - s0);                     // bytes from wp to the end of the sequence
     const i64 pend = sh + (s1 - s0);                        // stream positions [sh, pend) start a window of the range
+    const i64 nbytes = min(sh + (len - s0), pend + k);      // bytes from wp that a window of the range can touch
     // words that hold no base of the sequence are not loaded and decode as valid 'AAAA' (no window in range reaches them)
     auto load_word = [&](i64 widx) -> u32 { return 4 * widx < nbytes ? __ldg(wp + widx) : 0x41414141u; };
     const u32 cmask2 = (1u << (2 * k)) - 1u, kmask = (1u << k) - 1u;
@@ -880,7 +880,13 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
 //
 // Dynamic shared memory (u32 units): [nwarps x lcap lists][MEMO_HIST_WORDS histogram][hs_cap keys][hs_cap counts][rpad counters]
 struct MemoBlockScratch { u32 part[32]; u32 bin, before; int nz, take, kept, over; ArgmaxScratch as; };
-constexpr int MEMO_DELAY = 4;
+#ifndef MEMO_DELAY_ROUNDS
+#define MEMO_DELAY_ROUNDS 4
+#endif
+#ifndef MEMO_BLOCK_MIN_BLOCKS
+#define MEMO_BLOCK_MIN_BLOCKS 3
+#endif
+constexpr int MEMO_DELAY = MEMO_DELAY_ROUNDS;
 
 // the bin in which the running count of hist[0, MEMO_BINS) reaches `target` (1-based), and the count before it
 RK_D void memo_find_bin(const u32* hist, u32 target, MemoBlockScratch* bs) {
@@ -906,7 +912,7 @@ RK_D void memo_find_bin(const u32* hist, u32 target, MemoBlockScratch* bs) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, MEMO_BLOCK_MIN_BLOCKS)
 classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* __restrict__ list,
                            const int* __restrict__ nlist_ptr, i64 nseq, int lcap, int hs_cap, int rpad,
                            u32* __restrict__ scratch, i64 scratch_stride, Hit* __restrict__ out) {
