@@ -447,8 +447,19 @@ def section_config2(args, R, gpu, refs, pins):
     hits_host[:] = 0
     packed_ms = R.timed(e2e_fixed, args.steps, w)
     same_packed = bool(np.array_equal(hits_host.view(np.int32), dev_hits.view(np.int32)))
+    # adaptive: a chunk is packed only while the link is busy with earlier chunks (link and cores both kept busy)
+    gpu.set_host_pack(2, threads)
+    hits_host[:] = 0
+    for _ in range(max(w, 2)):
+        e2e_fixed()
+    gpu.transfer_stats(reset=True)
+    adaptive_ms = R.timed(e2e_fixed, args.steps, 0)
+    xfer = gpu.transfer_stats(reset=True)
+    same_adaptive = bool(np.array_equal(hits_host.view(np.int32), dev_hits.view(np.int32)))
     gpu.set_host_pack(False)
-    return {"n": n, "hb": hb, "ho": ho, "kernel_ms": kernel_ms, "launches": launches, "prof": prof, "dev_hits": dev_hits,
+    return {"adaptive_ms": adaptive_ms, "same_adaptive": same_adaptive,
+            "adaptive_h2d": (xfer["plain_bytes"] + xfer["packed_bytes"]) // max(args.steps, 1),
+            "adaptive_packed_share": xfer["packed_chunks"] / max(xfer["packed_chunks"] + xfer["plain_chunks"], 1), "n": n, "hb": hb, "ho": ho, "kernel_ms": kernel_ms, "launches": launches, "prof": prof, "dev_hits": dev_hits,
             "e2e_ms": e2e_ms, "e2e_offs_ms": e2e_offs_ms, "same": same and same_offs, "ceiling_ms": ceiling_ms,
             "packed_ms": packed_ms, "same_packed": same_packed, "pack_threads": threads}
 
@@ -769,6 +780,9 @@ def main_ours(args, rank, world, local_rank):
         plain_ms = c2["e2e_ms"]
         use_packed = c2["same_packed"] and c2["packed_ms"] < plain_ms
         e2e_ms = c2["packed_ms"] if use_packed else plain_ms
+        use_adaptive = c2["same_adaptive"] and c2["adaptive_ms"] < e2e_ms
+        if use_adaptive:
+            e2e_ms = c2["adaptive_ms"]
         value = total_reads / (kernel_ms / 1e3)
         e2e_value = total_reads / (e2e_ms / 1e3)
         peaks = {}
@@ -816,12 +830,20 @@ def main_ours(args, rank, world, local_rank):
             "kmers_per_s": value * (READ_LEN - K),
             "kmers_note": "windows classified per second; on the memoised path they are looked up, murmur_path hashes them",
             "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": (int(12 * ((n * READ_LEN + 31) // 32)) if use_packed else h2d), "d2h_bytes_per_step": int(16 * n),
-                    "api": ("rkg_classify_fixed after rkg_set_host_pack: pinned host buffers of ASCII bases in, packed to 2-bit codes + "
+                    "h2d_bytes_per_step": (int(c2["adaptive_h2d"]) if use_adaptive else int(12 * ((n * READ_LEN + 31) // 32)) if use_packed else h2d),
+                    "d2h_bytes_per_step": int(16 * n),
+                    "api": ("rkg_classify_fixed after rkg_set_host_pack(2): pinned host buffers of ASCII bases in; the library packs a chunk "
+                            "to 2-bit codes + mask on the host cores INSIDE the timed call while the link is busy with earlier chunks and "
+                            "sends it as it is otherwise (h2d bytes are this rank's measured mix)"
+                            if use_adaptive else
+                            "rkg_classify_fixed after rkg_set_host_pack: pinned host buffers of ASCII bases in, packed to 2-bit codes + "
                             "mask by the library on the host cores INSIDE the timed call, 0.375 B/base over the link"
                             if use_packed else
                             "rkg_classify_fixed (pinned host buffers, fixed-length reads: no offsets cross the link)"),
-                    "matches_device_run": c2["same"] and (c2["same_packed"] or not use_packed),
+                    "matches_device_run": c2["same"] and (c2["same_packed"] or not use_packed) and (c2["same_adaptive"] or not use_adaptive),
+                    "adaptive_transfer": {"ms_per_step": c2["adaptive_ms"], "value": total_reads / (c2["adaptive_ms"] / 1e3),
+                                          "h2d_bytes_per_step": int(c2["adaptive_h2d"]), "packed_share_of_chunks": c2["adaptive_packed_share"],
+                                          "host_threads_per_rank": c2["pack_threads"], "matches_device_run": c2["same_adaptive"]},
                     "plain_transfer": {"ms_per_step": plain_ms, "value": total_reads / (plain_ms / 1e3), "h2d_bytes_per_step": h2d},
                     "packed_transfer": {"ms_per_step": c2["packed_ms"], "value": total_reads / (c2["packed_ms"] / 1e3),
                                         "h2d_bytes_per_step": int(12 * ((n * READ_LEN + 31) // 32)), "host_threads_per_rank": c2["pack_threads"],

@@ -142,9 +142,16 @@ int rkg_count_fixed(rkg_ctx* ctx, const char* bases, int64_t read_len, int64_t n
  * 2-bit codes and the invalid-base mask -- what its ingest kernel makes on the device -- on the HOST, with `threads` host
  * threads (0 = as many as the machine has, at most 16), chunk by chunk inside rkg_classify_batch / rkg_classify_fixed /
  * rkg_count_batch / rkg_count_fixed and the other host-buffer calls, and ship 0.375 bytes per base instead of 1.  Same
- * buffers in, same results out (upper-casing and the validity of a base are all the kernels take from a byte).  Off by
- * default: it pays when the caller's cores are otherwise idle. */
+ * buffers in, same results out (upper-casing and the validity of a base are all the kernels take from a byte).
+ * enable: 0 = off (the default), 1 = every chunk is packed (pays when the link is much slower than the caller's cores),
+ * 2 = adaptive: rkg_classify_batch / _fixed and rkg_count_batch / _fixed send a chunk as it is when the link would
+ * otherwise idle and pack it while the link is busy with earlier chunks, so that link and cores both stay busy whatever
+ * their speeds are (measured on the context's first chunks); 64 MB chunks, four in flight. */
 int rkg_set_host_pack(rkg_ctx* ctx, int enable, int threads);
+/* What the host-buffer calls sent since the context was created or `reset` was last passed non-zero:
+ * stats[0] = host-to-device bytes of chunks sent as they are, [1] = bytes of packed chunks (0.375 per base),
+ * [2] = chunks sent as they are, [3] = packed chunks. */
+int rkg_transfer_stats(rkg_ctx* ctx, int64_t stats[4], int reset);
 
 /* The same in two steps for callers that keep batches resident in HBM (and for kernel-only timing):
  * upload once, classify any number of times, fetch results. */

@@ -18,7 +18,7 @@ RKG_SYMBOLS = [
     "rkg_sketch_shard", "rkg_merge_sketches", "rkg_launch_count", "rkg_profile_enable", "rkg_profile_read",
     "rkg_set_memo", "rkg_memo_active", "rkg_count_partial", "rkg_classify_fixed", "rkg_count_fixed", "rkg_copy_probe",
     "rkg_load_ref_sets", "rkg_classify_sets", "rkg_load_ref_sketches", "rkg_count_export", "rkg_count_import",
-    "rkg_depth_begin", "rkg_depth_add", "rkg_depth_of_sequence", "rkg_depth_rescue", "rkg_set_host_pack",
+    "rkg_depth_begin", "rkg_depth_add", "rkg_depth_of_sequence", "rkg_depth_rescue", "rkg_set_host_pack", "rkg_transfer_stats",
 ]
 
 
@@ -58,6 +58,7 @@ def load():
     lib.rkg_classify_fixed.argtypes = [P, P, L, L, I, P]
     lib.rkg_count_fixed.argtypes = [P, P, L, L, I]
     lib.rkg_copy_probe.argtypes = [P, P, P, L, L, P]
+    lib.rkg_transfer_stats.argtypes = [P, P, C.c_int]
     lib.rkg_load_ref_sets.argtypes = [P, P, P, I]
     lib.rkg_load_ref_sketches.argtypes = [P, P, P, I]
     lib.rkg_count_export.argtypes = [P, I, P, P, U, C.POINTER(U)]

@@ -157,8 +157,15 @@ class RkmhGpu:
         self._check(self.lib.rkg_get_ref_sketches(self.handle, sk.ctypes.data, lens.ctypes.data))
         return sk, lens
 
+    def transfer_stats(self, reset=False):
+        """Bytes / chunks the host-buffer calls sent as they are and packed (rkg_transfer_stats)."""
+        st = (C.c_int64 * 4)()
+        self._check(self.lib.rkg_transfer_stats(self.handle, st, int(reset)))
+        return {"plain_bytes": int(st[0]), "packed_bytes": int(st[1]), "plain_chunks": int(st[2]), "packed_chunks": int(st[3])}
+
     def set_host_pack(self, enable=True, threads=0):
-        """Pack bases to 2 bits + mask on the host before every host-to-device copy (rkg_set_host_pack)."""
+        """Pack bases to 2 bits + mask on the host before the host-to-device copies (rkg_set_host_pack):
+        0 / False = off, 1 / True = every chunk, 2 = adaptive (a chunk is packed while the link is busy anyway)."""
         self._check(self.lib.rkg_set_host_pack(self.handle, int(enable), int(threads)))
 
     def set_memo(self, enable=True):

@@ -10,6 +10,7 @@
 #include <map>
 #include <string>
 #include <thread>
+#include <chrono>
 #include <vector>
 
 #include "../../include/rkmh_gpu.h"
@@ -69,6 +70,8 @@ struct rkg_batch {
     cudaEvent_t done = nullptr;
 };
 
+constexpr int NSLOTS = 4;
+
 struct rkg_ctx {
     int device = 0;
     int sm_count = 0;
@@ -94,12 +97,16 @@ struct rkg_ctx {
     DevBuf ref_sketches, ref_lens, tb_entries, tb_maxmult, tb_dupbase, tb_dupbits, tb_filter, tb_cursor;
     RefTable tb{};
     cudaStream_t stream = nullptr;
-    rkg_batch* slots[2] = {nullptr, nullptr};   // internal double buffer of rkg_classify_batch / count
+    rkg_batch* slots[NSLOTS] = {};       // internal buffers of rkg_classify_batch / count (two; four with adaptive packing)
     // packed transfer (rkg_set_host_pack): per slot, pinned staging for the codes and the mask packed on the host
-    bool host_pack = false;
+    int host_pack = 0;                   // 0 off, 1 every chunk, 2 adaptive: a chunk is packed when the link is busy anyway
     int pack_threads = 1;
-    void* stage[2] = {nullptr, nullptr};
-    size_t stage_cap[2] = {0, 0};
+    void* stage[NSLOTS] = {};
+    size_t stage_cap[NSLOTS] = {};
+    cudaEvent_t h2d_done[NSLOTS] = {};   // adaptive mode: recorded after a chunk's host-to-device copies
+    int64_t xfer[4] = {0, 0, 0, 0};       // rkg_transfer_stats
+    double pack_lead = 0.75;             // pack when the queued copies last at least this share of the packing time (RKMH_PACK_LEAD)
+    double pack_ms_per_byte = 0.0, dma_ms_per_byte = 0.0;      // adaptive mode: measured on this context's first chunks
     // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
     bool memo_enabled = true, memo_ready = false, sieve_enabled = true, group_kernel = false;
     DevBuf memo_tab, memo_ref, memo_hash, memo_counts, memo_tmp, memo_misc, memo_sieve, memo_cmap;
@@ -239,7 +246,8 @@ fixed_offs_kernel(i64* __restrict__ offs, i64 n, i64 base0, i64 len) {
 
 // Copy reads [r0, r1) of the caller's buffers into the batch (asynchronous on b->stream); packing is done on demand.
 // offs == nullptr: every read has `fixed_len` bases and read i starts at bases[i * fixed_len].
-int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* offs, i64 r0, i64 r1, i64 fixed_len = 0) {
+int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* offs, i64 r0, i64 r1, i64 fixed_len = 0,
+               int pack_mode = -1) {          // pack_mode: -1 = as the context says (host_pack == 1), 0 = plain, 1 = packed
     const i64 n = r1 - r0;
     const i64 base0 = offs ? offs[r0] : r0 * fixed_len, total = offs ? offs[r1] - base0 : n * fixed_len;
     b->nseq = n; b->total = total; b->base0 = base0;
@@ -251,8 +259,9 @@ int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* off
     CK(b->hits.ensure(sizeof(Hit) * (size_t)std::max<i64>(n, 1)));
     CK(b->redo.ensure(sizeof(int) * (size_t)std::max<i64>(n, 1)));
     CK(b->misc.ensure(256));
-    const int slot = (b == ctx->slots[0]) ? 0 : (b == ctx->slots[1]) ? 1 : -1;
-    const bool pack_here = ctx->host_pack && slot >= 0 && total > 0;
+    int slot = -1;
+    for (int i = 0; i < NSLOTS; ++i) if (b == ctx->slots[i]) slot = i;
+    const bool pack_here = (pack_mode < 0 ? ctx->host_pack == 1 : pack_mode == 1) && slot >= 0 && total > 0;
     if (pack_here) {
         // 0.375 bytes per base cross the link: codes (2 words per 32 bases) then the mask (1 word per 32 bases), packed by
         // the host's threads into this slot's pinned staging buffer (free again: the caller waited for the slot's stream)
@@ -268,9 +277,13 @@ int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* off
         u32* hc = static_cast<u32*>(ctx->stage[slot]);
         u32* hm = hc + mask_at;
         rk_pack_bases(bases + base0, total, hc, hm, ctx->pack_threads);
+        ctx->xfer[1] += 12 * nwords32; ++ctx->xfer[3];
         CK(cudaMemcpyAsync(b->codes.p, hc, sizeof(u32) * 2 * (size_t)nwords32, cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->nmask.p, hm, sizeof(u32) * (size_t)nwords32, cudaMemcpyHostToDevice, b->stream));
-    } else if (total > 0) CK(cudaMemcpyAsync(b->bases.p, bases + base0, (size_t)total, cudaMemcpyHostToDevice, b->stream));
+    } else if (total > 0) {
+        CK(cudaMemcpyAsync(b->bases.p, bases + base0, (size_t)total, cudaMemcpyHostToDevice, b->stream));
+        ctx->xfer[0] += total; ++ctx->xfer[2];
+    }
     if (offs) CK(cudaMemcpyAsync(b->offs.p, offs + r0, sizeof(i64) * (size_t)(n + 1), cudaMemcpyHostToDevice, b->stream));
     else {
         ++ctx->launches;
@@ -527,16 +540,16 @@ MemoGeom memo_geometry(const rkg_ctx* ctx, const rkg_batch* b) {
     const i64 want = std::min<i64>(most, std::max<i64>(128, ((i64)(0.4 * (double)ctx->s) + 31) / 32 * 32));
     for (int per_sm = 4; per_sm >= 1 && !g.ok; --per_sm) {
         const size_t budget = ctx->smem_optin / per_sm - 4608;     // static scratch + hit rings + the 1 KB reserve per block
-        if (fixed + 4 * 8 * (size_t)32 > budget) continue;
-        const i64 room = (i64)((budget - fixed) / (4 * 8)) / 32 * 32;
+        if (fixed + 4 * 8 * (size_t)64 > budget) continue;
+        const i64 room = (i64)((budget - fixed) / (4 * 8)) / 32 * 32 - 32;     // 32 words per warp catch an overflowing list
         if (room < want && per_sm > 1) continue;
         g.lcap = (int)std::min<i64>(want, room);
         g.block_per_sm = per_sm;
         g.ok = true;
     }
     if (!g.ok) return g;
-    g.scratch_stride = (std::max<i64>(b->max_ntotal, 1) + 32 * 8 + 31) / 32 * 32;      // the lists of the second attempt: every window
-    g.block_smem = fixed + 4 * 8 * (size_t)g.lcap;
+    g.scratch_stride = (std::max<i64>(b->max_ntotal, 1) + 64 * 8 + 31) / 32 * 32;      // the lists of the second attempt: every window
+    g.block_smem = fixed + 4 * 8 * (size_t)(g.lcap + 32);
     // warp kernel: the typical read keeps all its k-mers (n <= s)
     const i64 mean_n = std::max<i64>(b->total / b->nseq - ctx->kl.k[0], 0);
     g.rwords = (ctx->nrefs + 1) / 2;
@@ -764,8 +777,8 @@ int build_ref_table(rkg_ctx* ctx, int nrefs, cudaStream_t st) {
     return RKG_OK;
 }
 
-int ensure_slots(rkg_ctx* ctx) {
-    for (int i = 0; i < 2; ++i)
+int ensure_slots(rkg_ctx* ctx, int n = 2) {
+    for (int i = 0; i < n; ++i)
         if (!ctx->slots[i]) { int rc = batch_alloc(ctx, &ctx->slots[i]); if (rc) return rc; }
     return RKG_OK;
 }
@@ -848,8 +861,9 @@ void rkg_destroy(rkg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     profile_collect(ctx);
-    for (int i = 0; i < 2; ++i) batch_release(ctx->slots[i]);
-    for (int i = 0; i < 2; ++i) if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+    for (int i = 0; i < NSLOTS; ++i) batch_release(ctx->slots[i]);
+    for (int i = 0; i < NSLOTS; ++i) if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+    for (int i = 0; i < NSLOTS; ++i) if (ctx->h2d_done[i]) cudaEventDestroy(ctx->h2d_done[i]);
     for (DevBuf* d : {&ctx->depth_keys, &ctx->depth_counts, &ctx->depth_zero, &ctx->hash_lut, &ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
                       &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
                       &ctx->memo_tab, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
@@ -1156,18 +1170,68 @@ int rkg_count_lookup(rkg_ctx* ctx, const uint64_t* keys, int64_t n, int32_t* out
 static int host_pipeline(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t nreads, int mode, int arg,
                          rkg_hit* out, int64_t fixed_len = 0) {
     // mode 0: count (arg = count_zeros); mode 1: classify (arg = min_occ); mode 2: the copies of mode 1 without its kernels
-    int rc = ensure_slots(ctx);
+    // Adaptive packing (rkg_set_host_pack mode 2): a chunk either crosses the link as it is (no host work at all) or is
+    // packed to 0.375 bytes per base by the host's threads first.  Packing pays exactly while the link is busy with earlier
+    // chunks, so each chunk is packed when the copies still queued will last about as long as packing it takes, and sent
+    // plain otherwise: the link never waits for the packer and the packer never waits for the link, whatever their speeds
+    // are on this host (both are measured on the context's first chunks; `lead` is re-synchronised with the copy events).
+    const bool adaptive = ctx->host_pack == 2 && mode != 2;
+    const int ns = adaptive ? NSLOTS : 2;
+    int rc = ensure_slots(ctx, ns);
     if (rc) return rc;
+    const i64 chunk_bytes = adaptive ? (64LL << 20) : CHUNK_BYTES;
     std::vector<std::pair<i64, i64>> chunks;
-    if (offs) chunks = make_chunks(offs, nreads, CHUNK_BYTES, CHUNK_READS);
+    if (offs) chunks = make_chunks(offs, nreads, chunk_bytes, CHUNK_READS);
     else {
-        const i64 per = std::max<i64>(1, std::min<i64>(CHUNK_READS, CHUNK_BYTES / std::max<i64>(fixed_len, 1)));
+        const i64 per = std::max<i64>(1, std::min<i64>(CHUNK_READS, chunk_bytes / std::max<i64>(fixed_len, 1)));
         for (i64 r0 = 0; r0 < nreads; r0 += per) chunks.emplace_back(r0, std::min<i64>(nreads, r0 + per));
     }
+    using clk = std::chrono::steady_clock;
+    auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+    double lead = 0.0;                                       // estimated time the queued host-to-device copies still take
+    clk::time_point t_last = clk::now();
+    int last_copy_slot = -1;
+    if (adaptive)
+        for (int i = 0; i < ns; ++i)
+            if (!ctx->h2d_done[i]) CK(cudaEventCreateWithFlags(&ctx->h2d_done[i], cudaEventDisableTiming));
     for (size_t c = 0; c < chunks.size(); ++c) {
-        rkg_batch* b = ctx->slots[c & 1];
-        CK(cudaStreamSynchronize(b->stream));     // the slot's previous chunk (c - 2) is finished
-        if ((rc = batch_fill(ctx, b, bases, offs, chunks[c].first, chunks[c].second, fixed_len))) return rc;
+        const int slot = (int)(c % (size_t)ns);
+        rkg_batch* b = ctx->slots[slot];
+        CK(cudaStreamSynchronize(b->stream));     // the slot's previous chunk (c - ns) is finished
+        int pack_mode = -1;
+        if (adaptive) {
+            const i64 r0 = chunks[c].first, r1 = chunks[c].second;
+            const double bytes = (double)(offs ? offs[r1] - offs[r0] : (r1 - r0) * fixed_len);
+            lead = std::max(0.0, lead - ms_since(t_last));
+            t_last = clk::now();
+            if (last_copy_slot >= 0 && cudaEventQuery(ctx->h2d_done[last_copy_slot]) == cudaSuccess) lead = 0.0;
+            if (ctx->dma_ms_per_byte == 0.0) {
+                // first chunk of the context: plain and alone, to time the link
+                for (int i = 0; i < ns; ++i) CK(cudaStreamSynchronize(ctx->slots[i]->stream));
+                const clk::time_point t0 = clk::now();
+                if ((rc = batch_fill(ctx, b, bases, offs, r0, r1, fixed_len, 0))) return rc;
+                CK(cudaStreamSynchronize(b->stream));
+                if (bytes > 0) ctx->dma_ms_per_byte = std::max(ms_since(t0), 1e-3) / bytes;
+                pack_mode = 2;                               // filled already
+            } else if (ctx->pack_ms_per_byte == 0.0) {
+                pack_mode = 1;                               // second chunk: packed, to time the packer
+            } else {
+                pack_mode = lead >= ctx->pack_lead * ctx->pack_ms_per_byte * bytes ? 1 : 0;
+            }
+            if (pack_mode != 2) {
+                const clk::time_point t0 = clk::now();
+                if ((rc = batch_fill(ctx, b, bases, offs, r0, r1, fixed_len, pack_mode))) return rc;
+                if (pack_mode == 1 && bytes > 0) {
+                    const double per = ms_since(t0) / bytes;
+                    ctx->pack_ms_per_byte = ctx->pack_ms_per_byte == 0.0 ? per : 0.7 * ctx->pack_ms_per_byte + 0.3 * per;
+                }
+                lead = std::max(0.0, lead - ms_since(t_last));
+                t_last = clk::now();
+                lead += ctx->dma_ms_per_byte * bytes * (pack_mode == 1 ? 0.375 : 1.0);
+                CK(cudaEventRecord(ctx->h2d_done[slot], b->stream));
+                last_copy_slot = slot;
+            }
+        } else if ((rc = batch_fill(ctx, b, bases, offs, chunks[c].first, chunks[c].second, fixed_len))) return rc;
         if (mode == 0) {
             if ((rc = launch_count(ctx, b, ctx->read_ct, arg))) return rc;
         } else {
@@ -1176,7 +1240,7 @@ static int host_pipeline(rkg_ctx* ctx, const char* bases, const int64_t* offs, i
                                b->stream));
         }
     }
-    for (int i = 0; i < 2; ++i) CK(cudaStreamSynchronize(ctx->slots[i]->stream));
+    for (int i = 0; i < ns; ++i) CK(cudaStreamSynchronize(ctx->slots[i]->stream));
     return RKG_OK;
 }
 
@@ -1232,8 +1296,17 @@ int rkg_copy_probe(rkg_ctx* ctx, const char* bases, const int64_t* offs, int64_t
 
 int rkg_set_host_pack(rkg_ctx* ctx, int enable, int threads) {
     if (!ctx) return RKG_ERR_ARG;
-    ctx->host_pack = enable != 0;
+    if (enable < 0 || enable > 2) return fail(ctx, RKG_ERR_ARG, "rkg_set_host_pack: mode %d (0 off, 1 every chunk, 2 adaptive)", enable);
+    ctx->host_pack = enable;
     ctx->pack_threads = threads > 0 ? std::min(threads, 64) : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    ctx->pack_ms_per_byte = 0.0; ctx->dma_ms_per_byte = 0.0;                // measured again on the next chunks
+    if (const char* e = getenv("RKMH_PACK_LEAD")) ctx->pack_lead = atof(e);
+    return RKG_OK;
+}
+
+int rkg_transfer_stats(rkg_ctx* ctx, int64_t stats[4], int reset) {
+    if (!ctx || !stats) return RKG_ERR_ARG;
+    for (int i = 0; i < 4; ++i) { stats[i] = ctx->xfer[i]; if (reset) ctx->xfer[i] = 0; }
     return RKG_OK;
 }
 

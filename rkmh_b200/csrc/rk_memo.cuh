@@ -85,34 +85,36 @@ RK_D u32 sv_bad4(u32 bad) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// One warp walks the k-mer starts [s0, s1) of the sequence p[0, len), 32 starts per round, and calls
-// f(pos, code, in_range, valid) on every lane (warp-convergent; in_range = s0 <= pos < s1, valid = in_range and no
-// invalid base in the window).  k <= 12.
+// One warp walks the k-mer starts [s0, s1) of the sequence p[0, len), 128 starts per step, and calls
+// f(code, in_range, valid) four times per step on every lane (warp-convergent, straight-line: no branch between the
+// calls; in_range = this lane's window starts inside [s0, s1), valid = in_range and no invalid base in the window).
+// k <= 12, s1 - s0 < 2^31 - 256.  The order of the windows is not the order of the calls' lanes: stream position 0 is the
+// word-aligned byte at or before p + s0, the window of lane l in round r of a step starts at stream base 32 r + l, so the
+// first (address & 3) windows reported lie before s0 (out of range), and so do those of the last step beyond s1.
 //
 // The bytes are read as aligned 32-bit words, 128 bases of the stream per lane-wide load, three loads in flight (a warp
-// streams a long read straight from HBM).  Stream position 0 is the word-aligned byte at or before p + s0, so the
-// window that lane l handles in round r of a chunk starts at stream base 32 r + l = read position s0 - sh + ...:
-// the first sh positions of the stream lie before s0 and are reported out of range.
+// streams a long read straight from HBM) and never beyond the last byte a window of the range can touch.
 template <typename F>
 RK_D void memo_stream(const unsigned char* __restrict__ p, i64 len, int k, i64 s0, i64 s1, int lane, F&& f) {
     if (s0 >= s1) return;
     const unsigned char* q = p + s0;
     const int sh = (int)(reinterpret_cast<size_t>(q) & 3u);
     const u32* __restrict__ wp = reinterpret_cast<const u32*>(q - sh);
-    const i64 pend = sh + (s1 - s0);                        // stream positions [sh, pend) start a window of the range
-    const i64 nbytes = min(sh + (len - s0), pend + k);      // bytes from wp that a window of the range can touch
-    // words that hold no base of the sequence are not loaded and decode as valid 'AAAA' (no window in range reaches them)
-    auto load_word = [&](i64 widx) -> u32 { return 4 * widx < nbytes ? __ldg(wp + widx) : 0x41414141u; };
+    const int nrel = (int)(s1 - s0);
+    const int pend = sh + nrel;                             // stream positions [sh, pend) start a window of the range
+    const int nbytes = (int)min((i64)sh + (len - s0), (i64)pend + k);      // bytes from wp that such a window can touch
+    // words that hold no such byte are not loaded and decode as valid 'AAAA'
+    auto load_word = [&](int widx) -> u32 { return 4 * widx < nbytes ? __ldg(wp + widx) : 0x41414141u; };
     const u32 cmask2 = (1u << (2 * k)) - 1u, kmask = (1u << k) - 1u;
-    // window at stream position 32 r + lane of a chunk: pieces 8 r + (lane >> 2) .. + 3, from base (lane & 3) on
+    // window at stream position 32 r + lane of a step: pieces 8 r + (lane >> 2) .. + 3, from base (lane & 3) on
     const int src0 = lane >> 2;
     const u32 osh = 2u * (u32)(lane & 3), ish = (u32)(lane & 3);
-    // piece j + i of lane j comes from the next chunk when j + i >= 32 (byte 1 of the shuffled pair instead of byte 0)
+    // piece j + i of lane j comes from the next step when j + i >= 32 (byte 1 of the shuffled pair instead of byte 0)
     const u32 sel1 = lane >= 31 ? 0x3250u : 0x3240u, sel2 = lane >= 30 ? 0x3510u : 0x3410u, sel3 = lane >= 29 ? 0x5210u : 0x4210u;
     u32 wb = load_word(32 + lane), wc = load_word(64 + lane);
     u32 pc, bc;
     sv_decode(load_word(lane), pc, bc);
-    for (i64 c0 = 0; c0 < pend; c0 += 128) {
+    for (int c0 = 0; c0 < pend; c0 += 128) {
         u32 pn, bn;
         sv_decode(wb, pn, bn);
         wb = wc; wc = load_word((c0 >> 2) + 96 + lane);
@@ -122,25 +124,26 @@ RK_D void memo_stream(const unsigned char* __restrict__ p, i64 len, int k, i64 s
         Q = __byte_perm(Q, __shfl_sync(0xffffffffu, xq, (lane + 1) & 31), sel1);
         Q = __byte_perm(Q, __shfl_sync(0xffffffffu, xq, (lane + 2) & 31), sel2);
         Q = __byte_perm(Q, __shfl_sync(0xffffffffu, xq, (lane + 3) & 31), sel3);
-        u32 IQ = 0;                                          // the same for the invalid flags (one bit per base)
+        u32 code[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) code[r] = (__shfl_sync(0xffffffffu, Q, src0 + 8 * r) >> osh) & cmask2;
+        bool bad[4] = {false, false, false, false};          // the window of round r holds an invalid base
         if (slow) {
             const u32 xi = sv_bad4(bc) | (sv_bad4(bn) << 4);
-            IQ = xi & 15u;
+            u32 IQ = xi & 15u;                               // the invalid flags of the same 16 bases
 #pragma unroll
             for (int i = 1; i < 4; ++i) {
                 const u32 t = __shfl_sync(0xffffffffu, xi, (lane + i) & 31);
                 IQ |= ((lane + i < 32) ? (t & 15u) : (t >> 4)) << (4 * i);
             }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) bad[r] = ((__shfl_sync(0xffffffffu, IQ, src0 + 8 * r) >> ish) & kmask) != 0u;
         }
+        const int rel0 = c0 + lane - sh;                     // start of this lane's round-0 window, relative to s0
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            if (c0 + 32 * r >= pend) break;
-            const u32 code = (__shfl_sync(0xffffffffu, Q, src0 + 8 * r) >> osh) & cmask2;
-            bool inv = false;
-            if (slow) inv = ((__shfl_sync(0xffffffffu, IQ, src0 + 8 * r) >> ish) & kmask) != 0u;
-            const i64 pos = s0 + c0 + 32 * r + lane - sh;
-            const bool in = pos >= s0 && pos < s1;
-            f(pos, code, in, in && !inv);
+            const bool in = (u32)(rel0 + 32 * r) < (u32)nrel;
+            f(code[r], in, in && !bad[r]);
         }
         pc = pn; bc = bn;
     }
@@ -299,7 +302,7 @@ count_memo_kernel(SeqBatch sb, Memo mm, int count_zeros, int wpr) {
         const i64 n = nkmers(len, mm.k);
         const i64 per = ((((n + 31) >> 5) + wpr - 1) / wpr) << 5;          // k-mer starts per warp, whole rounds
         const i64 s0 = (i64)wt * per, s1 = min(n, s0 + per);
-        memo_stream(sb.bases + beg, len, mm.k, s0, s1, lane, [&](i64, u32 code, bool in, bool valid) {
+        memo_stream(sb.bases + beg, len, mm.k, s0, s1, lane, [&](u32 code, bool in, bool valid) {
             if (valid) atomicAdd(&mm.code_counts[code], 1);
             else if (in) ++inv;
         });
@@ -400,7 +403,7 @@ classify_memo_wide_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, int rwords,
             __syncwarp();
         };
 
-        memo_stream(sb.bases + beg, len, k, 0, n, lane, [&](i64, u32 code, bool, bool valid) {
+        memo_stream(sb.bases + beg, len, k, 0, n, lane, [&](u32 code, bool, bool valid) {
             u32 m = MEMO_ZERO;
             if (valid) m = __ldg(&mm.tab[code]);
             const bool counted = !(m & (MEMO_ZERO | MEMO_FAILM));
@@ -543,7 +546,7 @@ classify_memo_warp_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
         int nc = 0;
         u32 nz = 0;
         if (n > 0) {
-            memo_stream(p, len64, k, 0, n, lane, [&](i64, u32 code, bool, bool valid) {
+            memo_stream(p, len64, k, 0, n, lane, [&](u32 code, bool, bool valid) {
                 u32 m = MEMO_ZERO;
                 if (valid) m = __ldg(&tab[code]);
                 nz += !(m & (MEMO_ZERO | MEMO_FAILM));
@@ -878,7 +881,32 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
 //   resolve  the REF members are compacted into a per-warp ring and resolved against the reference table 32 at a time,
 //            exactly like the Murmur path does (copy number of a repeated hash from a per-block set of table slots).
 //
-// Dynamic shared memory (u32 units): [nwarps x lcap lists][MEMO_HIST_WORDS histogram][hs_cap keys][hs_cap counts][rpad counters]
+// Dynamic shared memory (u32 units): [nwarps x (lcap + 32) lists][MEMO_HIST_WORDS histogram][hs_cap keys][hs_cap counts][rpad counters]
+// ++ of a 32-bit word of shared memory at shared-window address `saddr` (the address conversion of a generic pointer
+// is not repeated at every use)
+RK_D void smem_inc(u32* base, u32 saddr_base, u32 idx) {
+#ifdef RK_EMU
+    (void)saddr_base;
+    atomicAdd(&base[idx], 1u);
+#else
+    (void)base;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr_base + 4u * idx) : "memory");
+#endif
+}
+RK_D u32 smem_addr(const void* p) {
+#ifdef RK_EMU
+    (void)p;
+    return 0u;
+#else
+    return (u32)__cvta_generic_to_shared(p);
+#endif
+}
+// zero `words` (a multiple of 4) 32-bit words at the 16-byte aligned p, the whole block
+RK_D void block_zero(u32* p, int words) {
+    uint4* v = reinterpret_cast<uint4*>(p);
+    for (int i = threadIdx.x; i < words / 4; i += blockDim.x) v[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 struct MemoBlockScratch { u32 part[32]; u32 bin, before; int nz, take, kept, over; ArgmaxScratch as; };
 #ifndef MEMO_DELAY_ROUNDS
 #define MEMO_DELAY_ROUNDS 4
@@ -912,6 +940,57 @@ RK_D void memo_find_bin(const u32* hist, u32 target, MemoBlockScratch* bs) {
     __syncthreads();
 }
 
+// Pass 1 of classify_memo_block_kernel for one warp: the table value of every window of [s0, s1), kept when it counts and
+// lies under `bound` (appended at L[cnt], or at L[cap + lane] once the list is full: cnt > cap tells), kept values into
+// the histogram of the top 12 rank bits.  SHARED: L is a shared-memory list (32-bit addressing, predicated stores: the loop
+// body is branch-free and the warp stays converged).  The table value of a window is consumed MEMO_DELAY rounds after its
+// lookup was issued (the 64 MB table does not fit one die's L2: a tenth of the lookups go to HBM; with two rounds ncu
+// showed 2.3 long-scoreboard stalls per issued instruction).
+template <bool SHARED>
+RK_D void memo_block_pass1(const unsigned char* __restrict__ p, i64 len, int k, i64 s0, i64 s1, int lane,
+                           const u32* __restrict__ tab, u32 bound, u32* L, int cap, u32* hist, u32 hist_s, int& cnt_out,
+                           u32& nz_out) {
+    const u32 ltm = (1u << lane) - 1u;
+    const u32 L_s = smem_addr(L);
+    u32 ring[MEMO_DELAY];
+#pragma unroll
+    for (int d = 0; d < MEMO_DELAY; ++d) ring[d] = MEMO_SKIP;
+    u32 local_nz = 0;
+    int cnt = 0;
+    auto consume = [&](u32 m) {
+        const bool ok = !(m & (MEMO_ZERO | MEMO_FAILM));            // MEMO_SKIP has every flag set
+        local_nz += ok;
+        const bool keep = ok && m < bound;
+        const u32 bal = __ballot_sync(0xffffffffu, keep);
+        const int at = cnt + __popc(bal & ltm);
+        const int idx = at < cap ? at : cap + lane;
+        const u32 hidx = memo_hidx(m >> 20);
+#ifndef RK_EMU
+        if (SHARED) {
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u32 [%1], %2;\n\t@p red.shared.add.u32 [%3], 1;\n\t}"
+                         ::"r"((u32)keep), "r"(L_s + 4u * (u32)idx), "r"(m), "r"(hist_s + 4u * hidx) : "memory");
+        } else
+#endif
+        if (keep) {
+            L[idx] = m;
+            smem_inc(hist, hist_s, hidx);
+        }
+        cnt += __popc(bal);
+    };
+    memo_stream(p, len, k, s0, s1, lane, [&](u32 code, bool, bool valid) {
+        u32 m = MEMO_SKIP;
+        if (valid) m = __ldg(&tab[code]);
+        consume(ring[MEMO_DELAY - 1]);
+#pragma unroll
+        for (int d = MEMO_DELAY - 1; d > 0; --d) ring[d] = ring[d - 1];
+        ring[0] = m;
+    });
+#pragma unroll
+    for (int d = MEMO_DELAY - 1; d >= 0; --d) consume(ring[d]);
+    cnt_out = cnt;
+    nz_out = warp_sum(local_nz);
+}
+
 __global__ void __launch_bounds__(256, MEMO_BLOCK_MIN_BLOCKS)
 classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* __restrict__ list,
                            const int* __restrict__ nlist_ptr, i64 nseq, int lcap, int hs_cap, int rpad,
@@ -924,11 +1003,13 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
     __shared__ MemoBlockScratch bs;
     __shared__ u32 wq[8][MEMO_RING];                         // per-warp ring of hit ranks (blocks of at most 256 threads)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
-    u32* lists = reinterpret_cast<u32*>(dsm);
-    u32* hist = lists + (size_t)nwb * lcap;
+    u32* lists = reinterpret_cast<u32*>(dsm);                // per warp lcap values + 32 that catch an overflowing list's stores
+    u32* hist = lists + (size_t)nwb * (lcap + 32);
     u32* hs_keys = hist + MEMO_HIST_WORDS;
     u32* hs_cnt = hs_keys + hs_cap;
     u32* counts = hs_cnt + hs_cap;
+    const u32 hist_s = smem_addr(hist);
+    const int zero_words = MEMO_HIST_WORDS + 2 * hs_cap + rpad;            // histogram, hit set and counters are contiguous
     const u32 hs_mask = (u32)hs_cap - 1;
     const u32 ltm = (1u << lane) - 1u;
     const int k = mm.k;
@@ -952,47 +1033,15 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
         u32* L;
         int cnt, nz;
         for (;;) {
-            L = wide ? scratch + (i64)blockIdx.x * scratch_stride + (i64)wib * per : lists + (size_t)wib * lcap;
+            L = wide ? scratch + (i64)blockIdx.x * scratch_stride + (i64)wib * (per + 32) : lists + (size_t)wib * (lcap + 32);
             const int cap = wide ? (int)per : lcap;
             if (threadIdx.x == 0) { bs.nz = 0; bs.take = 0; bs.kept = 0; bs.over = 0; }
-            for (int i = threadIdx.x; i < MEMO_HIST_WORDS; i += blockDim.x) hist[i] = 0;
-            for (int i = threadIdx.x; i < 2 * hs_cap; i += blockDim.x) hs_keys[i] = 0;
-            for (int i = threadIdx.x; i < rpad; i += blockDim.x) counts[i] = 0;
+            block_zero(hist, zero_words);
             __syncthreads();
             // ---- pass 1 ---------------------------------------------------------------------------------------------
-            // The table value of a window is consumed MEMO_DELAY rounds after its lookup was issued (the 64 MB table does
-            // not fit one die's L2: a tenth of the lookups go to HBM; with two rounds ncu showed 2.3 long-scoreboard
-            // stalls per issued instruction).
-            u32 ring[MEMO_DELAY];
-#pragma unroll
-            for (int d = 0; d < MEMO_DELAY; ++d) ring[d] = MEMO_SKIP;
-            u32 local_nz = 0;
-            cnt = 0;
-            auto consume = [&](u32 m) {
-                const bool ok = !(m & (MEMO_ZERO | MEMO_FAILM));            // MEMO_SKIP has every flag set
-                local_nz += ok;
-                const bool keep = ok && m < bound;
-                const u32 bal = __ballot_sync(0xffffffffu, keep);
-                if (bal) {
-                    const int at = cnt + __popc(bal & ltm);
-                    if (keep) {
-                        if (at < cap) L[at] = m;
-                        atomicAdd(&hist[memo_hidx(m >> 20)], 1u);
-                    }
-                    cnt += __popc(bal);
-                }
-            };
-            memo_stream(sb.bases + beg, len, k, s0, s1, lane, [&](i64, u32 code, bool, bool valid) {
-                u32 m = MEMO_SKIP;
-                if (valid) m = __ldg(&mm.tab[code]);
-                consume(ring[MEMO_DELAY - 1]);
-#pragma unroll
-                for (int d = MEMO_DELAY - 1; d > 0; --d) ring[d] = ring[d - 1];
-                ring[0] = m;
-            });
-#pragma unroll
-            for (int d = MEMO_DELAY - 1; d >= 0; --d) consume(ring[d]);
-            local_nz = warp_sum(local_nz);
+            u32 local_nz;
+            if (wide) memo_block_pass1<false>(sb.bases + beg, len, k, s0, s1, lane, mm.tab, bound, L, cap, hist, hist_s, cnt, local_nz);
+            else memo_block_pass1<true>(sb.bases + beg, len, k, s0, s1, lane, mm.tab, bound, L, cap, hist, hist_s, cnt, local_nz);
             if (lane == 0) {
                 if (local_nz) atomicAdd(&bs.nz, (int)local_nz);
                 if (cnt > cap) bs.over = 1; else if (cnt) atomicAdd(&bs.kept, cnt);
@@ -1013,11 +1062,11 @@ classify_memo_block_kernel(SeqBatch sb, int s, Memo mm, RefTable tb, const int* 
             memo_find_bin(hist, (u32)s, &bs);
             const u32 b1 = bs.bin, before1 = bs.before;
             __syncthreads();
-            for (int i = threadIdx.x; i < MEMO_HIST_WORDS; i += blockDim.x) hist[i] = 0;
+            block_zero(hist, MEMO_HIST_WORDS);
             __syncthreads();
             for (int i = lane; i < cnt; i += 32) {
                 const u32 m = L[i];
-                if ((m >> 20) == b1) atomicAdd(&hist[memo_hidx((m >> 8) & 0xFFFu)], 1u);
+                if ((m >> 20) == b1) smem_inc(hist, hist_s, memo_hidx((m >> 8) & 0xFFFu));
             }
             __syncthreads();
             memo_find_bin(hist, (u32)s - before1, &bs);

@@ -389,8 +389,8 @@ int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, con
         const i64 most = ((std::max<i64>(b.max_ntotal, 1) + 31) / 32 + nwb - 1) / nwb * 32;
         int lcap = (int)std::min<i64>(most, std::max<i64>(128, ((i64)(0.4 * s) + 31) / 32 * 32));
         if (vcap_limit > 0) lcap = std::min(lcap, vcap_limit);
-        const i64 stride = (std::max<i64>(b.max_ntotal, 1) + 32 * nwb + 31) / 32 * 32;
-        size_t smem = 4 * ((size_t)nwb * lcap + MEMO_HIST_WORDS + 2 * (size_t)hs_cap + rpad);
+        const i64 stride = (std::max<i64>(b.max_ntotal, 1) + 64 * nwb + 31) / 32 * 32;
+        size_t smem = 4 * ((size_t)nwb * (lcap + 32) + MEMO_HIST_WORDS + 2 * (size_t)hs_cap + rpad);
         std::vector<u32> scratch((size_t)grid * (size_t)stride + 8);
         u32* ps = scratch.data();
         const int* list = (path >= 1) ? predo : nullptr;

@@ -597,7 +597,8 @@ def test_packed_transfer_gives_the_same_records(oracle):
     """rkg_set_host_pack: the bases are packed to 2-bit codes + an invalid-base mask on the HOST and cross the link at
     0.375 B/base; the memoised kernels get them unpacked on the device (every invalid byte as N, every letter upper-cased).
     Records, count tables and sketches are those of the plain transfer: ragged reads with lower case, N, IUPAC and
-    punctuation bytes, reads shorter than k, fixed-length batches, both hashing paths, with and without -M."""
+    punctuation bytes, reads shorter than k, fixed-length batches, both hashing paths, with and without -M; and the same
+    with the adaptive mode (2), which packs some chunks and sends others as they are."""
     import rkmh_b200
     _, rs, _ = load_sequences([data_path("all_pave_ref.fa.gz")])
     _, aw, _ = load_sequences([data_path("awkward_reads.fq.gz"), data_path("minION25.fq.gz")])
@@ -607,7 +608,7 @@ def test_packed_transfer_gives_the_same_records(oracle):
     wb, wo = _pack(weird)
     for memo in (True, False):
         res = {}
-        for pack in (False, True):
+        for pack in (0, 1, 2):
             with rkmh_b200.RkmhGpu(0) as g:
                 g.set_memo(memo)
                 g.set_host_pack(pack, 3)
@@ -621,8 +622,24 @@ def test_packed_transfer_gives_the_same_records(oracle):
                 sk, ln = g.sketch_batch(wb, wo)
                 out += [sk, ln]
                 res[pack] = out
-        for a, b in zip(res[False], res[True]):
-            assert np.array_equal(a, b)
+        for mode in (1, 2):
+            for a, b in zip(res[0], res[mode]):
+                assert np.array_equal(a, b)
     sk, ln = oracle.sketch_batch(rs, [12], 1000)
     exp = oracle.classify_batch(weird, [12], 1000, sk, ln)
-    assert np.array_equal(res[True][2], _fields(exp))
+    assert np.array_equal(res[2][2], _fields(exp))
+    # several 64 MB chunks in flight: the adaptive mode mixes packed and plain chunks inside one call
+    big, bo = _synthetic_reads(rng, rs, 1_500_000, 150)
+    big[::997] = ord("N"); big[5::1201] = ord("a")
+    with rkmh_b200.RkmhGpu(0) as g:
+        g.set_params([12], 1000, read_table_size=rkmh_b200.STREAM_TABLE_SIZE)
+        g.load_refs(*_pack(rs))
+        plain = _fields(g.classify_fixed(big, 150))
+        g.count_reset(); g.count_fixed(big, 150)
+        ct = g.count_table_tensor().cpu().numpy().copy()
+        g.set_host_pack(2, 4)
+        for _ in range(3):
+            assert np.array_equal(_fields(g.classify_fixed(big, 150)), plain)
+        assert np.array_equal(_fields(g.classify_batch(big, bo)), plain)
+        g.count_reset(); g.count_fixed(big, 150)
+        assert np.array_equal(g.count_table_tensor().cpu().numpy(), ct)
