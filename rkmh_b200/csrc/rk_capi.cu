@@ -105,7 +105,7 @@ struct rkg_ctx {
     size_t stage_cap[NSLOTS] = {};
     cudaEvent_t h2d_done[NSLOTS] = {};   // adaptive mode: recorded after a chunk's host-to-device copies
     int64_t xfer[4] = {0, 0, 0, 0};       // rkg_transfer_stats
-    double pack_lead = 0.75;             // pack when the queued copies last at least this share of the packing time (RKMH_PACK_LEAD)
+    double pack_lead = 1.0;              // pack when the queued copies last at least this share of the packing time (RKMH_PACK_LEAD)
     double pack_ms_per_byte = 0.0, dma_ms_per_byte = 0.0;      // adaptive mode: measured on this context's first chunks
     // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
     bool memo_enabled = true, memo_ready = false, sieve_enabled = true, group_kernel = false;
@@ -246,6 +246,17 @@ fixed_offs_kernel(i64* __restrict__ offs, i64 n, i64 base0, i64 len) {
 
 // Copy reads [r0, r1) of the caller's buffers into the batch (asynchronous on b->stream); packing is done on demand.
 // offs == nullptr: every read has `fixed_len` bases and read i starts at bases[i * fixed_len].
+// pinned staging of a slot for the packed transfer
+int ensure_stage(rkg_ctx* ctx, int slot, size_t bytes) {
+    if (ctx->stage_cap[slot] >= bytes) return RKG_OK;
+    if (ctx->stage[slot]) cudaFreeHost(ctx->stage[slot]);
+    ctx->stage[slot] = nullptr; ctx->stage_cap[slot] = 0;
+    const size_t want = bytes + bytes / 8 + 4096;
+    CK(cudaHostAlloc(&ctx->stage[slot], want, cudaHostAllocPortable));
+    ctx->stage_cap[slot] = want;
+    return RKG_OK;
+}
+
 int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* offs, i64 r0, i64 r1, i64 fixed_len = 0,
                int pack_mode = -1) {          // pack_mode: -1 = as the context says (host_pack == 1), 0 = plain, 1 = packed
     const i64 n = r1 - r0;
@@ -267,13 +278,7 @@ int batch_fill(rkg_ctx* ctx, rkg_batch* b, const char* bases, const int64_t* off
         // the host's threads into this slot's pinned staging buffer (free again: the caller waited for the slot's stream)
         const size_t mask_at = ((size_t)2 * nwords32 + 7) & ~(size_t)7;      // the mask starts 32-byte aligned (streaming stores)
         const size_t words = mask_at + (size_t)nwords32;
-        if (ctx->stage_cap[slot] < words * 4) {
-            if (ctx->stage[slot]) cudaFreeHost(ctx->stage[slot]);
-            ctx->stage[slot] = nullptr; ctx->stage_cap[slot] = 0;
-            const size_t want = words * 4 + words / 2 + 4096;
-            CK(cudaHostAlloc(&ctx->stage[slot], want, cudaHostAllocPortable));
-            ctx->stage_cap[slot] = want;
-        }
+        { int rc = ensure_stage(ctx, slot, words * 4); if (rc) return rc; }
         u32* hc = static_cast<u32*>(ctx->stage[slot]);
         u32* hm = hc + mask_at;
         rk_pack_bases(bases + base0, total, hc, hm, ctx->pack_threads);
@@ -1204,26 +1209,39 @@ static int host_pipeline(rkg_ctx* ctx, const char* bases, const int64_t* offs, i
             const double bytes = (double)(offs ? offs[r1] - offs[r0] : (r1 - r0) * fixed_len);
             lead = std::max(0.0, lead - ms_since(t_last));
             t_last = clk::now();
-            if (last_copy_slot >= 0 && cudaEventQuery(ctx->h2d_done[last_copy_slot]) == cudaSuccess) lead = 0.0;
+            if (last_copy_slot >= 0) {
+                // the estimate against the truth: copies all done although some were expected to be left -> the link is
+                // faster than assumed; none expected but the last one is still under way -> slower
+                const bool done = cudaEventQuery(ctx->h2d_done[last_copy_slot]) == cudaSuccess;
+                if (done && lead > 0.25 * ctx->dma_ms_per_byte * bytes) ctx->dma_ms_per_byte *= 0.93;
+                if (!done && lead == 0.0) { ctx->dma_ms_per_byte *= 1.07; lead = 0.1 * ctx->dma_ms_per_byte * bytes; }
+                if (done) lead = 0.0;
+            }
+            // staging sized before anything is timed (page-locking it takes milliseconds)
+            if ((rc = ensure_stage(ctx, slot, (size_t)(bytes * 0.375) + (64 << 10)))) return rc;
             if (ctx->dma_ms_per_byte == 0.0) {
                 // first chunk of the context: plain and alone, to time the link
                 for (int i = 0; i < ns; ++i) CK(cudaStreamSynchronize(ctx->slots[i]->stream));
+                if ((rc = batch_fill(ctx, b, bases, offs, r0, r1, fixed_len, 0))) return rc;     // (first use: allocates the slot's device buffers)
+                CK(cudaStreamSynchronize(b->stream));
                 const clk::time_point t0 = clk::now();
-                if ((rc = batch_fill(ctx, b, bases, offs, r0, r1, fixed_len, 0))) return rc;
+                if (b->total > 0) CK(cudaMemcpyAsync(b->bases.p, bases + b->base0, (size_t)b->total, cudaMemcpyHostToDevice, b->stream));
                 CK(cudaStreamSynchronize(b->stream));
                 if (bytes > 0) ctx->dma_ms_per_byte = std::max(ms_since(t0), 1e-3) / bytes;
                 pack_mode = 2;                               // filled already
+                t_last = clk::now();
             } else if (ctx->pack_ms_per_byte == 0.0) {
                 pack_mode = 1;                               // second chunk: packed, to time the packer
             } else {
                 pack_mode = lead >= ctx->pack_lead * ctx->pack_ms_per_byte * bytes ? 1 : 0;
             }
             if (pack_mode != 2) {
+                const bool first_use = b->bases.cap == 0;   // the slot's device buffers are allocated inside: not a timing sample
                 const clk::time_point t0 = clk::now();
                 if ((rc = batch_fill(ctx, b, bases, offs, r0, r1, fixed_len, pack_mode))) return rc;
-                if (pack_mode == 1 && bytes > 0) {
+                if (pack_mode == 1 && bytes > 0 && !first_use) {
                     const double per = ms_since(t0) / bytes;
-                    ctx->pack_ms_per_byte = ctx->pack_ms_per_byte == 0.0 ? per : 0.7 * ctx->pack_ms_per_byte + 0.3 * per;
+                    ctx->pack_ms_per_byte = ctx->pack_ms_per_byte == 0.0 ? per : 0.5 * ctx->pack_ms_per_byte + 0.5 * per;
                 }
                 lead = std::max(0.0, lead - ms_since(t_last));
                 t_last = clk::now();

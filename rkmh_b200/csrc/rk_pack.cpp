@@ -7,8 +7,13 @@
 // AVX-512BW or AVX2 (+ BMI2) when the CPU has them (64 / 32 bases per step: two byte-to-mask moves give the two code bit
 // planes, PDEP interleaves them, four compares give the validity mask), a scalar loop otherwise.  Per-function target
 // attributes and run-time dispatch: the file needs no special compiler flags.
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -144,6 +149,71 @@ void pack_range(const unsigned char* b, int64_t n32, int64_t tail, uint32_t* cod
     pack_scalar(b, n32, tail, codes, nmask);
 }
 
+// The calling thread's helpers.  A chunk is packed in about a millisecond and the calls come every millisecond or two:
+// starting sixteen threads per call would cost a fifth of that, so the helpers persist (one pool per calling thread, i.e.
+// per GPU context's pipeline) and spin for a short while after a job before they go to sleep.
+class PackPool {
+  public:
+    ~PackPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; gen_.fetch_add(1, std::memory_order_release); }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // job(i) for i in [0, n): job(0) on the caller, the rest on helpers; returns when all are done
+    void run(int n, const std::function<void(int)>& job) {
+        while ((int)workers_.size() < n - 1) {
+            const int idx = (int)workers_.size() + 1;
+            workers_.emplace_back([this, idx] { work(idx); });
+        }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            job_ = &job; njobs_ = n;
+            pending_.store(n - 1, std::memory_order_relaxed);
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        cv_.notify_all();
+        job(0);
+        for (int spin = 0; pending_.load(std::memory_order_acquire) != 0; ++spin)
+            if (spin > 2000) std::this_thread::yield();
+    }
+
+  private:
+    void work(int idx) {
+        uint64_t seen = 0;
+        for (;;) {
+            // spin ~100 us for the next job, then block
+            const auto t0 = std::chrono::steady_clock::now();
+            while (gen_.load(std::memory_order_acquire) == seen) {
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(100)) {
+                    std::unique_lock<std::mutex> lk(m_);
+                    cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+                    break;
+                }
+            }
+            const std::function<void(int)>* job;
+            int n;
+            {
+                std::lock_guard<std::mutex> lk(m_);           // job_ / njobs_ were written under the lock before gen_ moved
+                seen = gen_.load(std::memory_order_acquire);
+                if (stop_) return;
+                job = job_; n = njobs_;
+            }
+            if (idx < n) {
+                (*job)(idx);
+                pending_.fetch_sub(1, std::memory_order_acq_rel);
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::atomic<uint64_t> gen_{0};
+    std::atomic<int> pending_{0};
+    const std::function<void(int)>* job_ = nullptr;
+    int njobs_ = 0;
+    bool stop_ = false;
+};
+
 }  // namespace
 
 // codes: 2 * ceil(n / 32) words, nmask: ceil(n / 32) words (bases beyond n read as invalid).  `threads` host threads.
@@ -152,11 +222,10 @@ extern "C" void rk_pack_bases(const char* bases, int64_t n, uint32_t* codes, uin
     const int64_t n32 = n / 32, tail = n - n32 * 32;
     threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n32 / 4096 + 1));
     if (threads == 1) { pack_range(b, n32, tail, codes, nmask); return; }
-    std::vector<std::thread> th;
-    for (int t = 0; t < threads; ++t) {
+    thread_local PackPool pool;
+    pool.run(threads, [=](int t) {
         // ranges start at multiples of 8 groups: the streaming stores want 32-byte aligned destinations
         const int64_t lo = (n32 * t / threads) & ~(int64_t)7, hi = t == threads - 1 ? n32 : ((n32 * (t + 1) / threads) & ~(int64_t)7);
-        th.emplace_back([=] { pack_range(b + lo * 32, hi - lo, t == threads - 1 ? tail : 0, codes + 2 * lo, nmask + lo); });
-    }
-    for (auto& x : th) x.join();
+        pack_range(b + lo * 32, hi - lo, t == threads - 1 ? tail : 0, codes + 2 * lo, nmask + lo);
+    });
 }
