@@ -105,7 +105,7 @@ struct rkg_ctx {
     size_t stage_cap[NSLOTS] = {};
     cudaEvent_t h2d_done[NSLOTS] = {};   // adaptive mode: recorded after a chunk's host-to-device copies
     int64_t xfer[4] = {0, 0, 0, 0};       // rkg_transfer_stats
-    double pack_lead = 1.0;              // pack when the queued copies last at least this share of the packing time (RKMH_PACK_LEAD)
+    double pack_lead = 0.75;             // pack when the queued copies last at least this share of the packing time (RKMH_PACK_LEAD)
     double pack_ms_per_byte = 0.0, dma_ms_per_byte = 0.0;      // adaptive mode: measured on this context's first chunks
     // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
     bool memo_enabled = true, memo_ready = false, sieve_enabled = true, group_kernel = false;
