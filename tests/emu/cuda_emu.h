@@ -57,7 +57,7 @@ struct Barrier {  // reusable counting barrier: futex waits (C++20 atomic wait),
             gen.store(g + 1, std::memory_order_release);
             gen.notify_all();
         } else {
-            for (int spin = 0; spin < 64 && gen.load(std::memory_order_acquire) == g; ++spin) sched_yield();
+            for (int spin = 0; spin < 8 && gen.load(std::memory_order_acquire) == g; ++spin) sched_yield();
             while (gen.load(std::memory_order_acquire) == g) gen.wait(g, std::memory_order_acquire);
         }
     }
