@@ -16,6 +16,10 @@
 #include <fcntl.h>
 #include <getopt.h>
 #include <sys/mman.h>
+#include <sys/prctl.h>
+#include <sys/wait.h>
+#include <csignal>
+#include <cerrno>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -808,11 +812,53 @@ void format_filter_record(std::string& out, const Options& o, const char* name, 
 // The end of a command: everything is written, so the process leaves without tearing down the CUDA contexts, the pinned
 // chunk pool and the device tables one by one (measured on the B200 box: more than a second for an 8 M-read run -- the
 // operating system reclaims all of it at once).  RKMH_CLEAN_EXIT=1 returns through the destructors instead (sanitizers).
+//
+// Even so the kernel needs ~0.6 s after _exit to unpin the pool and release the GPU contexts, and whoever waits for the
+// process waits for that too.  So the GPU commands run in a WORKER process (forked before anything touches CUDA); the
+// process the caller started only waits for the worker's one-byte "everything is written" message and leaves at once,
+// while the worker's teardown finishes on its own.  A worker that ends any other way (error exit, signal) is waited for and
+// its status passed on.  RKMH_NO_DETACH=1 runs everything in one process.
+int g_done_fd = -1;
+
 int leave(int rc) {
     tmark("done");
     if (getenv("RKMH_CLEAN_EXIT")) return rc;
     fflush(stdout); fflush(stderr);
+    if (g_done_fd >= 0) {
+        prctl(PR_SET_PDEATHSIG, 0);                  // the front process leaves first now: that is not a reason to die
+        close(1); close(2);                          // readers of our output see end-of-file now, not after the teardown
+        const unsigned char b = (unsigned char)rc;
+        if (write(g_done_fd, &b, 1) != 1) {}
+    }
     _exit(rc);
+}
+
+// Returns in the worker (and in the only process when detaching is off); the front process never returns.
+void detach_teardown() {
+    if (getenv("RKMH_NO_DETACH") || getenv("RKMH_CLEAN_EXIT")) return;
+    int fds[2];
+    if (pipe(fds) != 0) return;
+    fflush(stdout); fflush(stderr);
+    const pid_t pid = fork();
+    if (pid < 0) { close(fds[0]); close(fds[1]); return; }
+    if (pid == 0) {
+        close(fds[0]);
+        g_done_fd = fds[1];
+        prctl(PR_SET_PDEATHSIG, SIGTERM);            // a front process killed half-way takes the worker with it
+        return;
+    }
+    close(fds[1]);
+    unsigned char b = 0;
+    ssize_t n;
+    do { n = read(fds[0], &b, 1); } while (n < 0 && errno == EINTR);
+    if (n == 1) _exit((int)b);
+    int st = 0;
+    while (waitpid(pid, &st, 0) < 0 && errno == EINTR) {}
+    if (WIFSIGNALED(st)) {                           // e.g. the abort() of an unknown option: end the same way
+        signal(WTERMSIG(st), SIG_DFL);
+        raise(WTERMSIG(st));
+    }
+    _exit(WIFEXITED(st) ? WEXITSTATUS(st) : 1);
 }
 
 // ---- stream / classify: src/rkmh.cpp:584-989 ------------------------------------------------------------
@@ -1355,6 +1401,7 @@ int main_call(int argc, char** argv) {
 int main(int argc, char** argv) {
     if (argc <= 1) { usage(argv[0]); exit(1); }
     const std::string cmd = argv[1];
+    if (cmd == "classify" || cmd == "stream" || cmd == "filter" || cmd == "hash" || cmd == "hpv16" || cmd == "call") detach_teardown();
     if (cmd == "classify") {
         fprintf(stderr, "CLASSIFY COMMAND IS TEMPORARILY UNAVAILABLE: TRY rkmh stream INSTEAD.\n");   // src/rkmh.cpp:2746
         return main_stream(argc, argv);

@@ -19,7 +19,7 @@ with gzip.open("tests/golden/data/all_pave_ref.fa.gz", "rb") as fi, open(os.path
     shutil.copyfileobj(fi, fo)
 PY
 cat "$W/reads.fq" > /dev/null
-for t in 1 4 8 "8 RKMH_PARSE_MMAP=1" "4 RKMH_PARSE_MMAP=1"; do
+for t in 1 4 8 "8 RKMH_NO_DETACH=1" "8 RKMH_PARSE_MMAP=1"; do
   set -- $t; t=$1; extra=${2:-RKMH_NOP=1}
   best=999
   for rep in 1 2 3; do
