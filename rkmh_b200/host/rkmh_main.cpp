@@ -417,7 +417,16 @@ struct ChunkPool {
             RK(owner, rkg_host_alloc(owner, sizeof(rkg_hit) * cap_reads, &ph));
             c->pinned = true;
         } else {
-            pb = malloc(cap_bases); po = malloc(sizeof(int64_t) * (cap_reads + 1)); ph = malloc(sizeof(rkg_hit) * cap_reads);
+            // huge pages: 4 KB first-touch faults of eight parser threads (60 k of them for the pool) queue on the process's
+            // mmap lock together with the CUDA driver's start-up on its own thread and were seen to triple its time
+            auto big = [](size_t bytes) -> void* {
+                void* p = nullptr;
+                const size_t huge = (size_t)2 << 20, sz = (bytes + huge - 1) / huge * huge;
+                if (posix_memalign(&p, huge, sz) != 0) return nullptr;
+                madvise(p, sz, MADV_HUGEPAGE);
+                return p;
+            };
+            pb = big(cap_bases); po = big(sizeof(int64_t) * (cap_reads + 1)); ph = big(sizeof(rkg_hit) * cap_reads);
             if (!pb || !po || !ph) { fprintf(stderr, "rkmh: out of memory\n"); exit(2); }
         }
         c->bases = (char*)pb; c->offs = (int64_t*)po; c->hits = (rkg_hit*)ph;
