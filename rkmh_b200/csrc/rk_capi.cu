@@ -103,6 +103,10 @@ struct rkg_ctx {
     int pack_threads = 1;
     void* stage[NSLOTS] = {};
     size_t stage_cap[NSLOTS] = {};
+    DevBuf shard_scan, shard_cnt;        // rkg_sketch_shard: kept hashes and counters of the one-pass route
+    cudaStream_t copy_stream = nullptr;  // rkg_sketch_shard: the shard's pieces arrive here while earlier pieces are hashed
+    cudaEvent_t copy_event = nullptr;
+    bool shard_two_pass = false;         // RKMH_SHARD_TWO_PASS=1: always take the exact two-pass route (tests, comparison)
     cudaEvent_t h2d_done[NSLOTS] = {};   // adaptive mode: recorded after a chunk's host-to-device copies
     int64_t xfer[4] = {0, 0, 0, 0};       // rkg_transfer_stats
     double pack_lead = 0.75;             // pack when the queued copies last at least this share of the packing time (RKMH_PACK_LEAD)
@@ -835,6 +839,7 @@ int rkg_create(int device, rkg_ctx** out) {
     ctx->device = device;
     { const char* nm = getenv("RKMH_NO_MEMO"); ctx->memo_enabled = !(nm && nm[0] && nm[0] != '0'); }
     { const char* nm = getenv("RKMH_NO_SIEVE"); ctx->sieve_enabled = !(nm && nm[0] && nm[0] != '0'); }
+    { const char* nm = getenv("RKMH_SHARD_TWO_PASS"); ctx->shard_two_pass = nm && nm[0] && nm[0] != '0'; }
     { const char* nm = getenv("RKMH_GROUP_KERNEL"); ctx->group_kernel = nm && nm[0] && nm[0] != '0'; }   // round-1 Murmur fast path (A/B timing)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
@@ -869,7 +874,9 @@ void rkg_destroy(rkg_ctx* ctx) {
     for (int i = 0; i < NSLOTS; ++i) batch_release(ctx->slots[i]);
     for (int i = 0; i < NSLOTS; ++i) if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
     for (int i = 0; i < NSLOTS; ++i) if (ctx->h2d_done[i]) cudaEventDestroy(ctx->h2d_done[i]);
-    for (DevBuf* d : {&ctx->depth_keys, &ctx->depth_counts, &ctx->depth_zero, &ctx->hash_lut, &ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
+    if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (DevBuf* d : {&ctx->shard_scan, &ctx->shard_cnt, &ctx->depth_keys, &ctx->depth_counts, &ctx->depth_zero, &ctx->hash_lut, &ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
                       &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
                       &ctx->memo_tab, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
                       &ctx->memo_sieve, &ctx->memo_cmap})
@@ -1744,17 +1751,93 @@ int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t km
     if (rc) return rc;
     rkg_batch* b = ctx->slots[0];
     CK(cudaStreamSynchronize(b->stream));
-    const int64_t one[2] = {0, n + k};
-    if ((rc = batch_fill(ctx, b, bases, one, 0, 1))) return rc;
-    if ((rc = ensure_packed(ctx, b))) return rc;
+    // The shard arrives in 32 MB pieces on a copy stream; behind each piece the compute stream packs it (ingest_kernel) and
+    // hashes the windows whose k bases have arrived (shard_scan_kernel), so that copy and hashing overlap.
+    const i64 total = n + k;
+    const i64 nwords32 = (total + 31) / 32;
+    b->nseq = 1; b->total = total; b->base0 = 0; b->max_len = total; b->max_ntotal = n;
+    CK(b->bases.ensure((size_t)nwords32 * 32 + 64));
+    CK(b->codes.ensure(sizeof(u32) * (size_t)(2 * nwords32 + 8)));
+    CK(b->nmask.ensure(sizeof(u32) * (size_t)(nwords32 + 8)));
+    CK(b->misc.ensure(256));
+    if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->copy_event) CK(cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
+    CK(cudaMemsetAsync(b->codes.as<u32>() + 2 * nwords32, 0, sizeof(u32) * 8, b->stream));
+    CK(cudaMemsetAsync(b->nmask.as<u32>() + nwords32, 0xFF, sizeof(u32) * 8, b->stream));
+    const int grid = ctx->sm_count * 8;
+    const i64 lastw = 2 * nwords32 + 7, lastm = nwords32 + 7;               // 8 words of padding follow the record
+    // the guess: twice the s-th smallest of n uniform hashes; room for four times s kept hashes
+    u64 limit = ~0ULL;
+    if ((i64)ctx->s < n) {
+        const long double frac = 2.0L * (long double)ctx->s / (long double)n;
+        if (frac < 1.0L) limit = (u64)(frac * 18446744073709551615.0L);
+    }
+    const u64 cap = std::max<u64>(4ULL * (u64)ctx->s, 1ULL << 16);
+    DevBuf& d_scan = ctx->shard_scan;                                        // kept between calls (a cudaFree synchronises the device)
+    DevBuf& d_cnt = ctx->shard_cnt;
+    if (d_scan.ensure(sizeof(u64) * (size_t)next_pow2((i64)cap)) || d_cnt.ensure(64))
+        return fail(ctx, RKG_ERR_NOMEM, "rkg_sketch_shard: device allocation failed");
+    CK(cudaMemsetAsync(d_cnt.p, 0, 64, b->stream));
+    CK(cudaEventRecord(ctx->copy_event, b->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));          // the buffers are free (and sized) from here on
+    const i64 piece = 32LL << 20;
+    i64 w_lo = 0;
+    for (i64 off = 0; off < total; off += piece) {
+        const i64 plen = std::min<i64>(piece, total - off);
+        CK(cudaMemcpyAsync(b->bases.as<unsigned char>() + off, bases + off, (size_t)plen, cudaMemcpyHostToDevice, ctx->copy_stream));
+        ctx->xfer[0] += plen;
+        CK(cudaEventRecord(ctx->copy_event, ctx->copy_stream));
+        CK(cudaStreamWaitEvent(b->stream, ctx->copy_event, 0));
+        const i64 pw = (plen + 31) / 32;
+        {
+            Timed t(ctx, b->stream, K_INGEST);
+            ingest_kernel<<<(int)std::min<i64>((pw + 255) / 256, (i64)ctx->sm_count * 16), 256, 0, b->stream>>>(
+                b->bases.as<unsigned char>() + off, plen, b->codes.as<u32>() + 2 * (off / 32), b->nmask.as<u32>() + off / 32, pw);
+            ++ctx->launches;
+        }
+        const i64 w_hi = std::min<i64>(n, off + plen - k + 1);
+        if (w_hi > w_lo) {
+            Timed t(ctx, b->stream, K_SKETCH);
+            DISPATCH_KCSEL(ctx->kcsel, (shard_scan_kernel<KS><<<grid, 256, 0, b->stream>>>(b->codes.as<u32>(), b->nmask.as<u32>(), lastw, lastm, w_lo, w_hi,
+                                                                                         ctx->kl, limit, d_scan.as<u64>(),
+                                                                                         d_cnt.as<unsigned long long>(), cap)));
+            ++ctx->launches;
+            w_lo = w_hi;
+        }
+    }
+    ++ctx->xfer[2];
+    b->packed = true; b->ascii = true;
+    {
+        unsigned long long hc[2] = {0, 0};
+        cudaMemcpyAsync(hc, d_cnt.p, sizeof(hc), cudaMemcpyDeviceToHost, b->stream);
+        if (cudaStreamSynchronize(b->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+            return fail(ctx, RKG_ERR_CUDA, "rkg_sketch_shard: %s", cudaGetErrorString(cudaGetLastError()));
+        const u64 kept = hc[0], nonzero = hc[1];
+        if (kept <= cap && (kept >= (u64)ctx->s || kept == nonzero) && !ctx->shard_two_pass) {
+            // the guess held: the kept hashes contain the s smallest non-zero ones (or all of them)
+            rc = RKG_OK;
+            if (kept > 0) {
+                const int P = next_pow2((i64)std::max<u64>(kept, 2));
+                {
+                    Timed t(ctx, b->stream, K_SKETCH);
+                    shard_sort_kernel<<<1, 1024, 0, b->stream>>>(d_scan.as<u64>(), (int)kept, P);
+                    ++ctx->launches;
+                }
+                const int out_n = (int)std::min<u64>(kept, (u64)ctx->s);
+                cudaMemcpyAsync(sketch, d_scan.p, sizeof(u64) * (size_t)out_n, cudaMemcpyDeviceToHost, b->stream);
+                if (cudaStreamSynchronize(b->stream) != cudaSuccess) rc = fail(ctx, RKG_ERR_CUDA, "rkg_sketch_shard: %s", cudaGetErrorString(cudaGetLastError()));
+                else *len = out_n;
+            }
+            return rc;
+        }
+    }
+    // the exact two-pass route on the codes that are on the device now
     DevBuf d_hist, d_pick, d_cand;
     rc = RKG_OK;
     do {
         if (d_hist.ensure(sizeof(u32) * SHARD_BINS) || d_pick.ensure(64)) { rc = fail(ctx, RKG_ERR_NOMEM, "rkg_sketch_shard: device allocation failed"); break; }
         cudaMemsetAsync(d_hist.p, 0, sizeof(u32) * SHARD_BINS, b->stream);
         cudaMemsetAsync(d_pick.p, 0, 64, b->stream);
-        const int grid = ctx->sm_count * 8;
-        const i64 lastw = 2 * ((b->total + 31) / 32) + 7, lastm = (b->total + 31) / 32 + 7;   // batch_fill pads 8 words
         u64 hpick[2] = {0, 0};
         {
             Timed t(ctx, b->stream, K_SKETCH);

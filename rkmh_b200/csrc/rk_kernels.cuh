@@ -418,6 +418,10 @@ sketch_kernel(SeqBatch sb, const __grid_constant__ KList kl, int s, CountTable c
 // ------------------------------------------------------------------------------------------------
 // Bottom-s sketch of ONE long record (a shard of it) without materialising its hashes: `rkmh hash` on a
 // chromosome-scale sequence (minhashes(calc_hashes()), mkmh.hpp:505-532, 931-950).
+//   shard_scan_kernel   ONE hashing pass when the hashes behave like hashes: keep the non-zero hashes at or under a limit
+//                       guessed from s / n (twice the expected s-th smallest), count the non-zero ones.  At least s kept
+//                       (and room for them): they hold the sketch.  Otherwise (repeats, mostly invalid windows) the exact
+//                       two-pass route below runs on the same device-resident codes:
 //   shard_hist_kernel   hash every window, histogram of the top 16 hash bits (non-zero hashes only)
 //   shard_pick_kernel   the bin in which the running count reaches s, and the count through that bin
 //   shard_emit_kernel   hash again, keep the hashes whose top 16 bits are <= that bin (s plus one bin's worth)
@@ -437,6 +441,30 @@ shard_hist_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, 
         team_hash_k<KCSEL>(kl.kv[0], lut, codes, nmask, last_word, last_mword, w0, cnt, k, lane, 32,
                            [&](i64, u64 h) { if (h) atomicAdd(&hist[(u32)(h >> 48)], 1u); });
     }
+}
+
+// windows [w_begin, w_end) of the record; cnt[0] += kept hashes (cand[] holds the first `cap` of them), cnt[1] += non-zero hashes
+template <int KCSEL>
+__global__ void __launch_bounds__(256)
+shard_scan_kernel(const u32* __restrict__ codes, const u32* __restrict__ nmask, i64 last_word, i64 last_mword, i64 w_begin, i64 w_end,
+                  const __grid_constant__ KList kl, u64 limit, u64* __restrict__ cand, unsigned long long* __restrict__ cnt, u64 cap) {
+    const u64* lut = hash_lut_load(kl.lut);
+    const int lane = threadIdx.x & 31, k = kl.k[0];
+    const i64 warp = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    unsigned long long nz = 0;
+    for (i64 w0 = w_begin + warp * SHARD_SEG; w0 < w_end; w0 += nwarps * SHARD_SEG) {
+        const i64 c = min(SHARD_SEG, w_end - w0);
+        team_hash_k<KCSEL>(kl.kv[0], lut, codes, nmask, last_word, last_mword, w0, c, k, lane, 32, [&](i64, u64 h) {
+            if (h) {
+                ++nz;
+                if (h <= limit) {
+                    const unsigned long long at = atomicAdd(&cnt[0], 1ULL);
+                    if (at < cap) cand[at] = h;
+                }
+            }
+        });
+    }
+    if (nz) atomicAdd(&cnt[1], nz);
 }
 
 // out[0] = bin, out[1] = number of non-zero hashes with top 16 bits <= bin (all of them when fewer than s exist)

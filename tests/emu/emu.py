@@ -67,14 +67,16 @@ class Emu:
                             sk.ctypes.data, lens.ctypes.data, block, int(force_global_sort))
         return sk, lens
 
-    def sketch_shard(self, seq, n, k, s, block=64):
+    def sketch_shard(self, seq, n, k, s, block=64, scan_first=False, pieces=3, want_route=False):
+        """rkg_sketch_shard's kernels; scan_first: the one-pass route with the guessed limit first (route 1 when accepted)"""
         seq = np.ascontiguousarray(np.frombuffer(seq, np.uint8))
         out = np.zeros(s, np.uint64)
         m = np.zeros(1, np.int32)
+        route = np.zeros(1, np.int32)
         rc = self.lib.emu_sketch_shard(seq.ctypes.data, C.c_int64(seq.size), C.c_int64(n), int(k), int(s), out.ctypes.data,
-                                       m.ctypes.data, block)
+                                       m.ctypes.data, block, int(scan_first), int(pieces), route.ctypes.data)
         assert rc == 0, rc
-        return out[:m[0]]
+        return (out[:m[0]], int(route[0])) if want_route else out[:m[0]]
 
     def merge(self, parts, lens, s, block=64, in_smem=True):
         parts = np.ascontiguousarray(parts, np.uint64)

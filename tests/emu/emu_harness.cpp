@@ -167,8 +167,11 @@ int emu_sketch(const char* bases, const i64* offs, i64 nseq, const int* ks, int 
     return 0;
 }
 
-// rkg_sketch_shard's kernels (histogram of the top 16 hash bits, pick, emit, sort) on the first n windows of one record
-int emu_sketch_shard(const char* bases, i64 nbytes, i64 n, int k, int s, u64* out, int* out_len, int block) {
+// rkg_sketch_shard's kernels on the first n windows of one record.  scan_first != 0: the one-pass route with the guessed
+// limit (in `pieces` launches over consecutive window ranges, as the pieces of a shard arrive), *route = 1 when its result
+// was accepted; otherwise / else the exact route (histogram of the top 16 hash bits, pick, emit, sort), *route = 2.
+int emu_sketch_shard(const char* bases, i64 nbytes, i64 n, int k, int s, u64* out, int* out_len, int block, int scan_first,
+                     int pieces, int* route) {
     int ks[1] = {k}; int kcsel; KList kl = make_klist(ks, 1, &kcsel);
     const i64 offs[2] = {0, nbytes};
     HostBatch b; fill_batch(b, bases, offs, 1, kl, block);
@@ -176,6 +179,39 @@ int emu_sketch_shard(const char* bases, i64 nbytes, i64 n, int k, int s, u64* ou
     u64 pick[2] = {0, 0};
     const u32* pc = b.codes.data(); const u32* pm = b.nmask.data(); u32* ph = hist.data(); u64* pp = pick;
     const i64 lastw = (i64)b.codes.size() - 1, lastm = (i64)b.nmask.size() - 1;
+    *route = 2;
+    if (scan_first) {
+        u64 limit = ~0ULL;
+        if ((i64)s < n) {
+            const long double frac = 2.0L * (long double)s / (long double)n;
+            if (frac < 1.0L) limit = (u64)(frac * 18446744073709551615.0L);
+        }
+        const u64 cap = std::max<u64>(4ULL * (u64)s, 1ULL << 10);
+        std::vector<u64> sc(next_pow2((i64)cap), 0);
+        unsigned long long cnt[2] = {0, 0};
+        u64* psc = sc.data(); unsigned long long* pcnt = cnt;
+        pieces = std::max(pieces, 1);
+        for (int p = 0; p < pieces; ++p) {
+            const i64 lo = n * p / pieces, hi = n * (p + 1) / pieces;
+            if (hi <= lo) continue;
+            dispatch(kcsel, [&](auto tag) {
+                constexpr int KS = decltype(tag)::value;
+                emu::launch(dim3(2), dim3(block), 0, [=] { shard_scan_kernel<KS>(pc, pm, lastw, lastm, lo, hi, kl, limit, psc, pcnt, cap); });
+            });
+        }
+        const u64 kept = cnt[0];
+        if (kept <= cap && (kept >= (u64)s || kept == cnt[1])) {
+            *route = 1;
+            *out_len = 0;
+            if (kept == 0) return 0;
+            const int P = next_pow2((i64)std::max<u64>(kept, 2));
+            emu::launch(dim3(1), dim3(block), 0, [=] { shard_sort_kernel(psc, (int)kept, P); });
+            const int m = (int)std::min<u64>(kept, (u64)s);
+            std::copy(sc.begin(), sc.begin() + m, out);
+            *out_len = m;
+            return 0;
+        }
+    }
     dispatch(kcsel, [&](auto tag) {
         constexpr int KS = decltype(tag)::value;
         emu::launch(dim3(2), dim3(block), 0, [=] { shard_hist_kernel<KS>(pc, pm, lastw, lastm, n, kl, ph); });

@@ -209,3 +209,13 @@ def test_sketch_shard_kernels(emu, oracle):
     assert len(emu.sketch_shard(b"N" * 300, 279, 21, 50)) == 0
     rep = b"ACGT" * 2000
     assert np.array_equal(emu.sketch_shard(rep, len(rep) - 21, 21, 100), oracle.minhashes(oracle.calc_hashes(rep, [21]), 100))
+    # the one-pass route (hashes at or under a limit guessed from s / n, piece by piece) and its fall-back to the exact one
+    routes = {}
+    for name, sq, k, s in (("random", seq, 21, 500), ("random_k12", seq, 12, 64), ("k5", seq, 5, 3000), ("tiny", tiny, 21, 1000),
+                           ("allN", b"N" * 300, 21, 50), ("repeat", rep, 21, 100), ("mostlyN", b"N" * 9000 + seq[:1500], 21, 400),
+                           ("one_kmer", b"A" * 5000, 12, 10)):
+        got, route = emu.sketch_shard(sq, len(sq) - k, k, s, scan_first=True, pieces=4, want_route=True)
+        assert np.array_equal(got, oracle.minhashes(oracle.calc_hashes(sq, [k]), s)), name
+        routes[name] = route
+    assert routes["random"] == 1 and routes["tiny"] == 1 and routes["allN"] == 1     # guess accepted
+    assert routes["repeat"] == 2 and routes["mostlyN"] == 2                          # guess refused: exact route
