@@ -1731,6 +1731,13 @@ int rkg_merge_sketches(rkg_ctx* ctx, const uint64_t* parts, const int32_t* part_
     return rc;
 }
 
+static void launch_shard_sort(rkg_ctx* ctx, cudaStream_t st, u64* a, int m, int P) {
+    const size_t bytes = (size_t)P * 8;
+    const int in_smem = bytes + 1024 <= ctx->smem_optin ? 1 : 0;
+    if (in_smem) cudaFuncSetAttribute(shard_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    shard_sort_kernel<<<1, 1024, in_smem ? bytes : 0, st>>>(a, m, P, in_smem);
+}
+
 int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t kmer_begin, int64_t kmer_end,
                      int64_t record_len, uint64_t* sketch, int32_t* len) {
     if (!ctx || !bases || !sketch || !len) return RKG_ERR_ARG;
@@ -1766,10 +1773,11 @@ int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t km
     CK(cudaMemsetAsync(b->nmask.as<u32>() + nwords32, 0xFF, sizeof(u32) * 8, b->stream));
     const int grid = ctx->sm_count * 8;
     const i64 lastw = 2 * nwords32 + 7, lastm = nwords32 + 7;               // 8 words of padding follow the record
-    // the guess: twice the s-th smallest of n uniform hashes; room for four times s kept hashes
+    // the guess: 1.5 x the s-th smallest of n uniform hashes (s = 10 000: 15 000 +- 120 kept, a 16 k-entry sort in shared
+    // memory); room for four times s kept hashes
     u64 limit = ~0ULL;
     if ((i64)ctx->s < n) {
-        const long double frac = 2.0L * (long double)ctx->s / (long double)n;
+        const long double frac = 1.5L * (long double)ctx->s / (long double)n;
         if (frac < 1.0L) limit = (u64)(frac * 18446744073709551615.0L);
     }
     const u64 cap = std::max<u64>(4ULL * (u64)ctx->s, 1ULL << 16);
@@ -1782,14 +1790,75 @@ int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t km
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));          // the buffers are free (and sized) from here on
     const i64 piece = 32LL << 20;
     i64 w_lo = 0;
-    for (i64 off = 0; off < total; off += piece) {
+    // rkg_set_host_pack(2): a piece is packed on the host while the link is busy with earlier pieces (the policy of
+    // host_pipeline; the two rates are measured on the context's first pieces if they are not known yet)
+    const bool adaptive = ctx->host_pack == 2;
+    using clk = std::chrono::steady_clock;
+    auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+    double lead = 0.0;
+    clk::time_point t_last = clk::now();
+    int last_stage = -1, npiece = 0;
+    if (adaptive)
+        for (int i = 0; i < NSLOTS; ++i) {
+            if (!ctx->h2d_done[i]) CK(cudaEventCreateWithFlags(&ctx->h2d_done[i], cudaEventDisableTiming));
+            if ((rc = ensure_stage(ctx, i, (size_t)(piece * 3 / 8) + (64 << 10)))) return rc;
+        }
+    for (i64 off = 0; off < total; off += piece, ++npiece) {
         const i64 plen = std::min<i64>(piece, total - off);
-        CK(cudaMemcpyAsync(b->bases.as<unsigned char>() + off, bases + off, (size_t)plen, cudaMemcpyHostToDevice, ctx->copy_stream));
-        ctx->xfer[0] += plen;
+        const i64 pw = (plen + 31) / 32;
+        bool pack = false, time_link = false;
+        if (adaptive) {
+            lead = std::max(0.0, lead - ms_since(t_last));
+            t_last = clk::now();
+            if (last_stage >= 0) {
+                const bool done = cudaEventQuery(ctx->h2d_done[last_stage]) == cudaSuccess;
+                if (done && lead > 0.25 * ctx->dma_ms_per_byte * (double)plen) ctx->dma_ms_per_byte *= 0.93;
+                if (!done && lead == 0.0) { ctx->dma_ms_per_byte *= 1.07; lead = 0.1 * ctx->dma_ms_per_byte * (double)plen; }
+                if (done) lead = 0.0;
+            }
+            if (ctx->dma_ms_per_byte == 0.0) time_link = true;
+            else if (ctx->pack_ms_per_byte == 0.0) pack = true;
+            else pack = lead >= ctx->pack_lead * ctx->pack_ms_per_byte * (double)plen;
+        }
+        if (pack) {
+            const int st = npiece % NSLOTS;
+            CK(cudaEventSynchronize(ctx->h2d_done[st]));     // the staging buffer's previous copy has left it
+            const size_t mask_at = ((size_t)2 * pw + 7) & ~(size_t)7;
+            u32* hc = static_cast<u32*>(ctx->stage[st]);
+            u32* hm = hc + mask_at;
+            const clk::time_point t0 = clk::now();
+            rk_pack_bases(bases + off, plen, hc, hm, ctx->pack_threads);
+            const double per = ms_since(t0) / (double)plen;
+            ctx->pack_ms_per_byte = ctx->pack_ms_per_byte == 0.0 ? per : 0.5 * ctx->pack_ms_per_byte + 0.5 * per;
+            CK(cudaMemcpyAsync(b->codes.as<u32>() + 2 * (off / 32), hc, sizeof(u32) * 2 * (size_t)pw, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaMemcpyAsync(b->nmask.as<u32>() + off / 32, hm, sizeof(u32) * (size_t)pw, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->h2d_done[st], ctx->copy_stream));
+            last_stage = st;
+            ctx->xfer[1] += 12 * pw; ++ctx->xfer[3];
+        } else {
+            clk::time_point t0;
+            if (time_link) { CK(cudaStreamSynchronize(ctx->copy_stream)); t0 = clk::now(); }
+            CK(cudaMemcpyAsync(b->bases.as<unsigned char>() + off, bases + off, (size_t)plen, cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (time_link) {
+                CK(cudaStreamSynchronize(ctx->copy_stream));
+                ctx->dma_ms_per_byte = std::max(ms_since(t0), 1e-3) / (double)plen;
+            }
+            if (adaptive) {
+                const int st = npiece % NSLOTS;
+                CK(cudaEventSynchronize(ctx->h2d_done[st]));
+                CK(cudaEventRecord(ctx->h2d_done[st], ctx->copy_stream));
+                last_stage = st;
+            }
+            ctx->xfer[0] += plen; ++ctx->xfer[2];
+        }
+        if (adaptive) {
+            lead = std::max(0.0, lead - ms_since(t_last));
+            t_last = clk::now();
+            if (!time_link) lead += ctx->dma_ms_per_byte * (double)plen * (pack ? 0.375 : 1.0);
+        }
         CK(cudaEventRecord(ctx->copy_event, ctx->copy_stream));
         CK(cudaStreamWaitEvent(b->stream, ctx->copy_event, 0));
-        const i64 pw = (plen + 31) / 32;
-        {
+        if (!pack) {
             Timed t(ctx, b->stream, K_INGEST);
             ingest_kernel<<<(int)std::min<i64>((pw + 255) / 256, (i64)ctx->sm_count * 16), 256, 0, b->stream>>>(
                 b->bases.as<unsigned char>() + off, plen, b->codes.as<u32>() + 2 * (off / 32), b->nmask.as<u32>() + off / 32, pw);
@@ -1805,8 +1874,7 @@ int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t km
             w_lo = w_hi;
         }
     }
-    ++ctx->xfer[2];
-    b->packed = true; b->ascii = true;
+    b->packed = true; b->ascii = false;             // (some pieces may have arrived packed: the bytes are not all there)
     {
         unsigned long long hc[2] = {0, 0};
         cudaMemcpyAsync(hc, d_cnt.p, sizeof(hc), cudaMemcpyDeviceToHost, b->stream);
@@ -1820,7 +1888,7 @@ int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t km
                 const int P = next_pow2((i64)std::max<u64>(kept, 2));
                 {
                     Timed t(ctx, b->stream, K_SKETCH);
-                    shard_sort_kernel<<<1, 1024, 0, b->stream>>>(d_scan.as<u64>(), (int)kept, P);
+                    launch_shard_sort(ctx, b->stream, d_scan.as<u64>(), (int)kept, P);
                     ++ctx->launches;
                 }
                 const int out_n = (int)std::min<u64>(kept, (u64)ctx->s);
@@ -1858,7 +1926,7 @@ int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t km
             Timed t(ctx, b->stream, K_SKETCH);
             DISPATCH_KCSEL(ctx->kcsel, (shard_emit_kernel<KS><<<grid, 256, 0, b->stream>>>(b->codes.as<u32>(), b->nmask.as<u32>(), lastw, lastm, n, ctx->kl,
                                                                                          d_pick.as<u64>(), d_cand.as<u64>(), ncand, kept)));
-            shard_sort_kernel<<<1, 1024, 0, b->stream>>>(d_cand.as<u64>(), (int)kept, P);
+            launch_shard_sort(ctx, b->stream, d_cand.as<u64>(), (int)kept, P);
             ctx->launches += 2;
         }
         const int out_n = (int)std::min<u64>(kept, (u64)ctx->s);

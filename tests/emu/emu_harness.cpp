@@ -183,7 +183,7 @@ int emu_sketch_shard(const char* bases, i64 nbytes, i64 n, int k, int s, u64* ou
     if (scan_first) {
         u64 limit = ~0ULL;
         if ((i64)s < n) {
-            const long double frac = 2.0L * (long double)s / (long double)n;
+            const long double frac = 1.5L * (long double)s / (long double)n;
             if (frac < 1.0L) limit = (u64)(frac * 18446744073709551615.0L);
         }
         const u64 cap = std::max<u64>(4ULL * (u64)s, 1ULL << 10);
@@ -205,7 +205,7 @@ int emu_sketch_shard(const char* bases, i64 nbytes, i64 n, int k, int s, u64* ou
             *out_len = 0;
             if (kept == 0) return 0;
             const int P = next_pow2((i64)std::max<u64>(kept, 2));
-            emu::launch(dim3(1), dim3(block), 0, [=] { shard_sort_kernel(psc, (int)kept, P); });
+            emu::launch(dim3(1), dim3(block), (size_t)P * 8, [=] { shard_sort_kernel(psc, (int)kept, P, 1); });
             const int m = (int)std::min<u64>(kept, (u64)s);
             std::copy(sc.begin(), sc.begin() + m, out);
             *out_len = m;
@@ -229,7 +229,7 @@ int emu_sketch_shard(const char* bases, i64 nbytes, i64 n, int k, int s, u64* ou
         emu::launch(dim3(2), dim3(block), 0, [=] { shard_emit_kernel<KS>(pc, pm, lastw, lastm, n, kl, pp, pcand, pn, kept); });
     });
     if (ncand != kept) return -2;
-    emu::launch(dim3(1), dim3(block), 0, [=] { shard_sort_kernel(pcand, (int)kept, P); });
+    emu::launch(dim3(1), dim3(block), 0, [=] { shard_sort_kernel(pcand, (int)kept, P, 0); });
     const int m = (int)std::min<u64>(kept, (u64)s);
     std::copy(cand.begin(), cand.begin() + m, out);
     *out_len = m;
