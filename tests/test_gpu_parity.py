@@ -262,6 +262,57 @@ def test_sharded_sketch_equals_whole(gpu, oracle):
     assert np.array_equal(gpu.sketch_shard(seq[:300_000], 0, 300_000 - 12, 300_000), m12)
 
 
+def test_shard_sketch_in_pieces(oracle, monkeypatch):
+    """rkg_sketch_shard copies a shard in 32 MB pieces and hashes behind the copies: a 110 Mbp record (four pieces, windows
+    across every piece boundary, invalid bases right at the boundaries) gives the same sketch through the one-pass route,
+    through the exact two-pass route (RKMH_SHARD_TWO_PASS), with pieces packed on the host (rkg_set_host_pack 2), and as
+    four shards merged; its first 2 Mbp are checked against the oracle."""
+    import rkmh_b200
+    rng = np.random.default_rng(17)
+    n = 110_000_000
+    seq = rng.integers(0, 4, size=n, dtype=np.uint8)
+    seq = np.frombuffer(b"ACGT", np.uint8)[seq]
+    piece = 32 << 20
+    for j in (1, 2, 3):
+        seq[j * piece - 3:j * piece + 2] = ord("N")
+        seq[j * piece - 40] = ord("a")
+    k, s = 21, 10000
+    nk = n - k
+    out = {}
+    for name, env, pack in (("one_pass", None, 0), ("two_pass", "1", 0), ("adaptive", None, 2)):
+        if env:
+            monkeypatch.setenv("RKMH_SHARD_TWO_PASS", env)
+        else:
+            monkeypatch.delenv("RKMH_SHARD_TWO_PASS", raising=False)
+        with rkmh_b200.RkmhGpu(0) as g:
+            g.set_params([k], s)
+            g.set_host_pack(pack, 4)
+            g.profile_enable(True)
+            res = [g.sketch_shard(seq, 0, nk, n) for _ in range(3 if pack else 1)]
+            launches = g.profile_read(reset=True)["sketch_kernel"]["launches"]
+            assert all(np.array_equal(r, res[0]) for r in res)
+            out[name] = res[0]
+            if name == "one_pass":
+                assert launches == 4 + 1, launches                     # one hashing launch per piece + the sort
+                parts, lens = [], []
+                for r in range(4):
+                    b, e = nk * r // 4, nk * (r + 1) // 4
+                    sk = g.sketch_shard(seq[b:min(e + k, n)], b, e, n)
+                    row = np.zeros(s, np.uint64); row[:len(sk)] = sk
+                    parts.append(row); lens.append(len(sk))
+                out["merged"] = g.merge_sketches(np.stack(parts), lens)
+                out["head"] = g.sketch_shard(seq[:2_000_000], 0, 2_000_000 - k, 2_000_000)
+            if name == "two_pass":
+                assert launches > 4 + 1, launches
+            if pack:
+                st = g.transfer_stats()
+                assert st["packed_chunks"] > 0 and st["plain_chunks"] > 0, st
+    assert len(out["one_pass"]) == s and np.all(np.diff(out["one_pass"].astype(np.float64)) >= 0)
+    for name in ("two_pass", "adaptive", "merged"):
+        assert np.array_equal(out[name], out["one_pass"]), name
+    assert np.array_equal(out["head"], oracle.minhashes(oracle.calc_hashes(seq[:2_000_000].tobytes(), [k]), s))
+
+
 def test_full_size_properties(gpu, oracle):
     """BASELINE config 2 at a tenth of its size (1 M reads) through size-independent properties: results do not
     depend on batch order or chunking, a spot sample equals the oracle, and every best <= sketch_len <= s."""
