@@ -78,6 +78,13 @@ class Emu:
         assert rc == 0, rc
         return (out[:m[0]], int(route[0])) if want_route else out[:m[0]]
 
+    def unpack(self, codes, nmask, block=64):
+        """unpack_kernel: 32 ASCII bytes per code pair / mask word"""
+        codes = np.ascontiguousarray(codes, np.uint32); nmask = np.ascontiguousarray(nmask, np.uint32)
+        out = np.zeros(32 * nmask.size, np.uint8)
+        self.lib.emu_unpack(codes.ctypes.data, nmask.ctypes.data, out.ctypes.data, C.c_int64(nmask.size), block)
+        return out
+
     def merge(self, parts, lens, s, block=64, in_smem=True):
         parts = np.ascontiguousarray(parts, np.uint64)
         lens = np.ascontiguousarray(lens, np.int32)

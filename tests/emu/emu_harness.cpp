@@ -236,6 +236,12 @@ int emu_sketch_shard(const char* bases, i64 nbytes, i64 n, int k, int s, u64* ou
     return 0;
 }
 
+// unpack_kernel (what the memoised kernels read after a packed transfer) on host-packed codes / mask
+int emu_unpack(const u32* codes, const u32* nmask, unsigned char* bases, i64 nwords32, int block) {
+    emu::launch(dim3(2), dim3(block), 0, [=] { unpack_kernel(codes, nmask, bases, nwords32); });
+    return 0;
+}
+
 int emu_merge(const u64* parts, const int* part_lens, int nparts, int s, u64* out, int* out_len, int block, int in_smem) {
     const int P = next_pow2(std::max(s, 2));
     std::vector<u64> scr(P);
