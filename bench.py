@@ -637,6 +637,16 @@ def section_cfg4(args, R):
         hits = pin_h.view(HIT_DTYPE, n)
         e2e_ms = R.timed(lambda: g.classify_fixed_raw(pin_b.ptr, L, n, -1, pin_h.ptr), args.steps, 2)
         same = R.all_true(bool(np.array_equal(hits.view(np.int32), dev_hits.view(np.int32))))
+        # the same call with the adaptive packed transfer (on the Murmur path a packed chunk also skips the ingest kernel)
+        e2e_plain_ms = e2e_ms
+        g.set_host_pack(2, max(1, host_cores() // max(R.world, 1)))
+        hits[:] = 0
+        e2e_adaptive_ms = R.timed(lambda: g.classify_fixed_raw(pin_b.ptr, L, n, -1, pin_h.ptr), args.steps, 3)
+        same_adaptive = R.all_true(bool(np.array_equal(hits.view(np.int32), dev_hits.view(np.int32))))
+        g.set_host_pack(0)
+        if same_adaptive and e2e_adaptive_ms < e2e_ms:
+            e2e_ms = e2e_adaptive_ms
+        out["e2e_transfers"] = {"plain_ms": e2e_plain_ms, "adaptive_ms": e2e_adaptive_ms, "adaptive_matches_device_run": same_adaptive}
         # rkmh filter keeps a read iff sketch_len > 0, best >= N and best - prev > D (src/rkmh.cpp:1292-1298)
         best, prev = np.maximum(dev_hits["best"], 0), np.maximum(dev_hits["prev"], 0)
         keep = (dev_hits["sketch_len"] > 0) & (best >= N4) & (best - prev > 0)
