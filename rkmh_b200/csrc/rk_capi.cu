@@ -103,9 +103,6 @@ struct rkg_ctx {
     int pack_threads = 1;
     void* stage[NSLOTS] = {};
     size_t stage_cap[NSLOTS] = {};
-    DevBuf memo_order, memo_slot_o;      // memoised path: codes in count-table slot order and their slots (memo_slot_order)
-    u64 memo_order_size = 0;             // the table size that order was made for
-    u32 memo_order_codes = 0;
     DevBuf shard_scan, shard_cnt;        // rkg_sketch_shard: kept hashes and counters of the one-pass route
     cudaStream_t copy_stream = nullptr;  // rkg_sketch_shard: the shard's pieces arrive here while earlier pieces are hashed
     cudaEvent_t copy_event = nullptr;
@@ -333,7 +330,6 @@ SeqBatch seq_view(const rkg_batch* b) {
 // Build hash / rank / REF tables over all 4^k codes.  Called at the end of rkg_load_refs (the reference table exists).
 int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     ctx->memo_ready = false;
-    ctx->memo_order_size = 0;
     if (!ctx->memo_enabled || ctx->kl.nk != 1 || ctx->kl.k[0] > MEMO_MAX_K) return RKG_OK;
     const int k = ctx->kl.k[0];
     const u32 ncodes = 1u << (2 * k);
@@ -430,45 +426,14 @@ int memo_build(rkg_ctx* ctx, cudaStream_t st) {
     return RKG_OK;
 }
 
-// The codes grouped by the region of the read count table their slot lies in (rk_memo.cuh: slot order), for the current
-// table size; false when the order is not available (no table, a table of 2^32 slots or more): the unordered kernels serve.
-bool memo_slot_order(rkg_ctx* ctx) {
-    if (!ctx->memo_ready || !ctx->read_ct.counts || ctx->read_ct.mod.d == 0 || ctx->read_ct.mod.d >= 0xFFFFFFFFull) return false;
-    if (ctx->memo_order_size == ctx->read_ct.mod.d && ctx->memo_order_codes == ctx->memo.ncodes) return true;
-    const u32 ncodes = ctx->memo.ncodes;
-    if (ctx->memo_order.ensure(sizeof(u32) * (size_t)ncodes) != cudaSuccess || ctx->memo_slot_o.ensure(sizeof(u32) * (size_t)ncodes) != cudaSuccess ||
-        ctx->memo_tmp.ensure(sizeof(u32) * ((size_t)3 * MEMO_SLOT_BUCKETS + ncodes)) != cudaSuccess) { cudaGetLastError(); return false; }
-    u32* bcount = ctx->memo_tmp.as<u32>();
-    u32* bstart = bcount + MEMO_SLOT_BUCKETS; u32* bfill = bstart + MEMO_SLOT_BUCKETS; u32* slot = bfill + MEMO_SLOT_BUCKETS;
-    int bits = 0; while ((1ull << bits) < ctx->read_ct.mod.d) ++bits;
-    const int shift = std::max(bits - 12, 0);                       // slot >> shift < MEMO_SLOT_BUCKETS
-    cudaStream_t st = ctx->stream;
-    cudaMemsetAsync(bcount, 0, sizeof(u32) * MEMO_SLOT_BUCKETS, st);
-    {
-        Timed t(ctx, st, K_MEMO_BUILD);
-        const int grid = (int)std::min<i64>(((i64)ncodes + 255) / 256, (i64)ctx->sm_count * 16);
-        memo_slot_count_kernel<<<grid, 256, 0, st>>>(ctx->memo.hash, ncodes, ctx->read_ct.mod, shift, slot, bcount);
-        memo_scan_kernel<<<1, 1024, 0, st>>>(bcount, bstart, bfill, MEMO_SLOT_BUCKETS, ctx->memo_misc.as<int>() + 12);   // (its bucket-size flag is not used here)
-        memo_slot_scatter_kernel<<<grid, 256, 0, st>>>(ncodes, slot, shift, bstart, bfill, ctx->memo_order.as<u32>(), ctx->memo_slot_o.as<u32>());
-        ctx->launches += 3;
-    }
-    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return false;
-    ctx->memo_order_size = ctx->read_ct.mod.d;
-    ctx->memo_order_codes = ncodes;
-    return true;
-}
-
 // Fold the per-code counters of pass 1 into the read count table (the table the reference keeps, rkmh.cpp:738-743).
 int memo_flush(rkg_ctx* ctx) {
     if (!ctx->memo_ready || !ctx->memo_pending) return RKG_OK;
     CK(cudaDeviceSynchronize());
-    const bool ordered = memo_slot_order(ctx);
     {
         Timed t(ctx, ctx->stream, K_MEMO_MAINT);
         const int grid = (int)std::min<i64>(((i64)ctx->memo.ncodes + 255) / 256, (i64)ctx->sm_count * 16);
-        if (ordered) memo_fold_ordered_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->memo, ctx->read_ct, ctx->memo_pending_zeros,
-                                                                           ctx->memo_order.as<u32>(), ctx->memo_slot_o.as<u32>());
-        else memo_fold_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->memo, ctx->read_ct, ctx->memo_pending_zeros);
+        memo_fold_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->memo, ctx->read_ct, ctx->memo_pending_zeros);
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
@@ -484,13 +449,10 @@ int memo_prepare(rkg_ctx* ctx, int min_occ) {
     const int want = min_occ >= 0 ? min_occ : INT_MIN;
     if (want == ctx->memo_occ && !(want != INT_MIN && ctx->memo_occ_stale)) return RKG_OK;
     CK(cudaDeviceSynchronize());
-    const bool ordered = min_occ >= 0 && memo_slot_order(ctx);
     {
         Timed t(ctx, ctx->stream, K_MEMO_MAINT);
         const int grid = (int)std::min<i64>(((i64)ctx->memo.ncodes + 255) / 256, (i64)ctx->sm_count * 16);
-        if (ordered) memo_apply_occ_ordered_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->memo, ctx->read_ct, min_occ, ctx->memo_order.as<u32>(),
-                                                                                ctx->memo_slot_o.as<u32>());
-        else memo_apply_occ_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->memo, ctx->read_ct, min_occ);
+        memo_apply_occ_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->memo, ctx->read_ct, min_occ);
     }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
@@ -914,7 +876,7 @@ void rkg_destroy(rkg_ctx* ctx) {
     for (int i = 0; i < NSLOTS; ++i) if (ctx->h2d_done[i]) cudaEventDestroy(ctx->h2d_done[i]);
     if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    for (DevBuf* d : {&ctx->memo_order, &ctx->memo_slot_o, &ctx->shard_scan, &ctx->shard_cnt, &ctx->depth_keys, &ctx->depth_counts, &ctx->depth_zero, &ctx->hash_lut, &ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
+    for (DevBuf* d : {&ctx->shard_scan, &ctx->shard_cnt, &ctx->depth_keys, &ctx->depth_counts, &ctx->depth_zero, &ctx->hash_lut, &ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
                       &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
                       &ctx->memo_tab, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
                       &ctx->memo_sieve, &ctx->memo_cmap})

@@ -289,68 +289,6 @@ memo_apply_occ_kernel(Memo mm, CountTable ct, int min_occ) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Slot order.  memo_fold_kernel and memo_apply_occ_kernel visit counts[hash % size] of every code: 16.7 M accesses spread at
-// random over an 800 MB table (0.67 ms each at k = 12: a DRAM row miss per access).  The slot of a code is fixed once the
-// table size is known, so the codes are grouped ONCE by the top bits of their slot (counting sort into MEMO_SLOT_BUCKETS
-// regions of the table, ~200 KB each); walked in that order both passes go through the table region by region -- every
-// sector comes from DRAM once, in address order -- while their accesses by code (code_counts, tab: 64 MB each) stay in L2.
-constexpr u32 MEMO_SLOT_BUCKETS = 4096;
-constexpr u32 MEMO_NO_SLOT = 0xFFFFFFFFu;        // codes whose hash is 0
-
-__global__ void __launch_bounds__(256)
-memo_slot_count_kernel(const u64* __restrict__ hash, u32 ncodes, FastMod mod, int shift, u32* __restrict__ slot, u32* __restrict__ bcount) {
-    for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < ncodes; c += gridDim.x * blockDim.x) {
-        const u64 h = hash[c];
-        const u32 s = h ? (u32)fastmod(h, mod) : MEMO_NO_SLOT;
-        slot[c] = s;
-        atomicAdd(&bcount[h ? (s >> shift) : MEMO_SLOT_BUCKETS - 1], 1u);
-    }
-}
-
-__global__ void __launch_bounds__(256)
-memo_slot_scatter_kernel(u32 ncodes, const u32* __restrict__ slot, int shift, const u32* __restrict__ start, u32* __restrict__ fill,
-                         u32* __restrict__ order, u32* __restrict__ slot_o) {
-    for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < ncodes; c += gridDim.x * blockDim.x) {
-        const u32 s = slot[c];
-        const u32 b = s != MEMO_NO_SLOT ? (s >> shift) : MEMO_SLOT_BUCKETS - 1;
-        const u32 pos = start[b] + atomicAdd(&fill[b], 1u);
-        order[pos] = c;
-        slot_o[pos] = s;
-    }
-}
-
-// memo_fold_kernel in slot order
-__global__ void __launch_bounds__(256)
-memo_fold_ordered_kernel(Memo mm, CountTable ct, int count_zeros, const u32* __restrict__ order, const u32* __restrict__ slot_o) {
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < mm.ncodes; i += gridDim.x * blockDim.x) {
-        const u32 c = order[i];
-        const int n = mm.code_counts[c];
-        if (n == 0) continue;
-        mm.code_counts[c] = 0;
-        const u32 s = slot_o[i];
-        if (s != MEMO_NO_SLOT) atomicAdd(&ct.counts[s], n);
-        else if (count_zeros) atomicAdd(&ct.counts[0], n);
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const u32 inv = *mm.inval;
-        *mm.inval = 0;
-        if (count_zeros && inv) atomicAdd(&ct.counts[0], (int)inv);     // an invalid window hashes to 0 (rkmh.cpp:331-336)
-    }
-}
-
-// memo_apply_occ_kernel in slot order (min_occ >= 0 and a count table present)
-__global__ void __launch_bounds__(256)
-memo_apply_occ_ordered_kernel(Memo mm, CountTable ct, int min_occ, const u32* __restrict__ order, const u32* __restrict__ slot_o) {
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < mm.ncodes; i += gridDim.x * blockDim.x) {
-        const u32 c = order[i], s = slot_o[i];
-        const u32 t = mm.tab[c];
-        const u32 fail = (s != MEMO_NO_SLOT && !(min_occ <= ct.counts[s])) ? MEMO_FAILM : 0u;
-        const u32 nt = (t & ~MEMO_FAILM) | fail;
-        if (nt != t) mm.tab[c] = nt;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // count_memo_kernel: -M pass 1.  `wpr` warps share one read (1 for short reads, a whole block for long ones).
 __global__ void __launch_bounds__(256)
 count_memo_kernel(SeqBatch sb, Memo mm, int count_zeros, int wpr) {

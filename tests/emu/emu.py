@@ -78,10 +78,6 @@ class Emu:
         assert rc == 0, rc
         return (out[:m[0]], int(route[0])) if want_route else out[:m[0]]
 
-    def set_ordered(self, on):
-        """fold / mask passes of the memoised path in count-table slot order (the product's default) or code order"""
-        self.lib.emu_set_ordered(int(on))
-
     def unpack(self, codes, nmask, block=64):
         """unpack_kernel: 32 ASCII bytes per code pair / mask word"""
         codes = np.ascontiguousarray(codes, np.uint32); nmask = np.ascontiguousarray(nmask, np.uint32)

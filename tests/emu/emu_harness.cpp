@@ -363,29 +363,7 @@ static void build_memo(HostMemo& hm, int k, const RefTable& tb, int block) {
     }
 }
 
-// The codes in count-table slot order (memo_slot_order of rk_capi.cu): used by the fold and mask passes unless switched off.
-static int g_ordered = 1;
-struct SlotOrder { std::vector<u32> order, slot_o; bool ok = false; };
-static void build_slot_order(SlotOrder& so, const Memo& mm, const CountTable& ct, int block) {
-    so.ok = false;
-    if (!g_ordered || ct.counts == nullptr || ct.mod.d == 0 || ct.mod.d >= 0xFFFFFFFFull) return;
-    const u32 ncodes = mm.ncodes;
-    so.order.assign(ncodes, 0); so.slot_o.assign(ncodes, 0);
-    std::vector<u32> slot(ncodes), bcount(MEMO_SLOT_BUCKETS, 0), bstart(MEMO_SLOT_BUCKETS), bfill(MEMO_SLOT_BUCKETS);
-    int bits = 0; while ((1ull << bits) < ct.mod.d) ++bits;
-    const int shift = std::max(bits - 12, 0);
-    int err = 0;
-    u32 *ps = slot.data(), *pc = bcount.data(), *pst = bstart.data(), *pf = bfill.data(), *po = so.order.data(), *pso = so.slot_o.data();
-    const u64* hash = mm.hash; FastMod mod = ct.mod; int* perr = &err;
-    emu::launch(dim3(2), dim3(block), 0, [=] { memo_slot_count_kernel(hash, ncodes, mod, shift, ps, pc); });
-    emu::launch(dim3(1), dim3(1024), 0, [=] { memo_scan_kernel(pc, pst, pf, MEMO_SLOT_BUCKETS, perr); });
-    emu::launch(dim3(2), dim3(block), 0, [=] { memo_slot_scatter_kernel(ncodes, ps, shift, pst, pf, po, pso); });
-    so.ok = true;
-}
-
 extern "C" {
-
-void emu_set_ordered(int on) { g_ordered = on; }
 
 // -M pass 1 through the memoised count kernel + fold; counts must be zero-initialised by the caller
 int emu_count_memo(const char* bases, const i64* offs, i64 nseq, int k, int* counts, u64 size, int count_zeros, int wpr,
@@ -397,11 +375,7 @@ int emu_count_memo(const char* bases, const i64* offs, i64 nseq, int k, int* cou
     CountTable ct{counts, make_fastmod(size)};
     SeqBatch sb = b.view(); Memo mm = hm.mm;
     emu::launch(dim3(2), dim3(block), 0, [=] { count_memo_kernel(sb, mm, count_zeros, wpr); });
-    SlotOrder so; build_slot_order(so, mm, ct, block);
-    if (so.ok) {
-        const u32 *po = so.order.data(), *pso = so.slot_o.data();
-        emu::launch(dim3(2), dim3(block), 0, [=] { memo_fold_ordered_kernel(mm, ct, count_zeros, po, pso); });
-    } else emu::launch(dim3(2), dim3(block), 0, [=] { memo_fold_kernel(mm, ct, count_zeros); });
+    emu::launch(dim3(2), dim3(block), 0, [=] { memo_fold_kernel(mm, ct, count_zeros); });
     return 0;
 }
 
@@ -421,11 +395,7 @@ int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, con
     CountTable ct{const_cast<int*>(counts), make_fastmod(size ? size : 1)};
     if (!counts) min_occ = -1;
     Memo mm = hm.mm;
-    SlotOrder so; if (min_occ >= 0) build_slot_order(so, mm, ct, block);
-    if (so.ok) {
-        const u32 *po = so.order.data(), *pso = so.slot_o.data();
-        emu::launch(dim3(2), dim3(block), 0, [=] { memo_apply_occ_ordered_kernel(mm, ct, min_occ, po, pso); });
-    } else emu::launch(dim3(2), dim3(block), 0, [=] { memo_apply_occ_kernel(mm, ct, min_occ); });
+    emu::launch(dim3(2), dim3(block), 0, [=] { memo_apply_occ_kernel(mm, ct, min_occ); });
     SeqBatch sb = b.view();
     RefTable tb = ht.tb;
     std::vector<int> redo((size_t)std::max<i64>(nreads, 1)); int redo_count = 0;

@@ -194,28 +194,6 @@ def test_memo_count_and_min_occ(emu, oracle):
     _memo_case(emu, oracle, refs[:4], reads, 8, 200, counts=c, min_occ=30, path=4)     # falls back to the warp kernel
 
 
-def test_memo_fold_and_mask_in_code_order_too(emu, oracle):
-    """The fold and -M mask passes walk the codes in count-table slot order by default (memo_slot_order); the code-order
-    kernels that serve tables of 2^32 slots or more give the same table and the same records."""
-    _, refs, _ = load_sequences([data_path("new_refs.fa.gz")])
-    _, reads, _ = load_sequences([data_path("mix2k.fq.gz")])
-    reads = reads[:12] + [b"N" * 40, b"ACGTTGCA" * 30]
-    try:
-        for on in (1, 0):
-            emu.set_ordered(on)
-            for size in (10_007, 1 << 16, 3):
-                c1 = np.zeros(size, np.int32)
-                emu.count_memo(reads, 8, c1, count_zeros=True, wpr=1)
-                c2 = np.zeros(size, np.int32)
-                oracle.count_batch(reads, [8], c2, valid_only=False)
-                assert np.array_equal(c1, c2), (on, size)
-            c = np.zeros(10_007, np.int32)
-            oracle.count_batch(reads, [8], c)
-            _memo_case(emu, oracle, refs[:4], reads, 8, 200, counts=c, min_occ=20, path=0)
-    finally:
-        emu.set_ordered(1)
-
-
 def test_sketch_shard_kernels(emu, oracle):
     """rkg_sketch_shard's histogram / pick / emit / sort kernels == minhashes(calc_hashes()) of the oracle: more windows
     than s, fewer than s, invalid bases, a period-4 repeat whose few hashes occur thousands of times, and a middle shard."""
