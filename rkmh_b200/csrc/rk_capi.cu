@@ -103,8 +103,6 @@ struct rkg_ctx {
     int pack_threads = 1;
     void* stage[NSLOTS] = {};
     size_t stage_cap[NSLOTS] = {};
-    DevBuf part_entries, part_cursor;    // partitioned counting (count_part_kernel): bucket arrays and their cursors
-    int count_part = -1;                 // RKMH_COUNT_PART: 0 never, 1 always, unset: batches of 8 M bases or more
     DevBuf shard_scan, shard_cnt;        // rkg_sketch_shard: kept hashes and counters of the one-pass route
     cudaStream_t copy_stream = nullptr;  // rkg_sketch_shard: the shard's pieces arrive here while earlier pieces are hashed
     cudaEvent_t copy_event = nullptr;
@@ -495,30 +493,6 @@ int launch_count(rkg_ctx* ctx, rkg_batch* b, CountTable ct, int count_zeros) {
         const int wpr = (b->total / b->nseq > 2048) ? 8 : 1;            // a block per long read, a warp per short one
         const i64 teams = (b->nseq + 0) * 1;
         const int grid = (int)std::min<i64>((teams * wpr + 7) / 8, (i64)ctx->sm_count * 8);
-        // large batches: partition the windows by code first, count each partition in shared memory (rk_memo.cuh)
-        const size_t stage_smem = (size_t)PART_STAGE_ENTRIES * 2, hist_smem = (size_t)std::min<u32>(ctx->memo.ncodes, 1u << PART_CODE_BITS) * 4;
-        if (ctx->count_part != 0 && (ctx->count_part > 0 || b->total >= (8LL << 20)) && stage_smem + 4096 <= ctx->smem_optin &&
-            hist_smem + 1024 <= ctx->smem_optin) {
-            PartBuf pb;
-            pb.nb = (int)std::max<u32>(1u, ctx->memo.ncodes >> PART_CODE_BITS);
-            pb.cap = (b->total + b->total / 2) / pb.nb + 4096;
-            CK(ctx->part_entries.ensure(sizeof(unsigned short) * (size_t)pb.nb * (size_t)pb.cap));
-            CK(ctx->part_cursor.ensure(sizeof(unsigned long long) * PART_MAX_BUCKETS));
-            pb.entries = ctx->part_entries.as<unsigned short>();
-            pb.cursor = ctx->part_cursor.as<unsigned long long>();
-            CK(cudaMemsetAsync(pb.cursor, 0, sizeof(unsigned long long) * PART_MAX_BUCKETS, b->stream));
-            CK(cudaFuncSetAttribute(count_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_smem));
-            CK(cudaFuncSetAttribute(count_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-            const int pgrid = (int)std::max<i64>(1, std::min<i64>((teams * wpr + 15) / 16, (i64)ctx->sm_count));
-            {
-                Timed t(ctx, b->stream, K_COUNT_MEMO);
-                count_part_kernel<<<pgrid, 512, stage_smem, b->stream>>>(seq_view(b), ctx->memo, count_zeros, wpr, pb);
-                count_hist_kernel<<<std::min(pb.nb, ctx->sm_count), 1024, hist_smem, b->stream>>>(ctx->memo, pb);
-                ++ctx->launches;
-            }
-            CK(cudaGetLastError());
-            return RKG_OK;
-        }
         l2_window(ctx, b->stream, ctx->memo.code_counts, sizeof(int) * (size_t)ctx->memo.ncodes);
         {
             Timed t(ctx, b->stream, K_COUNT_MEMO);
@@ -865,7 +839,6 @@ int rkg_create(int device, rkg_ctx** out) {
     ctx->device = device;
     { const char* nm = getenv("RKMH_NO_MEMO"); ctx->memo_enabled = !(nm && nm[0] && nm[0] != '0'); }
     { const char* nm = getenv("RKMH_NO_SIEVE"); ctx->sieve_enabled = !(nm && nm[0] && nm[0] != '0'); }
-    { const char* nm = getenv("RKMH_COUNT_PART"); if (nm && nm[0]) ctx->count_part = atoi(nm) != 0 ? 1 : 0; }
     { const char* nm = getenv("RKMH_SHARD_TWO_PASS"); ctx->shard_two_pass = nm && nm[0] && nm[0] != '0'; }
     { const char* nm = getenv("RKMH_GROUP_KERNEL"); ctx->group_kernel = nm && nm[0] && nm[0] != '0'; }   // round-1 Murmur fast path (A/B timing)
     ctx->sm_count = prop.multiProcessorCount;
@@ -903,7 +876,7 @@ void rkg_destroy(rkg_ctx* ctx) {
     for (int i = 0; i < NSLOTS; ++i) if (ctx->h2d_done[i]) cudaEventDestroy(ctx->h2d_done[i]);
     if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    for (DevBuf* d : {&ctx->part_entries, &ctx->part_cursor, &ctx->shard_scan, &ctx->shard_cnt, &ctx->depth_keys, &ctx->depth_counts, &ctx->depth_zero, &ctx->hash_lut, &ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
+    for (DevBuf* d : {&ctx->shard_scan, &ctx->shard_cnt, &ctx->depth_keys, &ctx->depth_counts, &ctx->depth_zero, &ctx->hash_lut, &ctx->read_counts, &ctx->ref_counts, &ctx->ref_sketches, &ctx->ref_lens, &ctx->tb_entries,
                       &ctx->tb_maxmult, &ctx->tb_dupbase, &ctx->tb_dupbits, &ctx->tb_filter, &ctx->tb_cursor,
                       &ctx->memo_tab, &ctx->memo_ref, &ctx->memo_hash, &ctx->memo_counts, &ctx->memo_tmp, &ctx->memo_misc,
                       &ctx->memo_sieve, &ctx->memo_cmap})

@@ -64,31 +64,6 @@ RK_D u32 warp_max(u32 v) { return __reduce_max_sync(0xffffffffu, v); }
 RK_D u32 warp_or(u32 v) { return __reduce_or_sync(0xffffffffu, v); }
 #endif
 
-// ++ of a 32-bit word of shared memory at shared-window address `saddr` (the address conversion of a generic pointer
-// is not repeated at every use)
-RK_D void smem_inc(u32* base, u32 saddr_base, u32 idx) {
-#ifdef RK_EMU
-    (void)saddr_base;
-    atomicAdd(&base[idx], 1u);
-#else
-    (void)base;
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr_base + 4u * idx) : "memory");
-#endif
-}
-RK_D u32 smem_addr(const void* p) {
-#ifdef RK_EMU
-    (void)p;
-    return 0u;
-#else
-    return (u32)__cvta_generic_to_shared(p);
-#endif
-}
-// zero `words` (a multiple of 4) 32-bit words at the 16-byte aligned p, the whole block
-RK_D void block_zero(u32* p, int words) {
-    uint4* v = reinterpret_cast<uint4*>(p);
-    for (int i = threadIdx.x; i < words / 4; i += blockDim.x) v[i] = make_uint4(0u, 0u, 0u, 0u);
-}
-
 // Exactly the bytes canonical() accepts (valid_dna[], mkmh.hpp:137-152) as one bit test: A C G T a c g t.
 RK_D bool memo_base_invalid(u32 ch) {
     const u32 u = (ch & 0xDFu) - 65u;                       // 'A' -> 0 ... 'Z' -> 25 for either case
@@ -335,125 +310,6 @@ count_memo_kernel(SeqBatch sb, Memo mm, int count_zeros, int wpr) {
     if (count_zeros) {
         inv = warp_sum(inv);
         if (lane == 0 && inv) atomicAdd(mm.inval, inv);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Partitioned counting (-M pass 1 of large batches).  count_memo_kernel is bound by the L2's atomic units: one
-// atomicAdd per window, on a 64 MB table, is all it does (ncu: LTS throughput 74 %, issue 16 %).  Counting does not need
-// atomics on global memory at all if the windows are first PARTITIONED by the top bits of their code:
-//
-//   count_part_kernel   streams the reads like count_memo_kernel, but appends each window's code (its low 15 bits, as u16)
-//                       to one of nb = ncodes / 2^15 buckets: first into the block's shared-memory staging (one
-//                       shared-memory atomic per window), then, every PART_QUOTA windows per warp, bucket by bucket into
-//                       the global bucket arrays with coalesced stores -- one GLOBAL atomic (the bucket's cursor) per
-//                       bucket and step instead of one per window.  An entry that finds its staging row or its global
-//                       bucket full is counted straight into code_counts (exact either way).
-//   count_hist_kernel   one block per bucket: the bucket's 2^15 counters live in 128 KB of shared memory, every entry is one
-//                       shared-memory increment, the non-zero counters are then ADDED to code_counts with plain coalesced
-//                       read-modify-writes (one block per bucket: nobody else touches that range).
-constexpr int PART_CODE_BITS = 15;
-constexpr int PART_STAGE_ENTRIES = 65536;        // u16 staging entries per block (128 KB), shared evenly by the buckets
-constexpr int PART_MAX_BUCKETS = 512;            // 4^12 / 2^15
-constexpr int PART_QUOTA = 2048;                 // windows a warp streams between two flushes (16 warps: half the staging)
-
-struct PartBuf {
-    unsigned short* entries;                     // nb rows of `cap` entries
-    unsigned long long* cursor;                  // per bucket: entries appended (may exceed cap: the rest went to code_counts)
-    i64 cap;
-    int nb;
-};
-
-__global__ void __launch_bounds__(512, 1)
-count_part_kernel(SeqBatch sb, Memo mm, int count_zeros, int wpr, PartBuf pb) {
-#ifdef RK_EMU
-    unsigned short* stage = reinterpret_cast<unsigned short*>(EMU_DYN_SMEM());
-#else
-    extern __shared__ __align__(16) unsigned char dsm[];
-    unsigned short* stage = reinterpret_cast<unsigned short*>(dsm);
-#endif
-    __shared__ u32 scount[PART_MAX_BUCKETS];
-    __shared__ int s_more;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
-    const int nb = pb.nb;
-    const u32 cap = (u32)(PART_STAGE_ENTRIES / nb);
-    const i64 gw = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((i64)gridDim.x * blockDim.x) >> 5;
-    const i64 nteams = nw / wpr;
-    const int wt = (int)(gw % wpr);
-    i64 s = gw / wpr;                                        // this warp's next read
-    u32 inv = 0;
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) scount[i] = 0;
-    for (;;) {
-        if (threadIdx.x == 0) s_more = 0;
-        __syncthreads();
-        // ---- append: this warp's reads until its quota of windows is streamed -------------------------------------
-        i64 done = 0;
-        while (s < sb.nseq && done < PART_QUOTA) {
-            const i64 beg = sb.offs[s] - sb.base0, len = sb.offs[s + 1] - sb.offs[s];
-            const i64 n = nkmers(len, mm.k);
-            const i64 per = ((((n + 31) >> 5) + wpr - 1) / wpr) << 5;
-            const i64 s0 = (i64)wt * per, s1 = min(n, s0 + per);
-            memo_stream(sb.bases + beg, len, mm.k, s0, s1, lane, [&](u32 code, bool in, bool valid) {
-                if (valid) {
-                    const u32 b = code >> PART_CODE_BITS;
-                    const u32 pos = atomicAdd(&scount[b], 1u);
-                    if (pos < cap) stage[b * cap + pos] = (unsigned short)(code & ((1u << PART_CODE_BITS) - 1u));
-                    else atomicAdd(&mm.code_counts[code], 1);
-                } else if (in) ++inv;
-            });
-            done += s1 > s0 ? s1 - s0 : 1;
-            s += nteams;
-        }
-        if (lane == 0 && s < sb.nseq) s_more = 1;
-        __syncthreads();
-        // ---- flush: bucket by bucket, a warp per bucket, coalesced -------------------------------------------------
-        for (int b = wib; b < nb; b += nwb) {
-            const u32 cnt = min(scount[b], cap);
-            if (cnt == 0) continue;
-            unsigned long long gpos = 0;
-            if (lane == 0) gpos = atomicAdd(&pb.cursor[b], (unsigned long long)cnt);
-            gpos = __shfl_sync(0xffffffffu, gpos, 0);
-            unsigned short* dst = pb.entries + (i64)b * pb.cap;
-            for (u32 i = lane; i < cnt; i += 32) {
-                const unsigned short e = stage[b * cap + i];
-                const unsigned long long at = gpos + i;
-                if (at < (unsigned long long)pb.cap) dst[at] = e;
-                else atomicAdd(&mm.code_counts[((u32)b << PART_CODE_BITS) | e], 1);
-            }
-            __syncwarp();
-            if (lane == 0) scount[b] = 0;
-        }
-        const int more = s_more;
-        __syncthreads();
-        if (!more) break;
-    }
-    if (count_zeros) {
-        inv = warp_sum(inv);
-        if (lane == 0 && inv) atomicAdd(mm.inval, inv);
-    }
-}
-
-__global__ void __launch_bounds__(1024, 1)
-count_hist_kernel(Memo mm, PartBuf pb) {
-#ifdef RK_EMU
-    u32* hist = reinterpret_cast<u32*>(EMU_DYN_SMEM());
-#else
-    extern __shared__ __align__(16) unsigned char dsm[];
-    u32* hist = reinterpret_cast<u32*>(dsm);
-#endif
-    const u32 width = min(mm.ncodes, 1u << PART_CODE_BITS);      // codes per bucket
-    for (int b = blockIdx.x; b < pb.nb; b += gridDim.x) {
-        const unsigned long long have = pb.cursor[b];
-        const i64 n = (i64)(have < (unsigned long long)pb.cap ? have : (unsigned long long)pb.cap);
-        if (n == 0) continue;                                    // block-uniform
-        block_zero(hist, (int)width);
-        __syncthreads();
-        const unsigned short* src = pb.entries + (i64)b * pb.cap;
-        for (i64 i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[src[i]], 1u);
-        __syncthreads();
-        int* out = mm.code_counts + ((i64)b << PART_CODE_BITS);
-        for (u32 i = threadIdx.x; i < width; i += blockDim.x) { const u32 v = hist[i]; if (v) out[i] += (int)v; }
-        __syncthreads();
     }
 }
 
@@ -1026,6 +882,31 @@ classify_memo_sieve_kernel(SeqBatch sb, int s, Memo mm, RefTable tb,
 //            exactly like the Murmur path does (copy number of a repeated hash from a per-block set of table slots).
 //
 // Dynamic shared memory (u32 units): [nwarps x (lcap + 32) lists][MEMO_HIST_WORDS histogram][hs_cap keys][hs_cap counts][rpad counters]
+// ++ of a 32-bit word of shared memory at shared-window address `saddr` (the address conversion of a generic pointer
+// is not repeated at every use)
+RK_D void smem_inc(u32* base, u32 saddr_base, u32 idx) {
+#ifdef RK_EMU
+    (void)saddr_base;
+    atomicAdd(&base[idx], 1u);
+#else
+    (void)base;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr_base + 4u * idx) : "memory");
+#endif
+}
+RK_D u32 smem_addr(const void* p) {
+#ifdef RK_EMU
+    (void)p;
+    return 0u;
+#else
+    return (u32)__cvta_generic_to_shared(p);
+#endif
+}
+// zero `words` (a multiple of 4) 32-bit words at the 16-byte aligned p, the whole block
+RK_D void block_zero(u32* p, int words) {
+    uint4* v = reinterpret_cast<uint4*>(p);
+    for (int i = threadIdx.x; i < words / 4; i += blockDim.x) v[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 struct MemoBlockScratch { u32 part[32]; u32 bin, before; int nz, take, kept, over; ArgmaxScratch as; };
 #ifndef MEMO_DELAY_ROUNDS
 #define MEMO_DELAY_ROUNDS 4

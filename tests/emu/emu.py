@@ -111,15 +111,10 @@ class Emu:
         return hits[:len(reads)], rsk, rl, int(redo[0])
 
     # ---- memoised path (rk_memo.cuh) ----
-    def count_memo(self, seqs, k, counts, count_zeros=False, wpr=1, block=64, part=False, bucket_cap=0):
-        """-M pass 1 on the memoised path; part: through count_part_kernel + count_hist_kernel (partitioned counting)"""
+    def count_memo(self, seqs, k, counts, count_zeros=False, wpr=1, block=64):
         bases, offs = pack(seqs)
-        if part:
-            rc = self.lib.emu_count_memo_part(bases.ctypes.data, offs.ctypes.data, len(seqs), int(k), counts.ctypes.data,
-                                              C.c_uint64(counts.size), int(count_zeros), int(wpr), block, C.c_int64(bucket_cap))
-        else:
-            rc = self.lib.emu_count_memo(bases.ctypes.data, offs.ctypes.data, len(seqs), int(k), counts.ctypes.data,
-                                         C.c_uint64(counts.size), int(count_zeros), int(wpr), block)
+        rc = self.lib.emu_count_memo(bases.ctypes.data, offs.ctypes.data, len(seqs), int(k), counts.ctypes.data,
+                                     C.c_uint64(counts.size), int(count_zeros), int(wpr), block)
         assert rc == 0
 
     def classify_memo(self, refs, reads, k, s, counts=None, min_occ=-1, path=1, block=64, vcap_limit=0):

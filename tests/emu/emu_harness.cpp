@@ -379,28 +379,6 @@ int emu_count_memo(const char* bases, const i64* offs, i64 nseq, int k, int* cou
     return 0;
 }
 
-// the same through the partitioned route (count_part_kernel + count_hist_kernel); bucket_cap > 0 caps the global bucket rows
-// (forces the overflow path that counts straight into the per-code table)
-int emu_count_memo_part(const char* bases, const i64* offs, i64 nseq, int k, int* counts, u64 size, int count_zeros, int wpr,
-                        int block, i64 bucket_cap) {
-    int ks[1] = {k}; int kcsel; KList kl = make_klist(ks, 1, &kcsel);
-    HostBatch b; fill_batch(b, bases, offs, nseq, kl, block);
-    HostMemo hm; RefTable none{}; build_memo(hm, k, none, block);
-    if (hm.err) return -1;
-    CountTable ct{counts, make_fastmod(size)};
-    SeqBatch sb = b.view(); Memo mm = hm.mm;
-    PartBuf pb;
-    pb.nb = (int)std::max<u32>(1u, mm.ncodes >> PART_CODE_BITS);
-    pb.cap = bucket_cap > 0 ? bucket_cap : (b.total + b.total / 2) / pb.nb + 4096;
-    std::vector<unsigned short> entries((size_t)pb.nb * (size_t)pb.cap);
-    std::vector<unsigned long long> cursor(PART_MAX_BUCKETS, 0);
-    pb.entries = entries.data(); pb.cursor = cursor.data();
-    emu::launch(dim3(2), dim3(block), (size_t)PART_STAGE_ENTRIES * 2, [=] { count_part_kernel(sb, mm, count_zeros, wpr, pb); });
-    emu::launch(dim3(2), dim3(block), (size_t)std::min<u32>(mm.ncodes, 1u << PART_CODE_BITS) * 4, [=] { count_hist_kernel(mm, pb); });
-    emu::launch(dim3(2), dim3(block), 0, [=] { memo_fold_kernel(mm, ct, count_zeros); });
-    return 0;
-}
-
 // path: 0 = block kernel for every read, 1 = warp kernel + block kernel on its redo list.  vcap_limit > 0 caps the
 // per-warp shared-memory lists of the block kernel (forces its second attempt with global lists).
 int emu_classify_memo(const char* ref_bases, const i64* ref_offs, int nrefs, const char* bases, const i64* offs, i64 nreads,

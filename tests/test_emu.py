@@ -194,29 +194,6 @@ def test_memo_count_and_min_occ(emu, oracle):
     _memo_case(emu, oracle, refs[:4], reads, 8, 200, counts=c, min_occ=30, path=4)     # falls back to the warp kernel
 
 
-@pytest.mark.parametrize("k,wpr,block", [(8, 1, 64), (10, 2, 128), (9, 1, 256)])
-def test_partitioned_counting(emu, oracle, k, wpr, block):
-    """count_part_kernel + count_hist_kernel (windows partitioned by code, counted in shared memory) == the oracle's
-    count table: ragged reads with invalid bases, a read of one repeated k-mer longer than a staging row (staging overflow
-    path), several steps per warp, and global bucket rows capped to a few entries (bucket overflow path)."""
-    rng = np.random.default_rng(k)
-    def rnd(n, pn=0.02):
-        return rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=n, p=[(1 - pn) / 4] * 4 + [pn]).tobytes()
-    reads = [rnd(int(n)) for n in rng.integers(5, 700, size=60)] + [b"A" * 9000, rnd(7000), b"", b"ACG", b"N" * 100, b"ACGT" * 1500]
-    size = 10_007
-    want = np.zeros(size, np.int32)
-    oracle.count_batch(reads, [k], want, valid_only=False)
-    for cap in (0, 7):
-        got = np.zeros(size, np.int32)
-        emu.count_memo(reads, k, got, count_zeros=True, wpr=wpr, block=block, part=True, bucket_cap=cap)
-        assert np.array_equal(got, want), (k, cap)
-    want = np.zeros(size, np.int32)
-    oracle.count_batch(reads, [k], want)
-    got = np.zeros(size, np.int32)
-    emu.count_memo(reads, k, got, wpr=wpr, block=block, part=True)
-    assert np.array_equal(got, want)
-
-
 def test_sketch_shard_kernels(emu, oracle):
     """rkg_sketch_shard's histogram / pick / emit / sort kernels == minhashes(calc_hashes()) of the oracle: more windows
     than s, fewer than s, invalid bases, a period-4 repeat whose few hashes occur thousands of times, and a middle shard."""
