@@ -35,7 +35,9 @@ class Emu:
         lib.emu_count.argtypes = [P, P, L, P, I, P, U, I, I]
         lib.emu_sketch.argtypes = [P, P, L, P, I, I, P, U, I, I, P, P, I, I]
         lib.emu_merge.argtypes = [P, P, I, I, P, P, I, I]
-        lib.emu_sketch_shard.argtypes = [P, L, L, I, I, P, P, I]
+        lib.emu_sketch_shard.argtypes = [P, L, L, I, I, P, P, I, I, I, P]
+        lib.emu_unpack.argtypes = [P, P, P, L, I]
+        lib.emu_call_depth.argtypes = [P, P, L, P, L, I, P, P, L, P, I]
         lib.emu_classify.argtypes = [P, P, I, P, P, L, P, I, I, P, U, I, I, I, I, I, I, P, P, P, P]
         lib.emu_count_memo.argtypes = [P, P, L, I, P, U, I, I, I]
         lib.emu_classify_memo.argtypes = [P, P, I, P, P, L, I, I, P, U, I, I, I, I, P, P]
@@ -77,6 +79,19 @@ class Emu:
                                        m.ctypes.data, block, int(scan_first), int(pieces), route.ctypes.data)
         assert rc == 0, rc
         return (out[:m[0]], int(route[0])) if want_route else out[:m[0]]
+
+    def call_depth(self, reads, ref, k, windows, block=64):
+        """rk_call.cuh: (depth of every window of ref, depth of the 4 k single-base alternatives of the listed windows)"""
+        bases, offs = pack(reads)
+        refa = np.ascontiguousarray(np.frombuffer(ref, np.uint8))
+        n = max(len(ref) - k, 0)
+        depth = np.zeros(max(n, 1), np.int32)
+        win = np.ascontiguousarray(windows, np.int64)
+        resc = np.zeros(max(win.size * 4 * k, 1), np.int32)
+        rc = self.lib.emu_call_depth(bases.ctypes.data, offs.ctypes.data, len(reads), refa.ctypes.data, C.c_int64(refa.size), int(k),
+                                     depth.ctypes.data, win.ctypes.data, C.c_int64(win.size), resc.ctypes.data, block)
+        assert rc == 0
+        return depth[:n], resc[:win.size * 4 * k].reshape(win.size, 4 * k)
 
     def unpack(self, codes, nmask, block=64):
         """unpack_kernel: 32 ASCII bytes per code pair / mask word"""

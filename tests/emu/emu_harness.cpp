@@ -12,6 +12,7 @@ EMU_DEFINE_STATE
 #include "../../rkmh_b200/csrc/rk_kernels.cuh"
 #include "../../rkmh_b200/csrc/rk_memo.cuh"
 #include "../../rkmh_b200/csrc/rk_warp.cuh"
+#include "../../rkmh_b200/csrc/rk_call.cuh"
 
 using namespace rk;
 
@@ -233,6 +234,36 @@ int emu_sketch_shard(const char* bases, i64 nbytes, i64 n, int k, int s, u64* ou
     const int m = (int)std::min<u64>(kept, (u64)s);
     std::copy(cand.begin(), cand.begin() + m, out);
     *out_len = m;
+    return 0;
+}
+
+// `rkmh call` on the device (rk_call.cuh): the exact hash -> depth table of the reads' windows, the depth of every window of
+// `ref`, and for the listed windows of `ref` the depth of every single-base substitution / deletion (4 k values per window)
+int emu_call_depth(const char* bases, const i64* offs, i64 nreads, const char* ref, i64 ref_len, int k, int* depth,
+                   const i64* windows, i64 nwin, int* rescue, int block) {
+    int ks[1] = {k}; int kcsel; KList kl = make_klist(ks, 1, &kcsel);
+    HostBatch b; fill_batch(b, bases, offs, nreads, kl, block);
+    const u32 cap = (u32)next_pow2(std::max<i64>(2 * b.max_ntotal * std::max<i64>(nreads, 1), 64));
+    std::vector<u64> keys(cap, 0); std::vector<u32> counts(cap, 0); unsigned long long zero = 0;
+    DepthTable dt{keys.data(), counts.data(), &zero, cap - 1};
+    SeqBatch sb = b.view();
+    dispatch(kcsel, [&](auto tag) {
+        constexpr int KS = decltype(tag)::value;
+        emu::launch(dim3(2), dim3(block), 0, [=] { depth_add_kernel<KS>(sb, kl, dt); });
+    });
+    const i64 roffs[2] = {0, ref_len};
+    HostBatch rb; fill_batch(rb, ref, roffs, 1, kl, block);
+    SeqBatch rsb = rb.view();
+    const i64 n = std::max<i64>(ref_len - k, 0);
+    dispatch(kcsel, [&](auto tag) {
+        constexpr int KS = decltype(tag)::value;
+        emu::launch(dim3(2), dim3(block), 0, [=] { depth_lookup_kernel<KS>(rsb, kl, dt, n, depth); });
+    });
+    const unsigned char* rseq = reinterpret_cast<const unsigned char*>(ref);
+    dispatch(kl.kv[0], [&](auto tag) {
+        constexpr int KV = decltype(tag)::value < NUM_KV ? decltype(tag)::value : 0;
+        emu::launch(dim3(2), dim3(block), 0, [=] { depth_rescue_kernel<KV>(rseq, ref_len, kl, dt, windows, nwin, rescue); });
+    });
     return 0;
 }
 

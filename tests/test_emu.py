@@ -194,6 +194,54 @@ def test_memo_count_and_min_occ(emu, oracle):
     _memo_case(emu, oracle, refs[:4], reads, 8, 200, counts=c, min_occ=30, path=4)     # falls back to the warp kernel
 
 
+@pytest.mark.parametrize("k", [9, 16, 24])
+def test_call_depth_kernels(emu, oracle, k):
+    """rk_call.cuh (`rkmh call`, src/rkmh.cpp:1570-1858): the exact k-mer depth table of the reads, the depth of every window
+    of the reference, and the depth of every single-base substitution (rotate_snps order) and deletion of chosen windows,
+    against a dictionary built from the oracle's hashes."""
+    from collections import Counter
+    rng = np.random.default_rng(k)
+    ref = bytearray(rng.choice(np.frombuffer(b"ACGT", np.uint8), size=600).tobytes())
+    ref[100] = ord("N"); ref[300:303] = b"acg"
+    ref = bytes(ref)
+    up = oracle.to_upper(ref)
+    reads = []
+    for _ in range(30):
+        a = int(rng.integers(0, 450)); r = bytearray(up[a:a + int(rng.integers(k + 1, 150))])
+        if rng.random() < 0.5:
+            r[int(rng.integers(0, len(r)))] = ord("ACGT"[int(rng.integers(0, 4))])
+        reads.append(bytes(r))
+    reads += [b"N" * 40, b"ACG"]
+    table = Counter()
+    for r in reads:
+        table.update(int(h) for h in oracle.calc_hashes(r, [k]))
+    windows = np.array([0, 1, 57, 99, 250, 299, len(ref) - k - 1], np.int64)
+    depth, resc = emu.call_depth(reads, up, k, windows)
+    want = np.array([table.get(int(h), 0) for h in oracle.calc_hashes(up, [k])], np.int32)
+    assert np.array_equal(depth, want)
+    rot = {"A": "CTG", "C": "TGA", "T": "CGA", "G": "ACT"}
+    def dep(kmer):
+        return table.get(oracle.calc_hash(kmer) if oracle.canonical(kmer) else 0, 0)
+    for wi, j in enumerate(windows):
+        j = int(j)
+        for a in range(4 * k):
+            if a < 3 * k:
+                pos, which = divmod(a, 3)
+                orig = chr(up[j + pos])
+                if orig not in rot:
+                    exp = -1
+                else:
+                    km = bytearray(up[j:j + k]); km[pos] = ord(rot[orig][which]); exp = dep(bytes(km))
+            else:
+                d = a - 3 * k + 1
+                if j == 0:
+                    exp = -1
+                else:
+                    kp = up[j - 1:j + k]
+                    exp = dep(kp[:d] + kp[d + 1:])
+            assert resc[wi, a] == exp, (k, j, a)
+
+
 def test_sketch_shard_kernels(emu, oracle):
     """rkg_sketch_shard's histogram / pick / emit / sort kernels == minhashes(calc_hashes()) of the oracle: more windows
     than s, fewer than s, invalid bases, a period-4 repeat whose few hashes occur thousands of times, and a middle shard."""
