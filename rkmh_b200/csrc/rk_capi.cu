@@ -109,6 +109,7 @@ struct rkg_ctx {
     bool shard_two_pass = false;         // RKMH_SHARD_TWO_PASS=1: always take the exact two-pass route (tests, comparison)
     cudaEvent_t h2d_done[NSLOTS] = {};   // adaptive mode: recorded after a chunk's host-to-device copies
     int64_t xfer[4] = {0, 0, 0, 0};       // rkg_transfer_stats
+    double pack_max_ratio = 1.25;        // pack only while packing a chunk takes at most this many times its plain copy (RKMH_PACK_MAX_RATIO)
     double pack_lead = 0.75;             // pack when the queued copies last at least this share of the packing time (RKMH_PACK_LEAD)
     double pack_ms_per_byte = 0.0, dma_ms_per_byte = 0.0;      // adaptive mode: measured on this context's first chunks
     // memoised path (single k <= MEMO_MAX_K, rk_memo.cuh)
@@ -250,6 +251,13 @@ fixed_offs_kernel(i64* __restrict__ offs, i64 n, i64 base0, i64 len) {
 
 // Copy reads [r0, r1) of the caller's buffers into the batch (asynchronous on b->stream); packing is done on demand.
 // offs == nullptr: every read has `fixed_len` bases and read i starts at bases[i * fixed_len].
+// Adaptive packed transfer: mixing packed and plain chunks pays when the host packs a chunk in about the time the link
+// takes to send it as it is.  When packing is much slower (few threads per rank, or the ranks of a full box sharing the
+// host's memory bandwidth with each other's copies) only a few chunks could be packed, and the packer's memory traffic
+// slows the copies down by more than those chunks save: measured at N = 4 and N = 8.  Then every
+// chunk goes plain.
+bool pack_pays(const rkg_ctx* ctx) { return ctx->pack_ms_per_byte <= ctx->pack_max_ratio * ctx->dma_ms_per_byte; }
+
 // pinned staging of a slot for the packed transfer
 int ensure_stage(rkg_ctx* ctx, int slot, size_t bytes) {
     if (ctx->stage_cap[slot] >= bytes) return RKG_OK;
@@ -1240,7 +1248,7 @@ static int host_pipeline(rkg_ctx* ctx, const char* bases, const int64_t* offs, i
             } else if (ctx->pack_ms_per_byte == 0.0) {
                 pack_mode = 1;                               // second chunk: packed, to time the packer
             } else {
-                pack_mode = lead >= ctx->pack_lead * ctx->pack_ms_per_byte * bytes ? 1 : 0;
+                pack_mode = (pack_pays(ctx) && lead >= ctx->pack_lead * ctx->pack_ms_per_byte * bytes) ? 1 : 0;
             }
             if (pack_mode != 2) {
                 const bool first_use = b->bases.cap == 0;   // the slot's device buffers are allocated inside: not a timing sample
@@ -1266,6 +1274,10 @@ static int host_pipeline(rkg_ctx* ctx, const char* bases, const int64_t* offs, i
         }
     }
     for (int i = 0; i < ns; ++i) CK(cudaStreamSynchronize(ctx->slots[i]->stream));
+    if (adaptive && getenv("RKMH_PACK_DEBUG"))
+        fprintf(stderr, "rkmh: adaptive transfer: link %.3f ms, packer %.3f ms per 64 MB (ratio %.2f, packing %s)\n",
+                ctx->dma_ms_per_byte * 67108864.0, ctx->pack_ms_per_byte * 67108864.0,
+                ctx->dma_ms_per_byte > 0 ? ctx->pack_ms_per_byte / ctx->dma_ms_per_byte : 0.0, pack_pays(ctx) ? "on" : "off");
     return RKG_OK;
 }
 
@@ -1326,6 +1338,7 @@ int rkg_set_host_pack(rkg_ctx* ctx, int enable, int threads) {
     ctx->pack_threads = threads > 0 ? std::min(threads, 64) : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     ctx->pack_ms_per_byte = 0.0; ctx->dma_ms_per_byte = 0.0;                // measured again on the next chunks
     if (const char* e = getenv("RKMH_PACK_LEAD")) ctx->pack_lead = atof(e);
+    if (const char* e = getenv("RKMH_PACK_MAX_RATIO")) ctx->pack_max_ratio = atof(e);
     return RKG_OK;
 }
 
@@ -1818,7 +1831,7 @@ int rkg_sketch_shard(rkg_ctx* ctx, const char* bases, int64_t nbytes, int64_t km
             }
             if (ctx->dma_ms_per_byte == 0.0) time_link = true;
             else if (ctx->pack_ms_per_byte == 0.0) pack = true;
-            else pack = lead >= ctx->pack_lead * ctx->pack_ms_per_byte * (double)plen;
+            else pack = pack_pays(ctx) && lead >= ctx->pack_lead * ctx->pack_ms_per_byte * (double)plen;
         }
         if (pack) {
             const int st = npiece % NSLOTS;
