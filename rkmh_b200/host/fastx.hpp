@@ -14,27 +14,121 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <cstdlib>
 #include <cstring>
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace rkhost {
+
+// Blocked gzip (BGZF: bgzip, samtools, htslib): a series of gzip members of at most 64 KB, each of which states its
+// compressed size in an extra field ('B' 'C', RFC 1952 FEXTRA), so the members can be found without inflating anything and
+// inflated by several threads at once.  zlib alone reads such a file as one stream on one thread (about 0.3 GB/s of FASTQ);
+// this reader takes batches of members and inflates them in parallel, in order.  Anything that is not BGZF from its first
+// byte on is not touched (ByteStream then uses gzopen as before).
+class BgzfReader {
+  public:
+    ~BgzfReader() { if (fp_) fclose(fp_); }
+    // true when `path` is a regular file that starts with a BGZF member
+    bool open(const char* path, int threads) {
+        fp_ = fopen(path, "rb");
+        if (!fp_) return false;
+        unsigned char h[18];
+        const bool ok = fread(h, 1, 18, fp_) == 18 && member_size(h) > 0;
+        if (!ok || fseek(fp_, 0, SEEK_SET) != 0) { fclose(fp_); fp_ = nullptr; return false; }
+        threads_ = std::max(1, std::min(threads, 32));
+        return true;
+    }
+    // the next batch of inflated bytes appended to out (up to ~256 members); false at the end of the file or on a damaged member
+    bool next(std::vector<char>& out, size_t& out_len) {
+        if (!fp_ || done_) return false;
+        struct Member { size_t in_at, in_len, out_at, out_len; };
+        std::vector<Member> ms;
+        in_.clear();
+        size_t total_out = 0;
+        while (ms.size() < 256) {
+            unsigned char h[18];
+            const size_t got = fread(h, 1, 18, fp_);
+            if (got == 0) { done_ = true; break; }
+            const long bsize = got == 18 ? member_size(h) : -1;
+            if (bsize < 26) { done_ = true; bad_ = true; break; }             // not a BGZF member: stop here (truncated / foreign data)
+            const size_t at = in_.size();
+            in_.resize(at + (size_t)bsize);
+            memcpy(in_.data() + at, h, 18);
+            if (fread(in_.data() + at + 18, 1, (size_t)bsize - 18, fp_) != (size_t)bsize - 18) { in_.resize(at); done_ = true; bad_ = true; break; }
+            const unsigned char* tail = reinterpret_cast<const unsigned char*>(in_.data()) + at + bsize - 4;
+            const size_t isize = (size_t)tail[0] | ((size_t)tail[1] << 8) | ((size_t)tail[2] << 16) | ((size_t)tail[3] << 24);
+            ms.push_back(Member{at, (size_t)bsize, total_out, isize});
+            total_out += isize;
+        }
+        if (ms.empty()) return false;
+        if (out.size() < out_len + total_out) out.resize(out_len + total_out);
+        char* dst = out.data() + out_len;
+        std::atomic<bool> fail{false};
+        auto work = [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i) {
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(in_.data()) + ms[i].in_at;
+                const size_t xlen = (size_t)src[10] | ((size_t)src[11] << 8);
+                z_stream z{};
+                if (inflateInit2(&z, -15) != Z_OK) { fail = true; return; }
+                z.next_in = const_cast<unsigned char*>(src) + 12 + xlen;
+                z.avail_in = (unsigned)(ms[i].in_len - 12 - xlen - 8);
+                z.next_out = reinterpret_cast<unsigned char*>(dst + ms[i].out_at);
+                z.avail_out = (unsigned)ms[i].out_len;
+                const int rc = inflate(&z, Z_FINISH);
+                if (!(rc == Z_STREAM_END || (rc == Z_OK && ms[i].out_len == 0) || (rc == Z_BUF_ERROR && ms[i].out_len == 0)) || z.total_out != ms[i].out_len) fail = true;
+                inflateEnd(&z);
+            }
+        };
+        const size_t nt = std::min<size_t>((size_t)threads_, ms.size());
+        if (nt <= 1) work(0, ms.size());
+        else {
+            std::vector<std::thread> th;
+            for (size_t t = 0; t < nt; ++t) th.emplace_back(work, ms.size() * t / nt, ms.size() * (t + 1) / nt);
+            for (auto& x : th) x.join();
+        }
+        if (fail) { done_ = true; bad_ = true; return false; }
+        out_len += total_out;
+        return true;
+    }
+    bool damaged() const { return bad_; }
+
+  private:
+    // total size of the BGZF member whose first 18 bytes are h, or -1
+    static long member_size(const unsigned char* h) {
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return -1;
+        const unsigned xlen = h[10] | (h[11] << 8);
+        if (xlen < 6 || h[12] != 'B' || h[13] != 'C' || h[14] != 2 || h[15] != 0) return -1;      // bgzip writes BC first
+        return (long)(h[16] | (h[17] << 8)) + 1;
+    }
+    FILE* fp_ = nullptr;
+    int threads_ = 1;
+    bool done_ = false, bad_ = false;
+    std::vector<char> in_;
+};
 
 class ByteStream {
   public:
     // "-" reads standard input (gzip or plain, like any other path)
     explicit ByteStream(const char* path, long long offset = 0) : buf_(1 << 22) {
         if (const char* e = getenv("RKMH_PARSE_BUF")) buf_.resize((size_t)std::max<long>(atol(e), 16));   // testing knob
-        fp_ = (path[0] == '-' && path[1] == 0) ? gzdopen(0, "r") : gzopen(path, "r");
+        const bool is_stdin = path[0] == '-' && path[1] == 0;
+        if (!is_stdin && offset == 0 && !getenv("RKMH_NO_BGZF")) {
+            int threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+            if (const char* e = getenv("RKMH_PARSE_THREADS")) threads = std::max(1, atoi(e));
+            if (bgzf_.open(path, threads)) { use_bgzf_ = true; return; }
+        }
+        fp_ = is_stdin ? gzdopen(0, "r") : gzopen(path, "r");
         if (fp_) gzbuffer(fp_, 1 << 20);
         if (fp_ && offset > 0 && gzseek(fp_, (z_off_t)offset, SEEK_SET) < 0) { gzclose(fp_); fp_ = nullptr; }
     }
     ~ByteStream() { if (fp_) gzclose(fp_); }
-    bool ok() const { return fp_ != nullptr; }
+    bool ok() const { return fp_ != nullptr || use_bgzf_; }
     int get() {
         if (pos_ >= len_ && fill(1) == 0) return -1;
         return (unsigned char)buf_[pos_++];
@@ -46,6 +140,10 @@ class ByteStream {
         if (pos_ > 0) { memmove(buf_.data(), buf_.data() + pos_, len_ - pos_); len_ -= pos_; pos_ = 0; }
         if (need > buf_.size()) buf_.resize(need + (need >> 1));
         while (len_ < need && !eof_) {
+            if (use_bgzf_) {
+                if (!bgzf_.next(buf_, len_)) eof_ = true;       // (grows buf_ by a batch of inflated members)
+                continue;
+            }
             const int got = gzread(fp_, buf_.data() + len_, (unsigned)std::min<size_t>(buf_.size() - len_, 1u << 30));
             if (got <= 0) eof_ = true; else len_ += (size_t)got;
         }
@@ -56,6 +154,8 @@ class ByteStream {
     bool at_eof() const { return eof_; }
   private:
     gzFile fp_ = nullptr;
+    BgzfReader bgzf_;
+    bool use_bgzf_ = false;
     std::vector<char> buf_;
     size_t pos_ = 0, len_ = 0;
     bool eof_ = false;

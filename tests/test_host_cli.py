@@ -61,6 +61,64 @@ def test_parser_odd_inputs(rkmh_bin, tmp_path):
         assert outz == out, fn
 
 
+def _bgzf(payload, block=60000, eof=True, level=6):
+    """`payload` as blocked gzip (BGZF, what bgzip / samtools write): members of at most `block` input bytes, each with its
+    compressed size in a 'BC' extra field, and the empty end-of-file member."""
+    import struct
+    import zlib
+    out = bytearray()
+    chunks = [payload[i:i + block] for i in range(0, len(payload), block)] + ([b""] if eof else [])
+    for c in chunks:
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        data = co.compress(c) + co.flush()
+        bsize = 12 + 6 + len(data) + 8
+        out += struct.pack("<4BI2BH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+        out += data + struct.pack("<II", zlib.crc32(c) & 0xFFFFFFFF, len(c) & 0xFFFFFFFF)
+    return bytes(out)
+
+
+def test_bgzf_input_is_inflated_in_parallel_and_reads_the_same(rkmh_bin, tmp_path):
+    """Blocked gzip (BGZF) input is recognised by its first member and inflated by several threads, member batches in
+    order; every other gzip file still goes through zlib's single stream.  The records must be those of the plain file:
+    members that end inside records, tiny members, one thread, a tiny parse buffer, a file without the end-of-file member,
+    a file truncated inside a member (the records before the damage, like zlib), and RKMH_NO_BGZF=1 (zlib reads BGZF too)."""
+    import gzip
+    import random
+    rnd = random.Random(5)
+    recs = []
+    for i in range(3000):
+        L = rnd.choice([30, 150, 150, 700, 9000])
+        recs.append(f"@r{i} x\n{''.join(rnd.choice('ACGTN') for _ in range(L))}\n+\n{''.join(chr(rnd.randint(33, 126)) for _ in range(L))}\n")
+    payload = "".join(recs).encode()
+    plain = tmp_path / "p.fq"
+    plain.write_bytes(payload)
+    exp = subprocess.run([rkmh_bin, "parse", str(plain)], stdout=subprocess.PIPE, check=True).stdout
+    assert exp.count(b"\n") == 3000
+    # Python's gzip module reads multi-member files: the helper above writes valid gzip
+    assert gzip.decompress(_bgzf(payload, 777)) == payload
+    for name, blob, envs in (("b60k", _bgzf(payload), [{}, {"RKMH_PARSE_THREADS": "1"}, {"RKMH_PARSE_BUF": "100"}, {"RKMH_NO_BGZF": "1"}]),
+                             ("b1k", _bgzf(payload, 1000, level=1), [{"RKMH_PARSE_THREADS": "5"}]),
+                             ("noeof", _bgzf(payload, 50000, eof=False), [{}]),
+                             ("gz", gzip.compress(payload), [{}])):
+        f = tmp_path / (name + ".fq.gz")
+        f.write_bytes(blob)
+        for env in envs:
+            out = subprocess.run([rkmh_bin, "parse", str(f)], stdout=subprocess.PIPE, check=True, env=dict(os.environ, **env)).stdout
+            assert out == exp, (name, env)
+        out = subprocess.run([rkmh_bin, "parse-stream", str(f)], stdout=subprocess.PIPE, check=True,
+                             env=dict(os.environ, RKMH_CHUNK_BYTES="20000")).stdout
+        assert out == exp, name
+    blob = _bgzf(payload)
+    cut = tmp_path / "cut.fq.gz"
+    cut.write_bytes(blob[:len(blob) * 2 // 3])
+    got = subprocess.run([rkmh_bin, "parse", str(cut)], stdout=subprocess.PIPE, check=True).stdout
+    ref = subprocess.run([rkmh_bin, "parse", str(cut)], stdout=subprocess.PIPE, check=True, env=dict(os.environ, RKMH_NO_BGZF="1")).stdout
+    lines, rlines = got.split(b"\n"), ref.split(b"\n")
+    assert 1000 < len(lines) < 3000 and exp.startswith(b"\n".join(lines[:-2]))
+    # zlib stops at the same damaged member, give or take the partial member it may have delivered
+    assert abs(len(lines) - len(rlines)) < 400
+
+
 def test_parser_fast_path_fuzz(rkmh_bin, tmp_path):
     """Well-formed four-line FASTQ takes a memchr fast path; records that deviate in any way fall back to the kseq
     state machine.  Both must agree with the Python restatement of the state machine on mutated inputs, also when the
