@@ -11,6 +11,7 @@
 //   * a truncated quality string ends the file (kseq returns -2 and the reference's loop stops).
 // Sequences are stored exactly as read: upper-casing (mkmh::to_upper) happens on the device.
 #pragma once
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -36,6 +37,8 @@ class BgzfReader {
     ~BgzfReader() { if (fp_) fclose(fp_); }
     // true when `path` is a regular file that starts with a BGZF member
     bool open(const char* path, int threads) {
+        struct stat st;
+        if (stat(path, &st) != 0 || !S_ISREG(st.st_mode)) return false;      // a FIFO or a device must not lose the bytes a probe reads
         fp_ = fopen(path, "rb");
         if (!fp_) return false;
         unsigned char h[18];

@@ -108,7 +108,16 @@ def test_bgzf_input_is_inflated_in_parallel_and_reads_the_same(rkmh_bin, tmp_pat
         out = subprocess.run([rkmh_bin, "parse-stream", str(f)], stdout=subprocess.PIPE, check=True,
                              env=dict(os.environ, RKMH_CHUNK_BYTES="20000")).stdout
         assert out == exp, name
+    # a FIFO is never probed for BGZF (the probe would eat its first bytes): zlib reads it, BGZF or not
+    import threading
+    fifo = tmp_path / "in.fifo"
+    os.mkfifo(fifo)
     blob = _bgzf(payload)
+    t = threading.Thread(target=lambda: open(fifo, "wb").write(blob), daemon=True)
+    t.start()
+    out = subprocess.run([rkmh_bin, "parse", str(fifo)], stdout=subprocess.PIPE, check=True, timeout=60).stdout
+    t.join(timeout=10)
+    assert out == exp
     cut = tmp_path / "cut.fq.gz"
     cut.write_bytes(blob[:len(blob) * 2 // 3])
     got = subprocess.run([rkmh_bin, "parse", str(cut)], stdout=subprocess.PIPE, check=True).stdout
