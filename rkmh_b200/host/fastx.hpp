@@ -17,6 +17,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cctype>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <cstdint>
@@ -34,7 +37,14 @@ namespace rkhost {
 // byte on is not touched (ByteStream then uses gzopen as before).
 class BgzfReader {
   public:
-    ~BgzfReader() { if (fp_) fclose(fp_); }
+    ~BgzfReader() {
+        if (!workers_.empty()) {
+            { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+            cv_.notify_all();
+            for (auto& t : workers_) t.join();
+        }
+        if (fp_) fclose(fp_);
+    }
     // true when `path` is a regular file that starts with a BGZF member
     bool open(const char* path, int threads) {
         struct stat st;
@@ -88,12 +98,26 @@ class BgzfReader {
                 inflateEnd(&z);
             }
         };
+        // The helpers persist for the life of the reader: creating threads maps and unmaps their stacks, and while the CUDA
+        // driver starts up on its own thread those calls queue on the process's mmap lock (a batch then took as long as
+        // zlib's single stream).
         const size_t nt = std::min<size_t>((size_t)threads_, ms.size());
         if (nt <= 1) work(0, ms.size());
         else {
-            std::vector<std::thread> th;
-            for (size_t t = 0; t < nt; ++t) th.emplace_back(work, ms.size() * t / nt, ms.size() * (t + 1) / nt);
-            for (auto& x : th) x.join();
+            while (workers_.size() + 1 < (size_t)threads_) {
+                const size_t idx = workers_.size() + 1;
+                workers_.emplace_back([this, idx] { helper(idx); });
+            }
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                job_ = [&, nt](size_t t) { if (t < nt) work(ms.size() * t / nt, ms.size() * (t + 1) / nt); };
+                pending_ = workers_.size();
+                ++gen_;
+            }
+            cv_.notify_all();
+            work(0, ms.size() / nt);                         // the caller is helper 0
+            std::unique_lock<std::mutex> lk(m_);
+            done_cv_.wait(lk, [&] { return pending_ == 0; });
         }
         if (fail) { done_ = true; bad_ = true; return false; }
         out_len += total_out;
@@ -109,10 +133,35 @@ class BgzfReader {
         if (xlen < 6 || h[12] != 'B' || h[13] != 'C' || h[14] != 2 || h[15] != 0) return -1;      // bgzip writes BC first
         return (long)(h[16] | (h[17] << 8)) + 1;
     }
+    void helper(size_t idx) {
+        unsigned long seen = 0;
+        for (;;) {
+            std::function<void(size_t)> job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                job = job_;
+            }
+            job(idx);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_cv_.notify_one();
+            }
+        }
+    }
     FILE* fp_ = nullptr;
     int threads_ = 1;
     bool done_ = false, bad_ = false;
     std::vector<char> in_;
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    std::function<void(size_t)> job_;
+    size_t pending_ = 0;
+    unsigned long gen_ = 0;
+    bool stop_ = false;
 };
 
 class ByteStream {
