@@ -37,6 +37,7 @@ class Emu:
         lib.emu_merge.argtypes = [P, P, I, I, P, P, I, I]
         lib.emu_sketch_shard.argtypes = [P, L, L, I, I, P, P, I, I, I, P]
         lib.emu_unpack.argtypes = [P, P, P, L, I]
+        lib.emu_classify_sets.argtypes = [P, P, I, P, P, L, I, P, U, I, I, I, I, P, P]
         lib.emu_call_depth.argtypes = [P, P, L, P, L, I, P, P, L, P, I]
         lib.emu_classify.argtypes = [P, P, I, P, P, L, P, I, I, P, U, I, I, I, I, I, I, P, P, P, P]
         lib.emu_count_memo.argtypes = [P, P, L, I, P, U, I, I, I]
@@ -79,6 +80,22 @@ class Emu:
                                        m.ctypes.data, block, int(scan_first), int(pieces), route.ctypes.data)
         assert rc == 0, rc
         return (out[:m[0]], int(route[0])) if want_route else out[:m[0]]
+
+    def classify_sets(self, sets, reads, k, ntypes, counts=None, min_occ=-1, block=64, hbuf_global=False):
+        """rkg_load_ref_sets + rkg_classify_sets: (hits over sets[:ntypes], counts [n, len(sets) - ntypes] of the rest)"""
+        so = np.zeros(len(sets) + 1, np.int64)
+        so[1:] = np.cumsum([len(x) for x in sets])
+        sh = np.ascontiguousarray(np.concatenate([np.asarray(x, np.uint64) for x in sets] + [np.zeros(1, np.uint64)]))
+        bases, offs = pack(reads)
+        out = np.zeros(max(len(reads), 1), HIT)
+        nextra = len(sets) - ntypes
+        extra = np.zeros((max(len(reads), 1), max(nextra, 1)), np.int32)
+        rc = self.lib.emu_classify_sets(sh.ctypes.data, so.ctypes.data, len(sets), bases.ctypes.data, offs.ctypes.data, len(reads), int(k),
+                                        counts.ctypes.data if counts is not None else None,
+                                        C.c_uint64(counts.size if counts is not None else 0), int(min_occ), int(ntypes), block,
+                                        int(hbuf_global), out.ctypes.data, extra.ctypes.data)
+        assert rc == 0
+        return out[:len(reads)], extra[:len(reads), :nextra]
 
     def call_depth(self, reads, ref, k, windows, block=64):
         """rk_call.cuh: (depth of every window of ref, depth of the 4 k single-base alternatives of the listed windows)"""

@@ -348,6 +348,48 @@ int emu_classify(const char* ref_bases, const i64* ref_offs, int nrefs, const ch
     return 0;
 }
 
+// `rkmh hpv16` on the device (rkg_load_ref_sets + rkg_classify_sets): a SET table from full hash sets (table_insert_set_kernel)
+// and the exact block kernel in set mode with an unbounded sketch size: hits over sets [0, ntypes), per-read counts of the rest
+extern "C" int emu_classify_sets(const u64* hashes, const i64* set_offs, int nsets, const char* bases, const i64* offs, i64 nreads,
+                                 int k, const int* counts, u64 size, int min_occ, int ntypes, int block, int hbuf_global, Hit* out,
+                                 int* extra) {
+    int ks[1] = {k}; int kcsel; KList kl = make_klist(ks, 1, &kcsel);
+    const i64 nent = set_offs[nsets] - set_offs[0];
+    const u32 cap = (u32)next_pow2(std::max<i64>(2 * nent, 1024));
+    RefTable tb{};
+    tb.cap_mask = cap - 1; tb.nb = (u32)((nsets + 63) / 64); tb.stride = 1 + tb.nb; tb.nrefs = (u32)nsets;
+    int flog2 = 10;
+    while (flog2 < 20 && (1LL << flog2) < 16 * nent) ++flog2;
+    tb.filter_log2 = (u32)flog2;
+    std::vector<u64> entries((size_t)cap * tb.stride, 0), dupbits(8, 0);
+    std::vector<u32> maxmult(cap, 0), dupbase(cap, 0), filter(((size_t)1 << flog2) / 32, 0);
+    tb.entries = entries.data(); tb.maxmult = maxmult.data(); tb.dup_base = dupbase.data(); tb.dup_bits = dupbits.data(); tb.filter = filter.data();
+    std::vector<i64> rel((size_t)nsets + 1);
+    for (int i = 0; i <= nsets; ++i) rel[i] = set_offs[i] - set_offs[0];
+    const u64* ph = hashes + set_offs[0]; const i64* prel = rel.data(); u32* pf = filter.data();
+    emu::launch(dim3(2), dim3(block), 0, [=] { table_insert_set_kernel(ph, prel, nsets, tb, pf); });
+    HostBatch b; fill_batch(b, bases, offs, nreads, kl, block);
+    CountTable ct{const_cast<int*>(counts), make_fastmod(size ? size : 1)};
+    if (!counts) { ct.counts = nullptr; min_occ = -1; }
+    SeqBatch sb = b.view();
+    const int s_all = 1 << 30, grid = 2;
+    const int hs_cap = next_pow2(2 * std::max<i64>(b.max_ntotal, 1));
+    const int rpad = (nsets + 63) / 64 * 64;
+    const i64 hbuf_cap = hbuf_global ? 0 : b.max_ntotal;
+    const i64 stride = hbuf_global ? std::max<i64>(b.max_ntotal, 1) : 0;
+    const size_t smem = (size_t)hbuf_cap * 8 + (size_t)hs_cap * 8 + (size_t)rpad * 4;
+    std::vector<u64> scratch((size_t)grid * (size_t)(stride + hs_cap) + 8);
+    u64* ps = scratch.data();
+    dispatch(kcsel, [&](auto tag) {
+        constexpr int KS = decltype(tag)::value;
+        emu::launch(dim3(grid), dim3(block), smem, [=] {
+            classify_block_kernel<KS>(sb, kl, s_all, ct, min_occ, tb, nullptr, nullptr, nreads, (int)hbuf_cap, hs_cap, 1, rpad, ps, stride,
+                                      out, 1, ntypes, extra);
+        });
+    });
+    return 0;
+}
+
 // ---- memoised path (rk_memo.cuh) -------------------------------------------------------------------------
 struct HostMemo {
     std::vector<u32> tab, ref, tmp, sieve;

@@ -194,6 +194,37 @@ def test_memo_count_and_min_occ(emu, oracle):
     _memo_case(emu, oracle, refs[:4], reads, 8, 200, counts=c, min_occ=30, path=4)     # falls back to the warp kernel
 
 
+@pytest.mark.parametrize("hbuf_global", [False, True])
+def test_classify_sets_kernels(emu, oracle, hbuf_global):
+    """The engine of `rkmh hpv16` (rkg_load_ref_sets + rkg_classify_sets): a set table built from FULL hash sets (with the
+    zeros and duplicates the reference's arrays carry) and the exact block kernel in set mode == the oracle's restatement of
+    src/rkmh.cpp:2643-2706 (hash_set_intersection_size for the type sets, per-read counts of the lineage sets), with and
+    without a -M mask, hash buffer in shared memory and in global scratch."""
+    k = 10
+    _, refs, _ = load_sequences([data_path("hpv_16_allFasta.fa.gz")])
+    _, reads, _ = load_sequences([data_path("minION25.fq.gz")])
+    reads = reads[:6] + [b"N" * 50, b"ACGT", refs[0][100:400]]
+    sets = []
+    for r in refs[:5]:
+        h = np.sort(oracle.calc_hashes(oracle.to_upper(r[:3000]), [k]))
+        sets.append(h)                                             # ascending, zeros and duplicates kept
+    lineage = [np.unique(s[s != 0])[::7] for s in sets[:3]]        # "specific hash" style subsets as the extra sets
+    allsets = sets + lineage
+    ntypes = len(sets)
+    hits, extra = emu.classify_sets(allsets, reads, k, ntypes, hbuf_global=hbuf_global)
+    oh, oe = oracle.classify_sets(reads, [k], allsets, ntypes)
+    for f in ("ref_id", "best"):                                   # (main_hpv16 keeps no runner-up: `prev` is not part of it)
+        assert np.array_equal(hits[f], oh[f]), f
+    assert np.array_equal(extra, oe)
+    c = np.zeros(10_007, np.int32)
+    oracle.count_batch(reads, [k], c)
+    hits, extra = emu.classify_sets(allsets, reads, k, ntypes, counts=c, min_occ=2, hbuf_global=hbuf_global)
+    oh, oe = oracle.classify_sets(reads, [k], allsets, ntypes, counts=c, min_occ=2)
+    for f in ("ref_id", "best"):
+        assert np.array_equal(hits[f], oh[f]), ("M", f)
+    assert np.array_equal(extra, oe)
+
+
 @pytest.mark.parametrize("k", [9, 16, 24])
 def test_call_depth_kernels(emu, oracle, k):
     """rk_call.cuh (`rkmh call`, src/rkmh.cpp:1570-1858): the exact k-mer depth table of the reads, the depth of every window
